@@ -1,0 +1,61 @@
+"""Build recipes (in-tree, so the .so files travel to the GPU box with the snapshot)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(HERE)
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build_gpu(force=False):
+    """libsybilgpu.so: hand-written sm_100a kernels + runtime, cudart linked statically."""
+    out = os.path.join(CSRC, "libsybilgpu.so")
+    srcs = [os.path.join(CSRC, f) for f in ("sg_kernels.cu", "sg_runtime.cu")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("sg_internal.h", "sg_hist.h")] + [
+        os.path.join(ROOT, "include", "sybilgpu.h")]
+    if not force and not _newer(out, deps):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    _run([nvcc] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress",
+                               "186", "-o", out] + srcs + ["-ldl"])
+    return out
+
+
+def build_blockgen(force=False):
+    out = os.path.join(CSRC, "libsybilblockgen.so")
+    src = os.path.join(CSRC, "blockgen.cpp")
+    if not force and not _newer(out, [src, os.path.join(ROOT, "include", "sybilgpu.h")]):
+        return out
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", out, src])
+    return out
+
+
+def build_oracle(force=False):
+    """oracle/liboracle.so — the CPU restatement (test infrastructure, never loaded by the product)."""
+    odir = os.path.join(ROOT, "oracle")
+    out = os.path.join(odir, "liboracle.so")
+    src = os.path.join(odir, "oracle.cpp")
+    if not force and not _newer(out, [src, os.path.join(ROOT, "include", "sybilgpu.h")]):
+        return out
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", out, src])
+    return out
+
+
+def build_all(force=False):
+    return [build_gpu(force), build_blockgen(force), build_oracle(force)]

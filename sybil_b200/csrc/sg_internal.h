@@ -1,0 +1,132 @@
+// sg_internal.h — structures shared by the host runtime (sg_runtime.cu) and the
+// scan kernels (sg_kernels.cu).  Not part of the C ABI.
+#pragma once
+#include <cstdint>
+
+#include "../../include/sybilgpu.h"
+
+namespace sg {
+
+// ---- device-resident block format ---------------------------------------------
+// One DevCol per (block, column slot).  The encoded arrays are the reference's
+// post-gob arrays copied verbatim into HBM (16-byte aligned); decode happens in
+// the scan kernel.
+enum : uint32_t {
+  COL_DELTA_IDS = 1u,     // SavedIntColumn.DeltaEncodedIDs
+  COL_DELTA_VALUES = 2u,  // SavedIntColumn.ValueEncoded
+  COL_IS_STR = 4u,
+  COL_BROKEN = 8u,        // "BLOCK SIZE CHANGED DURING QUERY" found at staging
+};
+
+struct DevCol {
+  uint32_t enc;     // sg_encoding
+  uint32_t flags;   // COL_*
+  uint32_t nbins;   // non-empty bins (BUCKET)
+  uint32_t nitems;  // record ids (BUCKET) or values (VALUES)
+  uint32_t nremap;  // str: dictionary size; int BUCKET: nbins
+  int32_t oob_gid;  // str: global id used for a local id outside the dictionary
+  const int64_t* bin_values;    // [nbins] int value, or local string id widened
+  const uint32_t* bin_offsets;  // [nbins+1]
+  const void* data;             // record ids u32[] | values i64[] | values i32[]
+  const int32_t* remap;         // str: local id -> global id; int BUCKET: bin -> value-dict code
+};
+static_assert(sizeof(DevCol) == 56, "DevCol layout");
+
+struct DevBlock {
+  int64_t block_index;
+  uint32_t num_records;
+  uint32_t _pad;
+};
+
+// ---- query plan (device copy read by the kernels) ---------------------------------
+constexpr int MAX_SUBHISTS = 64;
+
+struct KFilter {
+  int32_t col;
+  int32_t is_str;
+  int32_t op;       // sg_filter_op
+  int32_t str_gid;  // EQ/NEQ literal as a global id (-1: not in the dictionary)
+  int64_t ival;
+  const uint32_t* lut;  // RE/NRE: bitset over global ids
+  int64_t lut_bits;
+};
+
+struct KGroup {
+  int32_t col;
+  int32_t is_str;
+  uint32_t stride;  // slot += (code + 1) * stride ; code 0 is "missing"
+  uint32_t radix;
+};
+
+struct KSubHist {  // one BasicHist bucket layout (hist_basic.go:34-70)
+  int64_t lo, hi;  // Info.Min / Info.Max of this (sub)hist
+  int64_t reject_hi;  // Info.Max * 10, wrapping (hist_basic.go:104)
+  int64_t bsize;      // BucketSize
+  uint32_t nvals;     // len(Values)
+  uint32_t base;      // offset of its counters inside the agg's counter row
+};
+
+struct KAgg {
+  int32_t col;
+  int32_t nsub;  // 0: no buckets (avg mode); 1: BasicHist; >1: MultiHist subhists
+  int64_t info_min, info_max;
+  int64_t reject_hi;
+  uint32_t nvals_total;
+  uint32_t _pad;
+  uint64_t* buckets;  // [nslots][nvals_total]
+  uint64_t* hcount;   // [nslots]
+  uint64_t* sum;      // [nslots]
+  int64_t* vmax;      // [nslots] max accepted value above info_max (INT64_MIN if none)
+  int64_t* vmin;      // [nslots] (avg-mode min tracking; unused in v1)
+  KSubHist sub[MAX_SUBHISTS];
+};
+
+struct Plan {
+  int32_t nfilters, ngroups, naggs;
+  int32_t ncolslots;
+  int32_t time_col;  // -1 none
+  int32_t hist_mode; // op_mode == HIST
+  int64_t time_bucket;
+  int64_t time_first;  // trunc(time_min / bucket)
+  uint32_t time_radix;  // number of dense time buckets + 1 (0 = unused code)
+  uint32_t time_stride;
+  uint32_t gbits;       // low bits of a slot word holding the group slot
+  uint32_t pass_target; // value of (slot >> gbits) for a row that passed everything
+  uint32_t finc;        // 1 << gbits : added per passed filter
+  uint32_t time_ok;     // bit added when the time column is a populated int
+  uint32_t filt_target; // (slot >> gbits) & filt_mask == filt_target : passed all filters
+  uint32_t filt_mask;
+  uint32_t nslots;      // dense group slots
+  uint32_t acc_words;   // smem words per slot: 1 + 3*naggs
+  uint32_t acc_repl;    // replication (power of two, <= 32); 0 = accumulate in global memory
+  uint32_t _pad;
+  uint64_t* count;      // [nslots]
+  uint64_t* scalars;    // [0] matched rows, [1] broken blocks, [2] time overflow rows, [3] blocks done
+  uint32_t* block_status;  // per table block: 1 = broken in this query
+  KFilter filters[SG_MAX_FILTERS];
+  KGroup groups[SG_MAX_GROUPS];
+  KAgg aggs[SG_MAX_AGGS];
+};
+
+struct LaunchParams {
+  const Plan* plan;
+  const DevBlock* blocks;
+  const DevCol* cols;         // [nblocks_table][ncolslots]
+  const uint32_t* block_list; // blocks to scan
+  uint32_t nlist;
+  uint32_t slot_bytes;        // 1, 2 (shared memory) or 4 (global scratch)
+  uint32_t* work_counter;
+  uint32_t* gslots;           // slot_bytes == 4: [grid][SG_BLOCK_ROWS]
+  uint32_t* gbinpay;          // [grid][SG_BLOCK_ROWS] per-bin payload spill
+  uint32_t smem_bytes;
+  uint32_t acc_smem;          // accumulators replicated in shared memory (plan.acc_repl > 0)
+};
+
+// host-callable launcher (sg_kernels.cu)
+int launch_scan(const LaunchParams& lp, int grid, void* stream);
+int scan_threads();
+// shared memory the kernel needs besides slots and accumulators
+uint32_t scan_fixed_smem();
+constexpr uint32_t SMEM_BINS = 5120;  // per-bin payload entries kept in shared memory
+
+}  // namespace sg

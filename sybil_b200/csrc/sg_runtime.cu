@@ -1,0 +1,1499 @@
+// sg_runtime.cu — host runtime of libsybilgpu.so: context, HBM-resident tables,
+// query planning, kernel launches, NCCL merge, result finalisation, C ABI.
+//
+// Mirrors the host half of Table.LoadAndQueryRecords (src/lib/table_query.go:18-422):
+//   block enumeration + zone-map skip   table_query.go:96-131, table_block_io.go:110-182
+//   LoadBlockFromDir                    table_block_io.go:225-310   -> sg_table_add_block (staging)
+//   per-block FilterAndAggRecords       aggregate.go:56-282         -> scan kernel (sg_kernels.cu)
+//   CombineResults / SortResults        aggregate.go:414-467,497-525 -> device accumulators shared by
+//                                        all blocks (+ NCCL all-reduce across GPUs) and build_result()
+//   translate_group_by                  aggregate.go:284-324        -> render_key() over the global dictionary
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "sg_hist.h"
+#include "sg_internal.h"
+
+using namespace sg;
+
+// ---------------------------------------------------------------------------
+// NCCL, bound lazily so the library loads on machines without it
+// ---------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt64 = 4, ncclUint64 = 5 };  // nccl.h ncclDataType_t
+enum { ncclSum = 0, ncclMax = 2 };       // nccl.h ncclRedOp_t
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (auto n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+  }
+};
+NcclApi g_nccl;
+
+constexpr size_t ARENA_CHUNK = (size_t)512 << 20;
+constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+constexpr uint32_t MAX_DYN_SMEM = 227 * 1024;
+constexpr int64_t MAX_SLOTS = (int64_t)1 << 26;
+constexpr int64_t INT_DICT_CAP = (int64_t)1 << 22;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+}  // namespace
+
+struct sg_ctx {
+  int device = -1;
+  bool has_device = false;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::string err;
+  std::mutex mu;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  char devname[256] = {0};
+  void set_err(const std::string& s) { err = s; }
+};
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      (ctx)->set_err(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+      return SG_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+namespace {
+
+struct StrDict {
+  std::unordered_map<std::string, int32_t> map;
+  std::vector<std::string> strs;
+  int32_t intern(const char* p, size_t n) {
+    std::string s(p, n);
+    auto it = map.find(s);
+    if (it != map.end()) return it->second;
+    int32_t id = (int32_t)strs.size();
+    map.emplace(s, id);
+    strs.push_back(std::move(s));
+    return id;
+  }
+  int32_t find(const std::string& s) const {
+    auto it = map.find(s);
+    return it == map.end() ? -1 : it->second;
+  }
+};
+struct IntDict {
+  std::unordered_map<int64_t, int32_t> map;
+  std::vector<int64_t> vals;
+  bool overflow = false;
+  int32_t intern(int64_t v) {
+    auto it = map.find(v);
+    if (it != map.end()) return it->second;
+    if ((int64_t)vals.size() >= INT_DICT_CAP) {
+      overflow = true;
+      return 0;
+    }
+    int32_t id = (int32_t)vals.size();
+    map.emplace(v, id);
+    vals.push_back(v);
+    return id;
+  }
+};
+
+struct HostBlock {
+  int64_t block_index = 0;
+  uint32_t num_records = 0;
+  std::vector<sg_int_info> info;
+};
+
+struct Stage {
+  char* host = nullptr;
+  size_t used = 0;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+};
+
+}  // namespace
+
+struct sg_table {
+  sg_ctx* ctx = nullptr;
+  int ncols = 0;
+  std::vector<int32_t> types;
+  std::vector<HostBlock> blocks;
+  std::vector<DevCol> cols;  // [nblocks][ncols] host mirror (device pointers inside)
+  std::vector<StrDict> sdict;
+  std::vector<IntDict> idict;
+  std::vector<char> has_values_int;  // an int column that is value-array encoded somewhere
+  std::vector<char*> chunks;
+  size_t chunk_used = 0, chunk_cap = 0;
+  Stage stage[2];
+  int cur_stage = 0;
+  int64_t total_rows = 0;
+  int64_t device_bytes = 0;
+  int64_t encoded_bytes = 0;
+  int64_t h2d_bytes = 0;
+  // device mirrors of blocks / cols, refreshed when dirty
+  DevBlock* d_blocks = nullptr;
+  DevCol* d_cols = nullptr;
+  size_t d_blocks_cap = 0;
+  bool dirty = true;
+};
+
+namespace {
+
+int arena_alloc(sg_table* t, size_t bytes, char** out) {
+  bytes = align_up(bytes, 256);
+  if (t->chunks.empty() || t->chunk_used + bytes > t->chunk_cap) {
+    size_t cap = std::max(ARENA_CHUNK, bytes);
+    char* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {
+      t->ctx->set_err(std::string("cudaMalloc arena: ") + cudaGetErrorString(e));
+      return SG_ERR_NOMEM;
+    }
+    t->chunks.push_back(p);
+    t->chunk_used = 0;
+    t->chunk_cap = cap;
+    t->device_bytes += (int64_t)cap;
+  }
+  *out = t->chunks.back() + t->chunk_used;
+  t->chunk_used += bytes;
+  return SG_OK;
+}
+
+// One block's arrays are packed into a slab: host copy in pinned staging, same
+// layout in the device arena, one cudaMemcpyAsync per block.
+struct SlabWriter {
+  std::vector<std::pair<const void*, size_t>> parts;  // source, bytes
+  std::vector<size_t> offs;
+  size_t total = 0;
+  size_t add(const void* src, size_t bytes) {
+    size_t off = total;
+    parts.emplace_back(src, bytes);
+    offs.push_back(off);
+    total = align_up(total + bytes, 128);
+    return off;
+  }
+};
+
+}  // namespace
+
+// ===========================================================================
+// context
+// ===========================================================================
+extern "C" {
+
+int sg_abi_version(void) { return SG_ABI_VERSION; }
+
+sg_ctx* sg_create(int device, int* status_out) {
+  sg_ctx* c = new sg_ctx();
+  c->device = device;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    c->set_err(e != cudaSuccess ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)
+                                : std::string("no such CUDA device"));
+    if (status_out) *status_out = SG_ERR_CUDA;
+    // the context is still returned so the message can be read; every call that
+    // needs the GPU fails loudly (there is no CPU fallback)
+    return c;
+  }
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  c->sm_count = prop.multiProcessorCount;
+  snprintf(c->devname, sizeof(c->devname), "%s", prop.name);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    c->set_err("cudaStreamCreate failed");
+    if (status_out) *status_out = SG_ERR_CUDA;
+    return c;
+  }
+  c->has_device = true;
+  if (status_out) *status_out = SG_OK;
+  return c;
+}
+
+void sg_destroy(sg_ctx* c) {
+  if (!c) return;
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+const char* sg_last_error(sg_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int sg_device_sm_count(sg_ctx* c) { return c ? c->sm_count : 0; }
+
+void* sg_pinned_alloc(sg_ctx* c, size_t bytes) {
+  if (!c || !c->has_device) return nullptr;
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    c->set_err("cudaHostAlloc failed");
+    return nullptr;
+  }
+  return p;
+}
+void sg_pinned_free(sg_ctx* c, void* p) {
+  (void)c;
+  if (p) cudaFreeHost(p);
+}
+
+int sg_comm_unique_id(sg_ctx* c, char id_out[128]) {
+  if (!c) return SG_ERR_INVALID;
+  if (!g_nccl.load()) {
+    c->set_err("libnccl.so.2 not found");
+    return SG_ERR_NCCL;
+  }
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != 0) {
+    c->set_err("ncclGetUniqueId failed");
+    return SG_ERR_NCCL;
+  }
+  memcpy(id_out, id.internal, 128);
+  return SG_OK;
+}
+int sg_comm_init(sg_ctx* c, const char id[128], int rank, int nranks) {
+  if (!c || !c->has_device) return SG_ERR_CUDA;
+  if (!g_nccl.load()) {
+    c->set_err("libnccl.so.2 not found");
+    return SG_ERR_NCCL;
+  }
+  cudaSetDevice(c->device);
+  ncclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, uid, rank);
+  if (r != 0) {
+    c->set_err(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    c->comm = nullptr;
+    return SG_ERR_NCCL;
+  }
+  c->rank = rank;
+  c->nranks = nranks;
+  return SG_OK;
+}
+
+// ===========================================================================
+// table
+// ===========================================================================
+sg_table* sg_table_create(sg_ctx* c, int32_t num_col_slots, const int32_t* col_types) {
+  if (!c) return nullptr;
+  if (!c->has_device) {
+    c->set_err("sg_table_create: no CUDA device (libsybilgpu has no CPU path)");
+    return nullptr;
+  }
+  if (num_col_slots <= 0 || num_col_slots > SG_MAX_COLS) {
+    c->set_err("sg_table_create: num_col_slots out of range");
+    return nullptr;
+  }
+  sg_table* t = new sg_table();
+  t->ctx = c;
+  t->ncols = num_col_slots;
+  t->types.assign(col_types, col_types + num_col_slots);
+  t->sdict.resize((size_t)num_col_slots);
+  t->idict.resize((size_t)num_col_slots);
+  t->has_values_int.assign((size_t)num_col_slots, 0);
+  cudaSetDevice(c->device);
+  for (int i = 0; i < 2; i++) {
+    if (cudaHostAlloc((void**)&t->stage[i].host, STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->stage[i].done, cudaEventDisableTiming) != cudaSuccess) {
+      c->set_err("sg_table_create: staging allocation failed");
+      delete t;
+      return nullptr;
+    }
+  }
+  return t;
+}
+
+void sg_table_free(sg_table* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->copy_stream);
+  for (auto p : t->chunks) cudaFree(p);
+  for (int i = 0; i < 2; i++) {
+    if (t->stage[i].host) cudaFreeHost(t->stage[i].host);
+    if (t->stage[i].done) cudaEventDestroy(t->stage[i].done);
+  }
+  if (t->d_blocks) cudaFree(t->d_blocks);
+  if (t->d_cols) cudaFree(t->d_cols);
+  delete t;
+}
+
+int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
+  if (!t || !b) return SG_ERR_INVALID;
+  sg_ctx* c = t->ctx;
+  if (b->num_records <= 0 || b->num_records > SG_BLOCK_ROWS) {
+    c->set_err("add_block: num_records out of range");
+    return SG_ERR_INVALID;
+  }
+  if (b->ncols < 0 || (b->ncols > 0 && !b->cols)) {
+    c->set_err("add_block: bad column list");
+    return SG_ERR_INVALID;
+  }
+  cudaSetDevice(c->device);
+  const uint32_t nrec = (uint32_t)b->num_records;
+  std::vector<DevCol> dcs((size_t)t->ncols);
+  memset(dcs.data(), 0, sizeof(DevCol) * dcs.size());
+  // host-side temporaries that must live until the slab is packed
+  struct Tmp {
+    std::vector<int64_t> bin_values;
+    std::vector<uint32_t> bin_offsets;
+    std::vector<int32_t> remap;
+    size_t off_bv = 0, off_bo = 0, off_data = 0, off_remap = 0;
+    bool has_bv = false, has_bo = false, has_data = false, has_remap = false;
+  };
+  std::vector<Tmp> tmp((size_t)b->ncols);
+  SlabWriter sw;
+  int64_t enc_bytes = 0;
+
+  for (int ci = 0; ci < b->ncols; ci++) {
+    const sg_column_desc& cd = b->cols[ci];
+    if (cd.col_slot < 0 || cd.col_slot >= t->ncols) {
+      c->set_err("add_block: col_slot out of range");
+      return SG_ERR_INVALID;
+    }
+    if (cd.col_type != t->types[(size_t)cd.col_slot]) {
+      c->set_err("add_block: column type differs from the table's KeyTypes");
+      return SG_ERR_INVALID;
+    }
+    if (cd.col_type != SG_COL_INT && cd.col_type != SG_COL_STR) {
+      c->set_err("add_block: unsupported column type (set columns are out of scope)");
+      return SG_ERR_UNSUPPORTED;
+    }
+    DevCol& dc = dcs[(size_t)cd.col_slot];
+    Tmp& tm = tmp[(size_t)ci];
+    const bool is_str = cd.col_type == SG_COL_STR;
+    dc.enc = (uint32_t)cd.encoding;
+    dc.flags = (cd.delta_ids ? COL_DELTA_IDS : 0u) | (cd.delta_values ? COL_DELTA_VALUES : 0u) |
+               (is_str ? COL_IS_STR : 0u);
+    dc.oob_gid = -1;
+    if (cd.encoding == SG_ENC_ABSENT) continue;
+    if (is_str) {
+      // unpackStrCol: a string table longer than the block is "BLOCK SIZE CHANGED" (:524)
+      if (cd.ndict > nrec) dc.flags |= COL_BROKEN;
+      if (cd.ndict > 0 && (!cd.dict_bytes || !cd.dict_offsets)) {
+        c->set_err("add_block: string table missing");
+        return SG_ERR_INVALID;
+      }
+      StrDict& sd = t->sdict[(size_t)cd.col_slot];
+      tm.remap.resize(cd.ndict);
+      // duplicate strings inside one table keep the first id (bucket_replace, :536-545)
+      for (uint32_t k = 0; k < cd.ndict; k++) {
+        uint32_t o0 = cd.dict_offsets[k], o1 = cd.dict_offsets[k + 1];
+        if (o1 < o0) {
+          c->set_err("add_block: string offsets not monotone");
+          return SG_ERR_INVALID;
+        }
+        tm.remap[k] = sd.intern(cd.dict_bytes + o0, o1 - o0);
+      }
+      dc.oob_gid = sd.intern("", 0);
+      dc.nremap = cd.ndict;
+    }
+    if (cd.encoding == SG_ENC_BUCKET) {
+      if (cd.nbins > 0 && (!cd.bin_values || !cd.bin_offsets)) {
+        c->set_err("add_block: bucket arrays missing");
+        return SG_ERR_INVALID;
+      }
+      if (cd.nrecord_ids > 0 && !cd.record_ids) {
+        c->set_err("add_block: record ids missing");
+        return SG_ERR_INVALID;
+      }
+      if (cd.nbins > 0 && (cd.bin_offsets[0] != 0 || cd.bin_offsets[cd.nbins] != cd.nrecord_ids)) {
+        c->set_err("add_block: bin_offsets do not span record_ids");
+        return SG_ERR_INVALID;
+      }
+      if (cd.nrecord_ids > SG_BLOCK_ROWS) {
+        // more (bin,row) pairs than a block has rows: some row would be listed twice
+        c->set_err("add_block: more record ids than rows in a block");
+        return SG_ERR_INVALID;
+      }
+      // drop empty bins (the kernel's head-bit scheme needs non-empty bins)
+      tm.bin_values.reserve(cd.nbins);
+      tm.bin_offsets.reserve(cd.nbins + 1);
+      for (uint32_t k = 0; k < cd.nbins; k++) {
+        uint32_t o0 = cd.bin_offsets[k], o1 = cd.bin_offsets[k + 1];
+        if (o1 < o0) {
+          c->set_err("add_block: bin_offsets not monotone");
+          return SG_ERR_INVALID;
+        }
+        if (o1 == o0) continue;
+        int64_t v = cd.bin_values[k];
+        // a string bin whose id is outside the table decodes to id 0 in the
+        // reference (Go map zero value, column_store_io.go:557-562)
+        if (is_str && (v < 0 || v >= (int64_t)cd.ndict)) v = 0;
+        tm.bin_values.push_back(v);
+        tm.bin_offsets.push_back(o0);
+      }
+      tm.bin_offsets.push_back(cd.nrecord_ids);
+      dc.nbins = (uint32_t)tm.bin_values.size();
+      dc.nitems = cd.nrecord_ids;
+      if (dc.nbins == 0) {
+        dc.enc = SG_ENC_ABSENT;
+        continue;
+      }
+      if (!is_str) {
+        IntDict& id = t->idict[(size_t)cd.col_slot];
+        tm.remap.resize(dc.nbins);
+        for (uint32_t k = 0; k < dc.nbins; k++) tm.remap[k] = id.intern(tm.bin_values[k]);
+        dc.nremap = dc.nbins;
+      }
+      tm.off_bv = sw.add(tm.bin_values.data(), tm.bin_values.size() * 8);
+      tm.off_bo = sw.add(tm.bin_offsets.data(), tm.bin_offsets.size() * 4);
+      tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * 4);
+      tm.has_bv = tm.has_bo = tm.has_data = true;
+      enc_bytes += (int64_t)(tm.bin_values.size() * 8 + tm.bin_offsets.size() * 4 + (size_t)cd.nrecord_ids * 4);
+    } else if (cd.encoding == SG_ENC_VALUES) {
+      dc.nitems = cd.nvalues;
+      if (cd.nvalues > nrec) {
+        dc.flags |= COL_BROKEN;  // unpackIntCol :752 / unpackStrCol :592
+        dc.nitems = 0;
+      } else if (cd.nvalues > 0) {
+        if (is_str) {
+          if (!cd.values_i32) {
+            c->set_err("add_block: values_i32 missing");
+            return SG_ERR_INVALID;
+          }
+          tm.off_data = sw.add(cd.values_i32, (size_t)cd.nvalues * 4);
+          enc_bytes += (int64_t)cd.nvalues * 4;
+        } else {
+          if (!cd.values_i64) {
+            c->set_err("add_block: values_i64 missing");
+            return SG_ERR_INVALID;
+          }
+          tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * 8);
+          enc_bytes += (int64_t)cd.nvalues * 8;
+          t->has_values_int[(size_t)cd.col_slot] = 1;
+        }
+        tm.has_data = true;
+      }
+    } else {
+      c->set_err("add_block: unknown encoding");
+      return SG_ERR_INVALID;
+    }
+    if (!tm.remap.empty()) {
+      tm.off_remap = sw.add(tm.remap.data(), tm.remap.size() * 4);
+      tm.has_remap = true;
+    }
+  }
+
+  // ---- stage + copy ------------------------------------------------------------
+  char* dev = nullptr;
+  if (sw.total > 0) {
+    if (sw.total > STAGE_BYTES) {
+      c->set_err("add_block: block larger than the staging buffer");
+      return SG_ERR_INVALID;
+    }
+    int rc = arena_alloc(t, sw.total, &dev);
+    if (rc != SG_OK) return rc;
+    Stage* st = &t->stage[t->cur_stage];
+    if (st->used + sw.total > STAGE_BYTES) {
+      CUDA_TRY(c, cudaEventRecord(st->done, c->copy_stream));
+      st->pending = true;
+      t->cur_stage ^= 1;
+      st = &t->stage[t->cur_stage];
+      if (st->pending) {
+        CUDA_TRY(c, cudaEventSynchronize(st->done));
+        st->pending = false;
+      }
+      st->used = 0;
+    }
+    char* hostp = st->host + st->used;
+    for (size_t i = 0; i < sw.parts.size(); i++) memcpy(hostp + sw.offs[i], sw.parts[i].first, sw.parts[i].second);
+    CUDA_TRY(c, cudaMemcpyAsync(dev, hostp, sw.total, cudaMemcpyHostToDevice, c->copy_stream));
+    st->used += align_up(sw.total, 256);
+    t->h2d_bytes += (int64_t)sw.total;
+  }
+  for (int ci = 0; ci < b->ncols; ci++) {
+    const sg_column_desc& cd = b->cols[ci];
+    DevCol& dc = dcs[(size_t)cd.col_slot];
+    Tmp& tm = tmp[(size_t)ci];
+    if (tm.has_bv) dc.bin_values = (const int64_t*)(dev + tm.off_bv);
+    if (tm.has_bo) dc.bin_offsets = (const uint32_t*)(dev + tm.off_bo);
+    if (tm.has_data) dc.data = dev + tm.off_data;
+    if (tm.has_remap) dc.remap = (const int32_t*)(dev + tm.off_remap);
+  }
+  HostBlock hb;
+  hb.block_index = b->block_index;
+  hb.num_records = nrec;
+  for (int i = 0; i < b->ninfo; i++) hb.info.push_back(b->info[i]);
+  t->blocks.push_back(std::move(hb));
+  t->cols.insert(t->cols.end(), dcs.begin(), dcs.end());
+  t->total_rows += nrec;
+  t->encoded_bytes += enc_bytes;
+  t->dirty = true;
+  return SG_OK;
+}
+
+int sg_table_sync(sg_table* t) {
+  if (!t) return SG_ERR_INVALID;
+  cudaSetDevice(t->ctx->device);
+  CUDA_TRY(t->ctx, cudaStreamSynchronize(t->ctx->copy_stream));
+  t->stage[0].pending = t->stage[1].pending = false;
+  t->stage[0].used = t->stage[1].used = 0;
+  return SG_OK;
+}
+int64_t sg_table_num_blocks(sg_table* t) { return t ? (int64_t)t->blocks.size() : 0; }
+int64_t sg_table_num_rows(sg_table* t) { return t ? t->total_rows : 0; }
+int64_t sg_table_device_bytes(sg_table* t) { return t ? t->device_bytes : 0; }
+int64_t sg_table_dict_size(sg_table* t, int32_t col) {
+  if (!t || col < 0 || col >= t->ncols) return -1;
+  return (int64_t)t->sdict[(size_t)col].strs.size();
+}
+int sg_table_dict_get(sg_table* t, int32_t col, int64_t id, const char** bytes, int64_t* len) {
+  if (!t || col < 0 || col >= t->ncols) return SG_ERR_INVALID;
+  auto& sd = t->sdict[(size_t)col];
+  if (id < 0 || id >= (int64_t)sd.strs.size()) return SG_ERR_INVALID;
+  *bytes = sd.strs[(size_t)id].data();
+  *len = (int64_t)sd.strs[(size_t)id].size();
+  return SG_OK;
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// query
+// ===========================================================================
+namespace {
+
+struct GroupDim {  // one axis of the dense slot space
+  int col = -1;
+  bool is_str = false;
+  bool is_time = false;
+  uint32_t radix = 1, stride = 1;
+};
+
+struct ResultGroup {
+  std::vector<uint64_t> key;
+  std::string skey;
+  int64_t count = 0;
+  // per agg
+  std::vector<int64_t> hcount, sum, vmin, vmax;
+  std::vector<std::vector<int64_t>> values;  // bucket counters per agg
+};
+
+}  // namespace
+
+struct sg_result {
+  sg_query* q = nullptr;  // not owned
+  std::vector<HistLayout> layouts;
+  bool hist_mode = false;
+  int ngroups_cols = 0;
+  int naggs = 0;
+  std::vector<ResultGroup> groups;  // sorted
+  ResultGroup total;                // Cumulative
+  int64_t matched = 0, broken = 0, skipped = 0;
+  std::vector<int64_t> time_keys;
+  std::vector<std::unique_ptr<sg_result>> time_slices;
+  bool has_total_hists = true;
+};
+
+struct sg_query {
+  sg_ctx* ctx = nullptr;
+  sg_table* table = nullptr;
+  bool own_table = false;
+  // copied descriptor
+  sg_query_desc d;
+  std::vector<sg_filter_desc> filters;
+  std::vector<std::string> filter_strs;
+  std::vector<sg_group_desc> groups;
+  std::vector<sg_agg_desc> aggs;
+  std::vector<std::vector<uint32_t>> luts;  // per filter (host copy)
+  std::vector<int64_t> lut_bits;
+  // plan
+  bool planned = false;
+  Plan plan;
+  std::vector<GroupDim> dims;
+  std::vector<HistLayout> layouts;
+  uint32_t slot_bytes = 2;
+  uint32_t smem_bytes = 0;
+  // device state
+  Plan* d_plan = nullptr;
+  uint64_t* d_acc = nullptr;  // one allocation: scalars | count | per agg hcount,sum,vmax | buckets
+  size_t acc_words = 0;
+  size_t off_count = 0;
+  std::vector<size_t> off_hcount, off_sum, off_vmax, off_buckets;
+  uint32_t* d_block_status = nullptr;
+  uint32_t* d_block_list = nullptr;
+  uint32_t* d_work = nullptr;
+  uint32_t* d_gslots = nullptr;
+  uint32_t* d_gbinpay = nullptr;
+  std::vector<uint32_t*> d_luts;
+  size_t block_cap = 0;
+  int grid = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // stats
+  double kernel_ms = 0;
+  int64_t launches = 0;
+  int64_t skipped = 0, broken_staged = 0;
+  int64_t rows_scanned = 0, blocks_scanned = 0;
+  int64_t d2h_bytes = 0;
+  bool ran = false;
+  std::vector<uint32_t> last_list;
+};
+
+namespace {
+
+void free_device(sg_query* q) {
+  if (q->d_plan) cudaFree(q->d_plan);
+  if (q->d_acc) cudaFree(q->d_acc);
+  if (q->d_block_status) cudaFree(q->d_block_status);
+  if (q->d_block_list) cudaFree(q->d_block_list);
+  if (q->d_work) cudaFree(q->d_work);
+  if (q->d_gslots) cudaFree(q->d_gslots);
+  if (q->d_gbinpay) cudaFree(q->d_gbinpay);
+  for (auto p : q->d_luts)
+    if (p) cudaFree(p);
+  q->d_luts.clear();
+  q->d_plan = nullptr;
+  q->d_acc = nullptr;
+  q->d_block_status = q->d_block_list = q->d_work = q->d_gslots = q->d_gbinpay = nullptr;
+}
+
+uint32_t bits_for(uint64_t n) {  // bits to hold values 0..n-1
+  uint32_t b = 0;
+  while (((uint64_t)1 << b) < n) b++;
+  return b;
+}
+
+// ShouldLoadBlockFromDir (table_block_io.go:110-182) over the staged block info
+bool should_load(const sg_query* q, const std::vector<sg_int_info>& info) {
+  if (info.empty()) return true;
+  bool add = true;
+  for (auto& f : q->filters) {
+    if (f.col_type != SG_COL_INT) continue;
+    const sg_int_info* fi = nullptr;
+    for (auto& i : info)
+      if (i.col_slot == f.col_slot) fi = &i;
+    if (f.op == SG_OP_GT || f.op == SG_OP_LT) {
+      bool pmin = false, pmax = false;
+      if (fi) {
+        pmin = f.op == SG_OP_GT ? fi->min > f.int_value : fi->min < f.int_value;
+        pmax = f.op == SG_OP_GT ? fi->max > f.int_value : fi->max < f.int_value;
+      }
+      if (!pmin && !pmax) add = false;
+    } else if (f.op == SG_OP_EQ) {
+      if (!fi || fi->min > f.int_value || fi->max < f.int_value) add = false;
+    }
+  }
+  return add;
+}
+
+int upload_table(sg_table* t) {
+  sg_ctx* c = t->ctx;
+  if (!t->dirty && t->d_blocks) return SG_OK;
+  size_t nb = t->blocks.size();
+  if (nb > t->d_blocks_cap) {
+    if (t->d_blocks) cudaFree(t->d_blocks);
+    if (t->d_cols) cudaFree(t->d_cols);
+    t->d_blocks = nullptr;
+    t->d_cols = nullptr;
+    size_t cap = std::max<size_t>(nb * 2, 1024);
+    CUDA_TRY(c, cudaMalloc(&t->d_blocks, cap * sizeof(DevBlock)));
+    CUDA_TRY(c, cudaMalloc(&t->d_cols, cap * (size_t)t->ncols * sizeof(DevCol)));
+    t->d_blocks_cap = cap;
+  }
+  std::vector<DevBlock> hb(nb);
+  for (size_t i = 0; i < nb; i++) {
+    hb[i].block_index = t->blocks[i].block_index;
+    hb[i].num_records = t->blocks[i].num_records;
+    hb[i]._pad = 0;
+  }
+  if (nb) {
+    CUDA_TRY(c, cudaMemcpy(t->d_blocks, hb.data(), nb * sizeof(DevBlock), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(t->d_cols, t->cols.data(), nb * (size_t)t->ncols * sizeof(DevCol), cudaMemcpyHostToDevice));
+  }
+  t->dirty = false;
+  return SG_OK;
+}
+
+// Build the dense slot space and the device plan from the table's dictionaries.
+int make_plan(sg_query* q) {
+  sg_ctx* c = q->ctx;
+  sg_table* t = q->table;
+  Plan& P = q->plan;
+  memset(&P, 0, sizeof(P));
+  P.nfilters = (int32_t)q->filters.size();
+  P.ngroups = (int32_t)q->groups.size();
+  P.naggs = (int32_t)q->aggs.size();
+  P.ncolslots = t->ncols;
+  P.hist_mode = q->d.op_mode == SG_MODE_HIST;
+  const bool time_mode = q->d.time_col_slot >= 0 && q->d.time_bucket > 0;
+  P.time_col = time_mode ? q->d.time_col_slot : -1;
+
+  auto col_ok = [&](int col) { return col >= 0 && col < t->ncols; };
+  // ---- slot space ------------------------------------------------------------
+  q->dims.clear();
+  uint64_t stride = 1;
+  for (size_t i = 0; i < q->groups.size(); i++) {
+    GroupDim gd;
+    gd.col = q->groups[i].col_slot;
+    if (!col_ok(gd.col)) {
+      c->set_err("query: group column out of range");
+      return SG_ERR_INVALID;
+    }
+    gd.is_str = t->types[(size_t)gd.col] == SG_COL_STR;
+    if (!gd.is_str && (t->has_values_int[(size_t)gd.col] || t->idict[(size_t)gd.col].overflow)) {
+      c->set_err("query: group-by on a value-array encoded int column needs the hash path (not in this build)");
+      return SG_ERR_UNSUPPORTED;
+    }
+    uint64_t card = gd.is_str ? t->sdict[(size_t)gd.col].strs.size() : t->idict[(size_t)gd.col].vals.size();
+    gd.radix = (uint32_t)(card + 1);
+    gd.stride = (uint32_t)stride;
+    stride *= gd.radix;
+    if (stride > (uint64_t)MAX_SLOTS) {
+      c->set_err("query: group-by cardinality product exceeds the dense slot space");
+      return SG_ERR_UNSUPPORTED;
+    }
+    q->dims.push_back(gd);
+    P.groups[i].col = gd.col;
+    P.groups[i].is_str = gd.is_str;
+    P.groups[i].stride = gd.stride;
+    P.groups[i].radix = gd.radix;
+  }
+  if (time_mode) {
+    if (!col_ok(P.time_col) || t->types[(size_t)P.time_col] != SG_COL_INT) {
+      c->set_err("query: time column must be an int column");
+      return SG_ERR_INVALID;
+    }
+    // extents: the query's table IntInfo widened by the staged block infos
+    int64_t tmin = q->d.time_min, tmax = q->d.time_max;
+    for (auto& hb : t->blocks)
+      for (auto& ii : hb.info)
+        if (ii.col_slot == P.time_col) {
+          tmin = std::min(tmin, ii.min);
+          tmax = std::max(tmax, ii.max);
+        }
+    if (tmax < tmin) {
+      c->set_err("query: time_max < time_min");
+      return SG_ERR_INVALID;
+    }
+    P.time_bucket = q->d.time_bucket;
+    P.time_first = tmin / P.time_bucket;
+    int64_t nb = tmax / P.time_bucket - P.time_first + 1;
+    if (nb <= 0 || (uint64_t)nb * stride > (uint64_t)MAX_SLOTS) {
+      c->set_err("query: time axis too large for the dense slot space");
+      return SG_ERR_UNSUPPORTED;
+    }
+    P.time_radix = (uint32_t)nb + 1;
+    P.time_stride = (uint32_t)stride;
+    GroupDim gd;
+    gd.col = P.time_col;
+    gd.is_time = true;
+    gd.radix = P.time_radix;
+    gd.stride = P.time_stride;
+    q->dims.push_back(gd);
+    stride *= P.time_radix;
+  }
+  P.nslots = (uint32_t)stride;
+  P.gbits = bits_for(stride);
+  const uint32_t fbits = bits_for((uint64_t)P.nfilters + 1);
+  const uint32_t tbit = time_mode ? 1u : 0u;
+  const uint32_t total_bits = P.gbits + fbits + tbit;
+  if (total_bits > 32) {
+    c->set_err("query: slot word wider than 32 bits");
+    return SG_ERR_UNSUPPORTED;
+  }
+  q->slot_bytes = total_bits <= 8 ? 1u : (total_bits <= 16 ? 2u : 4u);
+  P.finc = 1u << P.gbits;
+  P.filt_mask = (1u << fbits) - 1u;
+  P.filt_target = (uint32_t)P.nfilters;
+  P.time_ok = time_mode ? (1u << (P.gbits + fbits)) : 0u;
+  P.pass_target = (uint32_t)P.nfilters | (time_mode ? (1u << fbits) : 0u);
+
+  // ---- filters -----------------------------------------------------------------
+  for (int i = 0; i < P.nfilters; i++) {
+    const sg_filter_desc& f = q->filters[(size_t)i];
+    if (!col_ok(f.col_slot)) {
+      c->set_err("query: filter column out of range");
+      return SG_ERR_INVALID;
+    }
+    KFilter& kf = P.filters[i];
+    kf.col = f.col_slot;
+    kf.is_str = t->types[(size_t)f.col_slot] == SG_COL_STR;
+    if ((f.col_type == SG_COL_STR) != (kf.is_str != 0)) {
+      c->set_err("query: filter type does not match the column's KeyTypes");
+      return SG_ERR_INVALID;
+    }
+    kf.op = f.op;
+    kf.ival = f.int_value;
+    kf.str_gid = -1;
+    kf.lut = nullptr;
+    kf.lut_bits = 0;
+    if (kf.is_str) {
+      if (f.op == SG_OP_EQ || f.op == SG_OP_NEQ) {
+        kf.str_gid = t->sdict[(size_t)f.col_slot].find(q->filter_strs[(size_t)i]);
+      } else if (f.op == SG_OP_RE || f.op == SG_OP_NRE) {
+        if (q->lut_bits[(size_t)i] < 0) {
+          c->set_err("query: regex filter without sg_query_set_str_lut");
+          return SG_ERR_STATE;
+        }
+        kf.lut = q->d_luts[(size_t)i];
+        kf.lut_bits = q->lut_bits[(size_t)i];
+      } else {
+        c->set_err("query: op not valid for a str filter");
+        return SG_ERR_INVALID;
+      }
+    } else if (f.op > SG_OP_NEQ) {
+      c->set_err("query: op not valid for an int filter");
+      return SG_ERR_INVALID;
+    }
+  }
+
+  // ---- aggregations ----------------------------------------------------------------
+  q->layouts.clear();
+  size_t words = 8;  // scalars
+  q->off_count = words;
+  words += P.nslots;
+  q->off_hcount.clear();
+  q->off_sum.clear();
+  q->off_vmax.clear();
+  q->off_buckets.clear();
+  for (int i = 0; i < P.naggs; i++) {
+    const sg_agg_desc& a = q->aggs[(size_t)i];
+    if (!col_ok(a.col_slot)) {
+      c->set_err("query: aggregation column out of range");
+      return SG_ERR_INVALID;
+    }
+    HistLayout L;
+    if (!make_layout(a.info_min, a.info_max, P.hist_mode != 0, q->d.hist_kind == SG_HIST_MULTI, q->d.hist_bucket, L)) {
+      c->set_err("query: IntInfo extents give no usable histogram layout");
+      return SG_ERR_INVALID;
+    }
+    q->layouts.push_back(L);
+    KAgg& ka = P.aggs[i];
+    ka.col = a.col_slot;
+    ka.info_min = a.info_min;
+    ka.info_max = a.info_max;
+    ka.reject_hi = wmul10(a.info_max);
+    ka.nsub = (int32_t)L.subs.size();
+    ka.nvals_total = L.nvals_total;
+    for (size_t s = 0; s < L.subs.size(); s++) ka.sub[s] = L.subs[s];
+    q->off_hcount.push_back(words);
+    words += P.nslots;
+    q->off_sum.push_back(words);
+    words += P.nslots;
+    q->off_vmax.push_back(words);
+    words += P.nslots;
+    q->off_buckets.push_back(words);
+    words += (size_t)P.nslots * L.nvals_total;
+    if (words * 8 > ((size_t)24 << 30)) {
+      c->set_err("query: accumulators exceed 24 GiB (groups x histogram buckets); needs the sparse path");
+      return SG_ERR_UNSUPPORTED;
+    }
+  }
+  q->acc_words = words;
+
+  // ---- shared memory budget ----------------------------------------------------------
+  P.acc_words = 1 + 3 * (uint32_t)P.naggs;
+  const uint32_t fixed = scan_fixed_smem() + (q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u);
+  const uint32_t avail = MAX_DYN_SMEM > fixed ? MAX_DYN_SMEM - fixed : 0u;
+  uint32_t repl = 32;
+  while (repl >= 1 && (uint64_t)P.nslots * P.acc_words * repl * 4 > avail) repl >>= 1;
+  P.acc_repl = repl;  // 0: accumulate straight into global memory
+  q->smem_bytes = fixed + P.nslots * P.acc_words * repl * 4;
+  if (repl == 0) q->smem_bytes = fixed;
+  return SG_OK;
+}
+
+int alloc_device(sg_query* q) {
+  sg_ctx* c = q->ctx;
+  sg_table* t = q->table;
+  cudaSetDevice(c->device);
+  if (q->d_acc) cudaFree(q->d_acc);
+  q->d_acc = nullptr;
+  CUDA_TRY(c, cudaMalloc(&q->d_acc, q->acc_words * 8));
+  if (!q->d_plan) CUDA_TRY(c, cudaMalloc(&q->d_plan, sizeof(Plan)));
+  if (!q->d_work) CUDA_TRY(c, cudaMalloc(&q->d_work, 64));
+  size_t nb = std::max<size_t>(t->blocks.size(), 1);
+  if (nb > q->block_cap) {
+    if (q->d_block_status) cudaFree(q->d_block_status);
+    if (q->d_block_list) cudaFree(q->d_block_list);
+    q->d_block_status = q->d_block_list = nullptr;
+    CUDA_TRY(c, cudaMalloc(&q->d_block_status, nb * 4));
+    CUDA_TRY(c, cudaMalloc(&q->d_block_list, nb * 4));
+    q->block_cap = nb;
+  }
+  q->grid = c->sm_count > 0 ? c->sm_count : 1;
+  if (!q->d_gbinpay) CUDA_TRY(c, cudaMalloc(&q->d_gbinpay, (size_t)q->grid * SG_BLOCK_ROWS * 4));
+  if (q->slot_bytes == 4 && !q->d_gslots) CUDA_TRY(c, cudaMalloc(&q->d_gslots, (size_t)q->grid * SG_BLOCK_ROWS * 4));
+  if (!q->ev0) {
+    CUDA_TRY(c, cudaEventCreate(&q->ev0));
+    CUDA_TRY(c, cudaEventCreate(&q->ev1));
+  }
+  // point the plan at the accumulators
+  Plan& P = q->plan;
+  P.scalars = q->d_acc;
+  P.count = q->d_acc + q->off_count;
+  P.block_status = q->d_block_status;
+  for (int i = 0; i < P.naggs; i++) {
+    P.aggs[i].hcount = q->d_acc + q->off_hcount[(size_t)i];
+    P.aggs[i].sum = q->d_acc + q->off_sum[(size_t)i];
+    P.aggs[i].vmax = (int64_t*)(q->d_acc + q->off_vmax[(size_t)i]);
+    P.aggs[i].vmin = nullptr;
+    P.aggs[i].buckets = q->d_acc + q->off_buckets[(size_t)i];
+  }
+  return SG_OK;
+}
+
+__global__ void fill_i64(int64_t* p, size_t n, int64_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int reset_accumulators(sg_query* q) {
+  sg_ctx* c = q->ctx;
+  CUDA_TRY(c, cudaMemsetAsync(q->d_acc, 0, q->acc_words * 8, c->stream));
+  for (int i = 0; i < q->plan.naggs; i++) {
+    size_t n = q->plan.nslots;
+    fill_i64<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int64_t*)(q->d_acc + q->off_vmax[(size_t)i]), n,
+                                                                  INT64_MIN);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return SG_OK;
+}
+
+// one launch of the scan kernel over `list`
+int run_list(sg_query* q, const std::vector<uint32_t>& list) {
+  sg_ctx* c = q->ctx;
+  sg_table* t = q->table;
+  if (!list.empty())
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(q->d_work, 0, 64, c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(q->d_block_status, 0, std::max<size_t>(t->blocks.size(), 1) * 4, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(q->d_plan, &q->plan, sizeof(Plan), cudaMemcpyHostToDevice, c->stream));
+  LaunchParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.plan = q->d_plan;
+  lp.blocks = t->d_blocks;
+  lp.cols = t->d_cols;
+  lp.block_list = q->d_block_list;
+  lp.nlist = (uint32_t)list.size();
+  lp.slot_bytes = q->slot_bytes;
+  lp.work_counter = q->d_work;
+  lp.gslots = q->d_gslots;
+  lp.gbinpay = q->d_gbinpay;
+  lp.smem_bytes = q->smem_bytes;
+  lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
+  int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(list.size(), 1));
+  CUDA_TRY(c, cudaEventRecord(q->ev0, c->stream));
+  int rc = launch_scan(lp, grid, c->stream);
+  if (rc != 0) {
+    c->set_err(std::string("scan kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return SG_ERR_CUDA;
+  }
+  CUDA_TRY(c, cudaEventRecord(q->ev1, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CUDA_TRY(c, cudaEventElapsedTime(&ms, q->ev0, q->ev1));
+  q->kernel_ms += ms;
+  q->launches += 1;
+  return SG_OK;
+}
+
+std::string render_key(const sg_query* q, const std::vector<uint64_t>& key) {
+  // translate_group_by (aggregate.go:284-324)
+  std::string s;
+  const sg_table* t = q->table;
+  if (q->groups.empty()) return "total";
+  for (size_t i = 0; i < q->groups.size(); i++) {
+    uint64_t v = key[i];
+    if (v != SG_MISSING_KEY) {
+      int col = q->groups[i].col_slot;
+      if (t->types[(size_t)col] == SG_COL_INT)
+        s += std::to_string((int64_t)v);
+      else if (v < t->sdict[(size_t)col].strs.size())
+        s += t->sdict[(size_t)col].strs[(size_t)v];
+    }
+    s += "\t";
+  }
+  return s;
+}
+
+void merge_group(ResultGroup& into, const ResultGroup& g, int naggs, const std::vector<HistLayout>& L, bool with_hists) {
+  into.count += g.count;
+  if (!with_hists) return;
+  for (int a = 0; a < naggs; a++) {
+    if (g.hcount[(size_t)a] == 0) continue;
+    into.hcount[(size_t)a] += g.hcount[(size_t)a];
+    into.sum[(size_t)a] = (int64_t)((uint64_t)into.sum[(size_t)a] + (uint64_t)g.sum[(size_t)a]);
+    into.vmax[(size_t)a] = std::max(into.vmax[(size_t)a], g.vmax[(size_t)a]);
+    if (L[(size_t)a].nvals_total) {
+      if (into.values[(size_t)a].empty()) into.values[(size_t)a].assign(L[(size_t)a].nvals_total, 0);
+      for (uint32_t k = 0; k < L[(size_t)a].nvals_total; k++) into.values[(size_t)a][k] += g.values[(size_t)a][k];
+    }
+  }
+}
+
+void init_group(ResultGroup& g, int naggs) {
+  g.hcount.assign((size_t)naggs, 0);
+  g.sum.assign((size_t)naggs, 0);
+  g.vmin.assign((size_t)naggs, 0);
+  g.vmax.assign((size_t)naggs, INT64_MIN);
+  g.values.assign((size_t)naggs, {});
+}
+
+void sort_groups(std::vector<ResultGroup>& v) {
+  // SortResults with OrderBy = $COUNT (aggregate.go:43-54,497-525); Go's sort is
+  // unstable, ties are broken by the rendered key ascending
+  std::sort(v.begin(), v.end(), [](const ResultGroup& a, const ResultGroup& b) {
+    if (a.count != b.count) return a.count > b.count;
+    return a.skey < b.skey;
+  });
+}
+
+int build_result(sg_query* q, sg_result** out) {
+  sg_ctx* c = q->ctx;
+  const Plan& P = q->plan;
+  std::vector<uint64_t> h(q->acc_words);
+  CUDA_TRY(c, cudaMemcpy(h.data(), q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost));
+  q->d2h_bytes += (int64_t)q->acc_words * 8;
+  std::unique_ptr<sg_result> r(new sg_result());
+  r->q = q;
+  r->layouts = q->layouts;
+  r->hist_mode = P.hist_mode != 0;
+  r->ngroups_cols = P.ngroups;
+  r->naggs = P.naggs;
+  r->matched = (int64_t)h[0];
+  r->broken = q->broken_staged + (int64_t)h[1];
+  r->skipped = q->skipped;
+  const bool time_mode = P.time_col >= 0;
+  const int naggs = P.naggs;
+  init_group(r->total, naggs);
+  r->total.skey = "TOTAL";
+  for (int i = 1; i < P.ngroups; i++) r->total.skey += "\t";
+  r->has_total_hists = !time_mode;
+
+  std::map<std::vector<uint64_t>, size_t> by_key;                    // Results in time mode
+  std::map<int64_t, std::unique_ptr<sg_result>> slices;              // TimeResults
+  const uint64_t* cnt = h.data() + q->off_count;
+  for (uint32_t s = 0; s < P.nslots; s++) {
+    if (cnt[s] == 0) continue;
+    ResultGroup g;
+    init_group(g, naggs);
+    g.count = (int64_t)cnt[s];
+    int64_t tbucket = 0;
+    for (auto& d : q->dims) {
+      uint32_t code = (s / d.stride) % d.radix;
+      if (d.is_time) {
+        tbucket = (P.time_first + (int64_t)code - 1) * P.time_bucket;
+        continue;
+      }
+      if (code == 0)
+        g.key.push_back(SG_MISSING_KEY);
+      else if (d.is_str)
+        g.key.push_back((uint64_t)(code - 1));
+      else
+        g.key.push_back((uint64_t)q->table->idict[(size_t)d.col].vals[code - 1]);
+    }
+    g.skey = render_key(q, g.key);
+    for (int a = 0; a < naggs; a++) {
+      g.hcount[(size_t)a] = (int64_t)h[q->off_hcount[(size_t)a] + s];
+      g.sum[(size_t)a] = (int64_t)h[q->off_sum[(size_t)a] + s];
+      g.vmax[(size_t)a] = (int64_t)h[q->off_vmax[(size_t)a] + s];
+      uint32_t nv = q->layouts[(size_t)a].nvals_total;
+      if (nv && g.hcount[(size_t)a]) {
+        const uint64_t* src = h.data() + q->off_buckets[(size_t)a] + (size_t)s * nv;
+        g.values[(size_t)a].assign(src, src + nv);
+      }
+    }
+    if (!time_mode) {
+      merge_group(r->total, g, naggs, q->layouts, true);
+      r->groups.push_back(std::move(g));
+    } else {
+      // Results[key]: Count/Samples only (aggregate.go:156-171); hists live per bucket
+      auto it = by_key.find(g.key);
+      if (it == by_key.end()) {
+        ResultGroup base;
+        init_group(base, naggs);
+        base.key = g.key;
+        base.skey = g.skey;
+        by_key[g.key] = r->groups.size();
+        r->groups.push_back(std::move(base));
+        it = by_key.find(g.key);
+      }
+      r->groups[it->second].count += g.count;
+      r->total.count += g.count;
+      auto& sl = slices[tbucket];
+      if (!sl) {
+        sl.reset(new sg_result());
+        sl->q = q;
+        sl->layouts = q->layouts;
+        sl->hist_mode = r->hist_mode;
+        sl->ngroups_cols = P.ngroups;
+        sl->naggs = naggs;
+        init_group(sl->total, naggs);
+      }
+      sl->groups.push_back(std::move(g));
+    }
+  }
+  sort_groups(r->groups);
+  for (auto& kv : slices) {
+    sort_groups(kv.second->groups);
+    r->time_keys.push_back(kv.first);
+    r->time_slices.push_back(std::move(kv.second));
+  }
+  *out = r.release();
+  return SG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+sg_query* sg_query_begin(sg_ctx* c, sg_table* t, const sg_query_desc* d) {
+  if (!c || !d) return nullptr;
+  if (!c->has_device) {
+    c->set_err("sg_query_begin: no CUDA device (libsybilgpu has no CPU path)");
+    return nullptr;
+  }
+  if (d->abi_version != SG_ABI_VERSION) {
+    c->set_err("sg_query_begin: ABI version mismatch");
+    return nullptr;
+  }
+  if (d->nfilters < 0 || d->nfilters > SG_MAX_FILTERS || d->ngroups < 0 || d->ngroups > SG_MAX_GROUPS ||
+      d->naggs < 0 || d->naggs > SG_MAX_AGGS) {
+    c->set_err("sg_query_begin: too many filters / groups / aggregations for this build");
+    return nullptr;
+  }
+  if (d->weight_col_slot >= 0) {
+    c->set_err("sg_query_begin: weighted queries (OPTS.WEIGHT_COL) are not supported in this build");
+    return nullptr;
+  }
+  if (!t) {
+    c->set_err("sg_query_begin: table is NULL");
+    return nullptr;
+  }
+  sg_query* q = new sg_query();
+  q->ctx = c;
+  q->table = t;
+  q->d = *d;
+  if (d->nfilters) q->filters.assign(d->filters, d->filters + d->nfilters);
+  if (d->ngroups) q->groups.assign(d->groups, d->groups + d->ngroups);
+  if (d->naggs) q->aggs.assign(d->aggs, d->aggs + d->naggs);
+  q->filter_strs.resize(q->filters.size());
+  for (size_t i = 0; i < q->filters.size(); i++) {
+    if (q->filters[i].str_value && q->filters[i].str_len > 0)
+      q->filter_strs[i].assign(q->filters[i].str_value, (size_t)q->filters[i].str_len);
+    q->filters[i].str_value = nullptr;
+  }
+  q->luts.resize(q->filters.size());
+  q->lut_bits.assign(q->filters.size(), -1);
+  q->d_luts.assign(q->filters.size(), nullptr);
+  q->d.filters = nullptr;
+  q->d.groups = nullptr;
+  q->d.aggs = nullptr;
+  return q;
+}
+
+void sg_query_free(sg_query* q) {
+  if (!q) return;
+  cudaSetDevice(q->ctx->device);
+  free_device(q);
+  if (q->ev0) cudaEventDestroy(q->ev0);
+  if (q->ev1) cudaEventDestroy(q->ev1);
+  delete q;
+}
+
+int sg_query_set_str_lut(sg_query* q, int32_t fi, const uint32_t* bits, int64_t nbits) {
+  if (!q || fi < 0 || (size_t)fi >= q->filters.size() || nbits < 0) return SG_ERR_INVALID;
+  sg_ctx* c = q->ctx;
+  cudaSetDevice(c->device);
+  size_t words = (size_t)((nbits + 31) / 32);
+  q->luts[(size_t)fi].assign(bits, bits + words);
+  q->lut_bits[(size_t)fi] = nbits;
+  if (q->d_luts[(size_t)fi]) cudaFree(q->d_luts[(size_t)fi]);
+  q->d_luts[(size_t)fi] = nullptr;
+  CUDA_TRY(c, cudaMalloc(&q->d_luts[(size_t)fi], std::max<size_t>(words, 1) * 4));
+  if (words) CUDA_TRY(c, cudaMemcpy(q->d_luts[(size_t)fi], bits, words * 4, cudaMemcpyHostToDevice));
+  q->planned = false;
+  return SG_OK;
+}
+
+int sg_query_should_load(sg_query* q, const sg_block_desc* b) {
+  if (!q || !b) return SG_ERR_INVALID;
+  std::vector<sg_int_info> info(b->info, b->info + b->ninfo);
+  return should_load(q, info) ? 1 : 0;
+}
+
+int sg_query_run(sg_query* q) {
+  if (!q) return SG_ERR_INVALID;
+  sg_ctx* c = q->ctx;
+  sg_table* t = q->table;
+  cudaSetDevice(c->device);
+  int rc = sg_table_sync(t);
+  if (rc != SG_OK) return rc;
+  rc = upload_table(t);
+  if (rc != SG_OK) return rc;
+  rc = make_plan(q);
+  if (rc != SG_OK) return rc;
+  rc = alloc_device(q);
+  if (rc != SG_OK) return rc;
+  q->planned = true;
+
+  // block list: zone-map pruning + blocks already known broken for a referenced column
+  std::vector<char> wanted((size_t)t->ncols, 0);
+  for (auto& f : q->filters) wanted[(size_t)f.col_slot] = 1;
+  for (auto& g : q->groups) wanted[(size_t)g.col_slot] = 1;
+  for (auto& a : q->aggs) wanted[(size_t)a.col_slot] = 1;
+  if (q->plan.time_col >= 0) wanted[(size_t)q->plan.time_col] = 1;
+  std::vector<uint32_t> list;
+  q->skipped = 0;
+  q->broken_staged = 0;
+  q->rows_scanned = 0;
+  for (size_t i = 0; i < t->blocks.size(); i++) {
+    if (!should_load(q, t->blocks[i].info)) {
+      q->skipped++;
+      continue;
+    }
+    bool broken = false;
+    for (int cidx = 0; cidx < t->ncols; cidx++)
+      if (wanted[(size_t)cidx] && (t->cols[i * (size_t)t->ncols + (size_t)cidx].flags & COL_BROKEN)) broken = true;
+    if (broken) {
+      q->broken_staged++;
+      continue;
+    }
+    list.push_back((uint32_t)i);
+    q->rows_scanned += t->blocks[i].num_records;
+  }
+  q->blocks_scanned = (int64_t)list.size();
+
+  // a block found broken by the kernel ("BLOCK SIZE CHANGED", row id >= NumRecords)
+  // must contribute nothing: rerun without it (rare path)
+  for (int attempt = 0; attempt < 8; attempt++) {
+    rc = reset_accumulators(q);
+    if (rc != SG_OK) return rc;
+    rc = run_list(q, list);
+    if (rc != SG_OK) return rc;
+    uint64_t scal[8];
+    CUDA_TRY(c, cudaMemcpy(scal, q->d_acc, sizeof(scal), cudaMemcpyDeviceToHost));
+    if (scal[2] != 0) {
+      c->set_err("query: rows fall outside the planned time axis (time_min/time_max too narrow)");
+      return SG_ERR_INVALID;
+    }
+    if (scal[1] == 0) break;
+    std::vector<uint32_t> status(t->blocks.size());
+    CUDA_TRY(c, cudaMemcpy(status.data(), q->d_block_status, status.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> next;
+    for (uint32_t b : list) {
+      if (status[b]) {
+        q->broken_staged++;
+        q->rows_scanned -= t->blocks[b].num_records;
+      } else {
+        next.push_back(b);
+      }
+    }
+    list.swap(next);
+  }
+  q->last_list = list;
+  q->ran = true;
+  return SG_OK;
+}
+
+int sg_query_submit_block(sg_query* q, const sg_block_desc* b) {
+  // streaming path: the block is staged into the query's table (H2D on the copy
+  // stream) and scanned by sg_query_finish; zone-map pruning happens before staging
+  if (!q || !b) return SG_ERR_INVALID;
+  std::vector<sg_int_info> info(b->info, b->info + b->ninfo);
+  if (!should_load(q, info)) {
+    q->skipped++;
+    return SG_OK;
+  }
+  return sg_table_add_block(q->table, b);
+}
+
+int sg_query_allreduce(sg_query* q) {
+  if (!q || !q->ran) return SG_ERR_STATE;
+  sg_ctx* c = q->ctx;
+  if (!c->comm || c->nranks <= 1) return SG_OK;
+  cudaSetDevice(c->device);
+  // CombineResults across GPUs: every rank holds the same dense layout (same
+  // dictionaries, same histogram extents), so the merge is element-wise.
+  // sums: scalars, count, hcount, sum, buckets; max: vmax.
+  const Plan& P = q->plan;
+  auto ar = [&](uint64_t* p, size_t n, int dtype, int op) -> int {
+    ncclResult_t r = g_nccl.AllReduce(p, p, n, dtype, op, c->comm, c->stream);
+    if (r != 0) {
+      c->set_err(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+      return SG_ERR_NCCL;
+    }
+    return SG_OK;
+  };
+  int rc = ar(q->d_acc, 8 + (size_t)P.nslots, ncclUint64, ncclSum);
+  for (int i = 0; i < P.naggs && rc == SG_OK; i++) {
+    rc = ar(q->d_acc + q->off_hcount[(size_t)i], 2 * (size_t)P.nslots, ncclUint64, ncclSum);
+    if (rc == SG_OK) rc = ar(q->d_acc + q->off_vmax[(size_t)i], P.nslots, ncclInt64, ncclMax);
+    if (rc == SG_OK && q->layouts[(size_t)i].nvals_total)
+      rc = ar(q->d_acc + q->off_buckets[(size_t)i], (size_t)P.nslots * q->layouts[(size_t)i].nvals_total, ncclUint64,
+              ncclSum);
+  }
+  if (rc != SG_OK) return rc;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return SG_OK;
+}
+
+int sg_query_finish(sg_query* q, sg_result** out) {
+  if (!q || !out) return SG_ERR_INVALID;
+  if (!q->ran) {
+    int rc = sg_query_run(q);
+    if (rc != SG_OK) return rc;
+  }
+  cudaSetDevice(q->ctx->device);
+  return build_result(q, out);
+}
+
+double sg_query_kernel_ms(sg_query* q) { return q ? q->kernel_ms : 0; }
+int64_t sg_query_kernel_launches(sg_query* q) { return q ? q->launches : 0; }
+
+int sg_query_stats(sg_query* q, sg_stats* s) {
+  if (!q || !s) return SG_ERR_INVALID;
+  memset(s, 0, sizeof(*s));
+  s->kernel_ms = q->kernel_ms;
+  s->kernel_launches = q->launches;
+  s->h2d_bytes = q->table->h2d_bytes;
+  s->d2h_bytes = q->d2h_bytes;
+  s->rows_scanned = q->rows_scanned;
+  s->blocks_scanned = q->blocks_scanned;
+  s->encoded_bytes = q->table->encoded_bytes;
+  return SG_OK;
+}
+
+// ===========================================================================
+// result accessors
+// ===========================================================================
+void sg_result_free(sg_result* r) { delete r; }
+int64_t sg_result_matched_count(sg_result* r) { return r ? r->matched : 0; }
+int64_t sg_result_num_groups(sg_result* r) { return r ? (int64_t)r->groups.size() : 0; }
+int64_t sg_result_num_broken(sg_result* r) { return r ? r->broken : 0; }
+int64_t sg_result_num_skipped(sg_result* r) { return r ? r->skipped : 0; }
+
+static ResultGroup* pick_group(sg_result* r, int64_t i) {
+  if (!r) return nullptr;
+  if (i == -1) return &r->total;
+  if (i < 0 || (size_t)i >= r->groups.size()) return nullptr;
+  return &r->groups[(size_t)i];
+}
+
+int sg_result_group(sg_result* r, int64_t i, uint64_t* key_out, int64_t* count, int64_t* samples) {
+  ResultGroup* g = pick_group(r, i);
+  if (!g) return SG_ERR_INVALID;
+  if (key_out)
+    for (size_t k = 0; k < g->key.size(); k++) key_out[k] = g->key[k];
+  if (count) *count = g->count;
+  if (samples) *samples = g->count;  // unweighted: Samples == Count (aggregate.go:202-203)
+  return SG_OK;
+}
+int sg_result_group_key(sg_result* r, int64_t i, const char** bytes, int64_t* len) {
+  ResultGroup* g = pick_group(r, i);
+  if (!g) return SG_ERR_INVALID;
+  *bytes = g->skey.data();
+  *len = (int64_t)g->skey.size();
+  return SG_OK;
+}
+
+// hist Min/Max as the reference tracks them (hist_basic.go:34-41,120-126;
+// hist_multi.go:31-33): hist mode and MultiHist start at the table extents;
+// BasicHist in avg mode starts at 0 and is not tracked by this build.
+static void hist_minmax(sg_result* r, const ResultGroup* g, int a, int64_t* mn, int64_t* mx) {
+  const HistLayout& L = r->layouts[(size_t)a];
+  if (L.tracked || L.multi) {
+    *mn = L.info_min;
+    *mx = std::max(L.info_max, g->vmax[(size_t)a]);
+  } else {
+    *mn = 0;
+    *mx = 0;
+  }
+}
+
+int sg_result_hist(sg_result* r, int64_t i, int32_t a, sg_hist_view* out) {
+  ResultGroup* g = pick_group(r, i);
+  if (!g || a < 0 || a >= r->naggs || !out) return SG_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  if (i == -1 && !r->has_total_hists) return 0;
+  if (g->hcount[(size_t)a] == 0) return 0;  // no hist for this aggregation (Q7)
+  const HistLayout& L = r->layouts[(size_t)a];
+  out->count = g->hcount[(size_t)a];
+  out->sum = g->sum[(size_t)a];
+  hist_minmax(r, g, a, &out->min, &out->max);
+  out->avg = (double)out->sum / (double)out->count;
+  out->num_buckets = (int32_t)L.num_buckets;
+  out->bucket_size = L.subs.size() == 1 ? (int32_t)L.subs[0].bsize : 0;
+  out->nvalues = (int32_t)L.nvals_total;
+  out->nsubhists = L.multi ? (int32_t)L.subs.size() : 0;
+  out->values = g->values[(size_t)a].empty() ? nullptr : g->values[(size_t)a].data();
+  return 1;
+}
+
+int sg_result_percentiles(sg_result* r, int64_t i, int32_t a, int64_t* out100) {
+  ResultGroup* g = pick_group(r, i);
+  if (!g || a < 0 || a >= r->naggs) return SG_ERR_INVALID;
+  if (g->hcount[(size_t)a] == 0 || g->values[(size_t)a].empty()) return 0;
+  int64_t mn, mx;
+  hist_minmax(r, g, a, &mn, &mx);
+  return percentiles(r->layouts[(size_t)a], g->values[(size_t)a].data(), g->hcount[(size_t)a], mn, out100);
+}
+
+double sg_result_stddev(sg_result* r, int64_t i, int32_t a) {
+  ResultGroup* g = pick_group(r, i);
+  if (!g || a < 0 || a >= r->naggs || g->hcount[(size_t)a] == 0 || g->values[(size_t)a].empty()) return NAN;
+  int64_t mn, mx;
+  hist_minmax(r, g, a, &mn, &mx);
+  double avg = (double)g->sum[(size_t)a] / (double)g->hcount[(size_t)a];
+  return stddev(r->layouts[(size_t)a], g->values[(size_t)a].data(), g->hcount[(size_t)a], avg, mn);
+}
+
+int64_t sg_result_sparse_buckets(sg_result* r, int64_t i, int32_t a, int64_t* edges, int64_t* counts, int64_t cap) {
+  ResultGroup* g = pick_group(r, i);
+  if (!g || a < 0 || a >= r->naggs) return SG_ERR_INVALID;
+  if (g->hcount[(size_t)a] == 0 || g->values[(size_t)a].empty()) return 0;
+  auto m = sparse_buckets(r->layouts[(size_t)a], g->values[(size_t)a].data());
+  int64_t n = 0;
+  for (auto& kv : m) {
+    if (edges && n < cap) {
+      edges[n] = kv.first;
+      counts[n] = kv.second;
+    }
+    n++;
+  }
+  return n;
+}
+
+int64_t sg_result_num_time_buckets(sg_result* r) { return r ? (int64_t)r->time_keys.size() : 0; }
+int64_t sg_result_time_bucket(sg_result* r, int64_t b) {
+  if (!r || b < 0 || (size_t)b >= r->time_keys.size()) return 0;
+  return r->time_keys[(size_t)b];
+}
+sg_result* sg_result_time_slice(sg_result* r, int64_t b) {
+  if (!r || b < 0 || (size_t)b >= r->time_slices.size()) return nullptr;
+  return r->time_slices[(size_t)b].get();
+}
+
+}  // extern "C"

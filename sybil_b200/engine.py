@@ -1,0 +1,409 @@
+"""Host-side mirror of sybil's query interface over the C ABI of libsybilgpu.so.
+
+Names, argument meaning and results follow the reference so that the parity tests
+read like src/lib/*_test.go:
+
+    Table.LoadAndQueryRecords(loadSpec, querySpec)   src/lib/table_query.go:18
+    Table.IntFilter / StrFilter                      src/lib/filter.go:287-310
+    Table.Grouping / Aggregation                     src/lib/query_spec.go:195-235
+    QuerySpec / QueryParams / Result                 src/lib/query_spec.go:11-105
+    Histogram interface                              src/lib/hist.go:9-25
+    FLAGS.OP / LOG_HIST / HIST_BUCKET / TIME_*       src/lib/config.go:30-100
+
+In production this layer is Go (see go/sybilgpu and INTEGRATION.md); the Go
+toolchain is not in the build image, so the mirror is Python over ctypes.  All
+compute goes through the CUDA library: there is no CPU path here.
+"""
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import _ffi as F
+
+
+class _Flags:
+    """The globals of config.go the hot path reads (config.go:123-176 defaults)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.OP = "avg"
+        self.LOG_HIST = False
+        self.HIST_BUCKET = 0
+        self.TIME_COL = ""
+        self.TIME_BUCKET = 0
+        self.LIMIT = 100
+
+
+FLAGS = _Flags()
+
+
+class SybilGpuError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("libsybilgpu status %d: %s" % (status, msg))
+        self.status = status
+
+
+_CTX = {}
+
+
+class Context:
+    """sg_ctx: one per process and GPU."""
+
+    def __init__(self, device=0):
+        self.lib = F.lib()
+        st = C.c_int(0)
+        self.h = self.lib.sg_create(device, C.byref(st))
+        if st.value != F.SG_OK:
+            msg = self.lib.sg_last_error(self.h).decode()
+            self.lib.sg_destroy(self.h)
+            self.h = None
+            raise SybilGpuError(st.value, msg)
+        self.device = device
+
+    def err(self):
+        return self.lib.sg_last_error(self.h).decode()
+
+    def check(self, rc):
+        if rc < 0:
+            raise SybilGpuError(rc, self.err())
+        return rc
+
+    def sm_count(self):
+        return self.lib.sg_device_sm_count(self.h)
+
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self.check(self.lib.sg_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, uid, rank, nranks):
+        self.check(self.lib.sg_comm_init(self.h, uid, rank, nranks))
+
+
+def get_context(device=0):
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]
+
+
+# ---- filters / groupings / aggregations -------------------------------------------
+class IntFilter:  # filter.go:143-150
+    def __init__(self, Field, FieldId, Op, Value):
+        self.Field, self.FieldId, self.Op, self.Value = Field, FieldId, Op, int(Value)
+
+
+class StrFilter:  # filter.go:152-160
+    def __init__(self, Field, FieldId, Op, Value):
+        self.Field, self.FieldId, self.Op, self.Value = Field, FieldId, Op, Value
+        self.regex = re.compile(Value) if Op in ("re", "nre") else None
+
+
+class Grouping:  # query_spec.go:73-76
+    def __init__(self, Name, name_id):
+        self.Name, self.name_id = Name, name_id
+
+
+class Aggregation:  # query_spec.go:78-83
+    def __init__(self, Name, name_id, Op):
+        self.Name, self.name_id, self.Op = Name, name_id, Op
+        self.HistType = ""
+        if Op == "hist":
+            self.HistType = "multi" if FLAGS.LOG_HIST else "basic"
+
+
+class LoadSpec:  # table_load_spec.go:5-72
+    def __init__(self, table):
+        self.table = table
+        self.columns = {}
+        self.files = {}
+
+    def Int(self, name):
+        self.columns[name] = True
+        self.files["int_" + name + ".db"] = True
+
+    def Str(self, name):
+        self.columns[name] = True
+        self.files["str_" + name + ".db"] = True
+
+
+class Hist:
+    """Histogram interface (hist.go:9-25) over the merged counters of one (group, aggregation)."""
+
+    def __init__(self, res, gi, ai):
+        self._r, self._gi, self._ai = res, gi, ai
+        v = F.sg_hist_view()
+        rc = res.lib.sg_result_hist(res.h, gi, ai, C.byref(v))
+        if rc != 1:
+            raise KeyError("no histogram")
+        self.Count, self.ExactSum = v.count, v.sum
+        self._min, self._max, self.Avg = v.min, v.max, v.avg
+        self.NumBuckets, self.BucketSize = v.num_buckets, v.bucket_size
+        self.nsubhists = v.nsubhists
+        self.Values = np.ctypeslib.as_array(v.values, (v.nvalues,)).copy() if v.values else np.zeros(0, np.int64)
+
+    def Mean(self):
+        return self.Avg
+
+    def TotalCount(self):
+        return self.Count
+
+    def Min(self):
+        return self._min
+
+    def Max(self):
+        return self._max
+
+    def Sum(self):  # exact int64 (the reference's Sum() is int64(Avg*Count), hist_basic.go:97-99)
+        return self.ExactSum
+
+    def GetPercentiles(self):
+        out = (C.c_int64 * 100)()
+        n = self._r.lib.sg_result_percentiles(self._r.h, self._gi, self._ai, out)
+        return [out[i] for i in range(n)]
+
+    def StdDev(self):
+        return self._r.lib.sg_result_stddev(self._r.h, self._gi, self._ai)
+
+    def GetIntBuckets(self):
+        n = self._r.lib.sg_result_sparse_buckets(self._r.h, self._gi, self._ai, None, None, 0)
+        e, c = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
+        self._r.lib.sg_result_sparse_buckets(self._r.h, self._gi, self._ai, e, c, n)
+        return {e[i]: c[i] for i in range(n)}
+
+
+class Result:  # query_spec.go:85-93
+    def __init__(self):
+        self.Hists = {}
+        self.GroupByKey = ""
+        self.BinaryByKey = ()
+        self.Count = 0
+        self.Samples = 0
+
+
+class _ResultHandle:
+    def __init__(self, lib, h, owner=None):
+        self.lib, self.h, self.owner = lib, h, owner
+
+    def groups(self, aggs, with_total):
+        out = []
+        n = self.lib.sg_result_num_groups(self.h)
+        idx = ([-1] if with_total else []) + list(range(n))
+        for gi in idx:
+            r = Result()
+            kb, kl = C.c_void_p(), C.c_int64()
+            self.lib.sg_result_group_key(self.h, gi, C.byref(kb), C.byref(kl))
+            r.GroupByKey = C.string_at(kb, kl.value).decode("utf-8", "replace")
+            cnt, smp = C.c_int64(), C.c_int64()
+            key = (C.c_uint64 * F.SG_MAX_GROUPS)()
+            self.lib.sg_result_group(self.h, gi, key, C.byref(cnt), C.byref(smp))
+            r.Count, r.Samples = cnt.value, smp.value
+            r.BinaryByKey = tuple(key[i] for i in range(F.SG_MAX_GROUPS))
+            for ai, a in enumerate(aggs):
+                try:
+                    r.Hists[a.Name] = Hist(self, gi, ai)
+                except KeyError:
+                    pass
+            out.append(r)
+        return out
+
+
+class QueryParams:  # query_spec.go:25-41
+    def __init__(self, Filters=None, Groups=None, Aggregations=None, TimeBucket=0, OrderBy="$COUNT", Limit=100):
+        self.Filters = Filters or []
+        self.Groups = Groups or []
+        self.Aggregations = Aggregations or []
+        self.TimeBucket = TimeBucket
+        self.OrderBy = OrderBy
+        self.Limit = Limit
+
+
+class QuerySpec:  # query_spec.go:60-67
+    def __init__(self, params=None, **kw):
+        self.QueryParams = params or QueryParams(**kw)
+        for k in ("Filters", "Groups", "Aggregations", "TimeBucket", "OrderBy", "Limit"):
+            setattr(self, k, getattr(self.QueryParams, k))
+        self.Results = {}
+        self.TimeResults = {}
+        self.Cumulative = None
+        self.MatchedCount = 0
+        self.Sorted = []
+        self.BrokenBlocks = 0
+        self.SkippedBlocks = 0
+        self.stats = None
+
+
+
+def make_query_desc(KeyTable, KeyTypes, IntInfo, qs):
+    """sg_query_desc for a QuerySpec + the FLAGS globals (usable without a GPU context)."""
+    nf, ng, na = len(qs.Filters), len(qs.Groups), len(qs.Aggregations)
+    fl = (F.sg_filter_desc * max(nf, 1))()
+    keep = []
+    for i, f in enumerate(qs.Filters):
+        fl[i].col_slot = f.FieldId
+        fl[i].op = F.OPS[f.Op]
+        if isinstance(f, IntFilter):
+            fl[i].col_type = F.SG_COL_INT
+            fl[i].int_value = f.Value
+        else:
+            fl[i].col_type = F.SG_COL_STR
+            b = f.Value if isinstance(f.Value, bytes) else f.Value.encode()
+            keep.append(b)
+            fl[i].str_value = b
+            fl[i].str_len = len(b)
+    gr = (F.sg_group_desc * max(ng, 1))()
+    for i, g in enumerate(qs.Groups):
+        gr[i].col_slot = g.name_id
+        gr[i].col_type = KeyTypes[g.name_id]
+    ag = (F.sg_agg_desc * max(na, 1))()
+    for i, a in enumerate(qs.Aggregations):
+        ag[i].col_slot = a.name_id
+        mn, mx = IntInfo.get(a.Name, (0, 0))
+        ag[i].info_min, ag[i].info_max = mn, mx
+    d = F.sg_query_desc()
+    d.abi_version = F.SG_ABI_VERSION
+    d.op_mode = F.SG_MODE_HIST if FLAGS.OP == "hist" else F.SG_MODE_AVG
+    d.hist_kind = F.SG_HIST_MULTI if FLAGS.LOG_HIST else F.SG_HIST_BASIC
+    d.hist_bucket = FLAGS.HIST_BUCKET
+    d.nfilters, d.ngroups, d.naggs = nf, ng, na
+    d.filters = C.cast(fl, C.POINTER(F.sg_filter_desc))
+    d.groups = C.cast(gr, C.POINTER(F.sg_group_desc))
+    d.aggs = C.cast(ag, C.POINTER(F.sg_agg_desc))
+    d.weight_col_slot = -1
+    d.time_col_slot = -1
+    if qs.TimeBucket and FLAGS.TIME_COL:
+        d.time_col_slot = KeyTable[FLAGS.TIME_COL]
+        d.time_bucket = qs.TimeBucket
+        mn, mx = IntInfo.get(FLAGS.TIME_COL, (0, 0))
+        d.time_min, d.time_max = mn, mx
+    return d, (fl, gr, ag, keep)
+
+
+class Table:
+    """sybil.Table as far as the query path needs it: KeyTable, KeyTypes, IntInfo and the blocks.
+
+    Blocks arrive through add_block() (in sybil they are block directories on disk,
+    gob-decoded by the Go host); they are staged once into HBM and stay resident.
+    """
+
+    def __init__(self, name, key_table, ctx=None):
+        self.Name = name
+        self.ctx = ctx or get_context()
+        self.lib = self.ctx.lib
+        self.KeyTable = {}  # name -> column slot (table.go:10-41)
+        self.KeyTypes = {}  # slot -> INT_VAL / STR_VAL
+        for slot, (n, typ) in enumerate(key_table):
+            self.KeyTable[n] = slot
+            self.KeyTypes[slot] = typ
+        self.IntInfo = {}  # name -> (Min, Max): table info.db (table_column_info.go:18-24)
+        types = (C.c_int32 * len(key_table))(*[t for _, t in key_table])
+        self.h = self.lib.sg_table_create(self.ctx.h, len(key_table), types)
+        if not self.h:
+            raise SybilGpuError(F.SG_ERR_CUDA, self.ctx.err())
+
+    def close(self):
+        if self.h:
+            self.lib.sg_table_free(self.h)
+            self.h = None
+
+    def get_key_id(self, name):
+        return self.KeyTable[name]
+
+    def add_block(self, blk):
+        d = blk.desc() if hasattr(blk, "desc") else blk
+        self.ctx.check(self.lib.sg_table_add_block(self.h, C.byref(d) if not isinstance(d, C._Pointer) else d))
+
+    def add_block_desc_ptr(self, p):
+        self.ctx.check(self.lib.sg_table_add_block(self.h, p))
+
+    def sync(self):
+        self.ctx.check(self.lib.sg_table_sync(self.h))
+
+    def NumRows(self):
+        return self.lib.sg_table_num_rows(self.h)
+
+    def dict_strings(self, name):
+        slot = self.KeyTable[name]
+        n = self.lib.sg_table_dict_size(self.h, slot)
+        out = []
+        for i in range(n):
+            b, l = C.c_void_p(), C.c_int64()
+            self.lib.sg_table_dict_get(self.h, slot, i, C.byref(b), C.byref(l))
+            out.append(C.string_at(b, l.value))
+        return out
+
+    # filter.go:287-310, query_spec.go:195-235, table_load_spec.go:59-72
+    def IntFilter(self, name, op, value):
+        return IntFilter(name, self.get_key_id(name), op, value)
+
+    def StrFilter(self, name, op, value):
+        return StrFilter(name, self.get_key_id(name), op, value)
+
+    def Grouping(self, name):
+        return Grouping(name, self.get_key_id(name))
+
+    def Aggregation(self, name, op):
+        return Aggregation(name, self.get_key_id(name), op)
+
+    def NewLoadSpec(self):
+        return LoadSpec(self)
+
+    def _desc(self, qs):
+        return make_query_desc(self.KeyTable, self.KeyTypes, self.IntInfo, qs)
+
+    def LoadAndQueryRecords(self, loadSpec, querySpec, allreduce=False):
+        """Table.LoadAndQueryRecords (table_query.go:18-422).  Returns the matched row count and
+        fills querySpec.{Results, TimeResults, Cumulative, MatchedCount, Sorted}."""
+        qs = querySpec
+        if loadSpec is not None:
+            for what, name in ([("filter", f.Field) for f in qs.Filters] + [("group", g.Name) for g in qs.Groups] +
+                               [("aggregation", a.Name) for a in qs.Aggregations]):
+                if name not in loadSpec.columns:
+                    raise ValueError("%s column %r is not in the LoadSpec: sybil would not load it" % (what, name))
+        d, keep = self._desc(qs)
+        q = self.lib.sg_query_begin(self.ctx.h, self.h, C.byref(d))
+        if not q:
+            raise SybilGpuError(F.SG_ERR_INVALID, self.ctx.err())
+        try:
+            for i, f in enumerate(qs.Filters):
+                if isinstance(f, StrFilter) and f.regex is not None:
+                    # the host evaluates the regexp once per distinct string (filter.go:215-237)
+                    strs = self.dict_strings(f.Field)
+                    bits = np.zeros((len(strs) + 31) // 32 + 1, np.uint32)
+                    for gid, s in enumerate(strs):
+                        if f.regex.search(s.decode("utf-8", "replace")):
+                            bits[gid >> 5] |= np.uint32(1 << (gid & 31))
+                    self.ctx.check(self.lib.sg_query_set_str_lut(q, i, bits.ctypes.data, len(strs)))
+            self.ctx.check(self.lib.sg_query_run(q))
+            if allreduce:
+                self.ctx.check(self.lib.sg_query_allreduce(q))
+            rp = C.c_void_p()
+            self.ctx.check(self.lib.sg_query_finish(q, C.byref(rp)))
+            st = F.sg_stats()
+            self.lib.sg_query_stats(q, C.byref(st))
+            qs.stats = st
+            try:
+                self._fill(qs, rp)
+            finally:
+                self.lib.sg_result_free(rp)
+        finally:
+            self.lib.sg_query_free(q)
+        return qs.MatchedCount
+
+    def _fill(self, qs, rp):
+        lib = self.lib
+        rh = _ResultHandle(lib, rp)
+        qs.MatchedCount = lib.sg_result_matched_count(rp)
+        qs.BrokenBlocks = lib.sg_result_num_broken(rp)
+        qs.SkippedBlocks = lib.sg_result_num_skipped(rp)
+        allg = rh.groups(qs.Aggregations, True)
+        qs.Cumulative = allg[0]
+        qs.Sorted = allg[1:]
+        qs.Results = {r.GroupByKey: r for r in qs.Sorted}
+        qs.TimeResults = {}
+        for b in range(lib.sg_result_num_time_buckets(rp)):
+            tb = lib.sg_result_time_bucket(rp, b)
+            sl = _ResultHandle(lib, lib.sg_result_time_slice(rp, b))
+            qs.TimeResults[tb] = {r.GroupByKey: r for r in sl.groups(qs.Aggregations, False)}
