@@ -199,6 +199,16 @@ int64_t sg_table_device_bytes(sg_table* t);
  * rendering keys): number of strings / i-th string */
 int64_t sg_table_dict_size(sg_table* t, int32_t col_slot);
 int sg_table_dict_get(sg_table* t, int32_t col_slot, int64_t id, const char** bytes, int64_t* len);
+/* value dictionary of a bucket-encoded int column (dense group-by axis) */
+int64_t sg_table_intdict_size(sg_table* t, int32_t col_slot);
+int sg_table_intdict_get(sg_table* t, int32_t col_slot, int64_t id, int64_t* value);
+/* Multi-GPU: every rank must number group keys identically before the dense
+ * partials are all-reduced.  Seed the dictionaries (e.g. with rank 0's, or with the
+ * table's StrInfo) BEFORE staging blocks; later strings append after the seed. */
+int sg_table_dict_seed_str(sg_table* t, int32_t col_slot, const char* bytes, const uint32_t* offsets, int64_t n);
+int sg_table_dict_seed_int(sg_table* t, int32_t col_slot, const int64_t* values, int64_t n);
+int64_t sg_table_encoded_bytes(sg_table* t); /* bytes of encoded column arrays resident */
+int64_t sg_table_h2d_bytes(sg_table* t);     /* bytes copied host->device while staging */
 
 /* ---- query ---------------------------------------------------------------
  * sg_query_begin .. sg_query_finish bracket what LoadAndQueryRecords does between

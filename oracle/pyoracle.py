@@ -22,6 +22,12 @@ def _i64(x):
     return x - (1 << 64) if x >= (1 << 63) else x
 
 
+def _fdiv(a, b):  # Go float64 division: x/0 is +-Inf or NaN, never a panic
+    if b == 0.0:
+        return float("nan") if a == 0.0 or a != a else math.copysign(float("inf"), a)
+    return a / b
+
+
 def _tdiv(a, b):  # Go integer division truncates toward zero
     q = abs(a) // abs(b)
     return q if (a >= 0) == (b >= 0) else -q
@@ -73,7 +79,7 @@ class PyBasicHist:
         for k, v in enumerate(o.Values):
             self.Values[k] += v
         tot = self.Count + o.Count
-        self.Avg = self.Avg * (float(self.Count) / float(tot)) + o.Avg * (float(o.Count) / float(tot))
+        self.Avg = self.Avg * _fdiv(float(self.Count), float(tot)) + o.Avg * _fdiv(float(o.Count), float(tot))
         self.Min, self.Max = min(self.Min, o.Min), max(self.Max, o.Max)
         self.Count = tot
         self.ExactSum = _i64(self.ExactSum + o.ExactSum)
@@ -151,7 +157,7 @@ class PyMultiHist:
         for a, b in zip(self.subs, o.subs):
             a.combine(b)
         tot = self.Count + o.Count
-        self.Avg = self.Avg * (float(self.Count) / float(tot)) + o.Avg * (float(o.Count) / float(tot))
+        self.Avg = self.Avg * _fdiv(float(self.Count), float(tot)) + o.Avg * _fdiv(float(o.Count), float(tot))
         self.Min, self.Max = min(self.Min, o.Min), max(self.Max, o.Max)
         self.Count = tot
         self.ExactSum = _i64(self.ExactSum + o.ExactSum)

@@ -99,6 +99,12 @@ SYMBOLS = {
     "sg_table_device_bytes": (C.c_int64, [P]),
     "sg_table_dict_size": (C.c_int64, [P, C.c_int32]),
     "sg_table_dict_get": (C.c_int, [P, C.c_int32, C.c_int64, C.POINTER(P), C.POINTER(C.c_int64)]),
+    "sg_table_intdict_size": (C.c_int64, [P, C.c_int32]),
+    "sg_table_intdict_get": (C.c_int, [P, C.c_int32, C.c_int64, C.POINTER(C.c_int64)]),
+    "sg_table_dict_seed_str": (C.c_int, [P, C.c_int32, P, P, C.c_int64]),
+    "sg_table_dict_seed_int": (C.c_int, [P, C.c_int32, P, C.c_int64]),
+    "sg_table_encoded_bytes": (C.c_int64, [P]),
+    "sg_table_h2d_bytes": (C.c_int64, [P]),
     "sg_query_begin": (P, [P, P, C.POINTER(sg_query_desc)]),
     "sg_query_free": (None, [P]),
     "sg_query_set_str_lut": (C.c_int, [P, C.c_int32, P, C.c_int64]),

@@ -80,7 +80,14 @@ struct sg_ctx {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   char devname[256] = {0};
+  std::vector<std::pair<const char*, size_t>> pinned;  // sg_pinned_alloc ranges (DMA without a bounce copy)
   void set_err(const std::string& s) { err = s; }
+  bool is_pinned(const void* p, size_t n) const {
+    const char* c = (const char*)p;
+    for (auto& r : pinned)
+      if (c >= r.first && c + n <= r.first + r.second) return true;
+    return false;
+  }
 };
 
 #define CUDA_TRY(ctx, expr)                                                                   \
@@ -195,12 +202,16 @@ int arena_alloc(sg_table* t, size_t bytes, char** out) {
 struct SlabWriter {
   std::vector<std::pair<const void*, size_t>> parts;  // source, bytes
   std::vector<size_t> offs;
+  std::vector<char> direct;  // source already pinned: DMA straight from the caller's buffer
   size_t total = 0;
-  size_t add(const void* src, size_t bytes) {
+  size_t staged = 0;
+  size_t add(const void* src, size_t bytes, bool is_direct = false) {
     size_t off = total;
     parts.emplace_back(src, bytes);
     offs.push_back(off);
+    direct.push_back(is_direct ? 1 : 0);
     total = align_up(total + bytes, 128);
+    if (!is_direct) staged = total;
     return off;
   }
 };
@@ -260,11 +271,21 @@ void* sg_pinned_alloc(sg_ctx* c, size_t bytes) {
     c->set_err("cudaHostAlloc failed");
     return nullptr;
   }
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->pinned.emplace_back((const char*)p, bytes);
   return p;
 }
 void sg_pinned_free(sg_ctx* c, void* p) {
-  (void)c;
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  if (c) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (size_t i = 0; i < c->pinned.size(); i++)
+      if (c->pinned[i].first == (const char*)p) {
+        c->pinned.erase(c->pinned.begin() + (long)i);
+        break;
+      }
+  }
+  cudaFreeHost(p);
 }
 
 int sg_comm_unique_id(sg_ctx* c, char id_out[128]) {
@@ -468,7 +489,7 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
       }
       tm.off_bv = sw.add(tm.bin_values.data(), tm.bin_values.size() * 8);
       tm.off_bo = sw.add(tm.bin_offsets.data(), tm.bin_offsets.size() * 4);
-      tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * 4);
+      tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * 4, c->is_pinned(cd.record_ids, (size_t)cd.nrecord_ids * 4));
       tm.has_bv = tm.has_bo = tm.has_data = true;
       enc_bytes += (int64_t)(tm.bin_values.size() * 8 + tm.bin_offsets.size() * 4 + (size_t)cd.nrecord_ids * 4);
     } else if (cd.encoding == SG_ENC_VALUES) {
@@ -482,14 +503,14 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
             c->set_err("add_block: values_i32 missing");
             return SG_ERR_INVALID;
           }
-          tm.off_data = sw.add(cd.values_i32, (size_t)cd.nvalues * 4);
+          tm.off_data = sw.add(cd.values_i32, (size_t)cd.nvalues * 4, c->is_pinned(cd.values_i32, (size_t)cd.nvalues * 4));
           enc_bytes += (int64_t)cd.nvalues * 4;
         } else {
           if (!cd.values_i64) {
             c->set_err("add_block: values_i64 missing");
             return SG_ERR_INVALID;
           }
-          tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * 8);
+          tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * 8, c->is_pinned(cd.values_i64, (size_t)cd.nvalues * 8));
           enc_bytes += (int64_t)cd.nvalues * 8;
           t->has_values_int[(size_t)cd.col_slot] = 1;
         }
@@ -526,9 +547,27 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
       }
       st->used = 0;
     }
+    // staged parts: contiguous runs of non-direct parts are bounced through pinned
+    // staging and copied run by run; direct parts go straight from the caller's memory
     char* hostp = st->host + st->used;
-    for (size_t i = 0; i < sw.parts.size(); i++) memcpy(hostp + sw.offs[i], sw.parts[i].first, sw.parts[i].second);
-    CUDA_TRY(c, cudaMemcpyAsync(dev, hostp, sw.total, cudaMemcpyHostToDevice, c->copy_stream));
+    size_t i = 0;
+    while (i < sw.parts.size()) {
+      if (sw.direct[i]) {
+        CUDA_TRY(c, cudaMemcpyAsync(dev + sw.offs[i], sw.parts[i].first, sw.parts[i].second, cudaMemcpyHostToDevice,
+                                    c->copy_stream));
+        i++;
+        continue;
+      }
+      size_t j = i, run_begin = sw.offs[i], run_end = sw.offs[i];
+      while (j < sw.parts.size() && !sw.direct[j]) {
+        memcpy(hostp + sw.offs[j], sw.parts[j].first, sw.parts[j].second);
+        run_end = sw.offs[j] + sw.parts[j].second;
+        j++;
+      }
+      CUDA_TRY(c, cudaMemcpyAsync(dev + run_begin, hostp + run_begin, run_end - run_begin, cudaMemcpyHostToDevice,
+                                  c->copy_stream));
+      i = j;
+    }
     st->used += align_up(sw.total, 256);
     t->h2d_bytes += (int64_t)sw.total;
   }
@@ -576,6 +615,30 @@ int sg_table_dict_get(sg_table* t, int32_t col, int64_t id, const char** bytes, 
   *len = (int64_t)sd.strs[(size_t)id].size();
   return SG_OK;
 }
+
+int sg_table_dict_seed_str(sg_table* t, int32_t col, const char* bytes, const uint32_t* offsets, int64_t n) {
+  if (!t || col < 0 || col >= t->ncols || n < 0 || (n > 0 && (!bytes || !offsets))) return SG_ERR_INVALID;
+  for (int64_t i = 0; i < n; i++) t->sdict[(size_t)col].intern(bytes + offsets[i], offsets[i + 1] - offsets[i]);
+  return SG_OK;
+}
+int sg_table_dict_seed_int(sg_table* t, int32_t col, const int64_t* values, int64_t n) {
+  if (!t || col < 0 || col >= t->ncols || n < 0 || (n > 0 && !values)) return SG_ERR_INVALID;
+  for (int64_t i = 0; i < n; i++) t->idict[(size_t)col].intern(values[i]);
+  return SG_OK;
+}
+int64_t sg_table_intdict_size(sg_table* t, int32_t col) {
+  if (!t || col < 0 || col >= t->ncols) return -1;
+  return (int64_t)t->idict[(size_t)col].vals.size();
+}
+int sg_table_intdict_get(sg_table* t, int32_t col, int64_t id, int64_t* value) {
+  if (!t || col < 0 || col >= t->ncols || !value) return SG_ERR_INVALID;
+  auto& d = t->idict[(size_t)col];
+  if (id < 0 || id >= (int64_t)d.vals.size()) return SG_ERR_INVALID;
+  *value = d.vals[(size_t)id];
+  return SG_OK;
+}
+int64_t sg_table_encoded_bytes(sg_table* t) { return t ? t->encoded_bytes : 0; }
+int64_t sg_table_h2d_bytes(sg_table* t) { return t ? t->h2d_bytes : 0; }
 
 }  // extern "C"
 
@@ -653,7 +716,7 @@ struct sg_query {
   // stats
   double kernel_ms = 0;
   int64_t launches = 0;
-  int64_t skipped = 0, broken_staged = 0;
+  int64_t skipped = 0, broken_staged = 0, stream_skipped = 0;
   int64_t rows_scanned = 0, blocks_scanned = 0;
   int64_t d2h_bytes = 0;
   bool ran = false;
@@ -1266,7 +1329,7 @@ int sg_query_run(sg_query* q) {
   for (auto& a : q->aggs) wanted[(size_t)a.col_slot] = 1;
   if (q->plan.time_col >= 0) wanted[(size_t)q->plan.time_col] = 1;
   std::vector<uint32_t> list;
-  q->skipped = 0;
+  q->skipped = q->stream_skipped;
   q->broken_staged = 0;
   q->rows_scanned = 0;
   for (size_t i = 0; i < t->blocks.size(); i++) {
@@ -1324,7 +1387,7 @@ int sg_query_submit_block(sg_query* q, const sg_block_desc* b) {
   if (!q || !b) return SG_ERR_INVALID;
   std::vector<sg_int_info> info(b->info, b->info + b->ninfo);
   if (!should_load(q, info)) {
-    q->skipped++;
+    q->stream_skipped++;
     return SG_OK;
   }
   return sg_table_add_block(q->table, b);

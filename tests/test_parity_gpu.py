@@ -1,0 +1,222 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libsybilgpu.so), against the CPU
+oracle on the same seeded inputs.  Bit-exact: group keys, Count, Samples, hist Count, exact int64
+sums, Min/Max, every bucket counter, percentiles, MatchedCount.  Float tolerance (stated in
+tests/util.py): mean 1e-9, stddev 1e-9."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from sybil_b200 import _ffi as F
+from tests.util import INT, STR, Q, Spec, compare, random_spec, run_gpu, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def both(spec, q):
+    o = run_oracle(spec, q)
+    g = run_gpu(spec, q)
+    compare(g, o, q)
+    return g, o
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_group_by_avg(seed):
+    s = random_spec(seed, nrows=5000, block_rows=1500)
+    both(s, Q(s, groups=["host"], aggs=["age", "lat", "big"], op="avg"))
+
+
+def test_int_filters_like_filter_test_go():
+    # filter_test.go:9-150: eq / neq / lt / gt on an int column
+    s = random_spec(11, nrows=4000, block_rows=1000)
+    for op in ("eq", "neq", "lt", "gt"):
+        both(s, Q(s, int_filters=[("age", op, 20)], groups=["age"], aggs=["age"], op="avg"))
+
+
+def test_str_filters_eq_neq_re_nre_and_absent_literal():
+    s = random_spec(12, nrows=4000, block_rows=1000)
+    for op, lit in (("eq", "s3"), ("neq", "s3"), ("re", "^s1"), ("nre", "^s1"), ("eq", "nope"), ("neq", "nope")):
+        both(s, Q(s, str_filters=[("state", op, lit)], groups=["state"], aggs=["age"], op="avg"))
+
+
+def test_three_filters_two_groups_hist_like_config3():
+    s = random_spec(13, nrows=6000, block_rows=2000)
+    g, o = both(s, Q(s, int_filters=[("age", "gt", 12), ("big", "lt", 900000)], str_filters=[("state", "neq", "s3")],
+                     groups=["host", "age"], aggs=["lat"], op="hist"))
+    assert len(g.Results) > 50
+
+
+def test_histogram_percentiles_like_aggregate_test_go():
+    # aggregate_test.go:102-208: per-group percentiles equal the key when every value of a group is the key
+    n = 3000
+    rng = np.random.default_rng(5)
+    age = rng.integers(10, 30, n)
+    s = Spec([("age", INT), ("age_str", STR)])
+    s.add_rows({"age": age, "age_str": np.array([str(a) for a in age])}, block_rows=700)
+    q = Q(s, groups=["age_str"], aggs=["age"], op="hist")
+    g, o = both(s, q)
+    for k, r in g.Results.items():
+        p = r.Hists["age"].GetPercentiles()
+        key = int(k.strip("\t"))
+        assert p[25] == key and p[50] == key and p[75] == key
+
+
+def test_loghist_multihist():
+    s = random_spec(14, nrows=5000, block_rows=1700)
+    both(s, Q(s, groups=["host"], aggs=["big", "lat"], op="hist", loghist=True))
+    both(s, Q(s, groups=["host"], aggs=["big"], op="avg", loghist=True))
+
+
+def test_hist_bucket_override():
+    s = random_spec(15, nrows=3000, block_rows=1000)
+    both(s, Q(s, groups=["host"], aggs=["lat"], op="hist", hist_bucket=100))
+
+
+def test_time_series_like_aggregate_test_go():
+    # aggregate_test.go:211-279: at least one bucket, none empty
+    s = random_spec(16, nrows=6000, block_rows=2000)
+    g, o = both(s, Q(s, groups=["host"], aggs=["lat"], op="hist", time_col="time", time_bucket=600))
+    assert len(g.TimeResults) >= 1 and all(len(m) > 0 for m in g.TimeResults.values())
+    both(s, Q(s, aggs=["age"], op="avg", time_col="time", time_bucket=3600))
+
+
+def test_value_array_encodings_and_values_above_2_pow_32():
+    # table_query_test.go (CHUNK_SIZE = CARDINALITY_THRESHOLD+1) and column_store_test.go:143-211
+    s = random_spec(17, nrows=4000, block_rows=1300, threshold=50, wide=True)
+    both(s, Q(s, int_filters=[("big", "gt", 0)], groups=["host"], aggs=["big", "lat"], op="avg"))
+    both(s, Q(s, int_filters=[("big", "lt", 1 << 45)], groups=["host", "state"], aggs=["big"], op="hist"))
+    both(s, Q(s, groups=["uid"], aggs=["age", "big"], op="avg"))  # high-cardinality str key, value-array ids
+
+
+def test_no_groups_and_no_aggs():
+    s = random_spec(18, nrows=2000, block_rows=800)
+    g, o = both(s, Q(s, aggs=["age"], op="hist"))
+    assert list(g.Results) == ["total"]
+    both(s, Q(s, int_filters=[("age", "gt", 20)]))  # count(*) + one IntFilter (config 1's query shape)
+
+
+def test_filter_matching_nothing():
+    s = random_spec(19, nrows=1500, block_rows=500)
+    g, o = both(s, Q(s, int_filters=[("age", "gt", 1000)], groups=["host"], aggs=["age"], op="avg"))
+    assert g.MatchedCount == 0 and len(g.Results) == 0
+
+
+def test_missing_columns_and_group_on_missing_values():
+    # a column absent from some blocks; rows lacking the group column render an empty field (Q4)
+    rng = np.random.default_rng(20)
+    s = Spec([("a", INT), ("b", INT), ("h", STR)])
+    n = 1200
+    s.add_rows({"a": rng.integers(0, 10, n), "b": rng.integers(0, 100, n), "h": np.array(["x%d" % v for v in rng.integers(0, 4, n)])},
+               valid={"h": rng.random(n) > 0.3, "b": rng.random(n) > 0.5}, block_rows=400)
+    s.add_rows({"a": rng.integers(0, 10, n)}, block_rows=400)  # blocks without b and h at all
+    both(s, Q(s, groups=["h"], aggs=["b"], op="hist"))
+    both(s, Q(s, groups=["h", "a"], aggs=["b", "a"], op="avg"))
+    both(s, Q(s, int_filters=[("b", "neq", 5)], groups=["a"], aggs=["b"], op="avg"))
+
+
+def test_single_row_and_full_size_blocks():
+    rng = np.random.default_rng(21)
+    s = Spec([("v", INT), ("g", STR)])
+    s.add_rows({"v": np.array([42]), "g": np.array(["only"])})
+    n = F.SG_BLOCK_ROWS
+    s.add_rows({"v": rng.integers(0, 1 << 20, n), "g": np.array(["g%d" % x for x in rng.integers(0, 7, n)])})
+    s.add_rows({"v": rng.integers(0, 3000, n - 1), "g": np.array(["g%d" % x for x in rng.integers(0, 7, n - 1)])})
+    both(s, Q(s, groups=["g"], aggs=["v"], op="hist"))
+    both(s, Q(s, int_filters=[("v", "lt", 2000)], groups=["g"], aggs=["v"], op="avg"))
+
+
+def test_broken_block_is_skipped_like_table_query_test_go():
+    # table_query_test.go:11-158: a block whose NumRecords shrank under its row ids is dropped
+    # whole ("BLOCK SIZE CHANGED DURING QUERY") and the other blocks still answer
+    s = random_spec(22, nrows=3000, block_rows=1000)
+    s.blocks[1].num_records = 400
+    g, o = both(s, Q(s, groups=["host"], aggs=["age"], op="hist"))
+    assert g.BrokenBlocks == 1
+    s2 = random_spec(23, nrows=3000, block_rows=1000, threshold=50)
+    s2.blocks[2].num_records = 500  # value arrays longer than the block
+    g, o = both(s2, Q(s2, groups=["host"], aggs=["big"], op="avg"))
+    assert g.BrokenBlocks == 1
+
+
+def test_zone_map_pruning():
+    # ShouldLoadBlockFromDir (table_block_io.go:110-182): blocks whose [min,max] cannot match are skipped
+    rng = np.random.default_rng(24)
+    s = Spec([("t", INT), ("v", INT)])
+    for b in range(4):
+        s.add_rows({"t": rng.integers(b * 1000, b * 1000 + 1000, 500), "v": rng.integers(0, 50, 500)})
+    g, o = both(s, Q(s, int_filters=[("t", "gt", 2500)], groups=["v"], aggs=["t"], op="avg"))
+    assert g.SkippedBlocks == 2
+    g, o = both(s, Q(s, int_filters=[("t", "eq", 1200)], aggs=["v"], op="avg"))
+    assert g.SkippedBlocks == 3
+
+
+def test_negative_values_and_exact_sums():
+    rng = np.random.default_rng(25)
+    n = 5000
+    s = Spec([("x", INT), ("g", STR)])
+    s.add_rows({"x": rng.integers(-(1 << 62), 1 << 62, n), "g": np.array(["g%d" % v for v in rng.integers(0, 3, n)])},
+               threshold=10, block_rows=2000)
+    s.IntInfo["x"] = (-(1 << 62), (1 << 62) // 10)
+    both(s, Q(s, groups=["g"], aggs=["x"], op="avg"))
+    s2 = Spec([("x", INT), ("g", STR)])
+    s2.add_rows({"x": rng.integers(-500, 500, n), "g": np.array(["g%d" % v for v in rng.integers(0, 3, n)])}, block_rows=2000)
+    both(s2, Q(s2, groups=["g"], aggs=["x"], op="hist"))
+
+
+def test_many_groups_spills_accumulators_to_global_memory():
+    rng = np.random.default_rng(26)
+    n = 20000
+    s = Spec([("a", INT), ("b", INT), ("v", INT)])
+    s.add_rows({"a": rng.integers(0, 300, n), "b": rng.integers(0, 200, n), "v": rng.integers(0, 100000, n)}, block_rows=7000)
+    g, o = both(s, Q(s, groups=["a", "b"], aggs=["v"], op="avg"))
+    assert len(g.Results) > 10000
+
+
+def test_golden_rows_reproduce_reference_buckets():
+    # the reference's golden result (decoding_test.go fixture) through the CUDA path
+    from tests.test_oracle_golden import G, dense, golden_table
+    s = golden_table()
+    q = Q(s, groups=["browser", "device"], aggs=["pageload"], op="hist")
+    g = run_gpu(s, q)
+    assert g.MatchedCount == G["MatchedCount"]
+    assert [r.GroupByKey for r in g.Sorted] == G["Sorted"]
+    assert g.Cumulative.GroupByKey == "TOTAL\t"
+    assert np.array_equal(g.Cumulative.Hists["pageload"].Values, dense(G["Cumulative"]["hist"]))
+    for k, gold in G["Results"].items():
+        r = g.Results[k]
+        h = r.Hists["pageload"]
+        assert (r.Count, r.Samples, h.TotalCount()) == (gold["Count"], gold["Samples"], gold["hist"]["Count"])
+        assert (h.Min(), h.Max()) == (gold["hist"]["Min"], gold["hist"]["Max"])
+        assert (h.NumBuckets, h.BucketSize, len(h.Values)) == (1001, 23, 1002)
+        assert np.array_equal(h.Values, dense(gold["hist"]))
+
+
+@pytest.mark.parametrize("cfg,rows", [("c2", 300_000), ("c3", 400_000), ("c4", 300_000), ("c5", 300_000)])
+def test_benchmark_configs_at_reduced_size(cfg, rows):
+    """BASELINE.json configs 2-5 generated by the C++ generator at a size the oracle finishes in seconds."""
+    from sybil_b200 import engine as E
+    from sybil_b200 import synth
+    from oracle.oracle_ffi import OracleTable
+    spec = synth.config(cfg, total_rows=rows)
+    store = synth.generate(spec)
+    qd = synth.query_for(spec)
+    s = Spec(spec.key_table)
+    s.IntInfo = dict(spec.IntInfo)
+    q = Q(s, **qd)
+    t = E.Table(cfg, spec.key_table)
+    t.IntInfo = dict(spec.IntInfo)
+    ot = OracleTable(spec.key_table)
+    try:
+        for i in range(store.num_blocks()):
+            t.add_block_desc_ptr(store.block(i))
+            ot.add_block(store.block(i))
+        d, keep = q.desc()
+        o = ot.query(d, q.aggs, nthreads=4)
+        g = run_gpu(s, q, table=t)
+        compare(g, o, q)
+        assert g.MatchedCount > 0
+    finally:
+        t.close()
+        ot.close()
+        store.close()
