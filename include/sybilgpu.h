@@ -192,6 +192,8 @@ void sg_table_free(sg_table* t);
  * malformed descriptor (the block is not added). */
 int sg_table_add_block(sg_table* t, const sg_block_desc* block);
 int sg_table_sync(sg_table* t); /* wait for staged copies */
+/* forget the staged blocks, keep arena + dictionaries (re-staging without reallocation) */
+int sg_table_clear(sg_table* t);
 int64_t sg_table_num_blocks(sg_table* t);
 int64_t sg_table_num_rows(sg_table* t);
 int64_t sg_table_device_bytes(sg_table* t);

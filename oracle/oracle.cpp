@@ -897,6 +897,7 @@ struct orc_result {
   int64_t broken = 0, skipped = 0;
   double seconds = 0;
   std::vector<int64_t> time_keys;
+  bool merged_view = false;
   // scratch kept alive for pointer-returning accessors
   std::vector<int64_t> values_scratch;
 };
@@ -1117,12 +1118,25 @@ int64_t orc_result_hist_values(orc_result* r, int64_t tb, int64_t i, int32_t agg
     for (auto& sh : h.m.Subhists) emit(sh);
   return n;
 }
+// Q9: a group's final Result object is the first block's (ResultMap.Combine adopts it by
+// reference, query_spec.go:107-116) and so may still carry that block's Outliers, while every
+// later block is merged through BasicHist.Combine, which drops them.  With the merged view on,
+// the derived quantities are taken from a fresh clone + Combine — what the reference reports
+// for Cumulative and for any group whose first block had no outliers.
+void orc_result_set_merged_view(orc_result* r, int on) { r->merged_view = on != 0; }
+static Hist view_of(orc_result* r, const Hist& h) {
+  if (!r->merged_view) return h;
+  Hist nh = h.NewHist(&r->flags);
+  nh.Combine(h);
+  return nh;
+}
+
 int orc_result_percentiles(orc_result* r, int64_t tb, int64_t i, int32_t agg, int64_t* out100) {
   Result* x = pick(r, tb, i);
   if (!x) return -1;
   auto it = x->Hists.find(agg);
   if (it == x->Hists.end()) return 0;
-  auto p = it->second.GetPercentiles();
+  auto p = view_of(r, it->second).GetPercentiles();
   for (size_t k = 0; k < p.size() && k < 100; k++) out100[k] = p[k];
   return (int)p.size();
 }
@@ -1131,7 +1145,7 @@ double orc_result_stddev(orc_result* r, int64_t tb, int64_t i, int32_t agg) {
   if (!x) return NAN;
   auto it = x->Hists.find(agg);
   if (it == x->Hists.end()) return NAN;
-  return it->second.StdDev();
+  return view_of(r, it->second).StdDev();
 }
 int64_t orc_result_sparse_buckets(orc_result* r, int64_t tb, int64_t i, int32_t agg, int64_t* edges, int64_t* counts,
                                   int64_t cap) {
@@ -1139,7 +1153,7 @@ int64_t orc_result_sparse_buckets(orc_result* r, int64_t tb, int64_t i, int32_t 
   if (!x) return -1;
   auto it = x->Hists.find(agg);
   if (it == x->Hists.end()) return 0;
-  auto m = it->second.GetSparseBuckets();
+  auto m = view_of(r, it->second).GetSparseBuckets();
   int64_t n = 0;
   for (auto& kv : m) {
     if (edges && n < cap) {

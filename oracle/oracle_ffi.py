@@ -38,6 +38,7 @@ SYMBOLS = {
     "orc_result_percentiles": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int32, I64P]),
     "orc_result_stddev": (C.c_double, [P, C.c_int64, C.c_int64, C.c_int32]),
     "orc_result_sparse_buckets": (C.c_int64, [P, C.c_int64, C.c_int64, C.c_int32, I64P, I64P, C.c_int64]),
+    "orc_result_set_merged_view": (None, [P, C.c_int]),
     "orc_basic_layout": (None, [C.c_int64, C.c_int64, C.c_int32, I64P, I64P, I64P]),
     "orc_multi_layout": (C.c_int64, [C.c_int64, C.c_int64, I64P, C.c_int64]),
     "orc_basic_combine": (None, [C.c_int64, C.c_int64, C.c_int64, I64P, C.POINTER(C.c_double), I64P, C.c_int64, I64P,
@@ -112,6 +113,10 @@ class OracleTable:
             vals = np.zeros(max(nv.value, 1), np.int64)
             n = L.orc_result_hist_values(r, tb, gi, ai, vals.ctypes.data_as(I64P), len(vals))
             h.Values = vals[:n].copy()
+            # groups whose first-seen block result still holds Outliers (Q9): read the derived
+            # values from the merged view (fresh clone + Combine), which is what the reference
+            # reports whenever another block's result happens to be adopted first
+            L.orc_result_set_merged_view(r, 1 if h.noutliers else 0)
             p = (C.c_int64 * 100)()
             n = L.orc_result_percentiles(r, tb, gi, ai, p)
             h.Percentiles = [p[i] for i in range(n)]
@@ -120,6 +125,7 @@ class OracleTable:
             e, cc = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
             L.orc_result_sparse_buckets(r, tb, gi, ai, e, cc, n)
             h.IntBuckets = {e[i]: cc[i] for i in range(n)}
+            L.orc_result_set_merged_view(r, 0)
             o.Hists[name] = h
         return o
 

@@ -94,6 +94,7 @@ SYMBOLS = {
     "sg_table_free": (None, [P]),
     "sg_table_add_block": (C.c_int, [P, C.POINTER(sg_block_desc)]),
     "sg_table_sync": (C.c_int, [P]),
+    "sg_table_clear": (C.c_int, [P]),
     "sg_table_num_blocks": (C.c_int64, [P]),
     "sg_table_num_rows": (C.c_int64, [P]),
     "sg_table_device_bytes": (C.c_int64, [P]),

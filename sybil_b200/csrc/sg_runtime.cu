@@ -160,8 +160,8 @@ struct sg_table {
   std::vector<StrDict> sdict;
   std::vector<IntDict> idict;
   std::vector<char> has_values_int;  // an int column that is value-array encoded somewhere
-  std::vector<char*> chunks;
-  size_t chunk_used = 0, chunk_cap = 0;
+  std::vector<std::pair<char*, size_t>> chunks;  // device arena chunks (ptr, capacity)
+  size_t chunk_idx = 0, chunk_used = 0;
   Stage stage[2];
   int cur_stage = 0;
   int64_t total_rows = 0;
@@ -179,7 +179,11 @@ namespace {
 
 int arena_alloc(sg_table* t, size_t bytes, char** out) {
   bytes = align_up(bytes, 256);
-  if (t->chunks.empty() || t->chunk_used + bytes > t->chunk_cap) {
+  while (t->chunk_idx < t->chunks.size() && t->chunk_used + bytes > t->chunks[t->chunk_idx].second) {
+    t->chunk_idx++;
+    t->chunk_used = 0;
+  }
+  if (t->chunk_idx >= t->chunks.size()) {
     size_t cap = std::max(ARENA_CHUNK, bytes);
     char* p = nullptr;
     cudaError_t e = cudaMalloc(&p, cap);
@@ -187,12 +191,12 @@ int arena_alloc(sg_table* t, size_t bytes, char** out) {
       t->ctx->set_err(std::string("cudaMalloc arena: ") + cudaGetErrorString(e));
       return SG_ERR_NOMEM;
     }
-    t->chunks.push_back(p);
+    t->chunks.emplace_back(p, cap);
+    t->chunk_idx = t->chunks.size() - 1;
     t->chunk_used = 0;
-    t->chunk_cap = cap;
     t->device_bytes += (int64_t)cap;
   }
-  *out = t->chunks.back() + t->chunk_used;
+  *out = t->chunks[t->chunk_idx].first + t->chunk_used;
   t->chunk_used += bytes;
   return SG_OK;
 }
@@ -359,7 +363,7 @@ void sg_table_free(sg_table* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
   cudaStreamSynchronize(t->ctx->copy_stream);
-  for (auto p : t->chunks) cudaFree(p);
+  for (auto& p : t->chunks) cudaFree(p.first);
   for (int i = 0; i < 2; i++) {
     if (t->stage[i].host) cudaFreeHost(t->stage[i].host);
     if (t->stage[i].done) cudaEventDestroy(t->stage[i].done);
@@ -588,6 +592,26 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
   t->cols.insert(t->cols.end(), dcs.begin(), dcs.end());
   t->total_rows += nrec;
   t->encoded_bytes += enc_bytes;
+  t->dirty = true;
+  return SG_OK;
+}
+
+int sg_table_clear(sg_table* t) {
+  // drop the staged blocks but keep the device arena, the staging buffers and the
+  // dictionaries: the next sg_table_add_block reuses the memory
+  if (!t) return SG_ERR_INVALID;
+  cudaSetDevice(t->ctx->device);
+  CUDA_TRY(t->ctx, cudaStreamSynchronize(t->ctx->copy_stream));
+  CUDA_TRY(t->ctx, cudaStreamSynchronize(t->ctx->stream));
+  t->blocks.clear();
+  t->cols.clear();
+  t->chunk_idx = 0;
+  t->chunk_used = 0;
+  t->stage[0].pending = t->stage[1].pending = false;
+  t->stage[0].used = t->stage[1].used = 0;
+  t->total_rows = 0;
+  t->encoded_bytes = 0;
+  t->h2d_bytes = 0;
   t->dirty = true;
   return SG_OK;
 }
@@ -1041,6 +1065,7 @@ int reset_accumulators(sg_query* q) {
                                                                   INT64_MIN);
   }
   CUDA_TRY(c, cudaGetLastError());
+  q->launches += q->plan.naggs;
   return SG_OK;
 }
 

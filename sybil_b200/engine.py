@@ -143,6 +143,17 @@ class Hist:
         self.NumBuckets, self.BucketSize = v.num_buckets, v.bucket_size
         self.nsubhists = v.nsubhists
         self.Values = np.ctypeslib.as_array(v.values, (v.nvalues,)).copy() if v.values else np.zeros(0, np.int64)
+        # the sg_result is freed when LoadAndQueryRecords returns: derive everything now
+        lib, h = res.lib, res.h
+        out = (C.c_int64 * 100)()
+        n = lib.sg_result_percentiles(h, gi, ai, out)
+        self._percentiles = [out[i] for i in range(max(n, 0))]
+        self._stddev = lib.sg_result_stddev(h, gi, ai)
+        n = lib.sg_result_sparse_buckets(h, gi, ai, None, None, 0)
+        e, c = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
+        lib.sg_result_sparse_buckets(h, gi, ai, e, c, n)
+        self._buckets = {e[i]: c[i] for i in range(max(n, 0))}
+        self._r = None
 
     def Mean(self):
         return self.Avg
@@ -160,18 +171,13 @@ class Hist:
         return self.ExactSum
 
     def GetPercentiles(self):
-        out = (C.c_int64 * 100)()
-        n = self._r.lib.sg_result_percentiles(self._r.h, self._gi, self._ai, out)
-        return [out[i] for i in range(n)]
+        return list(self._percentiles)
 
     def StdDev(self):
-        return self._r.lib.sg_result_stddev(self._r.h, self._gi, self._ai)
+        return self._stddev
 
     def GetIntBuckets(self):
-        n = self._r.lib.sg_result_sparse_buckets(self._r.h, self._gi, self._ai, None, None, 0)
-        e, c = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
-        self._r.lib.sg_result_sparse_buckets(self._r.h, self._gi, self._ai, e, c, n)
-        return {e[i]: c[i] for i in range(n)}
+        return dict(self._buckets)
 
 
 class Result:  # query_spec.go:85-93

