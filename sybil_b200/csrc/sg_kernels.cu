@@ -7,24 +7,25 @@
 //   FilterAndAggRecords             src/lib/aggregate.go:56-282
 //   BasicHist/MultiHist.AddWeightedValue   src/lib/hist_basic.go:101-151, hist_multi.go:48-88
 //
-// Shape of the kernel (see DESIGN.md §3):
-//   * persistent grid, one CTA of 512 threads per SM; CTAs pull blocks from an
-//     atomic work counter;
-//   * per block the CTA keeps ONE word per row in shared memory ("slot": dense
-//     group index in the low bits, number of filters passed above them) and walks
-//     the referenced columns one after another.  The encoded arrays are streamed
-//     from HBM exactly once with 128-bit loads; nothing decoded is written back;
-//   * a bucket-encoded column (value -> delta-encoded row-id list) is decoded by
-//     a segmented prefix sum over the flat id array (segment heads = bin starts,
-//     kept as a 65,536-bit mask in shared memory) and scattered into the slot
-//     words with plain byte/halfword stores (a row appears in one bin only);
-//   * a value-array column is decoded by a block-wide int64 prefix sum in row
-//     order;
-//   * count / sum accumulators live in shared memory, replicated per lane so
-//     that the 32-bit shared atomics of a warp never collide (64-bit shared
-//     atomics are CAS loops on this architecture); sums are kept exact in two
-//     32-bit limbs with explicit carry.  Histogram bucket counters go to HBM/L2
-//     with 64-bit reductions (RED.ADD.64).
+// Shape of the kernel (DESIGN.md §3):
+//   * persistent grid, one CTA of 16 warps per SM; CTAs pull 65,536-row blocks from
+//     an atomic work counter;
+//   * per block the CTA keeps ONE word per row in shared memory ("slot": dense group
+//     index in the low bits, number of filters passed above them) and walks the
+//     referenced columns one after another.  The encoded arrays are streamed from
+//     HBM exactly once with 256-bit loads; nothing decoded is written back;
+//   * a column is cut into warp tiles (1024 row ids / 512 int64 values).  A warp
+//     loads its tile into registers, scans it (lane-serial + one warp scan), publishes
+//     the tile total in shared memory and picks up the totals of the 15 tiles between
+//     its previous tile and this one ("look-back"): there is no block-wide barrier in
+//     the streaming loops and the 16 warps' loads overlap each other's arithmetic;
+//   * bucket-encoded columns (value -> delta-encoded row-id list) use a segmented
+//     prefix sum (segment heads = bin starts, a 65,536-bit mask in shared memory) and
+//     scatter into the slot words with plain byte/halfword stores;
+//   * count / sum accumulators live in shared memory, replicated per lane so the
+//     32-bit shared atomics of a warp never collide (64-bit shared atomics are CAS
+//     loops on this architecture); sums are exact in two 32-bit limbs with explicit
+//     carry.  Histogram bucket counters go to L2/HBM with 64-bit reductions.
 // No tensor cores: this is integer / indexing work bound by HBM bandwidth.
 #include <cuda_runtime.h>
 
@@ -36,180 +37,202 @@ namespace sg {
 
 constexpr int THREADS = 512;
 constexpr int NWARPS = THREADS / 32;
-constexpr int U = 4;  // 128-bit loads in flight per lane per chunk
 constexpr uint32_t FLAG = 0x80000000u;
 constexpr uint32_t HEAD_WORDS = SG_BLOCK_ROWS / 32;  // 2048
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int BE = 32;  // row ids per lane in a bucket tile  (tile = 1024 ids, 4 KB)
+constexpr int VE = 16;  // int64 values per lane in a value tile (tile = 512 rows, 4 KB)
+constexpr int SE = 8;   // int32 string ids per lane (tile = 256 rows)
+constexpr uint32_t MAX_TILES = 128;
 
 int scan_threads() { return THREADS; }
 
-// fixed shared-memory carve-out (bytes), in this order after the dynamic base:
-//   headbits[2048] u32 | headprefix[2048] u16 | binpay[SMEM_BINS] u32 | wtot[2][NWARPS] u64 | misc[64] u32
-constexpr uint32_t OFF_HEADBITS = 0;
-constexpr uint32_t OFF_HEADPREFIX = OFF_HEADBITS + HEAD_WORDS * 4;
-constexpr uint32_t OFF_BINPAY = OFF_HEADPREFIX + HEAD_WORDS * 2;
-constexpr uint32_t OFF_WTOT = OFF_BINPAY + SMEM_BINS * 4;
-constexpr uint32_t OFF_MISC = OFF_WTOT + 2 * NWARPS * 8;
+// fixed shared-memory carve-out (bytes) ahead of the slot words and accumulators
+constexpr uint32_t OFF_HEADBITS = 0;                                   // u32[2048]
+constexpr uint32_t OFF_HEADPREFIX = OFF_HEADBITS + HEAD_WORDS * 4;     // u16[2048]
+constexpr uint32_t OFF_BINPAY = OFF_HEADPREFIX + HEAD_WORDS * 2;       // u32[SMEM_BINS]
+constexpr uint32_t OFF_PUBA = OFF_BINPAY + SMEM_BINS * 4;              // u64[MAX_TILES]
+constexpr uint32_t OFF_PUBB = OFF_PUBA + MAX_TILES * 8;                // u64[MAX_TILES]
+constexpr uint32_t OFF_MISC = OFF_PUBB + MAX_TILES * 8;                // u32[64]
 constexpr uint32_t FIXED_SMEM = OFF_MISC + 64 * 4;
 uint32_t scan_fixed_smem() { return FIXED_SMEM; }
 
-struct Ctx {  // per-CTA view of shared memory and the current block
+struct Ctx {
   uint32_t* headbits;
   uint16_t* headprefix;
   uint32_t* binpay_s;
-  unsigned long long* wtot;  // [2][NWARPS]
-  uint32_t* misc;            // [0] next block, [1] broken flag, [16..31] warp totals
-  uint32_t* acc;             // replicated accumulators (or nullptr)
+  volatile unsigned long long* pubA;
+  volatile unsigned long long* pubB;
+  volatile uint32_t* misc;  // [0] next block, [1] broken flag, [16..31] warp totals
+  uint32_t* acc;
   int tid, lane, warp;
+  uint32_t epoch;  // one per column pass; tags the published tile totals
 };
 
-__device__ __forceinline__ uint4 ldg128(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(p));
-  return r;
 }
-
-// 4 consecutive u32 starting at element idx (idx % 4 == 0), zero beyond n
-__device__ __forceinline__ uint4 load4_u32(const uint32_t* __restrict__ p, uint32_t idx, uint32_t n) {
-  if (idx + 4 <= n) return ldg128(p + idx);
-  uint4 r = make_uint4(0, 0, 0, 0);
-  if (idx < n) r.x = p[idx];
-  if (idx + 1 < n) r.y = p[idx + 1];
-  if (idx + 2 < n) r.z = p[idx + 2];
-  return r;
+__device__ __forceinline__ void ldg256(const void* p, unsigned long long* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3])
+               : "l"(p));
 }
 
 // ---------------------------------------------------------------------------
-// bucket-encoded column: visit(row, bin) for every (bin, row) pair
+// look-back over the tile totals other warps published for tiles t-15 .. t-1
 // ---------------------------------------------------------------------------
-template <class Visit>
-__device__ __forceinline__ void scan_bucket(const Ctx& cx, const DevCol& c, uint32_t nrec, Visit visit) {
+// segmented u32 flavour: returns the running segment sum entering tile t
+__device__ __forceinline__ uint32_t lookback_seg(const Ctx& cx, uint32_t t, uint32_t prev_incl) {
+  const int tt = (int)t - 15 + cx.lane;
+  const bool valid = cx.lane < 15 && tt >= 0;
+  uint32_t a = 0;
+  if (valid) {
+    unsigned long long w;
+    do {
+      w = cx.pubA[tt];
+    } while ((uint32_t)(w >> 32) != cx.epoch);
+    a = (uint32_t)w;
+  }
+  const uint32_t m = __ballot_sync(FULL, valid && (a & FLAG));
+  uint32_t contrib = valid ? (a & ~FLAG) : 0u;
+  uint32_t base = prev_incl;
+  if (m) {
+    const int js = 31 - __clz(m);
+    if (cx.lane < js) contrib = 0u;
+    base = 0u;
+  }
+  return base + __reduce_add_sync(FULL, contrib);
+}
+// plain u64 flavour: returns the sum of the totals of tiles t-15 .. t-1
+__device__ __forceinline__ unsigned long long lookback_sum(const Ctx& cx, uint32_t t) {
+  const int tt = (int)t - 15 + cx.lane;
+  unsigned long long v = 0;
+  if (cx.lane < 15 && tt >= 0) {
+    unsigned long long lo, hi;
+    do {
+      lo = cx.pubA[tt];
+    } while ((uint32_t)(lo >> 32) != cx.epoch);
+    do {
+      hi = cx.pubB[tt];
+    } while ((uint32_t)(hi >> 32) != cx.epoch);
+    v = (lo & 0xffffffffull) | (hi << 32);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// bucket-encoded column: on_bin(bin) whenever the bin of the lane's next entry
+// changes (and before its first entry), on_row(row) for every (bin,row) pair
+// ---------------------------------------------------------------------------
+template <class OnBin, class OnRow>
+__device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint32_t nrec, OnBin on_bin, OnRow on_row) {
   const uint32_t n = c.nitems;
+  const uint32_t nbins = c.nbins;
   const uint32_t* __restrict__ ids = reinterpret_cast<const uint32_t*>(c.data);
   const bool delta = (c.flags & COL_DELTA_IDS) != 0;
   const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
 
-  // segment heads: one bit per flat entry that starts a bin (bins are non-empty)
+  // segment heads: one bit per flat entry that starts a (non-empty) bin
   for (uint32_t i = tid; i < HEAD_WORDS; i += THREADS) cx.headbits[i] = 0;
   __syncthreads();
-  for (uint32_t b = tid; b < c.nbins; b += THREADS) {
-    uint32_t o = c.bin_offsets[b];
-    if (o < n) atomicOr(&cx.headbits[o >> 5], 1u << (o & 31));
+  {
+    const uint32_t* __restrict__ offs = c.bin_offsets;
+    for (uint32_t b = tid; b < nbins; b += THREADS) {
+      const uint32_t o = offs[b];
+      if (o < n) atomicOr(&cx.headbits[o >> 5], 1u << (o & 31));
+    }
   }
   __syncthreads();
   {  // exclusive prefix popcount per 32-entry word: 512 threads x 4 words
-    uint4 w = reinterpret_cast<const uint4*>(cx.headbits)[tid];
-    uint32_t p0 = __popc(w.x), p1 = __popc(w.y), p2 = __popc(w.z), p3 = __popc(w.w);
-    uint32_t tot = p0 + p1 + p2 + p3, inc = tot;
+    const uint4 w = reinterpret_cast<const uint4*>(cx.headbits)[tid];
+    const uint32_t p0 = __popc(w.x), p1 = __popc(w.y), p2 = __popc(w.z), p3 = __popc(w.w);
+    const uint32_t tot = p0 + p1 + p2 + p3;
+    uint32_t inc = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      const uint32_t t = __shfl_up_sync(FULL, inc, d);
       if (lane >= d) inc += t;
     }
     if (lane == 31) cx.misc[16 + warp] = inc;
     __syncthreads();
     uint32_t base = 0;
     for (int i = 0; i < warp; i++) base += cx.misc[16 + i];
-    uint32_t ex = base + inc - tot;
+    const uint32_t ex = base + inc - tot;
     cx.headprefix[tid * 4 + 0] = (uint16_t)ex;
     cx.headprefix[tid * 4 + 1] = (uint16_t)(ex + p0);
     cx.headprefix[tid * 4 + 2] = (uint16_t)(ex + p0 + p1);
     cx.headprefix[tid * 4 + 3] = (uint16_t)(ex + p0 + p1 + p2);
   }
+  cx.epoch++;
   __syncthreads();
 
-  constexpr uint32_t CH = THREADS * 4 * U;  // entries per chunk
-  uint32_t carry = 0;                       // running sum of the open segment at chunk start
-  int buf = 0;
-  for (uint32_t base = 0; base < n; base += CH, buf ^= 1) {
-    const uint32_t wbase = base + warp * (U * 128);
-    uint4 d[U];
+  const uint32_t ntiles = (n + (32 * BE - 1)) / (32 * BE);
+  uint32_t prev_incl = 0;  // running segment sum through this warp's previous tile
+  for (uint32_t t = warp; t < ntiles; t += NWARPS) {
+    const uint32_t idx0 = t * (32 * BE) + lane * BE;
+    uint32_t a[BE];
+    if (idx0 + BE <= n) {
 #pragma unroll
-    for (int u = 0; u < U; u++) d[u] = load4_u32(ids, wbase + u * 128 + lane * 4, n);
-
-    uint32_t y[U][4];
-    uint32_t nibs[U];   // head bits of the lane's 4 entries (true heads)
-    uint32_t openm[U];  // bit k: entry k still needs the cross-warp carry
-    uint32_t binb[U];   // heads strictly before the lane's first entry
-    uint32_t run_sum = 0, run_flag = 0;
+      for (int j = 0; j < BE / 8; j++) ldg256(ids + idx0 + 8 * j, a + 8 * j);
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint32_t idx = wbase + u * 128 + lane * 4;
-      uint32_t word = 0, hp = 0;
-      if (idx < n) {
-        word = cx.headbits[idx >> 5];
-        hp = cx.headprefix[idx >> 5];
-      }
-      const uint32_t sh = idx & 31;
-      const uint32_t nib_true = (word >> sh) & 0xFu;
-      binb[u] = hp + __popc(word & ((1u << sh) - 1u));
-      nibs[u] = nib_true;
-      const uint32_t nib = delta ? nib_true : 0xFu;  // absolute ids: every entry is its own segment
-      uint32_t a0 = d[u].x, a1 = d[u].y, a2 = d[u].z, a3 = d[u].w;
-      // a valid gap is < 65,536; anything larger marks the block broken (and is
-      // zeroed so that the packed scan word cannot overflow into the flag bit)
-      if ((a0 | a1 | a2 | a3) >= 0x10000u) {
+      for (int k = 0; k < BE; k++) a[k] = (idx0 + k < n) ? ids[idx0 + k] : 0u;
+    }
+    const uint32_t word = (idx0 < n) ? cx.headbits[idx0 >> 5] : 0u;
+    const uint32_t segw = delta ? word : FULL;  // absolute ids: every entry is its own segment
+    {
+      // a valid gap is < 65,536; anything larger marks the block broken and is masked so
+      // the packed (sum | flag) scan word cannot overflow into the flag bit
+      uint32_t orv = 0;
+#pragma unroll
+      for (int k = 0; k < BE; k++) orv |= a[k];
+      if (orv >= 0x10000u) {
         cx.misc[1] = 1;
-        a0 &= 0xFFFFu; a1 &= 0xFFFFu; a2 &= 0xFFFFu; a3 &= 0xFFFFu;
-      }
-      const uint32_t x0 = a0;
-      const uint32_t x1 = (nib & 2u) ? a1 : x0 + a1;
-      const uint32_t x2 = (nib & 4u) ? a2 : x1 + a2;
-      const uint32_t x3 = (nib & 8u) ? a3 : x2 + a3;
-      uint32_t agg = x3 | (nib ? FLAG : 0u);
 #pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, agg, dd);
-        if (lane >= dd && !(agg & FLAG)) agg += t;
+        for (int k = 0; k < BE; k++) a[k] &= 0xFFFFu;
       }
-      uint32_t excl = __shfl_up_sync(0xffffffffu, agg, 1);
-      if (lane == 0) excl = 0;
-      // segment sum entering this lane (without the cross-warp carry)
-      const uint32_t pre = (excl & FLAG) ? (excl & ~FLAG) : ((excl + run_sum) & ~FLAG);
-      const uint32_t pre_flag = (excl & FLAG) | run_flag;
-      y[u][0] = (nib & 1u) ? x0 : x0 + pre;
-      y[u][1] = (nib & 3u) ? x1 : x1 + pre;
-      y[u][2] = (nib & 7u) ? x2 : x2 + pre;
-      y[u][3] = (nib & 15u) ? x3 : x3 + pre;
-      uint32_t om = 0;
-      if (!pre_flag) {
-        om = (nib & 1u) ? 0u : 1u;
-        om |= (nib & 3u) ? 0u : 2u;
-        om |= (nib & 7u) ? 0u : 4u;
-        om |= (nib & 15u) ? 0u : 8u;
-      }
-      openm[u] = om;
-      const uint32_t last = __shfl_sync(0xffffffffu, agg, 31);
-      run_sum = (last & FLAG) ? (last & ~FLAG) : ((last + run_sum) & ~FLAG);
-      run_flag |= (last & FLAG);
     }
-    if (lane == 0) cx.wtot[buf * NWARPS + warp] = (unsigned long long)(run_sum | run_flag);
-    __syncthreads();
-    uint32_t cin = carry, call = carry;
+    // pass 1: lane total since the last head in the lane
+    uint32_t tot = 0;
 #pragma unroll
-    for (int i = 0; i < NWARPS; i++) {
-      const uint32_t t = (uint32_t)cx.wtot[buf * NWARPS + i];
-      call = (t & FLAG) ? (t & ~FLAG) : ((call + t) & ~FLAG);
-      if (i + 1 == warp) cin = call;
+    for (int k = 0; k < BE; k++) tot = ((segw >> k) & 1u) ? a[k] : tot + a[k];
+    uint32_t incl = tot | (segw ? FLAG : 0u);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d && !(incl & FLAG)) incl += v;
     }
-    if (warp == 0) cin = carry;
-    carry = call;
-
+    uint32_t excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 0;
+    const uint32_t tile_tot = __shfl_sync(FULL, incl, 31);
+    if (lane == 0) cx.pubA[t] = (unsigned long long)tile_tot | ((unsigned long long)cx.epoch << 32);
+    const uint32_t carry = lookback_seg(cx, t, prev_incl);
+    prev_incl = (tile_tot & FLAG) ? (tile_tot & ~FLAG) : ((carry + tile_tot) & ~FLAG);
+    uint32_t run = (excl & FLAG) ? (excl & ~FLAG) : ((excl + carry) & ~FLAG);
+    // pass 2: rows and bins
+    int bin = (int)((idx0 < n) ? cx.headprefix[idx0 >> 5] : 0) - 1;
+    const uint32_t cnt = (idx0 >= n) ? 0u : ((n - idx0 < BE) ? n - idx0 : BE);
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint32_t idx = wbase + u * 128 + lane * 4;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (idx + k < n) {
-          uint32_t row = y[u][k] + ((openm[u] >> k) & 1u ? cin : 0u);
-          uint32_t bin = binb[u] + __popc(nibs[u] & ((2u << k) - 1u)) - 1u;
-          if (row >= nrec || bin >= c.nbins) {
-            cx.misc[1] = 1;  // "BLOCK SIZE CHANGED DURING QUERY" (column_store_io.go:733)
-          } else {
-            visit(row, bin);
+    for (int k = 0; k < BE; k++) {
+      if (k < cnt) {
+        const bool head = (word >> k) & 1u;
+        if (head) bin++;
+        run = ((segw >> k) & 1u) ? a[k] : run + a[k];
+        if (head || k == 0) {
+          if ((uint32_t)bin >= nbins) {
+            cx.misc[1] = 1;
+            bin = 0;
           }
+          on_bin((uint32_t)bin);
         }
+        if (run >= nrec)
+          cx.misc[1] = 1;  // "BLOCK SIZE CHANGED DURING QUERY" (column_store_io.go:733)
+        else
+          on_row(run);
       }
     }
   }
@@ -220,66 +243,54 @@ __device__ __forceinline__ void scan_bucket(const Ctx& cx, const DevCol& c, uint
 // value-array int column (delta-encoded int64): visit(row, value) in row order
 // ---------------------------------------------------------------------------
 template <class Visit>
-__device__ __forceinline__ void scan_values_i64(const Ctx& cx, const DevCol& c, uint32_t nrec, Visit visit) {
+__device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const uint32_t nrec, Visit visit) {
   uint32_t n = c.nitems;
   if (n > nrec) n = nrec;  // staging already flags len(Values) > NumRecords as broken
   const unsigned long long* __restrict__ vals = reinterpret_cast<const unsigned long long*>(c.data);
   const bool delta = (c.flags & COL_DELTA_VALUES) != 0;
   const int lane = cx.lane, warp = cx.warp;
-  constexpr uint32_t CH = THREADS * 2 * U;
-  unsigned long long carry = 0;
-  int buf = 0;
-  for (uint32_t base = 0; base < n; base += CH, buf ^= 1) {
-    const uint32_t wbase = base + warp * (U * 64);
-    unsigned long long a[U][2];
+  cx.epoch++;
+  const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
+  unsigned long long prev_incl = 0;
+  for (uint32_t t = warp; t < ntiles; t += NWARPS) {
+    const uint32_t idx0 = t * (32 * VE) + lane * VE;
+    unsigned long long a[VE];
+    const bool full = idx0 + VE <= n;
+    if (full) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint32_t idx = wbase + u * 64 + lane * 2;
-      if (idx + 2 <= n) {
-        uint4 r = ldg128(vals + idx);
-        a[u][0] = (unsigned long long)r.x | ((unsigned long long)r.y << 32);
-        a[u][1] = (unsigned long long)r.z | ((unsigned long long)r.w << 32);
-      } else {
-        a[u][0] = idx < n ? vals[idx] : 0ull;
-        a[u][1] = 0ull;
-      }
+      for (int j = 0; j < VE / 4; j++) ldg256(vals + idx0 + 4 * j, a + 4 * j);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? vals[idx0 + k] : 0ull;
     }
     if (delta) {
-      unsigned long long run = 0;
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        a[u][1] += a[u][0];
-        unsigned long long inc = a[u][1];
+      for (int k = 1; k < VE; k++) a[k] += a[k - 1];
+      const unsigned long long tot = a[VE - 1];
+      unsigned long long incl = tot;
 #pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-          unsigned long long t = __shfl_up_sync(0xffffffffu, inc, dd);
-          if (lane >= dd) inc += t;
-        }
-        unsigned long long ex = inc - a[u][1] + run;
-        a[u][0] += ex;
-        a[u][1] += ex;
-        run += __shfl_sync(0xffffffffu, inc, 31);
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
       }
-      if (lane == 0) cx.wtot[buf * NWARPS + warp] = run;
-      __syncthreads();
-      unsigned long long cin = carry, call = carry;
-#pragma unroll
-      for (int i = 0; i < NWARPS; i++) {
-        if (i == warp) cin = call;
-        call += cx.wtot[buf * NWARPS + i];
+      const unsigned long long tile_tot = __shfl_sync(FULL, incl, 31);
+      if (lane == 0) {
+        cx.pubA[t] = (tile_tot & 0xffffffffull) | ((unsigned long long)cx.epoch << 32);
+        cx.pubB[t] = (tile_tot >> 32) | ((unsigned long long)cx.epoch << 32);
       }
-      carry = call;
+      const unsigned long long carry = prev_incl + lookback_sum(cx, t);
+      prev_incl = carry + tile_tot;
+      const unsigned long long base = incl - tot + carry;
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        a[u][0] += cin;
-        a[u][1] += cin;
-      }
+      for (int k = 0; k < VE; k++) a[k] += base;
     }
+    if (full) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint32_t idx = wbase + u * 64 + lane * 2;
-      if (idx < n) visit(idx, (long long)a[u][0]);
-      if (idx + 1 < n) visit(idx + 1, (long long)a[u][1]);
+      for (int k = 0; k < VE; k++) visit(idx0 + k, (long long)a[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VE; k++)
+        if (idx0 + k < n) visit(idx0 + k, (long long)a[k]);
     }
   }
   __syncthreads();
@@ -287,16 +298,21 @@ __device__ __forceinline__ void scan_values_i64(const Ctx& cx, const DevCol& c, 
 
 // value-array str column (raw int32 local ids): visit(row, local_id)
 template <class Visit>
-__device__ __forceinline__ void scan_values_i32(const Ctx& cx, const DevCol& c, uint32_t nrec, Visit visit) {
+__device__ __forceinline__ void scan_values_i32(Ctx& cx, const DevCol& c, const uint32_t nrec, Visit visit) {
   uint32_t n = c.nitems;
   if (n > nrec) n = nrec;
   const uint32_t* __restrict__ vals = reinterpret_cast<const uint32_t*>(c.data);
-  for (uint32_t idx = cx.tid * 4; idx < n; idx += THREADS * 4) {
-    uint4 r = load4_u32(vals, idx, n);
-    visit(idx, (int32_t)r.x);
-    if (idx + 1 < n) visit(idx + 1, (int32_t)r.y);
-    if (idx + 2 < n) visit(idx + 2, (int32_t)r.z);
-    if (idx + 3 < n) visit(idx + 3, (int32_t)r.w);
+  for (uint32_t idx0 = cx.tid * SE; idx0 < n; idx0 += THREADS * SE) {
+    uint32_t a[SE];
+    if (idx0 + SE <= n) {
+      ldg256(vals + idx0, a);
+#pragma unroll
+      for (int k = 0; k < SE; k++) visit(idx0 + k, (int32_t)a[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < SE; k++)
+        if (idx0 + k < n) visit(idx0 + k, (int32_t)vals[idx0 + k]);
+    }
   }
   __syncthreads();
 }
@@ -314,21 +330,25 @@ __device__ __forceinline__ bool int_pred(int op, long long v, long long lit) {
     default: return false;
   }
 }
-__device__ __forceinline__ bool str_pred(const KFilter& f, int32_t gid) {
-  // filter.go:199-250 on global ids: EQ/NEQ against the literal's id (a literal the
-  // dictionary does not hold matches nothing, Q3); RE/NRE through the host's bitset
-  switch (f.op) {
-    case SG_OP_EQ: return gid == f.str_gid;
-    case SG_OP_NEQ: return gid != f.str_gid;
-    case SG_OP_RE:
-    case SG_OP_NRE: {
-      bool m = false;
-      if (gid >= 0 && (long long)gid < f.lut_bits) m = (f.lut[gid >> 5] >> (gid & 31)) & 1u;
-      return f.op == SG_OP_RE ? m : !m;
+struct StrPred {  // filter.go:199-250 on global ids (registers, not plan memory)
+  int op;
+  int32_t gid;
+  const uint32_t* lut;
+  long long lut_bits;
+  __device__ __forceinline__ bool operator()(int32_t g) const {
+    switch (op) {
+      case SG_OP_EQ: return g == gid;  // a literal absent from the dictionary matches nothing (Q3)
+      case SG_OP_NEQ: return g != gid;
+      case SG_OP_RE:
+      case SG_OP_NRE: {
+        bool m = false;
+        if (g >= 0 && (long long)g < lut_bits) m = (lut[g >> 5] >> (g & 31)) & 1u;
+        return op == SG_OP_RE ? m : !m;
+      }
+      default: return false;
     }
-    default: return false;
   }
-}
+};
 __device__ __forceinline__ int32_t str_gid(const DevCol& c, long long local) {
   if (local < 0 || local >= (long long)c.nremap) return c.oob_gid;
   return c.remap[local];
@@ -336,51 +356,54 @@ __device__ __forceinline__ int32_t str_gid(const DevCol& c, long long local) {
 
 // time bucket code (aggregate.go:177: int(val)/TimeBucket*TimeBucket, truncating):
 // dense index 1.. of trunc(val/bucket) - first; 0 = outside the planned range
-__device__ __forceinline__ uint32_t time_code(const Plan& P, long long v) {
-  long long q = v / P.time_bucket - P.time_first;
-  if (q < 0 || q >= (long long)(P.time_radix - 1)) return 0u;
+__device__ __forceinline__ uint32_t time_code(long long v, long long bucket, long long first, uint32_t radix) {
+  const long long q = v / bucket - first;
+  if (q < 0 || q >= (long long)(radix - 1)) return 0u;
   return (uint32_t)q + 1u;
 }
 
 // ---------------------------------------------------------------------------
-// accumulation of one accepted/considered value
+// per-aggregation constants held in registers during a column pass
 // ---------------------------------------------------------------------------
-template <bool ACC_SMEM>
-__device__ __forceinline__ void agg_value(const Ctx& cx, const Plan& P, const KAgg& A, int ai, uint32_t g, long long v) {
-  // BasicHist/MultiHist.AddWeightedValue (hist_basic.go:104, hist_multi.go:52)
-  if (v > A.reject_hi || v < A.info_min) return;
-  if (ACC_SMEM) {
-    const uint32_t R = P.acc_repl;
-    uint32_t* w = cx.acc + ((size_t)g * P.acc_words + 1 + 3 * ai) * R + (cx.lane & (R - 1));
-    atomicAdd(w, 1u);
-    const uint32_t lo = (uint32_t)(unsigned long long)v;
-    uint32_t hi = (uint32_t)((unsigned long long)v >> 32);
-    const uint32_t old = atomicAdd(w + R, lo);
-    if (old > ~lo) hi += 1u;  // carry out of the low limb
-    if (hi) atomicAdd(w + 2 * R, hi);
-  } else {
-    atomicAdd(reinterpret_cast<unsigned long long*>(A.hcount) + g, 1ull);
-    atomicAdd(reinterpret_cast<unsigned long long*>(A.sum) + g, (unsigned long long)v);
+struct AggRegs {
+  long long info_min, info_max, reject_hi;
+  int nsub;
+  uint32_t nvals_total;
+  unsigned long long* buckets;
+  unsigned long long* hcount;
+  unsigned long long* sum;
+  long long* vmax;
+  const KSubHist* sub;
+  // first (only, for BasicHist) layout in registers
+  long long lo0;
+  uint32_t bsize0, nvals0;
+  bool fast32;  // BasicHist with a 32-bit bucket size: the common bucket path
+};
+
+__device__ __forceinline__ void hist_bucket_add(const AggRegs& A, uint32_t g, long long v) {
+  if (A.nsub == 1 && A.fast32) {
+    const unsigned long long x = (unsigned long long)v - (unsigned long long)A.lo0;
+    uint32_t b;
+    if (x < 0x100000000ull)
+      b = (uint32_t)x / A.bsize0;
+    else
+      b = (uint32_t)((x / (unsigned long long)A.bsize0) > 0xffffffffull ? 0xffffffffu : (x / A.bsize0));
+    if (b >= A.nvals0) b = A.nvals0 - 1;  // outlier: clamped into the last slot (hist_basic.go:134-137)
+    atomicAdd(A.buckets + ((size_t)g * A.nvals_total + b), 1ull);
+    return;
   }
-  if (v > A.info_max) atomicMax(reinterpret_cast<long long*>(A.vmax) + g, v);
-  if (A.nsub > 0) {
-    // BasicHist: the one layout; MultiHist: first sub-range containing v (hist_multi.go:81-86)
-    for (int s = 0; s < A.nsub; s++) {
-      const KSubHist& S = A.sub[s];
-      if (A.nsub > 1) {
-        if (v < S.lo || v > S.hi) continue;
-        if (v > S.reject_hi || v < S.lo) break;  // the subhist's own reject rule
-      }
-      unsigned long long x = (unsigned long long)v - (unsigned long long)S.lo;
-      unsigned long long b;
-      if (x < 0x100000000ull && (unsigned long long)S.bsize < 0x100000000ull)
-        b = (uint32_t)x / (uint32_t)S.bsize;
-      else
-        b = (unsigned long long)((long long)x / S.bsize);
-      if (b >= S.nvals) b = S.nvals - 1;  // outlier: clamped into the last slot (:134-137)
-      atomicAdd(reinterpret_cast<unsigned long long*>(A.buckets) + ((size_t)g * A.nvals_total + S.base + b), 1ull);
-      break;
+  // general BasicHist, or MultiHist: first sub-range containing v (hist_multi.go:81-86)
+  for (int s = 0; s < A.nsub; s++) {
+    const KSubHist S = A.sub[s];
+    if (A.nsub > 1) {
+      if (v < S.lo || v > S.hi) continue;
+      if (v > S.reject_hi || v < S.lo) break;  // the subhist's own reject rule
     }
+    long long b = (long long)((unsigned long long)v - (unsigned long long)S.lo) / S.bsize;
+    if (b >= (long long)S.nvals) b = (long long)S.nvals - 1;
+    if (b < 0) b = 0;
+    atomicAdd(A.buckets + ((size_t)g * A.nvals_total + S.base + (uint32_t)b), 1ull);
+    break;
   }
 }
 
@@ -390,16 +413,18 @@ __device__ __forceinline__ void agg_value(const Ctx& cx, const Plan& P, const KA
 template <typename SlotT, bool ACC_SMEM>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const Plan& P = *lp.plan;
+  const Plan* __restrict__ PP = lp.plan;
   Ctx cx;
   cx.tid = threadIdx.x;
   cx.lane = threadIdx.x & 31;
   cx.warp = threadIdx.x >> 5;
+  cx.epoch = 0;
   cx.headbits = reinterpret_cast<uint32_t*>(smem + OFF_HEADBITS);
   cx.headprefix = reinterpret_cast<uint16_t*>(smem + OFF_HEADPREFIX);
   cx.binpay_s = reinterpret_cast<uint32_t*>(smem + OFF_BINPAY);
-  cx.wtot = reinterpret_cast<unsigned long long*>(smem + OFF_WTOT);
-  cx.misc = reinterpret_cast<uint32_t*>(smem + OFF_MISC);
+  cx.pubA = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBA);
+  cx.pubB = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBB);
+  cx.misc = reinterpret_cast<volatile uint32_t*>(smem + OFF_MISC);
   SlotT* slot;
   uint32_t acc_off = FIXED_SMEM;
   if (sizeof(SlotT) == 4) {
@@ -408,12 +433,29 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     slot = reinterpret_cast<SlotT*>(smem + FIXED_SMEM);
     acc_off = FIXED_SMEM + SG_BLOCK_ROWS * sizeof(SlotT);
   }
-  cx.acc = ACC_SMEM ? reinterpret_cast<uint32_t*>(smem + acc_off) : nullptr;
-  uint32_t* gbinpay = lp.gbinpay + (size_t)blockIdx.x * SG_BLOCK_ROWS;
-  const uint32_t acc_total = ACC_SMEM ? P.nslots * P.acc_words * P.acc_repl : 0u;
+  cx.acc = reinterpret_cast<uint32_t*>(smem + acc_off);
+  uint32_t* const gbinpay = lp.gbinpay + (size_t)blockIdx.x * SG_BLOCK_ROWS;
+
+  // ---- plan scalars into registers (the plan lives in global memory; every shared
+  // atomic would otherwise force the compiler to reload it) -------------------------------
+  const int nfilters = PP->nfilters, ngroups = PP->ngroups, naggs = PP->naggs, ncolslots = PP->ncolslots;
+  const int time_col = PP->time_col;
+  const uint32_t gbits = PP->gbits, pass_target = PP->pass_target, finc = PP->finc, time_ok = PP->time_ok;
+  const uint32_t filt_target = PP->filt_target, filt_mask = PP->filt_mask, nslots = PP->nslots;
+  const uint32_t acc_words = PP->acc_words, R = ACC_SMEM ? PP->acc_repl : 1u;
+  const uint32_t gmask = (1u << gbits) - 1u;
+  const uint32_t gstride = acc_words * R;       // words between two slots' accumulators
+  const uint32_t lane_off = cx.lane & (R - 1);  // this lane's replica
+  unsigned long long* const g_count = reinterpret_cast<unsigned long long*>(PP->count);
+  unsigned long long* const g_scalars = reinterpret_cast<unsigned long long*>(PP->scalars);
+
+  const uint32_t acc_total = ACC_SMEM ? nslots * gstride : 0u;
   for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
+  for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
+    cx.pubA[i] = 0;
+    cx.pubB[i] = 0;
+  }
   unsigned long long matched = 0;
-  const uint32_t gmask = (1u << P.gbits) - 1u;
 
   for (;;) {
     __syncthreads();
@@ -426,117 +468,228 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     if (wi >= lp.nlist) break;
     const uint32_t bid = lp.block_list[wi];
     const uint32_t nrec = lp.blocks[bid].num_records;
-    const DevCol* cols = lp.cols + (size_t)bid * P.ncolslots;
+    const DevCol* __restrict__ cols = lp.cols + (size_t)bid * ncolslots;
 
     // every row starts as: group slot 0, no filter passed
-    for (uint32_t r = cx.tid; r < nrec; r += THREADS) slot[r] = 0;
+    if (sizeof(SlotT) < 4) {
+      uint4* s4 = reinterpret_cast<uint4*>(slot);
+      const uint32_t n16 = (nrec * (uint32_t)sizeof(SlotT) + 15u) / 16u;
+      for (uint32_t i = cx.tid; i < n16; i += THREADS) s4[i] = make_uint4(0, 0, 0, 0);
+    } else {
+      for (uint32_t r = cx.tid; r < nrec; r += THREADS) slot[r] = 0;
+    }
     __syncthreads();
 
     // ---- filters (aggregate.go:105-112; unpopulated -> false, Q1) -----------------
-    for (int fi = 0; fi < P.nfilters; fi++) {
-      const KFilter& F = P.filters[fi];
-      const DevCol& c = cols[F.col];
-      const SlotT finc = (SlotT)P.finc;
+    for (int fi = 0; fi < nfilters; fi++) {
+      const KFilter F = PP->filters[fi];
+      const DevCol c = cols[F.col];
+      const SlotT fincS = (SlotT)finc;
+      StrPred sp;
+      sp.op = F.op;
+      sp.gid = F.str_gid;
+      sp.lut = F.lut;
+      sp.lut_bits = F.lut_bits;
       if (c.enc == SG_ENC_BUCKET) {
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
         for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) {
           const long long bv = c.bin_values[b];
-          pay[b] = F.is_str ? (str_pred(F, str_gid(c, bv)) ? 1u : 0u) : (int_pred(F.op, bv, F.ival) ? 1u : 0u);
+          pay[b] = F.is_str ? (sp(str_gid(c, bv)) ? 1u : 0u) : (int_pred(F.op, bv, F.ival) ? 1u : 0u);
         }
         __syncthreads();
-        scan_bucket(cx, c, nrec, [&](uint32_t row, uint32_t bin) {
-          if (pay[bin]) slot[row] = (SlotT)(slot[row] + finc);
-        });
+        uint32_t cur = 0;
+        scan_bucket(
+            cx, c, nrec, [&](uint32_t bin) { cur = pay[bin]; },
+            [&](uint32_t row) {
+              if (cur) slot[row] = (SlotT)(slot[row] + fincS);
+            });
       } else if (c.enc == SG_ENC_VALUES) {
         if (F.is_str) {
           scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
-            if (str_pred(F, str_gid(c, local))) slot[row] = (SlotT)(slot[row] + finc);
+            if (sp(str_gid(c, local))) slot[row] = (SlotT)(slot[row] + fincS);
           });
         } else {
+          const int op = F.op;
+          const long long lit = F.ival;
           scan_values_i64(cx, c, nrec, [&](uint32_t row, long long v) {
-            if (int_pred(F.op, v, F.ival)) slot[row] = (SlotT)(slot[row] + finc);
+            if (int_pred(op, v, lit)) slot[row] = (SlotT)(slot[row] + fincS);
           });
         }
       }
     }
 
     // ---- group key (aggregate.go:125-143) as a dense mixed-radix index ---------------
-    for (int gi = 0; gi < P.ngroups; gi++) {
-      const KGroup& G = P.groups[gi];
-      const DevCol& c = cols[G.col];
+    for (int gi = 0; gi < ngroups; gi++) {
+      const KGroup G = PP->groups[gi];
+      const DevCol c = cols[G.col];
       if (c.enc == SG_ENC_BUCKET) {
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
         for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) {
-          int32_t code = G.is_str ? str_gid(c, c.bin_values[b]) : c.remap[b];
+          const int32_t code = G.is_str ? str_gid(c, c.bin_values[b]) : c.remap[b];
           pay[b] = ((uint32_t)code + 1u) * G.stride;
         }
         __syncthreads();
-        scan_bucket(cx, c, nrec, [&](uint32_t row, uint32_t bin) { slot[row] = (SlotT)(slot[row] + pay[bin]); });
+        SlotT cur = 0;
+        scan_bucket(
+            cx, c, nrec, [&](uint32_t bin) { cur = (SlotT)pay[bin]; },
+            [&](uint32_t row) { slot[row] = (SlotT)(slot[row] + cur); });
       } else if (c.enc == SG_ENC_VALUES && G.is_str) {
+        const uint32_t stride = G.stride;
         scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
-          slot[row] = (SlotT)(slot[row] + ((uint32_t)str_gid(c, local) + 1u) * G.stride);
+          slot[row] = (SlotT)(slot[row] + ((uint32_t)str_gid(c, local) + 1u) * stride);
         });
       }
       // VALUES int group columns are routed away from this kernel by the planner
     }
 
     // ---- time bucket (aggregate.go:146-183) ------------------------------------------
-    if (P.time_col >= 0) {
-      const DevCol& c = cols[P.time_col];
-      const SlotT tok = (SlotT)P.time_ok;
+    if (time_col >= 0) {
+      const DevCol c = cols[time_col];
+      const SlotT tok = (SlotT)time_ok;
+      const long long tb = PP->time_bucket, tf = PP->time_first;
+      const uint32_t tr = PP->time_radix, ts = PP->time_stride;
       if (c.enc == SG_ENC_BUCKET && !(c.flags & COL_IS_STR)) {
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
-        for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) pay[b] = time_code(P, c.bin_values[b]);
+        for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) pay[b] = time_code(c.bin_values[b], tb, tf, tr);
         __syncthreads();
-        scan_bucket(cx, c, nrec, [&](uint32_t row, uint32_t bin) {
-          const uint32_t tc = pay[bin];
-          if (tc)
-            slot[row] = (SlotT)(slot[row] + tc * P.time_stride + tok);
-          else
-            atomicAdd(reinterpret_cast<unsigned long long*>(P.scalars) + 2, 1ull);
-        });
+        uint32_t cur = 0;
+        scan_bucket(
+            cx, c, nrec, [&](uint32_t bin) { cur = pay[bin]; },
+            [&](uint32_t row) {
+              if (cur)
+                slot[row] = (SlotT)(slot[row] + cur * ts + tok);
+              else
+                atomicAdd(g_scalars + 2, 1ull);
+            });
       } else if (c.enc == SG_ENC_VALUES && !(c.flags & COL_IS_STR)) {
         scan_values_i64(cx, c, nrec, [&](uint32_t row, long long v) {
-          const uint32_t tc = time_code(P, v);
+          const uint32_t tc = time_code(v, tb, tf, tr);
           if (tc)
-            slot[row] = (SlotT)(slot[row] + tc * P.time_stride + tok);
+            slot[row] = (SlotT)(slot[row] + tc * ts + tok);
           else
-            atomicAdd(reinterpret_cast<unsigned long long*>(P.scalars) + 2, 1ull);
+            atomicAdd(g_scalars + 2, 1ull);
         });
       }
     }
     __syncthreads();
 
-    // ---- Count / Samples (aggregate.go:202-203) and MatchedCount (:117) --------------
+    // ---- Count / Samples (aggregate.go:202-203), MatchedCount (:117), aggregations
+    // (:246-261).  The count is taken inside the first aggregation pass when that column
+    // is a value array covering every row; otherwise in its own pass over the slot words.
     unsigned long long my_matched = 0;
-    for (uint32_t r = cx.tid; r < nrec; r += THREADS) {
-      const uint32_t s = (uint32_t)slot[r];
-      const uint32_t hi = s >> P.gbits;
-      if ((hi & P.filt_mask) == P.filt_target) my_matched++;
-      if (hi == P.pass_target) {
-        const uint32_t g = s & gmask;
-        if (ACC_SMEM)
-          atomicAdd(cx.acc + ((size_t)g * P.acc_words) * P.acc_repl + (cx.lane & (P.acc_repl - 1)), 1u);
-        else
-          atomicAdd(reinterpret_cast<unsigned long long*>(P.count) + g, 1ull);
-      }
-    }
+    bool counted = false;
+    uint32_t agg_mode_bits = 0;  // bit a: word0 of agg a counts NON-accepted rows (value arrays)
 
-    // ---- aggregations (aggregate.go:246-261) -------------------------------------------
-    for (int ai = 0; ai < P.naggs; ai++) {
-      const KAgg& A = P.aggs[ai];
-      const DevCol& c = cols[A.col];
+    for (int ai = -1; ai < naggs; ai++) {
+      if (ai < 0) {
+        // decide whether the first value-array aggregation can carry the count
+        bool fuse = false;
+        if (naggs > 0) {
+          const DevCol c0 = cols[PP->aggs[0].col];
+          fuse = c0.enc == SG_ENC_VALUES && !(c0.flags & COL_IS_STR);
+        }
+        if (fuse) continue;
+        for (uint32_t r = cx.tid; r < nrec; r += THREADS) {
+          const uint32_t s = (uint32_t)slot[r];
+          const uint32_t hi = s >> gbits;
+          if ((hi & filt_mask) == filt_target) my_matched++;
+          if (hi == pass_target) {
+            const uint32_t g = s & gmask;
+            if (ACC_SMEM)
+              atomicAdd(cx.acc + g * gstride + lane_off, 1u);
+            else
+              atomicAdd(g_count + g, 1ull);
+          }
+        }
+        counted = true;
+        continue;
+      }
+      const KAgg* __restrict__ KA = &PP->aggs[ai];
+      const DevCol c = cols[KA->col];
       if (c.flags & COL_IS_STR) continue;  // Populated != INT_VAL: no update
+      AggRegs A;
+      A.info_min = KA->info_min;
+      A.info_max = KA->info_max;
+      A.reject_hi = KA->reject_hi;
+      A.nsub = KA->nsub;
+      A.nvals_total = KA->nvals_total;
+      A.buckets = reinterpret_cast<unsigned long long*>(KA->buckets);
+      A.hcount = reinterpret_cast<unsigned long long*>(KA->hcount);
+      A.sum = reinterpret_cast<unsigned long long*>(KA->sum);
+      A.vmax = reinterpret_cast<long long*>(KA->vmax);
+      A.sub = KA->sub;
+      A.lo0 = KA->sub[0].lo;
+      A.bsize0 = (uint32_t)KA->sub[0].bsize;
+      A.nvals0 = KA->sub[0].nvals;
+      A.fast32 = KA->nsub == 1 && KA->sub[0].bsize > 0 && KA->sub[0].bsize < 0x100000000ll;
+      const uint32_t w0 = 1u + 3u * (uint32_t)ai;  // word0 of this aggregation inside a slot's accumulators
+      const bool do_count = !counted;              // only reachable for ai == 0 on a value array
+
+      // accept one populated value of a row that passed (AddWeightedValue, hist_basic.go:101-151)
+      auto accept = [&](uint32_t g, long long v, bool count_accepted) {
+        if (v > A.reject_hi || v < A.info_min) {  // hist_basic.go:104
+          if (ACC_SMEM && !count_accepted) atomicAdd(cx.acc + g * gstride + (w0 * R) + lane_off, 1u);
+          return;
+        }
+        if (ACC_SMEM) {
+          uint32_t* w = cx.acc + g * gstride + (w0 * R) + lane_off;
+          if (count_accepted) atomicAdd(w, 1u);
+          const uint32_t lo = (uint32_t)(unsigned long long)v;
+          uint32_t hi = (uint32_t)((unsigned long long)v >> 32);
+          const uint32_t old = atomicAdd(w + R, lo);
+          if (old > ~lo) hi += 1u;  // carry out of the low limb
+          if (hi) atomicAdd(w + 2 * R, hi);
+        } else {
+          atomicAdd(A.hcount + g, 1ull);
+          atomicAdd(A.sum + g, (unsigned long long)v);
+        }
+        if (v > A.info_max) atomicMax(A.vmax + g, v);
+        if (A.nsub > 0) hist_bucket_add(A, g, v);
+      };
+
       if (c.enc == SG_ENC_BUCKET) {
-        scan_bucket(cx, c, nrec, [&](uint32_t row, uint32_t bin) {
-          const uint32_t s = (uint32_t)slot[row];
-          if ((s >> P.gbits) == P.pass_target) agg_value<ACC_SMEM>(cx, P, A, ai, s & gmask, c.bin_values[bin]);
-        });
+        long long curv = 0;
+        scan_bucket(
+            cx, c, nrec, [&](uint32_t bin) { curv = c.bin_values[bin]; },
+            [&](uint32_t row) {
+              const uint32_t s = (uint32_t)slot[row];
+              if ((s >> gbits) == pass_target) accept(s & gmask, curv, true);
+            });
       } else if (c.enc == SG_ENC_VALUES) {
+        agg_mode_bits |= 1u << ai;
         scan_values_i64(cx, c, nrec, [&](uint32_t row, long long v) {
           const uint32_t s = (uint32_t)slot[row];
-          if ((s >> P.gbits) == P.pass_target) agg_value<ACC_SMEM>(cx, P, A, ai, s & gmask, v);
+          const uint32_t hi = s >> gbits;
+          if (do_count && (hi & filt_mask) == filt_target) my_matched++;
+          if (hi == pass_target) {
+            const uint32_t g = s & gmask;
+            if (do_count) {
+              if (ACC_SMEM)
+                atomicAdd(cx.acc + g * gstride + lane_off, 1u);
+              else
+                atomicAdd(g_count + g, 1ull);
+            }
+            accept(g, v, false);
+          }
         });
+        // rows past len(Values) are unpopulated for this column (Q6): they still count
+        const uint32_t nv = c.nitems < nrec ? c.nitems : nrec;
+        for (uint32_t r = nv + cx.tid; r < nrec; r += THREADS) {
+          const uint32_t s = (uint32_t)slot[r];
+          const uint32_t hi = s >> gbits;
+          if (do_count && (hi & filt_mask) == filt_target) my_matched++;
+          if (hi == pass_target) {
+            const uint32_t g = s & gmask;
+            if (do_count) {
+              if (ACC_SMEM)
+                atomicAdd(cx.acc + g * gstride + lane_off, 1u);
+              else
+                atomicAdd(g_count + g, 1ull);
+            }
+            if (ACC_SMEM) atomicAdd(cx.acc + g * gstride + (w0 * R) + lane_off, 1u);
+          }
+        }
+        counted = true;
       }
     }
     __syncthreads();
@@ -545,50 +698,48 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     const bool broken = cx.misc[1] != 0;
     if (broken) {
       if (cx.tid == 0) {
-        lp.plan->block_status[bid] = 1;
-        atomicAdd(reinterpret_cast<unsigned long long*>(P.scalars) + 1, 1ull);
+        PP->block_status[bid] = 1;
+        atomicAdd(g_scalars + 1, 1ull);
       }
     } else {
       matched += my_matched;
     }
     if (ACC_SMEM) {
-      const uint32_t R = P.acc_repl;
-      const uint32_t nw = P.nslots * P.acc_words;
-      for (uint32_t w = cx.tid; w < nw; w += THREADS) {
-        const uint32_t g = w / P.acc_words, k = w - g * P.acc_words;
-        if (k != 0 && ((k - 1) % 3) == 2) continue;  // high limbs are folded with their low limb
-        unsigned long long tot = 0;
-        for (uint32_t r = 0; r < R; r++) {
-          tot += cx.acc[(size_t)w * R + r];
-          cx.acc[(size_t)w * R + r] = 0;
-        }
-        if (k != 0 && ((k - 1) % 3) == 1) {
-          unsigned long long hi = 0;
+      // one thread per (slot, aggregation-or-count): fold the R replicas
+      const uint32_t per_slot = 1u + (uint32_t)naggs;
+      for (uint32_t i = cx.tid; i < nslots * per_slot; i += THREADS) {
+        const uint32_t g = i / per_slot, a = i - g * per_slot;  // a == 0: the count
+        uint32_t* base = cx.acc + g * gstride;
+        unsigned long long cnt = 0;
+        for (uint32_t r = 0; r < R; r++) cnt += base[r];
+        if (a == 0) {
+          if (cnt && !broken) atomicAdd(g_count + g, cnt);
+        } else {
+          const uint32_t w0 = 1u + 3u * (a - 1u);
+          unsigned long long word0 = 0, lo = 0, hi = 0;
           for (uint32_t r = 0; r < R; r++) {
-            hi += cx.acc[(size_t)(w + 1) * R + r];
-            cx.acc[(size_t)(w + 1) * R + r] = 0;
+            word0 += base[w0 * R + r];
+            lo += base[(w0 + 1) * R + r];
+            hi += base[(w0 + 2) * R + r];
           }
-          tot += hi << 32;
-        }
-        if (tot != 0 && !broken) {
-          unsigned long long* dst;
-          if (k == 0) {
-            dst = reinterpret_cast<unsigned long long*>(P.count) + g;
-          } else {
-            const KAgg& A = P.aggs[(k - 1) / 3];
-            dst = ((k - 1) % 3 == 0 ? reinterpret_cast<unsigned long long*>(A.hcount)
-                                    : reinterpret_cast<unsigned long long*>(A.sum)) + g;
+          const unsigned long long hc = ((agg_mode_bits >> (a - 1u)) & 1u) ? cnt - word0 : word0;
+          if (!broken) {
+            const KAgg* KA = &PP->aggs[a - 1u];
+            if (hc) atomicAdd(reinterpret_cast<unsigned long long*>(KA->hcount) + g, hc);
+            const unsigned long long sum = lo + (hi << 32);
+            if (sum) atomicAdd(reinterpret_cast<unsigned long long*>(KA->sum) + g, sum);
           }
-          atomicAdd(dst, tot);
         }
       }
+      __syncthreads();
+      for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
     }
   }
 
   // MatchedCount
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) matched += __shfl_xor_sync(0xffffffffu, matched, d);
-  if (cx.lane == 0 && matched) atomicAdd(reinterpret_cast<unsigned long long*>(P.scalars) + 0, matched);
+  for (int d = 16; d > 0; d >>= 1) matched += __shfl_xor_sync(FULL, matched, d);
+  if (cx.lane == 0 && matched) atomicAdd(g_scalars + 0, matched);
 }
 
 template <typename SlotT, bool ACC_SMEM>
@@ -604,10 +755,9 @@ int launch_scan(const LaunchParams& lp, int grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool acc_smem = lp.acc_smem != 0;
   const uint32_t sb = lp.slot_bytes;
-  const LaunchParams& p = lp;
-  if (sb == 1) return acc_smem ? launch_one<uint8_t, true>(p, grid, st) : launch_one<uint8_t, false>(p, grid, st);
-  if (sb == 2) return acc_smem ? launch_one<uint16_t, true>(p, grid, st) : launch_one<uint16_t, false>(p, grid, st);
-  return acc_smem ? launch_one<uint32_t, true>(p, grid, st) : launch_one<uint32_t, false>(p, grid, st);
+  if (sb == 1) return acc_smem ? launch_one<uint8_t, true>(lp, grid, st) : launch_one<uint8_t, false>(lp, grid, st);
+  if (sb == 2) return acc_smem ? launch_one<uint16_t, true>(lp, grid, st) : launch_one<uint16_t, false>(lp, grid, st);
+  return acc_smem ? launch_one<uint32_t, true>(lp, grid, st) : launch_one<uint32_t, false>(lp, grid, st);
 }
 
 }  // namespace sg
