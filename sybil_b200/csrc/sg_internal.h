@@ -118,6 +118,7 @@ struct LaunchParams {
   uint32_t* work_counter;
   uint32_t* gslots;           // slot_bytes == 4: [grid][SG_BLOCK_ROWS]
   uint32_t* gbinpay;          // [grid][SG_BLOCK_ROWS] per-bin payload spill
+  unsigned long long* gdummy; // [grid][32] sink for histogram reductions of rows that did not pass
   uint32_t smem_bytes;
   uint32_t acc_smem;          // accumulators replicated in shared memory (plan.acc_repl > 0)
 };

@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "sg_internal.h"
 
@@ -78,6 +79,18 @@ __device__ __forceinline__ void ldg256(const void* p, unsigned long long* r) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3])
                : "l"(p));
+}
+
+// shared-memory accumulators are addressed in the shared window (32-bit addresses): a generic
+// pointer would cost a window conversion per atomic
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sred_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t satom_add(uint32_t addr, uint32_t v) {
+  uint32_t o;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
+  return o;
 }
 
 // ---------------------------------------------------------------------------
@@ -213,28 +226,36 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     const uint32_t carry = lookback_seg(cx, t, prev_incl);
     prev_incl = (tile_tot & FLAG) ? (tile_tot & ~FLAG) : ((carry + tile_tot) & ~FLAG);
     uint32_t run = (excl & FLAG) ? (excl & ~FLAG) : ((excl + carry) & ~FLAG);
-    // pass 2: rows and bins
+    // pass 2: rows and bins.  A row id >= NumRecords marks the block broken
+    // ("BLOCK SIZE CHANGED DURING QUERY", column_store_io.go:733); ids are clamped so the
+    // scatter stays in range and the whole block is dropped at the end.
     int bin = (int)((idx0 < n) ? cx.headprefix[idx0 >> 5] : 0) - 1;
     const uint32_t cnt = (idx0 >= n) ? 0u : ((n - idx0 < BE) ? n - idx0 : BE);
-#pragma unroll
-    for (int k = 0; k < BE; k++) {
-      if (k < cnt) {
-        const bool head = (word >> k) & 1u;
-        if (head) bin++;
-        run = ((segw >> k) & 1u) ? a[k] : run + a[k];
-        if (head || k == 0) {
-          if ((uint32_t)bin >= nbins) {
-            cx.misc[1] = 1;
-            bin = 0;
-          }
-          on_bin((uint32_t)bin);
+    uint32_t maxrow = 0;
+    const uint32_t lastrow = nrec - 1u;
+    auto step = [&](int k) {
+      const bool head = (word >> k) & 1u;
+      if (head) bin++;
+      run = ((segw >> k) & 1u) ? a[k] : run + a[k];
+      if (head || k == 0) {
+        if ((uint32_t)bin >= nbins) {
+          cx.misc[1] = 1;
+          bin = 0;
         }
-        if (run >= nrec)
-          cx.misc[1] = 1;  // "BLOCK SIZE CHANGED DURING QUERY" (column_store_io.go:733)
-        else
-          on_row(run);
+        on_bin((uint32_t)bin);
       }
+      maxrow = max(maxrow, run);
+      on_row(min(run, lastrow));
+    };
+    if (cnt == BE) {
+#pragma unroll
+      for (int k = 0; k < BE; k++) step(k);
+    } else {
+#pragma unroll
+      for (int k = 0; k < BE; k++)
+        if (k < cnt) step(k);
     }
+    if (maxrow > lastrow) cx.misc[1] = 1;
   }
   __syncthreads();
 }
@@ -242,8 +263,8 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
 // ---------------------------------------------------------------------------
 // value-array int column (delta-encoded int64): visit(row, value) in row order
 // ---------------------------------------------------------------------------
-template <class Visit>
-__device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const uint32_t nrec, Visit visit) {
+template <class TileVisit>
+__device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const uint32_t nrec, TileVisit tile_visit) {
   uint32_t n = c.nitems;
   if (n > nrec) n = nrec;  // staging already flags len(Values) > NumRecords as broken
   const unsigned long long* __restrict__ vals = reinterpret_cast<const unsigned long long*>(c.data);
@@ -255,8 +276,7 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
   for (uint32_t t = warp; t < ntiles; t += NWARPS) {
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
     unsigned long long a[VE];
-    const bool full = idx0 + VE <= n;
-    if (full) {
+    if (idx0 + VE <= n) {
 #pragma unroll
       for (int j = 0; j < VE / 4; j++) ldg256(vals + idx0 + 4 * j, a + 4 * j);
     } else {
@@ -284,16 +304,59 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
 #pragma unroll
       for (int k = 0; k < VE; k++) a[k] += base;
     }
-    if (full) {
-#pragma unroll
-      for (int k = 0; k < VE; k++) visit(idx0 + k, (long long)a[k]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < VE; k++)
-        if (idx0 + k < n) visit(idx0 + k, (long long)a[k]);
-    }
+    const uint32_t nvalid = (idx0 >= n) ? 0u : ((n - idx0 < VE) ? n - idx0 : (uint32_t)VE);
+    tile_visit(idx0, a, nvalid);
   }
   __syncthreads();
+}
+
+// the slot words of VE consecutive rows starting at idx0 (idx0 % VE == 0), as 32-bit values
+template <typename SlotT>
+__device__ __forceinline__ void load_slots(const SlotT* slot, uint32_t idx0, uint32_t (&sw)[VE]) {
+  if (sizeof(SlotT) == 1) {
+    const uint4 q = *reinterpret_cast<const uint4*>(slot + idx0);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < VE; k++) sw[k] = __byte_perm(w[k >> 2], 0u, 0x4440u | (uint32_t)(k & 3));
+  } else if (sizeof(SlotT) == 2) {
+    const uint4 q0 = *reinterpret_cast<const uint4*>(slot + idx0);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(slot + idx0 + 8);
+    const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int k = 0; k < VE; k++) sw[k] = __byte_perm(w[k >> 1], 0u, (k & 1) ? 0x4432u : 0x4410u);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VE / 4; j++) {
+      const uint4 q = *reinterpret_cast<const uint4*>(slot + idx0 + 4 * j);
+      sw[4 * j + 0] = q.x;
+      sw[4 * j + 1] = q.y;
+      sw[4 * j + 2] = q.z;
+      sw[4 * j + 3] = q.w;
+    }
+  }
+}
+// add inc[k] (already positioned in the slot word's field) to the slot words of VE consecutive rows
+template <typename SlotT>
+__device__ __forceinline__ void add_slots(SlotT* slot, uint32_t idx0, const uint32_t (&inc)[VE]) {
+  if (sizeof(SlotT) == 1) {
+    uint4* p = reinterpret_cast<uint4*>(slot + idx0);
+    uint4 q = *p;
+    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < VE; k++) w[k >> 2] += inc[k] << (8 * (k & 3));
+    *p = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if (sizeof(SlotT) == 2) {
+    uint4* p = reinterpret_cast<uint4*>(slot + idx0);
+    uint4 q0 = p[0], q1 = p[1];
+    uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int k = 0; k < VE; k++) w[k >> 1] += inc[k] << (16 * (k & 1));
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VE; k++) slot[idx0 + k] = (SlotT)(slot[idx0 + k] + inc[k]);
+  }
 }
 
 // value-array str column (raw int32 local ids): visit(row, local_id)
@@ -363,9 +426,9 @@ __device__ __forceinline__ uint32_t time_code(long long v, long long bucket, lon
 }
 
 // ---------------------------------------------------------------------------
-// per-aggregation constants held in registers during a column pass
+// aggregation of one value: hot path inline in the kernel, everything rare out of line
 // ---------------------------------------------------------------------------
-struct AggRegs {
+struct AggSlow {  // what the out-of-line paths need (lives in local memory)
   long long info_min, info_max, reject_hi;
   int nsub;
   uint32_t nvals_total;
@@ -374,37 +437,50 @@ struct AggRegs {
   unsigned long long* sum;
   long long* vmax;
   const KSubHist* sub;
-  // first (only, for BasicHist) layout in registers
-  long long lo0;
-  uint32_t bsize0, nvals0;
-  bool fast32;  // BasicHist with a 32-bit bucket size: the common bucket path
+  uint32_t acc_w0_s;  // shared address of word0 of this aggregation for slot 0, this lane's replica
+  uint32_t gstride_b;  // bytes between two slots' accumulators
+  uint32_t R_b;        // bytes between two words' replicas
+  int acc_smem;
 };
 
-__device__ __forceinline__ void hist_bucket_add(const AggRegs& A, uint32_t g, long long v) {
-  if (A.nsub == 1 && A.fast32) {
-    const unsigned long long x = (unsigned long long)v - (unsigned long long)A.lo0;
-    uint32_t b;
-    if (x < 0x100000000ull)
-      b = (uint32_t)x / A.bsize0;
-    else
-      b = (uint32_t)((x / (unsigned long long)A.bsize0) > 0xffffffffull ? 0xffffffffu : (x / A.bsize0));
-    if (b >= A.nvals0) b = A.nvals0 - 1;  // outlier: clamped into the last slot (hist_basic.go:134-137)
-    atomicAdd(A.buckets + ((size_t)g * A.nvals_total + b), 1ull);
-    return;
-  }
-  // general BasicHist, or MultiHist: first sub-range containing v (hist_multi.go:81-86)
-  for (int s = 0; s < A.nsub; s++) {
-    const KSubHist S = A.sub[s];
-    if (A.nsub > 1) {
+// BasicHist with a 64-bit bucket size, or MultiHist: first sub-range containing v (hist_multi.go:81-86)
+__device__ __noinline__ void hist_bucket_general(const AggSlow* A, uint32_t g, long long v) {
+  for (int s = 0; s < A->nsub; s++) {
+    const KSubHist S = A->sub[s];
+    if (A->nsub > 1) {
       if (v < S.lo || v > S.hi) continue;
       if (v > S.reject_hi || v < S.lo) break;  // the subhist's own reject rule
     }
     long long b = (long long)((unsigned long long)v - (unsigned long long)S.lo) / S.bsize;
-    if (b >= (long long)S.nvals) b = (long long)S.nvals - 1;
+    if (b >= (long long)S.nvals) b = (long long)S.nvals - 1;  // outlier: last slot (hist_basic.go:134-137)
     if (b < 0) b = 0;
-    atomicAdd(A.buckets + ((size_t)g * A.nvals_total + S.base + (uint32_t)b), 1ull);
+    atomicAdd(A->buckets + ((size_t)g * A->nvals_total + S.base + (uint32_t)b), 1ull);
     break;
   }
+}
+
+// A value outside the fast range [max(info_min,0), min(info_max, 2^32-1)] of a row that passed:
+// the complete AddWeightedValue (hist_basic.go:101-151).  count_accepted: word0 counts accepted
+// values (bucket columns); otherwise it counts the NON-accepted ones (value arrays).
+__device__ __noinline__ void agg_slow(const AggSlow* A, uint32_t g, long long v, int count_accepted) {
+  if (v > A->reject_hi || v < A->info_min) {  // hist_basic.go:104
+    if (A->acc_smem && !count_accepted) sred_add(A->acc_w0_s + g * A->gstride_b, 1u);
+    return;
+  }
+  if (A->acc_smem) {
+    const uint32_t w = A->acc_w0_s + g * A->gstride_b;
+    if (count_accepted) sred_add(w, 1u);
+    const uint32_t lo = (uint32_t)(unsigned long long)v;
+    uint32_t hi = (uint32_t)((unsigned long long)v >> 32);
+    const uint32_t old = satom_add(w + A->R_b, lo);
+    if (old > ~lo) hi += 1u;  // carry out of the low limb
+    if (hi) sred_add(w + 2 * A->R_b, hi);
+  } else {
+    atomicAdd(A->hcount + g, 1ull);
+    atomicAdd(A->sum + g, (unsigned long long)v);
+  }
+  if (v > A->info_max) atomicMax(A->vmax + g, v);
+  if (A->nsub > 0) hist_bucket_general(A, g, v);
 }
 
 // ---------------------------------------------------------------------------
@@ -449,7 +525,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   unsigned long long* const g_count = reinterpret_cast<unsigned long long*>(PP->count);
   unsigned long long* const g_scalars = reinterpret_cast<unsigned long long*>(PP->scalars);
 
-  const uint32_t acc_total = ACC_SMEM ? nslots * gstride : 0u;
+  const uint32_t acc_total = ACC_SMEM ? (nslots + 1u) * gstride : 0u;  // + the trash slot
   for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
   for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
     cx.pubA[i] = 0;
@@ -511,8 +587,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         } else {
           const int op = F.op;
           const long long lit = F.ival;
-          scan_values_i64(cx, c, nrec, [&](uint32_t row, long long v) {
-            if (int_pred(op, v, lit)) slot[row] = (SlotT)(slot[row] + fincS);
+          scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+            uint32_t inc[VE];
+#pragma unroll
+            for (int k = 0; k < VE; k++) inc[k] = (k < nvalid && int_pred(op, (long long)a[k], lit)) ? finc : 0u;
+            add_slots(slot, idx0, inc);
           });
         }
       }
@@ -562,12 +641,20 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                 atomicAdd(g_scalars + 2, 1ull);
             });
       } else if (c.enc == SG_ENC_VALUES && !(c.flags & COL_IS_STR)) {
-        scan_values_i64(cx, c, nrec, [&](uint32_t row, long long v) {
-          const uint32_t tc = time_code(v, tb, tf, tr);
-          if (tc)
-            slot[row] = (SlotT)(slot[row] + tc * ts + tok);
-          else
-            atomicAdd(g_scalars + 2, 1ull);
+        scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+          uint32_t inc[VE];
+#pragma unroll
+          for (int k = 0; k < VE; k++) {
+            inc[k] = 0u;
+            if (k < nvalid) {
+              const uint32_t tc = time_code((long long)a[k], tb, tf, tr);
+              if (tc)
+                inc[k] = tc * ts + time_ok;
+              else
+                atomicAdd(g_scalars + 2, 1ull);
+            }
+          }
+          add_slots(slot, idx0, inc);
         });
       }
     }
@@ -577,6 +664,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     // (:246-261).  The count is taken inside the first aggregation pass when that column
     // is a value array covering every row; otherwise in its own pass over the slot words.
     unsigned long long my_matched = 0;
+    // MatchedCount differs from the sum of the group counts only in time mode (rows lacking
+    // the time column are matched but not counted, aggregate.go:117,146-154)
+    const bool count_matched = time_col >= 0;
     bool counted = false;
     uint32_t agg_mode_bits = 0;  // bit a: word0 of agg a counts NON-accepted rows (value arrays)
 
@@ -592,7 +682,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         for (uint32_t r = cx.tid; r < nrec; r += THREADS) {
           const uint32_t s = (uint32_t)slot[r];
           const uint32_t hi = s >> gbits;
-          if ((hi & filt_mask) == filt_target) my_matched++;
+          if (count_matched && (hi & filt_mask) == filt_target) my_matched++;
           if (hi == pass_target) {
             const uint32_t g = s & gmask;
             if (ACC_SMEM)
@@ -607,86 +697,196 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       const KAgg* __restrict__ KA = &PP->aggs[ai];
       const DevCol c = cols[KA->col];
       if (c.flags & COL_IS_STR) continue;  // Populated != INT_VAL: no update
-      AggRegs A;
-      A.info_min = KA->info_min;
-      A.info_max = KA->info_max;
-      A.reject_hi = KA->reject_hi;
-      A.nsub = KA->nsub;
-      A.nvals_total = KA->nvals_total;
-      A.buckets = reinterpret_cast<unsigned long long*>(KA->buckets);
-      A.hcount = reinterpret_cast<unsigned long long*>(KA->hcount);
-      A.sum = reinterpret_cast<unsigned long long*>(KA->sum);
-      A.vmax = reinterpret_cast<long long*>(KA->vmax);
-      A.sub = KA->sub;
-      A.lo0 = KA->sub[0].lo;
-      A.bsize0 = (uint32_t)KA->sub[0].bsize;
-      A.nvals0 = KA->sub[0].nvals;
-      A.fast32 = KA->nsub == 1 && KA->sub[0].bsize > 0 && KA->sub[0].bsize < 0x100000000ll;
       const uint32_t w0 = 1u + 3u * (uint32_t)ai;  // word0 of this aggregation inside a slot's accumulators
       const bool do_count = !counted;              // only reachable for ai == 0 on a value array
+      const uint32_t acc_s = smem_u32(cx.acc);
+      const uint32_t gstride_b = gstride * 4u, R_b = R * 4u;
+      const uint32_t cnt_s = acc_s + lane_off * 4u;            // + g*gstride_b: the slot's count word
+      const uint32_t w0_s = acc_s + (w0 * R + lane_off) * 4u;  // + g*gstride_b: this aggregation's word0
+      const uint32_t dummy_s = smem_u32(const_cast<uint32_t*>(cx.misc) + 32 + cx.lane);  // per-lane sink
+      AggSlow AS;
+      AS.info_min = KA->info_min;
+      AS.info_max = KA->info_max;
+      AS.reject_hi = KA->reject_hi;
+      AS.nsub = KA->nsub;
+      AS.nvals_total = KA->nvals_total;
+      AS.buckets = reinterpret_cast<unsigned long long*>(KA->buckets);
+      AS.hcount = reinterpret_cast<unsigned long long*>(KA->hcount);
+      AS.sum = reinterpret_cast<unsigned long long*>(KA->sum);
+      AS.vmax = reinterpret_cast<long long*>(KA->vmax);
+      AS.sub = KA->sub;
+      AS.acc_w0_s = w0_s;
+      AS.gstride_b = gstride_b;
+      AS.R_b = R_b;
+      AS.acc_smem = ACC_SMEM ? 1 : 0;
+      // fast range: values the hot path takes — accepted (>= info_min, <= info_max <= reject_hi),
+      // not above the table's max, and with a zero high limb
+      const long long fmin = AS.info_min > 0 ? AS.info_min : 0;
+      long long fmax = AS.info_max < 0xffffffffll ? AS.info_max : 0xffffffffll;
+      if (AS.reject_hi < fmax) fmax = AS.reject_hi;
+      const bool fast_any = ACC_SMEM && fmax >= fmin;
+      const unsigned long long fspan = fast_any ? (unsigned long long)(fmax - fmin) : 0ull;
+      // BasicHist with a 32-bit bucket size: bucket index in the hot path
+      const bool hist32 = KA->nsub == 1 && KA->sub[0].bsize > 0 && KA->sub[0].bsize < 0x100000000ll &&
+                          KA->sub[0].lo == AS.info_min && fast_any &&
+                          (unsigned long long)fmax - (unsigned long long)AS.info_min < 0x100000000ull;
+      const uint32_t bsize0 = (uint32_t)KA->sub[0].bsize, nvals0 = KA->sub[0].nvals;
+      const uint32_t hoff = (uint32_t)(fmin - AS.info_min);  // fast values: v - info_min = (v - fmin) + hoff
+      unsigned long long* const bkt = AS.buckets;
+      const uint32_t nvt = AS.nvals_total;
+      const int nsub = AS.nsub;
 
-      // accept one populated value of a row that passed (AddWeightedValue, hist_basic.go:101-151)
-      auto accept = [&](uint32_t g, long long v, bool count_accepted) {
-        if (v > A.reject_hi || v < A.info_min) {  // hist_basic.go:104
-          if (ACC_SMEM && !count_accepted) atomicAdd(cx.acc + g * gstride + (w0 * R) + lane_off, 1u);
-          return;
-        }
+      // Hot path (ACC_SMEM).  A row that did not pass, or whose value is outside the fast
+      // range, is steered to the TRASH slot (an extra accumulator row nobody reads) so that the
+      // shared atomics run unconditionally: no branch per row.  Carries out of the low limb and
+      // values that need the complete rule are collected in per-lane bit masks and handled
+      // after the tile.
+      const uint32_t trash = nslots;
+      const uint32_t passbits = pass_target << gbits;
+      const uint32_t fmin32 = (uint32_t)fmin, fspan32 = (uint32_t)fspan;
+      // no carry can leave a low limb inside one block when every hot-path value is below
+      // 2^32 / (rows one replica can receive per block): then the adds need no return value
+      const bool nocarry = fast_any && (unsigned long long)fmax * (unsigned long long)(SG_BLOCK_ROWS / R) < 0x100000000ull;
+      unsigned long long* const hdummy = lp.gdummy + (size_t)blockIdx.x * 32 + cx.lane;
+
+      // one populated value of a row whose slot word is s (bucket columns: row order is scattered)
+      auto accept_one = [&](uint32_t s, long long v) {
+        const uint32_t e = min(s ^ passbits, trash);
+        if (e == trash) return;
         if (ACC_SMEM) {
-          uint32_t* w = cx.acc + g * gstride + (w0 * R) + lane_off;
-          if (count_accepted) atomicAdd(w, 1u);
-          const uint32_t lo = (uint32_t)(unsigned long long)v;
-          uint32_t hi = (uint32_t)((unsigned long long)v >> 32);
-          const uint32_t old = atomicAdd(w + R, lo);
-          if (old > ~lo) hi += 1u;  // carry out of the low limb
-          if (hi) atomicAdd(w + 2 * R, hi);
-        } else {
-          atomicAdd(A.hcount + g, 1ull);
-          atomicAdd(A.sum + g, (unsigned long long)v);
+          const uint32_t vlo = (uint32_t)(unsigned long long)v, vhi = (uint32_t)((unsigned long long)v >> 32);
+          const bool fr = fast_any && vhi == 0u && (vlo - fmin32) <= fspan32;
+          if (fr) {
+            const uint32_t w = w0_s + e * gstride_b;
+            sred_add(w, 1u);
+            const uint32_t old = satom_add(w + R_b, vlo);
+            if (old > ~vlo) sred_add(w + 2 * R_b, 1u);
+            if (nsub > 0) {
+              if (hist32) {
+                uint32_t b = (vlo - fmin32 + hoff) / bsize0;
+                if (b >= nvals0) b = nvals0 - 1;
+                atomicAdd(bkt + ((size_t)e * nvt + b), 1ull);
+              } else {
+                hist_bucket_general(&AS, e, v);
+              }
+            }
+            return;
+          }
         }
-        if (v > A.info_max) atomicMax(A.vmax + g, v);
-        if (A.nsub > 0) hist_bucket_add(A, g, v);
+        agg_slow(&AS, e, v, 1);
       };
 
       if (c.enc == SG_ENC_BUCKET) {
         long long curv = 0;
         scan_bucket(
             cx, c, nrec, [&](uint32_t bin) { curv = c.bin_values[bin]; },
-            [&](uint32_t row) {
-              const uint32_t s = (uint32_t)slot[row];
-              if ((s >> gbits) == pass_target) accept(s & gmask, curv, true);
-            });
+            [&](uint32_t row) { accept_one((uint32_t)slot[row], curv); });
       } else if (c.enc == SG_ENC_VALUES) {
         agg_mode_bits |= 1u << ai;
-        scan_values_i64(cx, c, nrec, [&](uint32_t row, long long v) {
-          const uint32_t s = (uint32_t)slot[row];
-          const uint32_t hi = s >> gbits;
-          if (do_count && (hi & filt_mask) == filt_target) my_matched++;
-          if (hi == pass_target) {
-            const uint32_t g = s & gmask;
-            if (do_count) {
-              if (ACC_SMEM)
-                atomicAdd(cx.acc + g * gstride + lane_off, 1u);
-              else
-                atomicAdd(g_count + g, 1ull);
-            }
-            accept(g, v, false);
+        auto tile = [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid, auto do_count_tag,
+                        auto nocarry_tag) {
+          constexpr bool DO_COUNT = decltype(do_count_tag)::value;
+          constexpr bool NOCARRY = decltype(nocarry_tag)::value;
+          uint32_t sw[VE];
+          load_slots(slot, idx0, sw);
+          if (nvalid < VE) {
+#pragma unroll
+            for (int k = 0; k < VE; k++)
+              if (k >= nvalid) sw[k] = ~0u;  // rows past len(Values): handled by the tail loop below
           }
-        });
+          if (DO_COUNT && count_matched) {
+#pragma unroll
+            for (int k = 0; k < VE; k++)
+              if (((sw[k] >> gbits) & filt_mask) == filt_target && sw[k] != ~0u) my_matched++;
+          }
+          if (ACC_SMEM && fast_any) {
+            uint32_t cmask = 0, slow_any = 0;
+#pragma unroll
+            for (int k = 0; k < VE; k++) {
+              const uint32_t e = min(sw[k] ^ passbits, trash);  // passing row: its slot, else trash
+              if (DO_COUNT) sred_add(cnt_s + e * gstride_b, 1u);
+              const uint32_t vlo = (uint32_t)a[k], vhi = (uint32_t)(a[k] >> 32);
+              const bool fr = vhi == 0u && (vlo - fmin32) <= fspan32;
+              const uint32_t e2 = fr ? e : trash;
+              slow_any |= e ^ e2;  // non-zero: a passing row whose value needs the complete rule
+              if (NOCARRY) {
+                sred_add(w0_s + R_b + e2 * gstride_b, vlo);
+              } else {
+                const uint32_t old = satom_add(w0_s + R_b + e2 * gstride_b, vlo);
+                cmask |= (old > ~vlo) ? (1u << k) : 0u;
+              }
+              if (hist32) {
+                uint32_t b = (vlo - fmin32 + hoff) / bsize0;
+                if (b >= nvals0) b = nvals0 - 1;  // outlier: clamped into the last slot (hist_basic.go:134-137)
+                atomicAdd(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
+              }
+            }
+            if (cmask | slow_any) {  // rare
+#pragma unroll
+              for (int k = 0; k < VE; k++) {
+                const uint32_t e = min(sw[k] ^ passbits, trash);
+                const uint32_t vlo = (uint32_t)a[k], vhi = (uint32_t)(a[k] >> 32);
+                const bool fr = vhi == 0u && (vlo - fmin32) <= fspan32;
+                if ((cmask >> k) & 1u) sred_add(w0_s + 2 * R_b + (fr ? e : trash) * gstride_b, 1u);  // carry
+                if (!fr && e != trash) agg_slow(&AS, e, (long long)a[k], 0);
+              }
+            }
+            if (nsub > 0 && !hist32) {  // MultiHist / wide buckets: per-row general path
+#pragma unroll
+              for (int k = 0; k < VE; k++) {
+                const uint32_t e = min(sw[k] ^ passbits, trash);
+                const uint32_t vlo = (uint32_t)a[k], vhi = (uint32_t)(a[k] >> 32);
+                if (e != trash && fast_any && vhi == 0u && (vlo - fmin32) <= fspan32)
+                  hist_bucket_general(&AS, e, (long long)a[k]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < VE; k++) {
+              const uint32_t e = min(sw[k] ^ passbits, trash);
+              if (e != trash) {
+                if (DO_COUNT) {
+                  if (ACC_SMEM)
+                    sred_add(cnt_s + e * gstride_b, 1u);
+                  else
+                    atomicAdd(g_count + e, 1ull);
+                }
+                agg_slow(&AS, e, (long long)a[k], 0);
+              }
+            }
+          }
+        };
+        auto run = [&](auto dc, auto nc) {
+          scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+            tile(idx0, a, nvalid, dc, nc);
+          });
+        };
+        if (do_count) {
+          if (nocarry)
+            run(std::true_type(), std::true_type());
+          else
+            run(std::true_type(), std::false_type());
+        } else {
+          if (nocarry)
+            run(std::false_type(), std::true_type());
+          else
+            run(std::false_type(), std::false_type());
+        }
         // rows past len(Values) are unpopulated for this column (Q6): they still count
         const uint32_t nv = c.nitems < nrec ? c.nitems : nrec;
         for (uint32_t r = nv + cx.tid; r < nrec; r += THREADS) {
           const uint32_t s = (uint32_t)slot[r];
           const uint32_t hi = s >> gbits;
-          if (do_count && (hi & filt_mask) == filt_target) my_matched++;
+          if (do_count && count_matched && (hi & filt_mask) == filt_target) my_matched++;
           if (hi == pass_target) {
             const uint32_t g = s & gmask;
             if (do_count) {
               if (ACC_SMEM)
-                atomicAdd(cx.acc + g * gstride + lane_off, 1u);
+                sred_add(cnt_s + g * gstride_b, 1u);
               else
                 atomicAdd(g_count + g, 1ull);
             }
-            if (ACC_SMEM) atomicAdd(cx.acc + g * gstride + (w0 * R) + lane_off, 1u);
+            if (ACC_SMEM) sred_add(w0_s + g * gstride_b, 1u);
           }
         }
         counted = true;

@@ -81,6 +81,9 @@ struct sg_ctx {
   int rank = 0, nranks = 1;
   char devname[256] = {0};
   std::vector<std::pair<const char*, size_t>> pinned;  // sg_pinned_alloc ranges (DMA without a bounce copy)
+  // query-lifetime device buffers are recycled: cudaMalloc/cudaFree per query cost milliseconds
+  std::vector<std::pair<void*, size_t>> pool_free;
+  std::unordered_map<void*, size_t> pool_live;
   void set_err(const std::string& s) { err = s; }
   bool is_pinned(const void* p, size_t n) const {
     const char* c = (const char*)p;
@@ -90,6 +93,9 @@ struct sg_ctx {
   }
 };
 
+static cudaError_t pool_alloc(sg_ctx* c, void** out, size_t bytes);
+static void pool_release(sg_ctx* c, void* p);
+
 #define CUDA_TRY(ctx, expr)                                                                   \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -98,6 +104,42 @@ struct sg_ctx {
       return SG_ERR_CUDA;                                                                     \
     }                                                                                         \
   } while (0)
+
+static cudaError_t pool_alloc(sg_ctx* c, void** out, size_t bytes) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  size_t best = (size_t)-1;
+  for (size_t i = 0; i < c->pool_free.size(); i++)
+    if (c->pool_free[i].second >= bytes && (best == (size_t)-1 || c->pool_free[i].second < c->pool_free[best].second))
+      best = i;
+  if (best != (size_t)-1 && c->pool_free[best].second <= bytes * 2 + (1 << 20)) {
+    *out = c->pool_free[best].first;
+    c->pool_live[*out] = c->pool_free[best].second;
+    c->pool_free.erase(c->pool_free.begin() + (long)best);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaSuccess) c->pool_live[*out] = bytes;
+  return e;
+}
+static void pool_release(sg_ctx* c, void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->pool_live.find(p);
+  if (it == c->pool_live.end()) {
+    cudaFree(p);
+    return;
+  }
+  c->pool_free.emplace_back(p, it->second);
+  c->pool_live.erase(it);
+  // keep the cache bounded: drop the largest buffers beyond 16 entries
+  while (c->pool_free.size() > 16) {
+    size_t big = 0;
+    for (size_t i = 1; i < c->pool_free.size(); i++)
+      if (c->pool_free[i].second > c->pool_free[big].second) big = i;
+    cudaFree(c->pool_free[big].first);
+    c->pool_free.erase(c->pool_free.begin() + (long)big);
+  }
+}
 
 namespace {
 
@@ -261,6 +303,7 @@ sg_ctx* sg_create(int device, int* status_out) {
 void sg_destroy(sg_ctx* c) {
   if (!c) return;
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (auto& p : c->pool_free) cudaFree(p.first);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -733,6 +776,7 @@ struct sg_query {
   uint32_t* d_work = nullptr;
   uint32_t* d_gslots = nullptr;
   uint32_t* d_gbinpay = nullptr;
+  unsigned long long* d_gdummy = nullptr;
   std::vector<uint32_t*> d_luts;
   size_t block_cap = 0;
   int grid = 0;
@@ -750,18 +794,20 @@ struct sg_query {
 namespace {
 
 void free_device(sg_query* q) {
-  if (q->d_plan) cudaFree(q->d_plan);
-  if (q->d_acc) cudaFree(q->d_acc);
-  if (q->d_block_status) cudaFree(q->d_block_status);
-  if (q->d_block_list) cudaFree(q->d_block_list);
-  if (q->d_work) cudaFree(q->d_work);
-  if (q->d_gslots) cudaFree(q->d_gslots);
-  if (q->d_gbinpay) cudaFree(q->d_gbinpay);
-  for (auto p : q->d_luts)
-    if (p) cudaFree(p);
+  sg_ctx* c = q->ctx;
+  pool_release(c, q->d_plan);
+  pool_release(c, q->d_acc);
+  pool_release(c, q->d_block_status);
+  pool_release(c, q->d_block_list);
+  pool_release(c, q->d_work);
+  pool_release(c, q->d_gslots);
+  pool_release(c, q->d_gbinpay);
+  pool_release(c, q->d_gdummy);
+  for (auto p : q->d_luts) pool_release(c, p);
   q->d_luts.clear();
   q->d_plan = nullptr;
   q->d_acc = nullptr;
+  q->d_gdummy = nullptr;
   q->d_block_status = q->d_block_list = q->d_work = q->d_gslots = q->d_gbinpay = nullptr;
 }
 
@@ -1004,9 +1050,9 @@ int make_plan(sg_query* q) {
   const uint32_t fixed = scan_fixed_smem() + (q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u);
   const uint32_t avail = MAX_DYN_SMEM > fixed ? MAX_DYN_SMEM - fixed : 0u;
   uint32_t repl = 32;
-  while (repl >= 1 && (uint64_t)P.nslots * P.acc_words * repl * 4 > avail) repl >>= 1;
+  while (repl >= 1 && ((uint64_t)P.nslots + 1) * P.acc_words * repl * 4 > avail) repl >>= 1;  // + trash slot
   P.acc_repl = repl;  // 0: accumulate straight into global memory
-  q->smem_bytes = fixed + P.nslots * P.acc_words * repl * 4;
+  q->smem_bytes = fixed + (P.nslots + 1) * P.acc_words * repl * 4;
   if (repl == 0) q->smem_bytes = fixed;
   return SG_OK;
 }
@@ -1015,23 +1061,25 @@ int alloc_device(sg_query* q) {
   sg_ctx* c = q->ctx;
   sg_table* t = q->table;
   cudaSetDevice(c->device);
-  if (q->d_acc) cudaFree(q->d_acc);
+  pool_release(c, q->d_acc);
   q->d_acc = nullptr;
-  CUDA_TRY(c, cudaMalloc(&q->d_acc, q->acc_words * 8));
-  if (!q->d_plan) CUDA_TRY(c, cudaMalloc(&q->d_plan, sizeof(Plan)));
-  if (!q->d_work) CUDA_TRY(c, cudaMalloc(&q->d_work, 64));
+  CUDA_TRY(c, pool_alloc(c, (void**)&q->d_acc, q->acc_words * 8));
+  if (!q->d_plan) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_plan, sizeof(Plan)));
+  if (!q->d_work) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_work, 64));
   size_t nb = std::max<size_t>(t->blocks.size(), 1);
   if (nb > q->block_cap) {
-    if (q->d_block_status) cudaFree(q->d_block_status);
-    if (q->d_block_list) cudaFree(q->d_block_list);
+    pool_release(c, q->d_block_status);
+    pool_release(c, q->d_block_list);
     q->d_block_status = q->d_block_list = nullptr;
-    CUDA_TRY(c, cudaMalloc(&q->d_block_status, nb * 4));
-    CUDA_TRY(c, cudaMalloc(&q->d_block_list, nb * 4));
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_status, nb * 4));
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_list, nb * 4));
     q->block_cap = nb;
   }
   q->grid = c->sm_count > 0 ? c->sm_count : 1;
-  if (!q->d_gbinpay) CUDA_TRY(c, cudaMalloc(&q->d_gbinpay, (size_t)q->grid * SG_BLOCK_ROWS * 4));
-  if (q->slot_bytes == 4 && !q->d_gslots) CUDA_TRY(c, cudaMalloc(&q->d_gslots, (size_t)q->grid * SG_BLOCK_ROWS * 4));
+  if (!q->d_gbinpay) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gbinpay, (size_t)q->grid * SG_BLOCK_ROWS * 4));
+  if (!q->d_gdummy) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gdummy, (size_t)q->grid * 32 * 8));
+  if (q->slot_bytes == 4 && !q->d_gslots)
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gslots, (size_t)q->grid * SG_BLOCK_ROWS * 4));
   if (!q->ev0) {
     CUDA_TRY(c, cudaEventCreate(&q->ev0));
     CUDA_TRY(c, cudaEventCreate(&q->ev1));
@@ -1089,6 +1137,7 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.work_counter = q->d_work;
   lp.gslots = q->d_gslots;
   lp.gbinpay = q->d_gbinpay;
+  lp.gdummy = q->d_gdummy;
   lp.smem_bytes = q->smem_bytes;
   lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
   int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(list.size(), 1));
@@ -1243,6 +1292,13 @@ int build_result(sg_query* q, sg_result** out) {
       sl->groups.push_back(std::move(g));
     }
   }
+  if (!time_mode) {
+    // without a time column every matched row is counted in exactly one group, so the kernel
+    // does not count matches separately (MatchedCount, aggregate.go:117)
+    int64_t m = 0;
+    for (uint32_t s = 0; s < P.nslots; s++) m += (int64_t)cnt[s];
+    r->matched = m;
+  }
   sort_groups(r->groups);
   for (auto& kv : slices) {
     sort_groups(kv.second->groups);
@@ -1318,9 +1374,9 @@ int sg_query_set_str_lut(sg_query* q, int32_t fi, const uint32_t* bits, int64_t 
   size_t words = (size_t)((nbits + 31) / 32);
   q->luts[(size_t)fi].assign(bits, bits + words);
   q->lut_bits[(size_t)fi] = nbits;
-  if (q->d_luts[(size_t)fi]) cudaFree(q->d_luts[(size_t)fi]);
+  pool_release(c, q->d_luts[(size_t)fi]);
   q->d_luts[(size_t)fi] = nullptr;
-  CUDA_TRY(c, cudaMalloc(&q->d_luts[(size_t)fi], std::max<size_t>(words, 1) * 4));
+  CUDA_TRY(c, pool_alloc(c, (void**)&q->d_luts[(size_t)fi], std::max<size_t>(words, 1) * 4));
   if (words) CUDA_TRY(c, cudaMemcpy(q->d_luts[(size_t)fi], bits, words * 4, cudaMemcpyHostToDevice));
   q->planned = false;
   return SG_OK;
