@@ -47,6 +47,7 @@ static inline bool basic_layout(int64_t lo, int64_t hi, int32_t hist_bucket, KSu
   out.bsize = bs;
   out.nvals = (uint32_t)nvals;
   out.base = 0;
+  out.magic = (bs >= 2 && bs < ((int64_t)1 << 32)) ? (uint64_t)((((unsigned __int128)1) << 64) / (uint64_t)bs) + 1 : 0;
   if (num_buckets) *num_buckets = nb;
   return true;
 }

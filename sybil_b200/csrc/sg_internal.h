@@ -16,6 +16,7 @@ enum : uint32_t {
   COL_DELTA_VALUES = 2u,  // SavedIntColumn.ValueEncoded
   COL_IS_STR = 4u,
   COL_BROKEN = 8u,        // "BLOCK SIZE CHANGED DURING QUERY" found at staging
+  COL_STATS = 16u,        // vmin/vmax hold the exact extents of the decoded int values
 };
 
 struct DevCol {
@@ -29,8 +30,11 @@ struct DevCol {
   const uint32_t* bin_offsets;  // [nbins+1]
   const void* data;             // record ids u32[] | values i64[] | values i32[]
   const int32_t* remap;         // str: local id -> global id; int BUCKET: bin -> value-dict code
+  // exact extents of the decoded values (int columns), computed by the engine when the block is
+  // staged (bucket columns: on the host from the bin values; value arrays: stats kernel)
+  int64_t vmin, vmax;
 };
-static_assert(sizeof(DevCol) == 56, "DevCol layout");
+static_assert(sizeof(DevCol) == 72, "DevCol layout");
 
 struct DevBlock {
   int64_t block_index;
@@ -64,6 +68,8 @@ struct KSubHist {  // one BasicHist bucket layout (hist_basic.go:34-70)
   int64_t bsize;      // BucketSize
   uint32_t nvals;     // len(Values)
   uint32_t base;      // offset of its counters inside the agg's counter row
+  uint64_t magic;     // floor(2^64 / bsize) + 1 for bsize in [2, 2^32): x / bsize == umul64hi(x, magic), x < 2^32
+                      // (0: bsize == 1 or bsize >= 2^32, no magic)
 };
 
 struct KAgg {
@@ -123,8 +129,11 @@ struct LaunchParams {
   uint32_t acc_smem;          // accumulators replicated in shared memory (plan.acc_repl > 0)
 };
 
-// host-callable launcher (sg_kernels.cu)
+// host-callable launchers (sg_kernels.cu)
 int launch_scan(const LaunchParams& lp, int grid, void* stream);
+// extents of value-array int columns: items[i] = index into cols[] (block * ncolslots + slot)
+int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
+                 void* stream);
 int scan_threads();
 // shared memory the kernel needs besides slots and accumulators
 uint32_t scan_fixed_smem();

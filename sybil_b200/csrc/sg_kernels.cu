@@ -310,6 +310,73 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
   __syncthreads();
 }
 
+// exact x / d for x < 2^32 with the host-computed magic M = floor(2^64 / d) + 1 (d < 2^32):
+// x*M/2^64 = x/d + x*e/(d*2^64) with 0 < e <= d, and x*e < 2^64, so the floor is unchanged
+__device__ __forceinline__ uint32_t div_magic(uint32_t x, unsigned long long M) {
+  return (uint32_t)__umul64hi((unsigned long long)x, M);
+}
+
+// value-array int column whose decoded values are known (COL_STATS) to lie in [0, 2^32): the same
+// tiles and look-back, in 32-bit arithmetic.  tile_visit(idx0, a[VE] (uint32), nvalid)
+template <class TileVisit>
+__device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const uint32_t nrec, TileVisit tile_visit) {
+  uint32_t n = c.nitems;
+  if (n > nrec) n = nrec;
+  const unsigned long long* __restrict__ vals = reinterpret_cast<const unsigned long long*>(c.data);
+  const bool delta = (c.flags & COL_DELTA_VALUES) != 0;
+  const int lane = cx.lane, warp = cx.warp;
+  cx.epoch++;
+  const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
+  uint32_t prev_incl = 0;
+  for (uint32_t t = warp; t < ntiles; t += NWARPS) {
+    const uint32_t idx0 = t * (32 * VE) + lane * VE;
+    uint32_t a[VE];
+    if (idx0 + VE <= n) {
+#pragma unroll
+      for (int j = 0; j < VE / 4; j++) {
+        unsigned long long q[4];
+        ldg256(vals + idx0 + 4 * j, q);
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[4 * j + i] = (uint32_t)q[i];  // values < 2^32: the low limb is exact mod 2^32
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? (uint32_t)vals[idx0 + k] : 0u;
+    }
+    if (delta) {
+#pragma unroll
+      for (int k = 1; k < VE; k++) a[k] += a[k - 1];
+      const uint32_t tot = a[VE - 1];
+      uint32_t incl = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const uint32_t tile_tot = __shfl_sync(FULL, incl, 31);
+      if (lane == 0) cx.pubA[t] = (unsigned long long)tile_tot | ((unsigned long long)cx.epoch << 32);
+      // totals of tiles t-15 .. t-1 (other warps) on top of this warp's previous inclusive prefix
+      const int tt = (int)t - 15 + lane;
+      uint32_t contrib = 0;
+      if (lane < 15 && tt >= 0) {
+        unsigned long long w;
+        do {
+          w = cx.pubA[tt];
+        } while ((uint32_t)(w >> 32) != cx.epoch);
+        contrib = (uint32_t)w;
+      }
+      const uint32_t carry = prev_incl + __reduce_add_sync(FULL, contrib);
+      prev_incl = carry + tile_tot;
+      const uint32_t base = incl - tot + carry;
+#pragma unroll
+      for (int k = 0; k < VE; k++) a[k] += base;
+    }
+    const uint32_t nvalid = (idx0 >= n) ? 0u : ((n - idx0 < VE) ? n - idx0 : (uint32_t)VE);
+    tile_visit(idx0, a, nvalid);
+  }
+  __syncthreads();
+}
+
 // the slot words of VE consecutive rows starting at idx0 (idx0 % VE == 0), as 32-bit values
 template <typename SlotT>
 __device__ __forceinline__ void load_slots(const SlotT* slot, uint32_t idx0, uint32_t (&sw)[VE]) {
@@ -781,6 +848,98 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         scan_bucket(
             cx, c, nrec, [&](uint32_t bin) { curv = c.bin_values[bin]; },
             [&](uint32_t row) { accept_one((uint32_t)slot[row], curv); });
+      } else if (c.enc == SG_ENC_VALUES && ACC_SMEM && fast_any && (c.flags & COL_STATS) && c.vmin >= 0 &&
+                 c.vmax <= 0xffffffffll) {
+        // ---- value array whose decoded values provably fit 32 bits (staging statistics) ----
+        agg_mode_bits |= 1u << ai;
+        // every value inside the fast range and no carry possible: no per-row checks at all
+        const bool allfast = nocarry && c.vmin >= fmin && c.vmax <= fmax;
+        const unsigned long long magic0 = KA->sub[0].magic;
+        auto tile32 = [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid, auto do_count_tag, auto allfast_tag) {
+          constexpr bool DO_COUNT = decltype(do_count_tag)::value;
+          constexpr bool ALLFAST = decltype(allfast_tag)::value;
+          uint32_t sw[VE];
+          load_slots(slot, idx0, sw);
+          if (nvalid < VE) {
+#pragma unroll
+            for (int k = 0; k < VE; k++)
+              if (k >= nvalid) sw[k] = ~0u;  // rows past len(Values): handled by the tail loop below
+          }
+          if (DO_COUNT && count_matched) {
+#pragma unroll
+            for (int k = 0; k < VE; k++)
+              if (((sw[k] >> gbits) & filt_mask) == filt_target && sw[k] != ~0u) my_matched++;
+          }
+          uint32_t cmask = 0, slow_any = 0;
+#pragma unroll
+          for (int k = 0; k < VE; k++) {
+            const uint32_t e = min(sw[k] ^ passbits, trash);  // passing row: its slot, else trash
+            if (DO_COUNT) sred_add(cnt_s + e * gstride_b, 1u);
+            if (ALLFAST) {
+              sred_add(w0_s + R_b + e * gstride_b, a[k]);
+            } else {
+              const bool fr = (a[k] - fmin32) <= fspan32;
+              const uint32_t e2 = fr ? e : trash;
+              slow_any |= e ^ e2;
+              const uint32_t old = satom_add(w0_s + R_b + e2 * gstride_b, a[k]);
+              cmask |= (old > ~a[k]) ? (1u << k) : 0u;
+            }
+          }
+          if (!ALLFAST && (cmask | slow_any)) {  // rare
+#pragma unroll
+            for (int k = 0; k < VE; k++) {
+              const uint32_t e = min(sw[k] ^ passbits, trash);
+              const bool fr = (a[k] - fmin32) <= fspan32;
+              if ((cmask >> k) & 1u) sred_add(w0_s + 2 * R_b + (fr ? e : trash) * gstride_b, 1u);  // carry
+              if (!fr && e != trash) agg_slow(&AS, e, (long long)a[k], 0);
+            }
+          }
+          if (nsub > 0) {
+#pragma unroll
+            for (int k = 0; k < VE; k++) {
+              const uint32_t e = min(sw[k] ^ passbits, trash);
+              const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
+              const uint32_t e2 = fr ? e : trash;
+              if (hist32) {
+                const uint32_t x = a[k] - fmin32 + hoff;
+                uint32_t b = magic0 ? div_magic(x, magic0) : x / bsize0;
+                b = min(b, nvals0 - 1);  // outlier: clamped into the last slot (hist_basic.go:134-137)
+                atomicAdd(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
+              } else if (e2 != trash) {
+                hist_bucket_general(&AS, e2, (long long)a[k]);
+              }
+            }
+          }
+        };
+        auto run32 = [&](auto dc, auto af) {
+          scan_values_u32(cx, c, nrec, [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid) {
+            tile32(idx0, a, nvalid, dc, af);
+          });
+        };
+        if (do_count) {
+          if (allfast)
+            run32(std::true_type(), std::true_type());
+          else
+            run32(std::true_type(), std::false_type());
+        } else {
+          if (allfast)
+            run32(std::false_type(), std::true_type());
+          else
+            run32(std::false_type(), std::false_type());
+        }
+        // rows past len(Values) are unpopulated for this column (Q6): they still count
+        const uint32_t nv = c.nitems < nrec ? c.nitems : nrec;
+        for (uint32_t r = nv + cx.tid; r < nrec; r += THREADS) {
+          const uint32_t s = (uint32_t)slot[r];
+          const uint32_t hi = s >> gbits;
+          if (do_count && count_matched && (hi & filt_mask) == filt_target) my_matched++;
+          if (hi == pass_target) {
+            const uint32_t g = s & gmask;
+            if (do_count) sred_add(cnt_s + g * gstride_b, 1u);
+            sred_add(w0_s + g * gstride_b, 1u);
+          }
+        }
+        counted = true;
       } else if (c.enc == SG_ENC_VALUES) {
         agg_mode_bits |= 1u << ai;
         auto tile = [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid, auto do_count_tag,
@@ -940,6 +1099,82 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) matched += __shfl_xor_sync(FULL, matched, d);
   if (cx.lane == 0 && matched) atomicAdd(g_scalars + 0, matched);
+}
+
+// ---------------------------------------------------------------------------
+// staging-time statistics: exact min / max of the decoded values of value-array int
+// columns (one CTA per column of a block).  They let the scan kernel pick 32-bit
+// arithmetic and drop per-row range checks when a column provably needs neither.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const DevBlock* blocks,
+                                                           const uint32_t* items, uint32_t nitems,
+                                                           uint32_t ncolslots) {
+  __shared__ __align__(16) unsigned char smem_s[FIXED_SMEM];
+  __shared__ long long red_min[NWARPS], red_max[NWARPS];
+  Ctx cx;
+  cx.tid = threadIdx.x;
+  cx.lane = threadIdx.x & 31;
+  cx.warp = threadIdx.x >> 5;
+  cx.epoch = 0;
+  cx.headbits = reinterpret_cast<uint32_t*>(smem_s + OFF_HEADBITS);
+  cx.headprefix = reinterpret_cast<uint16_t*>(smem_s + OFF_HEADPREFIX);
+  cx.binpay_s = reinterpret_cast<uint32_t*>(smem_s + OFF_BINPAY);
+  cx.pubA = reinterpret_cast<volatile unsigned long long*>(smem_s + OFF_PUBA);
+  cx.pubB = reinterpret_cast<volatile unsigned long long*>(smem_s + OFF_PUBB);
+  cx.misc = reinterpret_cast<volatile uint32_t*>(smem_s + OFF_MISC);
+  cx.acc = nullptr;
+  for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
+    cx.pubA[i] = 0;
+    cx.pubB[i] = 0;
+  }
+  __syncthreads();
+  for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const uint32_t ci = items[it];
+    const DevCol c = cols[ci];
+    const uint32_t nrec = blocks[ci / ncolslots].num_records;
+    long long mn = 0x7fffffffffffffffll, mx = -0x7fffffffffffffffll - 1;
+    scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+#pragma unroll
+      for (int k = 0; k < VE; k++)
+        if (k < nvalid) {
+          const long long v = (long long)a[k];
+          mn = v < mn ? v : mn;
+          mx = v > mx ? v : mx;
+        }
+    });
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const long long omn = __shfl_xor_sync(FULL, mn, d), omx = __shfl_xor_sync(FULL, mx, d);
+      mn = omn < mn ? omn : mn;
+      mx = omx > mx ? omx : mx;
+    }
+    if (cx.lane == 0) {
+      red_min[cx.warp] = mn;
+      red_max[cx.warp] = mx;
+    }
+    __syncthreads();
+    if (cx.tid == 0) {
+      for (int w = 1; w < NWARPS; w++) {
+        mn = red_min[w] < mn ? red_min[w] : mn;
+        mx = red_max[w] > mx ? red_max[w] : mx;
+      }
+      cols[ci].vmin = mn;
+      cols[ci].vmax = mx;
+      cols[ci].flags = c.flags | COL_STATS;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
+                 void* stream) {
+  if (nitems == 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t grid = nitems < (uint32_t)sms * 2 ? nitems : (uint32_t)sms * 2;
+  stats_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(cols, blocks, items, nitems, ncolslots);
+  return (int)cudaGetLastError();
 }
 
 template <typename SlotT, bool ACC_SMEM>

@@ -202,6 +202,7 @@ struct sg_table {
   std::vector<StrDict> sdict;
   std::vector<IntDict> idict;
   std::vector<char> has_values_int;  // an int column that is value-array encoded somewhere
+  std::vector<uint32_t> pending_stats;  // value-array int columns whose extents are not computed yet
   std::vector<std::pair<char*, size_t>> chunks;  // device arena chunks (ptr, capacity)
   size_t chunk_idx = 0, chunk_used = 0;
   Stage stage[2];
@@ -210,6 +211,7 @@ struct sg_table {
   int64_t device_bytes = 0;
   int64_t encoded_bytes = 0;
   int64_t h2d_bytes = 0;
+  int64_t stats_launches = 0;
   // device mirrors of blocks / cols, refreshed when dirty
   DevBlock* d_blocks = nullptr;
   DevCol* d_cols = nullptr;
@@ -442,6 +444,7 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
   std::vector<Tmp> tmp((size_t)b->ncols);
   SlabWriter sw;
   int64_t enc_bytes = 0;
+  std::vector<uint32_t> stats_slots;
 
   for (int ci = 0; ci < b->ncols; ci++) {
     const sg_column_desc& cd = b->cols[ci];
@@ -531,8 +534,16 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
       if (!is_str) {
         IntDict& id = t->idict[(size_t)cd.col_slot];
         tm.remap.resize(dc.nbins);
-        for (uint32_t k = 0; k < dc.nbins; k++) tm.remap[k] = id.intern(tm.bin_values[k]);
+        int64_t mn = INT64_MAX, mx = INT64_MIN;
+        for (uint32_t k = 0; k < dc.nbins; k++) {
+          tm.remap[k] = id.intern(tm.bin_values[k]);
+          mn = std::min(mn, tm.bin_values[k]);
+          mx = std::max(mx, tm.bin_values[k]);
+        }
         dc.nremap = dc.nbins;
+        dc.vmin = mn;
+        dc.vmax = mx;
+        dc.flags |= COL_STATS;
       }
       tm.off_bv = sw.add(tm.bin_values.data(), tm.bin_values.size() * 8);
       tm.off_bo = sw.add(tm.bin_offsets.data(), tm.bin_offsets.size() * 4);
@@ -560,6 +571,7 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
           tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * 8, c->is_pinned(cd.values_i64, (size_t)cd.nvalues * 8));
           enc_bytes += (int64_t)cd.nvalues * 8;
           t->has_values_int[(size_t)cd.col_slot] = 1;
+          stats_slots.push_back((uint32_t)cd.col_slot);
         }
         tm.has_data = true;
       }
@@ -632,6 +644,7 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
   hb.num_records = nrec;
   for (int i = 0; i < b->ninfo; i++) hb.info.push_back(b->info[i]);
   t->blocks.push_back(std::move(hb));
+  for (uint32_t sl : stats_slots) t->pending_stats.push_back((uint32_t)(t->blocks.size() - 1) * (uint32_t)t->ncols + sl);
   t->cols.insert(t->cols.end(), dcs.begin(), dcs.end());
   t->total_rows += nrec;
   t->encoded_bytes += enc_bytes;
@@ -648,6 +661,7 @@ int sg_table_clear(sg_table* t) {
   CUDA_TRY(t->ctx, cudaStreamSynchronize(t->ctx->stream));
   t->blocks.clear();
   t->cols.clear();
+  t->pending_stats.clear();
   t->chunk_idx = 0;
   t->chunk_used = 0;
   t->stage[0].pending = t->stage[1].pending = false;
@@ -863,6 +877,25 @@ int upload_table(sg_table* t) {
   if (nb) {
     CUDA_TRY(c, cudaMemcpy(t->d_blocks, hb.data(), nb * sizeof(DevBlock), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(t->d_cols, t->cols.data(), nb * (size_t)t->ncols * sizeof(DevCol), cudaMemcpyHostToDevice));
+  }
+  if (!t->pending_stats.empty()) {
+    // exact extents of the newly staged value-array int columns (one more read of those
+    // arrays from HBM, once per staging): they select the 32-bit / check-free kernel paths
+    uint32_t* d_items = nullptr;
+    size_t n = t->pending_stats.size();
+    CUDA_TRY(c, pool_alloc(c, (void**)&d_items, n * 4));
+    CUDA_TRY(c, cudaMemcpyAsync(d_items, t->pending_stats.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_stats(t->d_cols, t->d_blocks, d_items, (uint32_t)n, (uint32_t)t->ncols, c->stream);
+    if (rc != 0) {
+      c->set_err(std::string("stats kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+      pool_release(c, d_items);
+      return SG_ERR_CUDA;
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(t->cols.data(), t->d_cols, nb * (size_t)t->ncols * sizeof(DevCol), cudaMemcpyDeviceToHost));
+    pool_release(c, d_items);
+    t->pending_stats.clear();
+    t->stats_launches++;
   }
   t->dirty = false;
   return SG_OK;
