@@ -450,6 +450,44 @@ __device__ __forceinline__ void scan_values_i32(Ctx& cx, const DevCol& c, const 
 // ---------------------------------------------------------------------------
 // predicates
 // ---------------------------------------------------------------------------
+// IntFilter (filter.go:177-189) as one unsigned range test: pass <=> ((v - lo) <=u span) != inv
+struct IntRange {
+  unsigned long long lo, span;
+  bool inv;   // NEQ: complement of the EQ range
+  bool none;  // empty range (e.g. "gt INT64_MAX")
+  __device__ __forceinline__ bool operator()(long long v) const {
+    return !none && ((((unsigned long long)v - lo) <= span) != inv);
+  }
+};
+__device__ __forceinline__ IntRange int_range(int op, long long lit) {
+  IntRange r;
+  r.lo = 0;
+  r.span = 0;
+  r.inv = false;
+  r.none = false;
+  const long long mn = -0x7fffffffffffffffll - 1, mx = 0x7fffffffffffffffll;
+  switch (op) {
+    case SG_OP_GT:
+      if (lit == mx) r.none = true;
+      r.lo = (unsigned long long)(lit + (lit == mx ? 0 : 1));
+      r.span = (unsigned long long)mx - r.lo;
+      break;
+    case SG_OP_LT:
+      if (lit == mn) r.none = true;
+      r.lo = (unsigned long long)mn;
+      r.span = (unsigned long long)(lit - (lit == mn ? 0 : 1)) - r.lo;
+      break;
+    case SG_OP_EQ:
+      r.lo = (unsigned long long)lit;
+      break;
+    case SG_OP_NEQ:
+      r.lo = (unsigned long long)lit;
+      r.inv = true;
+      break;
+    default: r.none = true; break;
+  }
+  return r;
+}
 __device__ __forceinline__ bool int_pred(int op, long long v, long long lit) {
   // filter.go:177-189
   switch (op) {
@@ -640,26 +678,41 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           pay[b] = F.is_str ? (sp(str_gid(c, bv)) ? 1u : 0u) : (int_pred(F.op, bv, F.ival) ? 1u : 0u);
         }
         __syncthreads();
-        uint32_t cur = 0;
+        SlotT cur = 0;  // finc for rows of a passing bin, else 0: the read-modify-write runs unconditionally
         scan_bucket(
-            cx, c, nrec, [&](uint32_t bin) { cur = pay[bin]; },
-            [&](uint32_t row) {
-              if (cur) slot[row] = (SlotT)(slot[row] + fincS);
-            });
+            cx, c, nrec, [&](uint32_t bin) { cur = pay[bin] ? fincS : (SlotT)0; },
+            [&](uint32_t row) { slot[row] = (SlotT)(slot[row] + cur); });
       } else if (c.enc == SG_ENC_VALUES) {
         if (F.is_str) {
           scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
             if (sp(str_gid(c, local))) slot[row] = (SlotT)(slot[row] + fincS);
           });
         } else {
-          const int op = F.op;
-          const long long lit = F.ival;
-          scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
-            uint32_t inc[VE];
+          const IntRange rg = int_range(F.op, F.ival);
+          const bool u32ok = (c.flags & COL_STATS) && c.vmin >= 0 && c.vmax <= 0xffffffffll;
+          // clip the range to [0, 2^32) for the 32-bit scan
+          const unsigned long long hi64 = rg.lo + rg.span;  // inclusive upper end (signed order = unsigned order
+                                                            // after the bias below)
+          const long long rlo = (long long)rg.lo, rhi = (long long)hi64;
+          const bool none32 = rg.none || rhi < 0 || rlo > 0xffffffffll;
+          const uint32_t lo32 = rlo < 0 ? 0u : (uint32_t)rlo;
+          const uint32_t span32 = none32 ? 0u : ((rhi > 0xffffffffll ? 0xffffffffu : (uint32_t)rhi) - lo32);
+          if (u32ok) {
+            scan_values_u32(cx, c, nrec, [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid) {
+              uint32_t inc[VE];
 #pragma unroll
-            for (int k = 0; k < VE; k++) inc[k] = (k < nvalid && int_pred(op, (long long)a[k], lit)) ? finc : 0u;
-            add_slots(slot, idx0, inc);
-          });
+              for (int k = 0; k < VE; k++)
+                inc[k] = (k < nvalid && !rg.none && ((!none32 && (a[k] - lo32) <= span32) != rg.inv)) ? finc : 0u;
+              add_slots(slot, idx0, inc);
+            });
+          } else {
+            scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+              uint32_t inc[VE];
+#pragma unroll
+              for (int k = 0; k < VE; k++) inc[k] = (k < nvalid && rg((long long)a[k])) ? finc : 0u;
+              add_slots(slot, idx0, inc);
+            });
+          }
         }
       }
     }

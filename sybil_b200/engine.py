@@ -404,6 +404,12 @@ class Table:
         qs.MatchedCount = lib.sg_result_matched_count(rp)
         qs.BrokenBlocks = lib.sg_result_num_broken(rp)
         qs.SkippedBlocks = lib.sg_result_num_skipped(rp)
+        qs.NumGroups = lib.sg_result_num_groups(rp)
+        if not getattr(qs, "materialize", True):
+            # counts only: the full result exists in the library (sg_result); building one
+            # Python object per group is harness work the caller asked to skip
+            qs.Cumulative, qs.Sorted, qs.Results, qs.TimeResults = None, [], {}, {}
+            return
         allg = rh.groups(qs.Aggregations, True)
         qs.Cumulative = allg[0]
         qs.Sorted = allg[1:]
