@@ -17,6 +17,7 @@ enum : uint32_t {
   COL_IS_STR = 4u,
   COL_BROKEN = 8u,        // "BLOCK SIZE CHANGED DURING QUERY" found at staging
   COL_STATS = 16u,        // vmin/vmax hold the exact extents of the decoded int values
+  COL_TMA = 32u,          // data_chunk/data_row locate `data` inside an arena tensor map
 };
 
 struct DevCol {
@@ -33,8 +34,10 @@ struct DevCol {
   // exact extents of the decoded values (int columns), computed by the engine when the block is
   // staged (bucket columns: on the host from the bin values; value arrays: stats kernel)
   int64_t vmin, vmax;
+  // `data` as a coordinate of the arena chunk's tensor map ({128 B, rows}): row = byte offset / 128
+  uint32_t data_chunk, data_row;
 };
-static_assert(sizeof(DevCol) == 72, "DevCol layout");
+static_assert(sizeof(DevCol) == 80, "DevCol layout");
 
 struct DevBlock {
   int64_t block_index;
@@ -127,6 +130,8 @@ struct LaunchParams {
   unsigned long long* gdummy; // [grid][32] sink for histogram reductions of rows that did not pass
   uint32_t smem_bytes;
   uint32_t acc_smem;          // accumulators replicated in shared memory (plan.acc_repl > 0)
+  const void* tmaps;          // CUtensorMap[chunks] in global memory (nullptr: plain vector loads)
+  uint32_t nstage;            // TMA staging depth per warp (1 or 2)
 };
 
 // host-callable launchers (sg_kernels.cu)
@@ -135,8 +140,9 @@ int launch_scan(const LaunchParams& lp, int grid, void* stream);
 int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
                  void* stream);
 int scan_threads();
-// shared memory the kernel needs besides slots and accumulators
-uint32_t scan_fixed_smem();
-constexpr uint32_t SMEM_BINS = 5120;  // per-bin payload entries kept in shared memory
+// shared memory the kernel needs besides slots and accumulators (nstage: TMA staging depth, 0 = none)
+uint32_t scan_fixed_smem(uint32_t nstage);
+constexpr uint32_t SMEM_BINS = 1024;  // per-bin payload entries kept in shared memory (more: global scratch)
+constexpr uint32_t TMA_TILE_BYTES = 4096;  // one warp tile: 32 rows of 128 bytes
 
 }  // namespace sg

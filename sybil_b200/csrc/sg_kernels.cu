@@ -48,15 +48,18 @@ constexpr uint32_t MAX_TILES = 128;
 
 int scan_threads() { return THREADS; }
 
-// fixed shared-memory carve-out (bytes) ahead of the slot words and accumulators
+// shared-memory carve-out (bytes).  The dynamic window is aligned up to 1 KiB at run time; first come
+// the per-warp TMA staging tiles (128B-swizzled, must sit on 1 KiB boundaries), then the fixed part
+// below, then the slot words and the accumulators.
 constexpr uint32_t OFF_HEADBITS = 0;                                   // u32[2048]
 constexpr uint32_t OFF_HEADPREFIX = OFF_HEADBITS + HEAD_WORDS * 4;     // u16[2048]
 constexpr uint32_t OFF_BINPAY = OFF_HEADPREFIX + HEAD_WORDS * 2;       // u32[SMEM_BINS]
 constexpr uint32_t OFF_PUBA = OFF_BINPAY + SMEM_BINS * 4;              // u64[MAX_TILES]
 constexpr uint32_t OFF_PUBB = OFF_PUBA + MAX_TILES * 8;                // u64[MAX_TILES]
-constexpr uint32_t OFF_MISC = OFF_PUBB + MAX_TILES * 8;                // u32[64]
+constexpr uint32_t OFF_MBAR = OFF_PUBB + MAX_TILES * 8;                // u64[NWARPS][2] mbarriers
+constexpr uint32_t OFF_MISC = OFF_MBAR + NWARPS * 2 * 8;               // u32[64]
 constexpr uint32_t FIXED_SMEM = OFF_MISC + 64 * 4;
-uint32_t scan_fixed_smem() { return FIXED_SMEM; }
+uint32_t scan_fixed_smem(uint32_t nstage) { return 1024u + NWARPS * TMA_TILE_BYTES * nstage + FIXED_SMEM; }
 
 struct Ctx {
   uint32_t* headbits;
@@ -64,11 +67,99 @@ struct Ctx {
   uint32_t* binpay_s;
   volatile unsigned long long* pubA;
   volatile unsigned long long* pubB;
-  volatile uint32_t* misc;  // [0] next block, [1] broken flag, [16..31] warp totals
+  volatile uint32_t* misc;  // [0] next block, [1] broken flag, [16..31] warp totals, [32..63] per-lane sinks
   uint32_t* acc;
   int tid, lane, warp;
   uint32_t epoch;  // one per column pass; tags the published tile totals
+  // TMA staging of this warp: nstage tiles of 4 KiB + one mbarrier each (shared-window addresses)
+  const unsigned char* tmaps;
+  uint32_t nstage;
+  uint32_t buf0, buf1, mbar0, mbar1, par0, par1;
+  __device__ __forceinline__ uint32_t buf(uint32_t st) const { return st ? buf1 : buf0; }
+  __device__ __forceinline__ uint32_t mbar(uint32_t st) const { return st ? mbar1 : mbar0; }
+  __device__ __forceinline__ uint32_t take_parity(uint32_t st) {
+    const uint32_t p = st ? par1 : par0;
+    if (st)
+      par1 ^= 1u;
+    else
+      par0 ^= 1u;
+    return p;
+  }
 };
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) -----------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar_s, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar_s, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_s, uint32_t parity) {
+  // try_wait suspends for a hardware-defined interval; a transfer that never completes (bad tensor
+  // map) traps instead of hanging the GPU
+  for (uint32_t spins = 0;; spins++) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(mbar_s), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) __trap();
+  }
+}
+// one 4 KiB tile = 32 rows x 128 bytes at row `row` of the arena chunk's tensor map
+__device__ __forceinline__ void tma_load_tile(uint32_t dst_s, const void* tmap, uint32_t row, uint32_t mbar_s) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          dst_s),
+      "l"(tmap), "r"(0), "r"(row), "r"(mbar_s)
+      : "memory");
+}
+// this lane's 128-byte row of a staged tile (32 words), undoing the 128B swizzle:
+// 16-byte chunk j of row r sits at chunk position j ^ (r & 7)
+__device__ __forceinline__ void read_staged_row(uint32_t buf_s, int lane, uint32_t (&w)[32]) {
+  const uint32_t rowbase = buf_s + (uint32_t)lane * 128u;
+  const uint32_t x = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint32_t addr = rowbase + ((((uint32_t)j) ^ x) << 4);
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w[4 * j + 0]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                 : "r"(addr));
+  }
+}
+// After a warp has read a staged tile with ordinary shared loads, the next TMA write into the same
+// buffer must not overtake those loads (they can sit in the load/store queue behind global
+// reductions for microseconds): every lane orders its generic-proxy reads before later async-proxy
+// accesses, then the warp converges, then lane 0 issues.
+__device__ __forceinline__ void staged_reads_done() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+}
+// the tile feed of one column pass: issue(tile) by lane 0, take(stage) by the whole warp
+struct Feed {
+  const void* tmap;
+  uint32_t row0;
+  bool on;
+};
+__device__ __forceinline__ Feed make_feed(const Ctx& cx, const DevCol& c) {
+  Feed f;
+  f.on = cx.tmaps != nullptr && (c.flags & COL_TMA) != 0;
+  f.tmap = cx.tmaps + (size_t)c.data_chunk * 128;
+  f.row0 = c.data_row;
+  return f;
+}
+__device__ __forceinline__ void feed_issue(const Ctx& cx, const Feed& f, uint32_t tile, uint32_t st) {
+  if (cx.lane == 0) {
+    mbar_expect_tx(cx.mbar(st), TMA_TILE_BYTES);
+    tma_load_tile(cx.buf(st), f.tmap, f.row0 + tile * 32u, cx.mbar(st));
+  }
+}
 
 __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -185,10 +276,28 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
 
   const uint32_t ntiles = (n + (32 * BE - 1)) / (32 * BE);
   uint32_t prev_incl = 0;  // running segment sum through this warp's previous tile
-  for (uint32_t t = warp; t < ntiles; t += NWARPS) {
+  const Feed feed = make_feed(cx, c);
+  if (feed.on)
+    for (uint32_t st = 0; st < cx.nstage; st++)
+      if (warp + st * NWARPS < ntiles) feed_issue(cx, feed, warp + st * NWARPS, st);
+  uint32_t it = 0;
+  for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * BE) + lane * BE;
     uint32_t a[BE];
-    if (idx0 + BE <= n) {
+    if (feed.on) {
+      // the tile was requested one (or two) iterations ago: TMA wrote it into this warp's staging
+      // buffer while the previous tile was being processed
+      const uint32_t st = it & (cx.nstage - 1u);
+      mbar_wait(cx.mbar(st), cx.take_parity(st));
+      read_staged_row(cx.buf(st), lane, a);
+      staged_reads_done();
+      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st);
+      if (idx0 + BE > n) {
+#pragma unroll
+        for (int k = 0; k < BE; k++)
+          if (idx0 + k >= n) a[k] = 0u;
+      }
+    } else if (idx0 + BE <= n) {
 #pragma unroll
       for (int j = 0; j < BE / 8; j++) ldg256(ids + idx0 + 8 * j, a + 8 * j);
     } else {
@@ -273,10 +382,25 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
   cx.epoch++;
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   unsigned long long prev_incl = 0;
-  for (uint32_t t = warp; t < ntiles; t += NWARPS) {
+  const Feed feed = make_feed(cx, c);
+  if (feed.on)
+    for (uint32_t st = 0; st < cx.nstage; st++)
+      if (warp + st * NWARPS < ntiles) feed_issue(cx, feed, warp + st * NWARPS, st);
+  uint32_t it = 0;
+  for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
     unsigned long long a[VE];
-    if (idx0 + VE <= n) {
+    if (feed.on) {
+      const uint32_t st = it & (cx.nstage - 1u);
+      mbar_wait(cx.mbar(st), cx.take_parity(st));
+      uint32_t raw[32];
+      read_staged_row(cx.buf(st), lane, raw);
+      staged_reads_done();
+      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st);
+#pragma unroll
+      for (int k = 0; k < VE; k++)
+        a[k] = (idx0 + k < n) ? ((unsigned long long)raw[2 * k] | ((unsigned long long)raw[2 * k + 1] << 32)) : 0ull;
+    } else if (idx0 + VE <= n) {
 #pragma unroll
       for (int j = 0; j < VE / 4; j++) ldg256(vals + idx0 + 4 * j, a + 4 * j);
     } else {
@@ -328,10 +452,24 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
   cx.epoch++;
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   uint32_t prev_incl = 0;
-  for (uint32_t t = warp; t < ntiles; t += NWARPS) {
+  const Feed feed = make_feed(cx, c);
+  if (feed.on)
+    for (uint32_t st = 0; st < cx.nstage; st++)
+      if (warp + st * NWARPS < ntiles) feed_issue(cx, feed, warp + st * NWARPS, st);
+  uint32_t it = 0;
+  for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
     uint32_t a[VE];
-    if (idx0 + VE <= n) {
+    if (feed.on) {
+      const uint32_t st = it & (cx.nstage - 1u);
+      mbar_wait(cx.mbar(st), cx.take_parity(st));
+      uint32_t raw[32];
+      read_staged_row(cx.buf(st), lane, raw);
+      staged_reads_done();
+      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st);
+#pragma unroll
+      for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? raw[2 * k] : 0u;  // low limbs: exact mod 2^32
+    } else if (idx0 + VE <= n) {
 #pragma unroll
       for (int j = 0; j < VE / 4; j++) {
         unsigned long long q[4];
@@ -593,19 +731,37 @@ __device__ __noinline__ void agg_slow(const AggSlow* A, uint32_t g, long long v,
 // ---------------------------------------------------------------------------
 template <typename SlotT, bool ACC_SMEM>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const Plan* __restrict__ PP = lp.plan;
   Ctx cx;
   cx.tid = threadIdx.x;
   cx.lane = threadIdx.x & 31;
   cx.warp = threadIdx.x >> 5;
   cx.epoch = 0;
+  // align the window to 1 KiB (the 128B swizzle pattern of the staged tiles repeats every 1 KiB)
+  unsigned char* const stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  cx.nstage = lp.tmaps ? lp.nstage : 0u;
+  cx.tmaps = reinterpret_cast<const unsigned char*>(lp.tmaps);
+  unsigned char* const smem = stage_base + NWARPS * TMA_TILE_BYTES * cx.nstage;
   cx.headbits = reinterpret_cast<uint32_t*>(smem + OFF_HEADBITS);
   cx.headprefix = reinterpret_cast<uint16_t*>(smem + OFF_HEADPREFIX);
   cx.binpay_s = reinterpret_cast<uint32_t*>(smem + OFF_BINPAY);
   cx.pubA = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBA);
   cx.pubB = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBB);
   cx.misc = reinterpret_cast<volatile uint32_t*>(smem + OFF_MISC);
+  {
+    const uint32_t per_warp = (cx.nstage ? cx.nstage : 1u) * TMA_TILE_BYTES;
+    cx.buf0 = smem_u32(stage_base) + (uint32_t)cx.warp * per_warp;
+    cx.buf1 = cx.buf0 + TMA_TILE_BYTES;
+    cx.mbar0 = smem_u32(smem + OFF_MBAR) + (uint32_t)cx.warp * 16u;
+    cx.mbar1 = cx.mbar0 + 8u;
+    cx.par0 = cx.par1 = 0;
+  }
+  if (cx.nstage && cx.lane == 0) {
+    mbar_init(cx.mbar0, 1);
+    mbar_init(cx.mbar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   SlotT* slot;
   uint32_t acc_off = FIXED_SMEM;
   if (sizeof(SlotT) == 4) {
@@ -1176,6 +1332,9 @@ __global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const D
   cx.pubB = reinterpret_cast<volatile unsigned long long*>(smem_s + OFF_PUBB);
   cx.misc = reinterpret_cast<volatile uint32_t*>(smem_s + OFF_MISC);
   cx.acc = nullptr;
+  cx.tmaps = nullptr;
+  cx.nstage = 0;
+  cx.buf0 = cx.buf1 = cx.mbar0 = cx.mbar1 = cx.par0 = cx.par1 = 0;
   for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
     cx.pubA[i] = 0;
     cx.pubB[i] = 0;

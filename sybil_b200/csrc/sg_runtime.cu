@@ -8,11 +8,13 @@
 //   CombineResults / SortResults        aggregate.go:414-467,497-525 -> device accumulators shared by
 //                                        all blocks (+ NCCL all-reduce across GPUs) and build_result()
 //   translate_group_by                  aggregate.go:284-324        -> render_key() over the global dictionary
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -59,6 +61,24 @@ struct NcclApi {
   }
 };
 NcclApi g_nccl;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link against libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encode_fn() {
+  static TmapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (TmapEncodeFn)p;
+  }
+  return fn;
+}
 
 constexpr size_t ARENA_CHUNK = (size_t)512 << 20;
 constexpr size_t STAGE_BYTES = (size_t)64 << 20;
@@ -212,6 +232,12 @@ struct sg_table {
   int64_t encoded_bytes = 0;
   int64_t h2d_bytes = 0;
   int64_t stats_launches = 0;
+  // one tensor map per arena chunk ({128 B, rows} bytes view, 128B swizzle, 32-row boxes)
+  std::vector<CUtensorMap> tmaps;
+  void* d_tmaps = nullptr;
+  size_t d_tmaps_cap = 0;
+  bool tmaps_dirty = false;
+  bool tma_ok = true;
   // device mirrors of blocks / cols, refreshed when dirty
   DevBlock* d_blocks = nullptr;
   DevCol* d_cols = nullptr;
@@ -239,6 +265,23 @@ int arena_alloc(sg_table* t, size_t bytes, char** out) {
     t->chunk_idx = t->chunks.size() - 1;
     t->chunk_used = 0;
     t->device_bytes += (int64_t)cap;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    TmapEncodeFn enc = getenv("SG_NO_TMA") ? nullptr : tmap_encode_fn();  // SG_NO_TMA=1: plain vector loads (A/B)
+    if (enc && t->tma_ok) {
+      const cuuint64_t gdim[2] = {128, (cuuint64_t)(cap / 128)};
+      const cuuint64_t gstr[1] = {128};
+      const cuuint32_t box[2] = {128, 32};
+      const cuuint32_t estr[2] = {1, 1};
+      if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+          CUDA_SUCCESS)
+        t->tma_ok = false;
+    } else {
+      t->tma_ok = false;
+    }
+    t->tmaps.push_back(tm);
+    t->tmaps_dirty = true;
   }
   *out = t->chunks[t->chunk_idx].first + t->chunk_used;
   t->chunk_used += bytes;
@@ -415,6 +458,7 @@ void sg_table_free(sg_table* t) {
   }
   if (t->d_blocks) cudaFree(t->d_blocks);
   if (t->d_cols) cudaFree(t->d_cols);
+  if (t->d_tmaps) cudaFree(t->d_tmaps);
   delete t;
 }
 
@@ -636,7 +680,14 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
     Tmp& tm = tmp[(size_t)ci];
     if (tm.has_bv) dc.bin_values = (const int64_t*)(dev + tm.off_bv);
     if (tm.has_bo) dc.bin_offsets = (const uint32_t*)(dev + tm.off_bo);
-    if (tm.has_data) dc.data = dev + tm.off_data;
+    if (tm.has_data) {
+      dc.data = dev + tm.off_data;
+      if (t->tma_ok) {
+        dc.data_chunk = (uint32_t)t->chunk_idx;
+        dc.data_row = (uint32_t)((size_t)(dev + tm.off_data - t->chunks[t->chunk_idx].first) / 128);
+        dc.flags |= COL_TMA;
+      }
+    }
     if (tm.has_remap) dc.remap = (const int32_t*)(dev + tm.off_remap);
   }
   HostBlock hb;
@@ -779,6 +830,7 @@ struct sg_query {
   std::vector<HistLayout> layouts;
   uint32_t slot_bytes = 2;
   uint32_t smem_bytes = 0;
+  uint32_t nstage = 0;
   // device state
   Plan* d_plan = nullptr;
   uint64_t* d_acc = nullptr;  // one allocation: scalars | count | per agg hcount,sum,vmax | buckets
@@ -856,6 +908,17 @@ bool should_load(const sg_query* q, const std::vector<sg_int_info>& info) {
 
 int upload_table(sg_table* t) {
   sg_ctx* c = t->ctx;
+  if (t->tmaps_dirty && t->tma_ok && !t->tmaps.empty()) {
+    if (t->tmaps.size() > t->d_tmaps_cap) {
+      if (t->d_tmaps) cudaFree(t->d_tmaps);
+      t->d_tmaps = nullptr;
+      size_t cap = t->tmaps.size() * 2 + 8;
+      CUDA_TRY(c, cudaMalloc(&t->d_tmaps, cap * sizeof(CUtensorMap)));
+      t->d_tmaps_cap = cap;
+    }
+    CUDA_TRY(c, cudaMemcpy(t->d_tmaps, t->tmaps.data(), t->tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    t->tmaps_dirty = false;
+  }
   if (!t->dirty && t->d_blocks) return SG_OK;
   size_t nb = t->blocks.size();
   if (nb > t->d_blocks_cap) {
@@ -1079,14 +1142,30 @@ int make_plan(sg_query* q) {
   q->acc_words = words;
 
   // ---- shared memory budget ----------------------------------------------------------
+  // TMA staging (per warp 4 KiB tiles, 1 or 2 deep) competes with the accumulator replicas:
+  // take two stages while at least 8 replicas still fit, else one, else plain loads
   P.acc_words = 1 + 3 * (uint32_t)P.naggs;
-  const uint32_t fixed = scan_fixed_smem() + (q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u);
-  const uint32_t avail = MAX_DYN_SMEM > fixed ? MAX_DYN_SMEM - fixed : 0u;
-  uint32_t repl = 32;
-  while (repl >= 1 && ((uint64_t)P.nslots + 1) * P.acc_words * repl * 4 > avail) repl >>= 1;  // + trash slot
+  const uint32_t slots_b = q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u;
+  auto repl_for = [&](uint32_t nstage) -> uint32_t {
+    const uint32_t fixed = scan_fixed_smem(nstage) + slots_b;
+    if (fixed > MAX_DYN_SMEM) return 0;
+    const uint32_t avail = MAX_DYN_SMEM - fixed;
+    uint32_t repl = 32;
+    while (repl >= 1 && ((uint64_t)P.nslots + 1) * P.acc_words * repl * 4 > avail) repl >>= 1;  // + trash slot
+    return repl;
+  };
+  uint32_t nstage = 0;
+  if (t->tma_ok && t->d_tmaps) {
+    if (repl_for(2) >= 8)
+      nstage = 2;
+    else if (repl_for(1) >= 2 || (repl_for(1) >= 1 && repl_for(0) <= 1))
+      nstage = 1;
+  }
+  if (scan_fixed_smem(nstage) + slots_b > MAX_DYN_SMEM) nstage = 0;
+  q->nstage = nstage;
+  const uint32_t repl = repl_for(nstage);
   P.acc_repl = repl;  // 0: accumulate straight into global memory
-  q->smem_bytes = fixed + (P.nslots + 1) * P.acc_words * repl * 4;
-  if (repl == 0) q->smem_bytes = fixed;
+  q->smem_bytes = scan_fixed_smem(nstage) + slots_b + (repl ? (P.nslots + 1) * P.acc_words * repl * 4 : 0u);
   return SG_OK;
 }
 
@@ -1173,6 +1252,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.gdummy = q->d_gdummy;
   lp.smem_bytes = q->smem_bytes;
   lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
+  lp.nstage = q->nstage;
+  lp.tmaps = q->nstage ? t->d_tmaps : nullptr;
   int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(list.size(), 1));
   CUDA_TRY(c, cudaEventRecord(q->ev0, c->stream));
   int rc = launch_scan(lp, grid, c->stream);
