@@ -191,6 +191,9 @@ void sg_table_free(sg_table* t);
  * values into the per-column value dictionary.  Returns SG_ERR_INVALID for a
  * malformed descriptor (the block is not added). */
 int sg_table_add_block(sg_table* t, const sg_block_desc* block);
+/* Batch form.  Arrays that lie inside one region from sg_pinned_alloc are mirrored into HBM with a
+ * few large copies instead of one per array (full PCIe rate); otherwise as n calls above. */
+int sg_table_add_blocks(sg_table* t, const sg_block_desc* const* blocks, int64_t n);
 int sg_table_sync(sg_table* t); /* wait for staged copies */
 /* forget the staged blocks, keep arena + dictionaries (re-staging without reallocation) */
 int sg_table_clear(sg_table* t);

@@ -93,6 +93,7 @@ SYMBOLS = {
     "sg_table_create": (P, [P, C.c_int32, C.POINTER(C.c_int32)]),
     "sg_table_free": (None, [P]),
     "sg_table_add_block": (C.c_int, [P, C.POINTER(sg_block_desc)]),
+    "sg_table_add_blocks": (C.c_int, [P, P, C.c_int64]),
     "sg_table_sync": (C.c_int, [P]),
     "sg_table_clear": (C.c_int, [P]),
     "sg_table_num_blocks": (C.c_int64, [P]),

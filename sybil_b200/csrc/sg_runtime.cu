@@ -462,7 +462,24 @@ void sg_table_free(sg_table* t) {
   delete t;
 }
 
-int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
+}  // extern "C"
+
+namespace {
+// A span of the caller's pinned memory mirrored into the arena by one large copy
+// (sg_table_add_blocks): arrays inside it are addressed in place, not copied again.
+struct Premap {
+  const char* host = nullptr;
+  char* dev = nullptr;
+  size_t bytes = 0;
+  size_t chunk = 0;
+  bool has(const void* p, size_t n) const {
+    const char* c = (const char*)p;
+    return host && c >= host && c + n <= host + bytes && ((size_t)(c - host) % 128) == 0;
+  }
+};
+}  // namespace
+
+static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm) {
   if (!t || !b) return SG_ERR_INVALID;
   sg_ctx* c = t->ctx;
   if (b->num_records <= 0 || b->num_records > SG_BLOCK_ROWS) {
@@ -484,6 +501,7 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
     std::vector<int32_t> remap;
     size_t off_bv = 0, off_bo = 0, off_data = 0, off_remap = 0;
     bool has_bv = false, has_bo = false, has_data = false, has_remap = false;
+    char* premapped = nullptr;  // the data array already sits in the arena (mirrored span)
   };
   std::vector<Tmp> tmp((size_t)b->ncols);
   SlabWriter sw;
@@ -591,7 +609,10 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
       }
       tm.off_bv = sw.add(tm.bin_values.data(), tm.bin_values.size() * 8);
       tm.off_bo = sw.add(tm.bin_offsets.data(), tm.bin_offsets.size() * 4);
-      tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * 4, c->is_pinned(cd.record_ids, (size_t)cd.nrecord_ids * 4));
+      if (pm.has(cd.record_ids, (size_t)cd.nrecord_ids * 4))
+        tm.premapped = pm.dev + ((const char*)cd.record_ids - pm.host);
+      else
+        tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * 4, c->is_pinned(cd.record_ids, (size_t)cd.nrecord_ids * 4));
       tm.has_bv = tm.has_bo = tm.has_data = true;
       enc_bytes += (int64_t)(tm.bin_values.size() * 8 + tm.bin_offsets.size() * 4 + (size_t)cd.nrecord_ids * 4);
     } else if (cd.encoding == SG_ENC_VALUES) {
@@ -605,14 +626,20 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
             c->set_err("add_block: values_i32 missing");
             return SG_ERR_INVALID;
           }
-          tm.off_data = sw.add(cd.values_i32, (size_t)cd.nvalues * 4, c->is_pinned(cd.values_i32, (size_t)cd.nvalues * 4));
+          if (pm.has(cd.values_i32, (size_t)cd.nvalues * 4))
+            tm.premapped = pm.dev + ((const char*)cd.values_i32 - pm.host);
+          else
+            tm.off_data = sw.add(cd.values_i32, (size_t)cd.nvalues * 4, c->is_pinned(cd.values_i32, (size_t)cd.nvalues * 4));
           enc_bytes += (int64_t)cd.nvalues * 4;
         } else {
           if (!cd.values_i64) {
             c->set_err("add_block: values_i64 missing");
             return SG_ERR_INVALID;
           }
-          tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * 8, c->is_pinned(cd.values_i64, (size_t)cd.nvalues * 8));
+          if (pm.has(cd.values_i64, (size_t)cd.nvalues * 8))
+            tm.premapped = pm.dev + ((const char*)cd.values_i64 - pm.host);
+          else
+            tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * 8, c->is_pinned(cd.values_i64, (size_t)cd.nvalues * 8));
           enc_bytes += (int64_t)cd.nvalues * 8;
           t->has_values_int[(size_t)cd.col_slot] = 1;
           stats_slots.push_back((uint32_t)cd.col_slot);
@@ -681,10 +708,12 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
     if (tm.has_bv) dc.bin_values = (const int64_t*)(dev + tm.off_bv);
     if (tm.has_bo) dc.bin_offsets = (const uint32_t*)(dev + tm.off_bo);
     if (tm.has_data) {
-      dc.data = dev + tm.off_data;
+      const size_t chunk = tm.premapped ? pm.chunk : t->chunk_idx;
+      char* dptr = tm.premapped ? tm.premapped : dev + tm.off_data;
+      dc.data = dptr;
       if (t->tma_ok) {
-        dc.data_chunk = (uint32_t)t->chunk_idx;
-        dc.data_row = (uint32_t)((size_t)(dev + tm.off_data - t->chunks[t->chunk_idx].first) / 128);
+        dc.data_chunk = (uint32_t)chunk;
+        dc.data_row = (uint32_t)((size_t)(dptr - t->chunks[chunk].first) / 128);
         dc.flags |= COL_TMA;
       }
     }
@@ -700,6 +729,67 @@ int sg_table_add_block(sg_table* t, const sg_block_desc* b) {
   t->total_rows += nrec;
   t->encoded_bytes += enc_bytes;
   t->dirty = true;
+  return SG_OK;
+}
+
+extern "C" {
+
+int sg_table_add_block(sg_table* t, const sg_block_desc* b) { return add_block_impl(t, b, Premap()); }
+
+int sg_table_add_blocks(sg_table* t, const sg_block_desc* const* blocks, int64_t n) {
+  // Batch staging.  When the big arrays of the batch lie densely inside one region from
+  // sg_pinned_alloc, the whole span is mirrored into the arena with a few large copies (full PCIe
+  // rate, one DMA setup per 64 MiB instead of one per array) and the per-block work below only
+  // handles dictionaries and the small per-bin arrays while that copy is in flight.
+  if (!t || (n > 0 && !blocks)) return SG_ERR_INVALID;
+  sg_ctx* c = t->ctx;
+  cudaSetDevice(c->device);
+  Premap pm;
+  const char* lo = nullptr;
+  const char* hi = nullptr;
+  size_t payload = 0;
+  auto see = [&](const void* p, size_t bytes) {
+    if (!p || !bytes || !c->is_pinned(p, bytes)) return;
+    const char* q = (const char*)p;
+    if (!lo || q < lo) lo = q;
+    if (!hi || q + bytes > hi) hi = q + bytes;
+    payload += bytes;
+  };
+  for (int64_t i = 0; i < n; i++) {
+    const sg_block_desc* b = blocks[i];
+    if (!b || b->ncols < 0 || (b->ncols > 0 && !b->cols)) continue;
+    for (int ci = 0; ci < b->ncols; ci++) {
+      const sg_column_desc& cd = b->cols[ci];
+      if (cd.encoding == SG_ENC_BUCKET)
+        see(cd.record_ids, (size_t)cd.nrecord_ids * 4);
+      else if (cd.encoding == SG_ENC_VALUES)
+        see(cd.col_type == SG_COL_STR ? (const void*)cd.values_i32 : (const void*)cd.values_i64,
+            (size_t)cd.nvalues * (cd.col_type == SG_COL_STR ? 4 : 8));
+    }
+  }
+  if (lo && payload >= ((size_t)1 << 20)) {
+    const char* base = (const char*)((uintptr_t)lo & ~(uintptr_t)127);
+    size_t span = (size_t)(hi - base);
+    if (span <= payload + payload / 2 + ((size_t)8 << 20)) {
+      char* dev = nullptr;
+      int rc = arena_alloc(t, span, &dev);
+      if (rc != SG_OK) return rc;
+      pm.host = base;
+      pm.dev = dev;
+      pm.bytes = span;
+      pm.chunk = t->chunk_idx;
+      const size_t piece = (size_t)64 << 20;
+      for (size_t off = 0; off < span; off += piece) {
+        size_t nb = std::min(piece, span - off);
+        CUDA_TRY(c, cudaMemcpyAsync(dev + off, base + off, nb, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      t->h2d_bytes += (int64_t)span;
+    }
+  }
+  for (int64_t i = 0; i < n; i++) {
+    int rc = add_block_impl(t, blocks[i], pm);
+    if (rc != SG_OK) return rc;
+  }
   return SG_OK;
 }
 
@@ -835,6 +925,7 @@ struct sg_query {
   Plan* d_plan = nullptr;
   uint64_t* d_acc = nullptr;  // one allocation: scalars | count | per agg hcount,sum,vmax | buckets
   size_t acc_words = 0;
+  size_t sum_words = 0;  // leading words merged by SUM; the rest (vmax) by MAX
   size_t off_count = 0;
   std::vector<size_t> off_hcount, off_sum, off_vmax, off_buckets;
   uint32_t* d_block_status = nullptr;
@@ -1098,6 +1189,8 @@ int make_plan(sg_query* q) {
   }
 
   // ---- aggregations ----------------------------------------------------------------
+  // accumulator layout: one SUM region (scalars | count | per agg hcount, sum | per agg buckets)
+  // followed by one MAX region (per agg vmax): the cross-GPU merge is two all-reduces
   q->layouts.clear();
   size_t words = 8;  // scalars
   q->off_count = words;
@@ -1130,14 +1223,19 @@ int make_plan(sg_query* q) {
     words += P.nslots;
     q->off_sum.push_back(words);
     words += P.nslots;
-    q->off_vmax.push_back(words);
-    words += P.nslots;
+  }
+  for (int i = 0; i < P.naggs; i++) {
     q->off_buckets.push_back(words);
-    words += (size_t)P.nslots * L.nvals_total;
+    words += (size_t)P.nslots * q->layouts[(size_t)i].nvals_total;
     if (words * 8 > ((size_t)24 << 30)) {
       c->set_err("query: accumulators exceed 24 GiB (groups x histogram buckets); needs the sparse path");
       return SG_ERR_UNSUPPORTED;
     }
+  }
+  q->sum_words = words;
+  for (int i = 0; i < P.naggs; i++) {
+    q->off_vmax.push_back(words);
+    words += P.nslots;
   }
   q->acc_words = words;
 
@@ -1218,14 +1316,13 @@ __global__ void fill_i64(int64_t* p, size_t n, int64_t v) {
 
 int reset_accumulators(sg_query* q) {
   sg_ctx* c = q->ctx;
-  CUDA_TRY(c, cudaMemsetAsync(q->d_acc, 0, q->acc_words * 8, c->stream));
-  for (int i = 0; i < q->plan.naggs; i++) {
-    size_t n = q->plan.nslots;
-    fill_i64<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int64_t*)(q->d_acc + q->off_vmax[(size_t)i]), n,
-                                                                  INT64_MIN);
+  CUDA_TRY(c, cudaMemsetAsync(q->d_acc, 0, q->sum_words * 8, c->stream));
+  if (q->acc_words > q->sum_words) {
+    size_t n = q->acc_words - q->sum_words;
+    fill_i64<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int64_t*)(q->d_acc + q->sum_words), n, INT64_MIN);
   }
   CUDA_TRY(c, cudaGetLastError());
-  q->launches += q->plan.naggs;
+  q->launches += (q->acc_words > q->sum_words) ? 1 : 0;
   return SG_OK;
 }
 
@@ -1605,14 +1702,10 @@ int sg_query_allreduce(sg_query* q) {
     }
     return SG_OK;
   };
-  int rc = ar(q->d_acc, 8 + (size_t)P.nslots, ncclUint64, ncclSum);
-  for (int i = 0; i < P.naggs && rc == SG_OK; i++) {
-    rc = ar(q->d_acc + q->off_hcount[(size_t)i], 2 * (size_t)P.nslots, ncclUint64, ncclSum);
-    if (rc == SG_OK) rc = ar(q->d_acc + q->off_vmax[(size_t)i], P.nslots, ncclInt64, ncclMax);
-    if (rc == SG_OK && q->layouts[(size_t)i].nvals_total)
-      rc = ar(q->d_acc + q->off_buckets[(size_t)i], (size_t)P.nslots * q->layouts[(size_t)i].nvals_total, ncclUint64,
-              ncclSum);
-  }
+  (void)P;
+  int rc = ar(q->d_acc, q->sum_words, ncclUint64, ncclSum);
+  if (rc == SG_OK && q->acc_words > q->sum_words)
+    rc = ar(q->d_acc + q->sum_words, q->acc_words - q->sum_words, ncclInt64, ncclMax);
   if (rc != SG_OK) return rc;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return SG_OK;

@@ -324,6 +324,10 @@ class Table:
     def add_block_desc_ptr(self, p):
         self.ctx.check(self.lib.sg_table_add_block(self.h, p))
 
+    def add_blocks(self, ptr_array, n):
+        """sg_table_add_blocks: ptr_array is a ctypes array of sg_block_desc pointers."""
+        self.ctx.check(self.lib.sg_table_add_blocks(self.h, ptr_array, n))
+
     def sync(self):
         self.ctx.check(self.lib.sg_table_sync(self.h))
 

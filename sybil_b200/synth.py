@@ -155,6 +155,14 @@ class Store:
     def block(self, i):
         return self.g.sbg_block(self.h, i)
 
+    def block_ptrs(self):
+        """(ctypes array of sg_block_desc*, n) for sg_table_add_blocks."""
+        n = self.num_blocks()
+        arr = (C.POINTER(F.sg_block_desc) * max(n, 1))()
+        for i in range(n):
+            arr[i] = self.block(i)
+        return arr, n
+
     def encoded_bytes(self):
         return self.g.sbg_encoded_bytes(self.h)
 
