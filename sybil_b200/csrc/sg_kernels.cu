@@ -178,6 +178,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void sred_add(uint32_t addr, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// global reductions spelled out in the global state space: a plain atomicAdd() on a pointer the
+// compiler cannot prove global becomes a generic ATOM that returns a predicate (round trip to L2)
+__device__ __forceinline__ void gred_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void gred_max(long long* p, long long v) {
+  asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t satom_add(uint32_t addr, uint32_t v) {
   uint32_t o;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
@@ -697,7 +705,7 @@ __device__ __noinline__ void hist_bucket_general(const AggSlow* A, uint32_t g, l
     long long b = (long long)((unsigned long long)v - (unsigned long long)S.lo) / S.bsize;
     if (b >= (long long)S.nvals) b = (long long)S.nvals - 1;  // outlier: last slot (hist_basic.go:134-137)
     if (b < 0) b = 0;
-    atomicAdd(A->buckets + ((size_t)g * A->nvals_total + S.base + (uint32_t)b), 1ull);
+    gred_add(A->buckets + ((size_t)g * A->nvals_total + S.base + (uint32_t)b), 1ull);
     break;
   }
 }
@@ -719,10 +727,10 @@ __device__ __noinline__ void agg_slow(const AggSlow* A, uint32_t g, long long v,
     if (old > ~lo) hi += 1u;  // carry out of the low limb
     if (hi) sred_add(w + 2 * A->R_b, hi);
   } else {
-    atomicAdd(A->hcount + g, 1ull);
-    atomicAdd(A->sum + g, (unsigned long long)v);
+    gred_add(A->hcount + g, 1ull);
+    gred_add(A->sum + g, (unsigned long long)v);
   }
-  if (v > A->info_max) atomicMax(A->vmax + g, v);
+  if (v > A->info_max) gred_max(A->vmax + g, v);
   if (A->nsub > 0) hist_bucket_general(A, g, v);
 }
 
@@ -914,7 +922,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               if (cur)
                 slot[row] = (SlotT)(slot[row] + cur * ts + tok);
               else
-                atomicAdd(g_scalars + 2, 1ull);
+                gred_add(g_scalars + 2, 1ull);
             });
       } else if (c.enc == SG_ENC_VALUES && !(c.flags & COL_IS_STR)) {
         scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
@@ -927,7 +935,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               if (tc)
                 inc[k] = tc * ts + time_ok;
               else
-                atomicAdd(g_scalars + 2, 1ull);
+                gred_add(g_scalars + 2, 1ull);
             }
           }
           add_slots(slot, idx0, inc);
@@ -962,9 +970,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           if (hi == pass_target) {
             const uint32_t g = s & gmask;
             if (ACC_SMEM)
-              atomicAdd(cx.acc + g * gstride + lane_off, 1u);
+              sred_add(smem_u32(cx.acc + g * gstride + lane_off), 1u);
             else
-              atomicAdd(g_count + g, 1ull);
+              gred_add(g_count + g, 1ull);
           }
         }
         counted = true;
@@ -1041,7 +1049,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               if (hist32) {
                 uint32_t b = (vlo - fmin32 + hoff) / bsize0;
                 if (b >= nvals0) b = nvals0 - 1;
-                atomicAdd(bkt + ((size_t)e * nvt + b), 1ull);
+                gred_add(bkt + ((size_t)e * nvt + b), 1ull);
               } else {
                 hist_bucket_general(&AS, e, v);
               }
@@ -1113,7 +1121,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                 const uint32_t x = a[k] - fmin32 + hoff;
                 uint32_t b = magic0 ? div_magic(x, magic0) : x / bsize0;
                 b = min(b, nvals0 - 1);  // outlier: clamped into the last slot (hist_basic.go:134-137)
-                atomicAdd(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
+                gred_add(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
               } else if (e2 != trash) {
                 hist_bucket_general(&AS, e2, (long long)a[k]);
               }
@@ -1186,7 +1194,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               if (hist32) {
                 uint32_t b = (vlo - fmin32 + hoff) / bsize0;
                 if (b >= nvals0) b = nvals0 - 1;  // outlier: clamped into the last slot (hist_basic.go:134-137)
-                atomicAdd(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
+                gred_add(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
               }
             }
             if (cmask | slow_any) {  // rare
@@ -1217,7 +1225,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                   if (ACC_SMEM)
                     sred_add(cnt_s + e * gstride_b, 1u);
                   else
-                    atomicAdd(g_count + e, 1ull);
+                    gred_add(g_count + e, 1ull);
                 }
                 agg_slow(&AS, e, (long long)a[k], 0);
               }
@@ -1252,7 +1260,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               if (ACC_SMEM)
                 sred_add(cnt_s + g * gstride_b, 1u);
               else
-                atomicAdd(g_count + g, 1ull);
+                gred_add(g_count + g, 1ull);
             }
             if (ACC_SMEM) sred_add(w0_s + g * gstride_b, 1u);
           }
@@ -1267,7 +1275,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     if (broken) {
       if (cx.tid == 0) {
         PP->block_status[bid] = 1;
-        atomicAdd(g_scalars + 1, 1ull);
+        gred_add(g_scalars + 1, 1ull);
       }
     } else {
       matched += my_matched;
@@ -1281,7 +1289,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         unsigned long long cnt = 0;
         for (uint32_t r = 0; r < R; r++) cnt += base[r];
         if (a == 0) {
-          if (cnt && !broken) atomicAdd(g_count + g, cnt);
+          if (cnt && !broken) gred_add(g_count + g, cnt);
         } else {
           const uint32_t w0 = 1u + 3u * (a - 1u);
           unsigned long long word0 = 0, lo = 0, hi = 0;
@@ -1293,9 +1301,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           const unsigned long long hc = ((agg_mode_bits >> (a - 1u)) & 1u) ? cnt - word0 : word0;
           if (!broken) {
             const KAgg* KA = &PP->aggs[a - 1u];
-            if (hc) atomicAdd(reinterpret_cast<unsigned long long*>(KA->hcount) + g, hc);
+            if (hc) gred_add(reinterpret_cast<unsigned long long*>(KA->hcount) + g, hc);
             const unsigned long long sum = lo + (hi << 32);
-            if (sum) atomicAdd(reinterpret_cast<unsigned long long*>(KA->sum) + g, sum);
+            if (sum) gred_add(reinterpret_cast<unsigned long long*>(KA->sum) + g, sum);
           }
         }
       }
@@ -1307,7 +1315,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   // MatchedCount
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) matched += __shfl_xor_sync(FULL, matched, d);
-  if (cx.lane == 0 && matched) atomicAdd(g_scalars + 0, matched);
+  if (cx.lane == 0 && matched) gred_add(g_scalars + 0, matched);
 }
 
 // ---------------------------------------------------------------------------
