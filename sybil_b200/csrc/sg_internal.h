@@ -81,7 +81,8 @@ struct KAgg {
   int64_t info_min, info_max;
   int64_t reject_hi;
   uint32_t nvals_total;
-  uint32_t _pad;
+  uint32_t _pad;      // bit 0: the plan proved hist Count == Count for every scanned block (the
+                      // kernel then skips the hist-Count reductions; accumulators-in-global plans only)
   uint64_t* buckets;  // [nslots][nvals_total]
   uint64_t* hcount;   // [nslots]
   uint64_t* sum;      // [nslots]

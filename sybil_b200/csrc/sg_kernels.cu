@@ -1157,6 +1157,44 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           }
         }
         counted = true;
+      } else if (c.enc == SG_ENC_VALUES && !ACC_SMEM && (c.flags & COL_STATS) && c.vmin >= 0 &&
+                 c.vmax <= 0xffffffffll) {
+        // ---- high-cardinality plan (accumulators in L2/HBM), 32-bit values: one RED per row for the
+        // count, one (two unless the plan proved hist Count == Count) per aggregation
+        const long long amin = AS.info_min, amax = AS.reject_hi < AS.info_max ? AS.reject_hi : AS.info_max;
+        const bool allin = c.vmin >= amin && c.vmax <= amax;  // every value accepted and not above info_max
+        const bool skip_hc = (KA->_pad & 1u) != 0;             // plan: hist Count == Count for this aggregation
+        unsigned long long* const g_hc = AS.hcount;
+        unsigned long long* const g_sum = AS.sum;
+        auto tile32g = [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid) {
+          uint32_t sw[VE];
+          load_slots(slot, idx0, sw);
+#pragma unroll
+          for (int k = 0; k < VE; k++) {
+            if (k >= nvalid) continue;
+            const uint32_t e = min(sw[k] ^ passbits, trash);
+            if (do_count && count_matched && ((sw[k] >> gbits) & filt_mask) == filt_target) my_matched++;
+            if (e == trash) continue;
+            if (do_count) gred_add(g_count + e, 1ull);
+            const long long v = (long long)a[k];
+            if (allin || (v >= amin && v <= amax)) {
+              if (!skip_hc) gred_add(g_hc + e, 1ull);
+              gred_add(g_sum + e, (unsigned long long)a[k]);
+              if (nsub > 0) hist_bucket_general(&AS, e, v);
+            } else {
+              agg_slow(&AS, e, v, 0);
+            }
+          }
+        };
+        scan_values_u32(cx, c, nrec, tile32g);
+        const uint32_t nv = c.nitems < nrec ? c.nitems : nrec;
+        for (uint32_t r = nv + cx.tid; r < nrec; r += THREADS) {
+          const uint32_t s = (uint32_t)slot[r];
+          const uint32_t hi = s >> gbits;
+          if (do_count && count_matched && (hi & filt_mask) == filt_target) my_matched++;
+          if (hi == pass_target && do_count) gred_add(g_count + (s & gmask), 1ull);
+        }
+        counted = true;
       } else if (c.enc == SG_ENC_VALUES) {
         agg_mode_bits |= 1u << ai;
         auto tile = [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid, auto do_count_tag,

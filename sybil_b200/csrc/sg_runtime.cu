@@ -163,22 +163,66 @@ static void pool_release(sg_ctx* c, void* p) {
 
 namespace {
 
+// String -> dense id.  Open addressing over (hash, id); lookups hash the caller's bytes in place
+// (a block of a high-cardinality column interns ~65,000 strings, a 1B-row table ~10^9 in all)
 struct StrDict {
-  std::unordered_map<std::string, int32_t> map;
   std::vector<std::string> strs;
+  std::vector<uint64_t> slots;  // (hash & ~0xffffffff) | (id + 1); 0 = empty
+  size_t mask = 0;
+  static uint64_t hash_bytes(const char* p, size_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
+    while (n >= 8) {
+      uint64_t w;
+      memcpy(&w, p, 8);
+      h = (h ^ w) * 0xff51afd7ed558ccdull;
+      h ^= h >> 32;
+      p += 8;
+      n -= 8;
+    }
+    uint64_t w = 0;
+    memcpy(&w, p, n);
+    h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 29;
+    return h;
+  }
+  void grow() {
+    size_t cap = slots.empty() ? 1024 : slots.size() * 2;
+    std::vector<uint64_t> ns(cap, 0);
+    size_t m = cap - 1;
+    for (size_t id = 0; id < strs.size(); id++) {
+      uint64_t h = hash_bytes(strs[id].data(), strs[id].size());
+      size_t i = (size_t)h & m;
+      while (ns[i]) i = (i + 1) & m;
+      ns[i] = (h & ~0xffffffffull) | (uint64_t)(id + 1);
+    }
+    slots.swap(ns);
+    mask = m;
+  }
+  int32_t lookup(const char* p, size_t n, uint64_t h) const {
+    if (slots.empty()) return -1;
+    size_t i = (size_t)h & mask;
+    while (slots[i]) {
+      if ((slots[i] & ~0xffffffffull) == (h & ~0xffffffffull)) {
+        const std::string& s = strs[(size_t)(slots[i] & 0xffffffffull) - 1];
+        if (s.size() == n && memcmp(s.data(), p, n) == 0) return (int32_t)((slots[i] & 0xffffffffull) - 1);
+      }
+      i = (i + 1) & mask;
+    }
+    return -1;
+  }
   int32_t intern(const char* p, size_t n) {
-    std::string s(p, n);
-    auto it = map.find(s);
-    if (it != map.end()) return it->second;
-    int32_t id = (int32_t)strs.size();
-    map.emplace(s, id);
-    strs.push_back(std::move(s));
+    const uint64_t h = hash_bytes(p, n);
+    int32_t id = lookup(p, n, h);
+    if (id >= 0) return id;
+    if ((strs.size() + 1) * 2 > slots.size()) grow();
+    id = (int32_t)strs.size();
+    strs.emplace_back(p, n);
+    size_t i = (size_t)h & mask;
+    while (slots[i]) i = (i + 1) & mask;
+    slots[i] = (h & ~0xffffffffull) | (uint64_t)(id + 1);
     return id;
   }
-  int32_t find(const std::string& s) const {
-    auto it = map.find(s);
-    return it == map.end() ? -1 : it->second;
-  }
+  int32_t find(const std::string& s) const { return lookup(s.data(), s.size(), hash_bytes(s.data(), s.size())); }
 };
 struct IntDict {
   std::unordered_map<int64_t, int32_t> map;
@@ -880,9 +924,19 @@ struct ResultGroup {
   std::vector<uint64_t> key;
   std::string skey;
   int64_t count = 0;
-  // per agg
-  std::vector<int64_t> hcount, sum, vmin, vmax;
-  std::vector<std::vector<int64_t>> values;  // bucket counters per agg
+  // per aggregation a: agg[3a] = hist Count, agg[3a+1] = exact sum, agg[3a+2] = max above info_max
+  // (one allocation per group: a high-cardinality result holds a million of these)
+  std::vector<int64_t> agg;
+  std::vector<std::vector<int64_t>> values;  // bucket counters per aggregation (hist mode only)
+  int64_t& hc(int a) { return agg[(size_t)a * 3]; }
+  int64_t& sm(int a) { return agg[(size_t)a * 3 + 1]; }
+  int64_t& vx(int a) { return agg[(size_t)a * 3 + 2]; }
+  int64_t hc(int a) const { return agg[(size_t)a * 3]; }
+  int64_t sm(int a) const { return agg[(size_t)a * 3 + 1]; }
+  int64_t vx(int a) const { return agg[(size_t)a * 3 + 2]; }
+  const std::vector<int64_t>* vals(int a) const {
+    return (size_t)a < values.size() && !values[(size_t)a].empty() ? &values[(size_t)a] : nullptr;
+  }
 };
 
 }  // namespace
@@ -946,6 +1000,7 @@ struct sg_query {
   int64_t d2h_bytes = 0;
   bool ran = false;
   std::vector<uint32_t> last_list;
+  std::vector<char> hc_is_count;
 };
 
 namespace {
@@ -1390,23 +1445,22 @@ void merge_group(ResultGroup& into, const ResultGroup& g, int naggs, const std::
   into.count += g.count;
   if (!with_hists) return;
   for (int a = 0; a < naggs; a++) {
-    if (g.hcount[(size_t)a] == 0) continue;
-    into.hcount[(size_t)a] += g.hcount[(size_t)a];
-    into.sum[(size_t)a] = (int64_t)((uint64_t)into.sum[(size_t)a] + (uint64_t)g.sum[(size_t)a]);
-    into.vmax[(size_t)a] = std::max(into.vmax[(size_t)a], g.vmax[(size_t)a]);
+    if (g.hc(a) == 0) continue;
+    into.hc(a) += g.hc(a);
+    into.sm(a) = (int64_t)((uint64_t)into.sm(a) + (uint64_t)g.sm(a));
+    into.vx(a) = std::max(into.vx(a), g.vx(a));
     if (L[(size_t)a].nvals_total) {
+      if (into.values.size() < (size_t)naggs) into.values.resize((size_t)naggs);
       if (into.values[(size_t)a].empty()) into.values[(size_t)a].assign(L[(size_t)a].nvals_total, 0);
-      for (uint32_t k = 0; k < L[(size_t)a].nvals_total; k++) into.values[(size_t)a][k] += g.values[(size_t)a][k];
+      if (const auto* gv = g.vals(a))
+        for (uint32_t k = 0; k < L[(size_t)a].nvals_total; k++) into.values[(size_t)a][k] += (*gv)[k];
     }
   }
 }
 
 void init_group(ResultGroup& g, int naggs) {
-  g.hcount.assign((size_t)naggs, 0);
-  g.sum.assign((size_t)naggs, 0);
-  g.vmin.assign((size_t)naggs, 0);
-  g.vmax.assign((size_t)naggs, INT64_MIN);
-  g.values.assign((size_t)naggs, {});
+  g.agg.assign((size_t)naggs * 3, 0);
+  for (int a = 0; a < naggs; a++) g.vx(a) = INT64_MIN;
 }
 
 void sort_groups(std::vector<ResultGroup>& v) {
@@ -1464,12 +1518,14 @@ int build_result(sg_query* q, sg_result** out) {
     }
     g.skey = render_key(q, g.key);
     for (int a = 0; a < naggs; a++) {
-      g.hcount[(size_t)a] = (int64_t)h[q->off_hcount[(size_t)a] + s];
-      g.sum[(size_t)a] = (int64_t)h[q->off_sum[(size_t)a] + s];
-      g.vmax[(size_t)a] = (int64_t)h[q->off_vmax[(size_t)a] + s];
+      g.hc(a) = (size_t)a < q->hc_is_count.size() && q->hc_is_count[(size_t)a] ? (int64_t)cnt[s]
+                                                                               : (int64_t)h[q->off_hcount[(size_t)a] + s];
+      g.sm(a) = (int64_t)h[q->off_sum[(size_t)a] + s];
+      g.vx(a) = (int64_t)h[q->off_vmax[(size_t)a] + s];
       uint32_t nv = q->layouts[(size_t)a].nvals_total;
-      if (nv && g.hcount[(size_t)a]) {
+      if (nv && g.hc(a)) {
         const uint64_t* src = h.data() + q->off_buckets[(size_t)a] + (size_t)s * nv;
+        if (g.values.size() < (size_t)naggs) g.values.resize((size_t)naggs);
         g.values[(size_t)a].assign(src, src + nv);
       }
     }
@@ -1640,6 +1696,27 @@ int sg_query_run(sg_query* q) {
     q->rows_scanned += t->blocks[i].num_records;
   }
   q->blocks_scanned = (int64_t)list.size();
+  // hist Count == Count for an aggregation when, in every scanned block, its column is a value
+  // array covering every row whose exact extents lie inside the accepted range: the kernel then
+  // skips that reduction (accumulators-in-global plans) and the result takes Count
+  q->hc_is_count.assign((size_t)q->plan.naggs, 0);
+  if (q->plan.acc_repl == 0 && c->nranks <= 1) {  // multi-GPU: ranks would have to agree first
+    for (int a = 0; a < q->plan.naggs; a++) {
+      const KAgg& ka = q->plan.aggs[a];
+      const int64_t amax = std::min(ka.reject_hi, ka.info_max);
+      bool ok = !list.empty();
+      for (uint32_t b : list) {
+        const DevCol& dc = t->cols[(size_t)b * (size_t)t->ncols + (size_t)ka.col];
+        if (dc.enc != SG_ENC_VALUES || (dc.flags & COL_IS_STR) || !(dc.flags & COL_STATS) ||
+            dc.nitems < t->blocks[b].num_records || dc.vmin < ka.info_min || dc.vmax > amax) {
+          ok = false;
+          break;
+        }
+      }
+      q->hc_is_count[(size_t)a] = ok ? 1 : 0;
+      q->plan.aggs[a]._pad = ok ? 1u : 0u;
+    }
+  }
 
   // a block found broken by the kernel ("BLOCK SIZE CHANGED", row id >= NumRecords)
   // must contribute nothing: rerun without it (rare path)
@@ -1777,7 +1854,7 @@ static void hist_minmax(sg_result* r, const ResultGroup* g, int a, int64_t* mn, 
   const HistLayout& L = r->layouts[(size_t)a];
   if (L.tracked || L.multi) {
     *mn = L.info_min;
-    *mx = std::max(L.info_max, g->vmax[(size_t)a]);
+    *mx = std::max(L.info_max, g->vx(a));
   } else {
     *mn = 0;
     *mx = 0;
@@ -1789,43 +1866,43 @@ int sg_result_hist(sg_result* r, int64_t i, int32_t a, sg_hist_view* out) {
   if (!g || a < 0 || a >= r->naggs || !out) return SG_ERR_INVALID;
   memset(out, 0, sizeof(*out));
   if (i == -1 && !r->has_total_hists) return 0;
-  if (g->hcount[(size_t)a] == 0) return 0;  // no hist for this aggregation (Q7)
+  if (g->hc(a) == 0) return 0;  // no hist for this aggregation (Q7)
   const HistLayout& L = r->layouts[(size_t)a];
-  out->count = g->hcount[(size_t)a];
-  out->sum = g->sum[(size_t)a];
+  out->count = g->hc(a);
+  out->sum = g->sm(a);
   hist_minmax(r, g, a, &out->min, &out->max);
   out->avg = (double)out->sum / (double)out->count;
   out->num_buckets = (int32_t)L.num_buckets;
   out->bucket_size = L.subs.size() == 1 ? (int32_t)L.subs[0].bsize : 0;
   out->nvalues = (int32_t)L.nvals_total;
   out->nsubhists = L.multi ? (int32_t)L.subs.size() : 0;
-  out->values = g->values[(size_t)a].empty() ? nullptr : g->values[(size_t)a].data();
+  out->values = g->vals(a) ? g->vals(a)->data() : nullptr;
   return 1;
 }
 
 int sg_result_percentiles(sg_result* r, int64_t i, int32_t a, int64_t* out100) {
   ResultGroup* g = pick_group(r, i);
   if (!g || a < 0 || a >= r->naggs) return SG_ERR_INVALID;
-  if (g->hcount[(size_t)a] == 0 || g->values[(size_t)a].empty()) return 0;
+  if (g->hc(a) == 0 || !g->vals(a)) return 0;
   int64_t mn, mx;
   hist_minmax(r, g, a, &mn, &mx);
-  return percentiles(r->layouts[(size_t)a], g->values[(size_t)a].data(), g->hcount[(size_t)a], mn, out100);
+  return percentiles(r->layouts[(size_t)a], g->vals(a)->data(), g->hc(a), mn, out100);
 }
 
 double sg_result_stddev(sg_result* r, int64_t i, int32_t a) {
   ResultGroup* g = pick_group(r, i);
-  if (!g || a < 0 || a >= r->naggs || g->hcount[(size_t)a] == 0 || g->values[(size_t)a].empty()) return NAN;
+  if (!g || a < 0 || a >= r->naggs || g->hc(a) == 0 || !g->vals(a)) return NAN;
   int64_t mn, mx;
   hist_minmax(r, g, a, &mn, &mx);
-  double avg = (double)g->sum[(size_t)a] / (double)g->hcount[(size_t)a];
-  return stddev(r->layouts[(size_t)a], g->values[(size_t)a].data(), g->hcount[(size_t)a], avg, mn);
+  double avg = (double)g->sm(a) / (double)g->hc(a);
+  return stddev(r->layouts[(size_t)a], g->vals(a)->data(), g->hc(a), avg, mn);
 }
 
 int64_t sg_result_sparse_buckets(sg_result* r, int64_t i, int32_t a, int64_t* edges, int64_t* counts, int64_t cap) {
   ResultGroup* g = pick_group(r, i);
   if (!g || a < 0 || a >= r->naggs) return SG_ERR_INVALID;
-  if (g->hcount[(size_t)a] == 0 || g->values[(size_t)a].empty()) return 0;
-  auto m = sparse_buckets(r->layouts[(size_t)a], g->values[(size_t)a].data());
+  if (g->hc(a) == 0 || !g->vals(a)) return 0;
+  auto m = sparse_buckets(r->layouts[(size_t)a], g->vals(a)->data());
   int64_t n = 0;
   for (auto& kv : m) {
     if (edges && n < cap) {
