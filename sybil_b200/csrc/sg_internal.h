@@ -107,7 +107,8 @@ struct Plan {
   uint32_t filt_target; // (slot >> gbits) & filt_mask == filt_target : passed all filters
   uint32_t filt_mask;
   uint32_t nslots;      // dense group slots
-  uint32_t acc_words;   // smem words per slot: 1 + 3*naggs
+  uint32_t acc_words;   // replicated smem words per slot: 1 + 2*naggs (count; per agg word0, sum low limb);
+                        // the sum high limbs (rarely touched) follow unreplicated
   uint32_t acc_repl;    // replication (power of two, <= 32); 0 = accumulate in global memory
   uint32_t _pad;
   uint64_t* count;      // [nslots]
@@ -133,6 +134,7 @@ struct LaunchParams {
   uint32_t acc_smem;          // accumulators replicated in shared memory (plan.acc_repl > 0)
   const void* tmaps;          // CUtensorMap[chunks] in global memory (nullptr: plain vector loads)
   uint32_t nstage;            // TMA staging depth per warp (1 or 2)
+  unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
 };
 
 // host-callable launchers (sg_kernels.cu)

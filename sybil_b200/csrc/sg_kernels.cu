@@ -58,7 +58,11 @@ constexpr uint32_t OFF_PUBA = OFF_BINPAY + SMEM_BINS * 4;              // u64[MA
 constexpr uint32_t OFF_PUBB = OFF_PUBA + MAX_TILES * 8;                // u64[MAX_TILES]
 constexpr uint32_t OFF_MBAR = OFF_PUBB + MAX_TILES * 8;                // u64[NWARPS][2] mbarriers
 constexpr uint32_t OFF_MISC = OFF_MBAR + NWARPS * 2 * 8;               // u32[64]
-constexpr uint32_t FIXED_SMEM = OFF_MISC + 64 * 4;
+constexpr uint32_t PL_MAX = 48;                                        // TMA-fed column passes of one block
+constexpr uint32_t OFF_PLIST = OFF_MISC + 64 * 4;                      // u32[PL_MAX][4]
+constexpr uint32_t OFF_PCAND = OFF_PLIST + PL_MAX * 16;                // u32[PL_MAX] candidate passes of the plan
+constexpr uint32_t OFF_PTMP = OFF_PCAND + PL_MAX * 4;                  // u32[PL_MAX][4] per-block scratch
+constexpr uint32_t FIXED_SMEM = OFF_PTMP + PL_MAX * 16;
 uint32_t scan_fixed_smem(uint32_t nstage) { return 1024u + NWARPS * TMA_TILE_BYTES * nstage + FIXED_SMEM; }
 
 struct Ctx {
@@ -75,6 +79,14 @@ struct Ctx {
   const unsigned char* tmaps;
   uint32_t nstage;
   uint32_t buf0, buf1, mbar0, mbar1, par0, par1;
+  // the TMA-fed column passes of the current block, in execution order: {chunk, row0, ntiles, -};
+  // a pass requests the first tiles of the NEXT pass before its end-of-pass barrier, so the HBM
+  // latency at the head of a pass overlaps the tail of the previous one
+  const uint32_t* plist;
+  uint32_t npass, pass_idx, pref_idx;
+  // SG_PHASE_TIMING: cycles warp 0 spent waiting for TMA tiles / for look-back totals
+  bool timing;
+  unsigned long long t_tma, t_lb;
   __device__ __forceinline__ uint32_t buf(uint32_t st) const { return st ? buf1 : buf0; }
   __device__ __forceinline__ uint32_t mbar(uint32_t st) const { return st ? mbar1 : mbar0; }
   __device__ __forceinline__ uint32_t take_parity(uint32_t st) {
@@ -158,6 +170,32 @@ __device__ __forceinline__ void feed_issue(const Ctx& cx, const Feed& f, uint32_
   if (cx.lane == 0) {
     mbar_expect_tx(cx.mbar(st), TMA_TILE_BYTES);
     tma_load_tile(cx.buf(st), f.tmap, f.row0 + tile * 32u, cx.mbar(st));
+  }
+}
+// start of a fed pass: request this warp's first tile(s) unless the previous pass already did
+__device__ __forceinline__ void feed_prologue(Ctx& cx, const Feed& f, uint32_t ntiles) {
+  if (!f.on) return;
+  const uint32_t* e = cx.plist + 4 * cx.pass_idx;
+  if (cx.pass_idx >= cx.npass || e[1] != f.row0 || e[2] != ntiles) __trap();  // pass list out of step
+  if (cx.pref_idx != cx.pass_idx)
+    for (uint32_t st = 0; st < cx.nstage; st++)
+      if (cx.warp + st * NWARPS < ntiles) feed_issue(cx, f, cx.warp + st * NWARPS, st);
+}
+// end of a fed pass (all of this warp's tiles consumed, both staging buffers free): request the
+// first tile(s) of the next fed pass of the block
+__device__ __forceinline__ void feed_epilogue(Ctx& cx, const Feed& f) {
+  if (!f.on) return;
+  cx.pass_idx++;
+  if (cx.pass_idx < cx.npass) {
+    const uint32_t* e = cx.plist + 4 * cx.pass_idx;
+    Feed nf;
+    nf.on = true;
+    nf.tmap = cx.tmaps + (size_t)e[0] * 128;
+    nf.row0 = e[1];
+    const uint32_t nt = e[2];
+    for (uint32_t st = 0; st < cx.nstage; st++)
+      if (cx.warp + st * NWARPS < nt) feed_issue(cx, nf, cx.warp + st * NWARPS, st);
+    cx.pref_idx = cx.pass_idx;
   }
 }
 
@@ -285,9 +323,7 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
   const uint32_t ntiles = (n + (32 * BE - 1)) / (32 * BE);
   uint32_t prev_incl = 0;  // running segment sum through this warp's previous tile
   const Feed feed = make_feed(cx, c);
-  if (feed.on)
-    for (uint32_t st = 0; st < cx.nstage; st++)
-      if (warp + st * NWARPS < ntiles) feed_issue(cx, feed, warp + st * NWARPS, st);
+  feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * BE) + lane * BE;
@@ -374,6 +410,7 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     }
     if (maxrow > lastrow) cx.misc[1] = 1;
   }
+  feed_epilogue(cx, feed);
   __syncthreads();
 }
 
@@ -391,9 +428,7 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   unsigned long long prev_incl = 0;
   const Feed feed = make_feed(cx, c);
-  if (feed.on)
-    for (uint32_t st = 0; st < cx.nstage; st++)
-      if (warp + st * NWARPS < ntiles) feed_issue(cx, feed, warp + st * NWARPS, st);
+  feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
@@ -439,6 +474,7 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
     const uint32_t nvalid = (idx0 >= n) ? 0u : ((n - idx0 < VE) ? n - idx0 : (uint32_t)VE);
     tile_visit(idx0, a, nvalid);
   }
+  feed_epilogue(cx, feed);
   __syncthreads();
 }
 
@@ -461,16 +497,16 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   uint32_t prev_incl = 0;
   const Feed feed = make_feed(cx, c);
-  if (feed.on)
-    for (uint32_t st = 0; st < cx.nstage; st++)
-      if (warp + st * NWARPS < ntiles) feed_issue(cx, feed, warp + st * NWARPS, st);
+  feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
     uint32_t a[VE];
     if (feed.on) {
       const uint32_t st = it & (cx.nstage - 1u);
+      const long long tw0 = cx.timing ? clock64() : 0;
       mbar_wait(cx.mbar(st), cx.take_parity(st));
+      if (cx.timing) cx.t_tma += (unsigned long long)(clock64() - tw0);
       uint32_t raw[32];
       read_staged_row(cx.buf(st), lane, raw);
       staged_reads_done();
@@ -504,6 +540,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
       // totals of tiles t-15 .. t-1 (other warps) on top of this warp's previous inclusive prefix
       const int tt = (int)t - 15 + lane;
       uint32_t contrib = 0;
+      const long long tl0 = cx.timing ? clock64() : 0;
       if (lane < 15 && tt >= 0) {
         unsigned long long w;
         do {
@@ -512,6 +549,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
         contrib = (uint32_t)w;
       }
       const uint32_t carry = prev_incl + __reduce_add_sync(FULL, contrib);
+      if (cx.timing) cx.t_lb += (unsigned long long)(clock64() - tl0);
       prev_incl = carry + tile_tot;
       const uint32_t base = incl - tot + carry;
 #pragma unroll
@@ -520,6 +558,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
     const uint32_t nvalid = (idx0 >= n) ? 0u : ((n - idx0 < VE) ? n - idx0 : (uint32_t)VE);
     tile_visit(idx0, a, nvalid);
   }
+  feed_epilogue(cx, feed);
   __syncthreads();
 }
 
@@ -689,6 +728,8 @@ struct AggSlow {  // what the out-of-line paths need (lives in local memory)
   long long* vmax;
   const KSubHist* sub;
   uint32_t acc_w0_s;  // shared address of word0 of this aggregation for slot 0, this lane's replica
+  uint32_t hi_s;      // shared address of the (unreplicated) sum high limb of this aggregation for slot 0
+  uint32_t hi_stride_b;  // bytes between two slots' high limbs
   uint32_t gstride_b;  // bytes between two slots' accumulators
   uint32_t R_b;        // bytes between two words' replicas
   int acc_smem;
@@ -725,7 +766,7 @@ __device__ __noinline__ void agg_slow(const AggSlow* A, uint32_t g, long long v,
     uint32_t hi = (uint32_t)((unsigned long long)v >> 32);
     const uint32_t old = satom_add(w + A->R_b, lo);
     if (old > ~lo) hi += 1u;  // carry out of the low limb
-    if (hi) sred_add(w + 2 * A->R_b, hi);
+    if (hi) sred_add(A->hi_s + g * A->hi_stride_b, hi);
   } else {
     gred_add(A->hcount + g, 1ull);
     gred_add(A->sum + g, (unsigned long long)v);
@@ -757,6 +798,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   cx.pubA = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBA);
   cx.pubB = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBB);
   cx.misc = reinterpret_cast<volatile uint32_t*>(smem + OFF_MISC);
+  uint32_t* const plist_w = reinterpret_cast<uint32_t*>(smem + OFF_PLIST);
+  cx.plist = plist_w;
+  cx.timing = lp.dbg != nullptr && cx.warp == 0;
+  cx.t_tma = cx.t_lb = 0;
+  cx.npass = cx.pass_idx = 0;
+  cx.pref_idx = 0xffffffffu;
   {
     const uint32_t per_warp = (cx.nstage ? cx.nstage : 1u) * TMA_TILE_BYTES;
     cx.buf0 = smem_u32(stage_base) + (uint32_t)cx.warp * per_warp;
@@ -794,13 +841,45 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   unsigned long long* const g_count = reinterpret_cast<unsigned long long*>(PP->count);
   unsigned long long* const g_scalars = reinterpret_cast<unsigned long long*>(PP->scalars);
 
-  const uint32_t acc_total = ACC_SMEM ? (nslots + 1u) * gstride : 0u;  // + the trash slot
+  // replicated words of (nslots + trash) slots, then one unreplicated high limb per (slot, aggregation)
+  const uint32_t acc_rep = ACC_SMEM ? (nslots + 1u) * gstride : 0u;
+  const uint32_t acc_total = ACC_SMEM ? acc_rep + (nslots + 1u) * (uint32_t)naggs : 0u;
   for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
+  // the CTA's running totals (64-bit) behind the replicated accumulators
+  unsigned long long* const ctot = reinterpret_cast<unsigned long long*>(cx.acc + ((acc_total + 1u) & ~1u));
+  const uint32_t ctot_n = ACC_SMEM ? nslots * (1u + 2u * (uint32_t)naggs) : 0u;
+  for (uint32_t i = cx.tid; i < ctot_n; i += THREADS) ctot[i] = 0;
   for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
     cx.pubA[i] = 0;
     cx.pubB[i] = 0;
   }
+  // candidate passes of the plan, in execution order: column | kind << 16 (0 filter, 1 group, 2 time,
+  // 3 aggregation) | (string filter) << 24.  Built once; each block only looks its columns up.
+  uint32_t* const pcand = reinterpret_cast<uint32_t*>(smem + OFF_PCAND);
+  uint32_t* const ptmp = reinterpret_cast<uint32_t*>(smem + OFF_PTMP);
+  if (cx.tid == 0) {
+    uint32_t nc = 0;
+    for (int fi = 0; fi < nfilters; fi++)
+      pcand[nc++] = (uint32_t)PP->filters[fi].col | (0u << 16) | (PP->filters[fi].is_str ? 1u << 24 : 0u);
+    for (int gi = 0; gi < ngroups; gi++) pcand[nc++] = (uint32_t)PP->groups[gi].col | (1u << 16);
+    if (time_col >= 0) pcand[nc++] = (uint32_t)time_col | (2u << 16);
+    for (int ai = 0; ai < naggs; ai++) pcand[nc++] = (uint32_t)PP->aggs[ai].col | (3u << 16);
+    cx.misc[3] = nc;
+  }
+  __syncthreads();
+  const uint32_t ncand = cx.misc[3];
   unsigned long long matched = 0;
+  // optional phase timing (thread 0 of each CTA): 0 init, 1 filters, 2 groups, 3 time, 4 count+aggs, 5 flush, 6 fetch
+  unsigned long long* const dbg = lp.dbg ? lp.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  long long tph = dbg ? clock64() : 0;
+  unsigned long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};  // registers of thread 0; written once at the end
+  auto phase = [&](int i) {
+    if (dbg && cx.tid == 0) {
+      const long long now = clock64();
+      tacc[i] += (unsigned long long)(now - tph);
+      tph = now;
+    }
+  };
 
   for (;;) {
     __syncthreads();
@@ -811,10 +890,33 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     __syncthreads();
     const uint32_t wi = cx.misc[0];
     if (wi >= lp.nlist) break;
+    phase(6);
     const uint32_t bid = lp.block_list[wi];
     const uint32_t nrec = lp.blocks[bid].num_records;
     const DevCol* __restrict__ cols = lp.cols + (size_t)bid * ncolslots;
 
+    // the block's TMA-fed passes in execution order (mirrors the pass sequence below): one thread
+    // per candidate looks its column up, warp 0 compacts after the barrier
+    if ((uint32_t)cx.tid < ncand) {
+      const uint32_t pc = pcand[cx.tid];
+      const uint32_t kind = (pc >> 16) & 0xffu;
+      const DevCol c = cols[pc & 0xffffu];
+      bool on = cx.tmaps != nullptr && (c.flags & COL_TMA);
+      bool bucket = c.enc == SG_ENC_BUCKET;
+      if (kind == 0) {
+        on = on && (bucket || (c.enc == SG_ENC_VALUES && !(pc >> 24)));
+      } else if (kind == 1) {
+        on = on && bucket;
+      } else {
+        on = on && !(c.flags & COL_IS_STR) && (bucket || c.enc == SG_ENC_VALUES);
+      }
+      uint32_t n = c.nitems;
+      if (!bucket && n > nrec) n = nrec;
+      ptmp[4 * cx.tid + 0] = on ? 1u : 0u;
+      ptmp[4 * cx.tid + 1] = c.data_chunk;
+      ptmp[4 * cx.tid + 2] = c.data_row;
+      ptmp[4 * cx.tid + 3] = bucket ? (n + (32 * BE - 1)) / (32 * BE) : (n + (32 * VE - 1)) / (32 * VE);
+    }
     // every row starts as: group slot 0, no filter passed
     if (sizeof(SlotT) < 4) {
       uint4* s4 = reinterpret_cast<uint4*>(slot);
@@ -824,6 +926,27 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       for (uint32_t r = cx.tid; r < nrec; r += THREADS) slot[r] = 0;
     }
     __syncthreads();
+    if (cx.warp == 0) {
+      uint32_t np = 0;
+      for (uint32_t b0 = 0; b0 < ncand; b0 += 32) {
+        const uint32_t i = b0 + cx.lane;
+        const bool on = i < ncand && ptmp[4 * i] != 0;
+        const uint32_t m = __ballot_sync(FULL, on);
+        if (on) {
+          const uint32_t pos = np + __popc(m & ((1u << cx.lane) - 1u));
+          plist_w[4 * pos + 0] = ptmp[4 * i + 1];
+          plist_w[4 * pos + 1] = ptmp[4 * i + 2];
+          plist_w[4 * pos + 2] = ptmp[4 * i + 3];
+        }
+        np += __popc(m);
+      }
+      if (cx.lane == 0) cx.misc[2] = np;
+    }
+    __syncthreads();
+    cx.npass = cx.misc[2];
+    cx.pass_idx = 0;
+    cx.pref_idx = 0xffffffffu;
+    phase(0);
 
     // ---- filters (aggregate.go:105-112; unpopulated -> false, Q1) -----------------
     for (int fi = 0; fi < nfilters; fi++) {
@@ -881,6 +1004,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       }
     }
 
+    phase(1);
     // ---- group key (aggregate.go:125-143) as a dense mixed-radix index ---------------
     for (int gi = 0; gi < ngroups; gi++) {
       const KGroup G = PP->groups[gi];
@@ -893,9 +1017,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         }
         __syncthreads();
         SlotT cur = 0;
-        scan_bucket(
-            cx, c, nrec, [&](uint32_t bin) { cur = (SlotT)pay[bin]; },
-            [&](uint32_t row) { slot[row] = (SlotT)(slot[row] + cur); });
+        if (nfilters == 0 && gi == 0) {
+          // first pass to touch the (zeroed) slot words: a store, not a read-modify-write
+          scan_bucket(
+              cx, c, nrec, [&](uint32_t bin) { cur = (SlotT)pay[bin]; }, [&](uint32_t row) { slot[row] = cur; });
+        } else {
+          scan_bucket(
+              cx, c, nrec, [&](uint32_t bin) { cur = (SlotT)pay[bin]; },
+              [&](uint32_t row) { slot[row] = (SlotT)(slot[row] + cur); });
+        }
       } else if (c.enc == SG_ENC_VALUES && G.is_str) {
         const uint32_t stride = G.stride;
         scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
@@ -905,6 +1035,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       // VALUES int group columns are routed away from this kernel by the planner
     }
 
+    phase(2);
     // ---- time bucket (aggregate.go:146-183) ------------------------------------------
     if (time_col >= 0) {
       const DevCol c = cols[time_col];
@@ -944,6 +1075,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     }
     __syncthreads();
 
+    phase(3);
     // ---- Count / Samples (aggregate.go:202-203), MatchedCount (:117), aggregations
     // (:246-261).  The count is taken inside the first aggregation pass when that column
     // is a value array covering every row; otherwise in its own pass over the slot words.
@@ -981,7 +1113,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       const KAgg* __restrict__ KA = &PP->aggs[ai];
       const DevCol c = cols[KA->col];
       if (c.flags & COL_IS_STR) continue;  // Populated != INT_VAL: no update
-      const uint32_t w0 = 1u + 3u * (uint32_t)ai;  // word0 of this aggregation inside a slot's accumulators
+      const uint32_t w0 = 1u + 2u * (uint32_t)ai;  // word0 of this aggregation inside a slot's replicated words
       const bool do_count = !counted;              // only reachable for ai == 0 on a value array
       const uint32_t acc_s = smem_u32(cx.acc);
       const uint32_t gstride_b = gstride * 4u, R_b = R * 4u;
@@ -1000,6 +1132,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       AS.vmax = reinterpret_cast<long long*>(KA->vmax);
       AS.sub = KA->sub;
       AS.acc_w0_s = w0_s;
+      const uint32_t hi_s = acc_s + (acc_rep + (uint32_t)ai) * 4u;  // + e * naggs * 4: this aggregation's high limb
+      const uint32_t hi_stride_b = (uint32_t)naggs * 4u;
+      AS.hi_s = hi_s;
+      AS.hi_stride_b = hi_stride_b;
       AS.gstride_b = gstride_b;
       AS.R_b = R_b;
       AS.acc_smem = ACC_SMEM ? 1 : 0;
@@ -1044,7 +1180,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             const uint32_t w = w0_s + e * gstride_b;
             sred_add(w, 1u);
             const uint32_t old = satom_add(w + R_b, vlo);
-            if (old > ~vlo) sred_add(w + 2 * R_b, 1u);
+            if (old > ~vlo) sred_add(hi_s + e * hi_stride_b, 1u);
             if (nsub > 0) {
               if (hist32) {
                 uint32_t b = (vlo - fmin32 + hoff) / bsize0;
@@ -1107,7 +1243,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             for (int k = 0; k < VE; k++) {
               const uint32_t e = min(sw[k] ^ passbits, trash);
               const bool fr = (a[k] - fmin32) <= fspan32;
-              if ((cmask >> k) & 1u) sred_add(w0_s + 2 * R_b + (fr ? e : trash) * gstride_b, 1u);  // carry
+              if ((cmask >> k) & 1u) sred_add(hi_s + (fr ? e : trash) * hi_stride_b, 1u);  // carry
               if (!fr && e != trash) agg_slow(&AS, e, (long long)a[k], 0);
             }
           }
@@ -1241,7 +1377,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                 const uint32_t e = min(sw[k] ^ passbits, trash);
                 const uint32_t vlo = (uint32_t)a[k], vhi = (uint32_t)(a[k] >> 32);
                 const bool fr = vhi == 0u && (vlo - fmin32) <= fspan32;
-                if ((cmask >> k) & 1u) sred_add(w0_s + 2 * R_b + (fr ? e : trash) * gstride_b, 1u);  // carry
+                if ((cmask >> k) & 1u) sred_add(hi_s + (fr ? e : trash) * hi_stride_b, 1u);  // carry
                 if (!fr && e != trash) agg_slow(&AS, e, (long long)a[k], 0);
               }
             }
@@ -1308,6 +1444,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     }
     __syncthreads();
 
+    phase(4);
     // ---- end of block: publish or discard ------------------------------------------------
     const bool broken = cx.misc[1] != 0;
     if (broken) {
@@ -1319,37 +1456,70 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       matched += my_matched;
     }
     if (ACC_SMEM) {
-      // one thread per (slot, aggregation-or-count): fold the R replicas
+      // one thread per (slot, aggregation-or-count): fold the R replicas into the CTA's running
+      // 64-bit totals (shared memory, no atomics).  The totals reach the global accumulators once,
+      // when the CTA runs out of blocks: per-block global reductions from 148 CTAs in lockstep
+      // serialise on the same few hundred L2 addresses right in front of a barrier.
       const uint32_t per_slot = 1u + (uint32_t)naggs;
+      const uint32_t tw = 1u + 2u * (uint32_t)naggs;  // totals per slot: count, then (hist count, sum) per agg
       for (uint32_t i = cx.tid; i < nslots * per_slot; i += THREADS) {
         const uint32_t g = i / per_slot, a = i - g * per_slot;  // a == 0: the count
-        uint32_t* base = cx.acc + g * gstride;
-        unsigned long long cnt = 0;
-        for (uint32_t r = 0; r < R; r++) cnt += base[r];
-        if (a == 0) {
-          if (cnt && !broken) gred_add(g_count + g, cnt);
-        } else {
-          const uint32_t w0 = 1u + 3u * (a - 1u);
-          unsigned long long word0 = 0, lo = 0, hi = 0;
-          for (uint32_t r = 0; r < R; r++) {
-            word0 += base[w0 * R + r];
-            lo += base[(w0 + 1) * R + r];
-            hi += base[(w0 + 2) * R + r];
+        const uint32_t* base = cx.acc + g * gstride;
+        // sum of the R replicas of word w (R is a power of two; 16-byte loads when R >= 4)
+        auto fold = [&](uint32_t w) -> unsigned long long {
+          unsigned long long t = 0;
+          if (R >= 4) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(base + w * R);
+#pragma unroll 8
+            for (uint32_t j = 0; j < R / 4; j++) {
+              const uint4 q = p4[j];
+              t += (unsigned long long)q.x + q.y + q.z + q.w;
+            }
+          } else {
+            for (uint32_t r = 0; r < R; r++) t += base[w * R + r];
           }
+          return t;
+        };
+        const unsigned long long cnt = fold(0);
+        if (a == 0) {
+          if (!broken) ctot[g * tw] += cnt;
+        } else {
+          const uint32_t w0 = 1u + 2u * (a - 1u);
+          const unsigned long long word0 = fold(w0), lo = fold(w0 + 1);
+          const unsigned long long hi = cx.acc[acc_rep + g * (uint32_t)naggs + (a - 1u)];
           const unsigned long long hc = ((agg_mode_bits >> (a - 1u)) & 1u) ? cnt - word0 : word0;
           if (!broken) {
-            const KAgg* KA = &PP->aggs[a - 1u];
-            if (hc) gred_add(reinterpret_cast<unsigned long long*>(KA->hcount) + g, hc);
-            const unsigned long long sum = lo + (hi << 32);
-            if (sum) gred_add(reinterpret_cast<unsigned long long*>(KA->sum) + g, sum);
+            ctot[g * tw + 1 + 2 * (a - 1u)] += hc;
+            ctot[g * tw + 2 + 2 * (a - 1u)] += lo + (hi << 32);
           }
         }
       }
       __syncthreads();
       for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
     }
+    phase(5);
   }
 
+  if (dbg && cx.tid == 0) {
+    for (int i = 0; i < 7; i++) dbg[i] = tacc[i];
+    dbg[7] = cx.t_tma;
+    dbg[8] = cx.t_lb;
+  }
+  if (ACC_SMEM) {
+    __syncthreads();
+    const uint32_t tw = 1u + 2u * (uint32_t)naggs;
+    for (uint32_t i = cx.tid; i < ctot_n; i += THREADS) {
+      const unsigned long long v = ctot[i];
+      if (!v) continue;
+      const uint32_t g = i / tw, k = i - g * tw;
+      if (k == 0) {
+        gred_add(g_count + g, v);
+      } else {
+        const KAgg* KA = &PP->aggs[(k - 1u) >> 1];
+        gred_add(reinterpret_cast<unsigned long long*>(((k - 1u) & 1u) ? KA->sum : KA->hcount) + g, v);
+      }
+    }
+  }
   // MatchedCount
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) matched += __shfl_xor_sync(FULL, matched, d);
@@ -1381,6 +1551,11 @@ __global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const D
   cx.tmaps = nullptr;
   cx.nstage = 0;
   cx.buf0 = cx.buf1 = cx.mbar0 = cx.mbar1 = cx.par0 = cx.par1 = 0;
+  cx.plist = nullptr;
+  cx.timing = false;
+  cx.t_tma = cx.t_lb = 0;
+  cx.npass = cx.pass_idx = 0;
+  cx.pref_idx = 0xffffffffu;
   for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
     cx.pubA[i] = 0;
     cx.pubB[i] = 0;

@@ -1297,19 +1297,21 @@ int make_plan(sg_query* q) {
   // ---- shared memory budget ----------------------------------------------------------
   // TMA staging (per warp 4 KiB tiles, 1 or 2 deep) competes with the accumulator replicas:
   // take two stages while at least 8 replicas still fit, else one, else plain loads
-  P.acc_words = 1 + 3 * (uint32_t)P.naggs;
+  P.acc_words = 1 + 2 * (uint32_t)P.naggs;
   const uint32_t slots_b = q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u;
   auto repl_for = [&](uint32_t nstage) -> uint32_t {
     const uint32_t fixed = scan_fixed_smem(nstage) + slots_b;
     if (fixed > MAX_DYN_SMEM) return 0;
     const uint32_t avail = MAX_DYN_SMEM - fixed;
     uint32_t repl = 32;
-    while (repl >= 1 && ((uint64_t)P.nslots + 1) * P.acc_words * repl * 4 > avail) repl >>= 1;  // + trash slot
+    const uint64_t ctot_b = (uint64_t)P.nslots * (1 + 2 * (uint64_t)P.naggs) * 8 + 8 +  // CTA-resident 64-bit totals
+                            ((uint64_t)P.nslots + 1) * (uint64_t)P.naggs * 4 + 8;      // unreplicated high limbs
+    while (repl >= 1 && ((uint64_t)P.nslots + 1) * P.acc_words * repl * 4 + ctot_b > avail) repl >>= 1;  // + trash slot
     return repl;
   };
   uint32_t nstage = 0;
   if (t->tma_ok && t->d_tmaps) {
-    if (repl_for(2) >= 8)
+    if (repl_for(2) >= 32)
       nstage = 2;
     else if (repl_for(1) >= 2 || (repl_for(1) >= 1 && repl_for(0) <= 1))
       nstage = 1;
@@ -1318,7 +1320,10 @@ int make_plan(sg_query* q) {
   q->nstage = nstage;
   const uint32_t repl = repl_for(nstage);
   P.acc_repl = repl;  // 0: accumulate straight into global memory
-  q->smem_bytes = scan_fixed_smem(nstage) + slots_b + (repl ? (P.nslots + 1) * P.acc_words * repl * 4 : 0u);
+  q->smem_bytes = scan_fixed_smem(nstage) + slots_b +
+                  (repl ? (P.nslots + 1) * P.acc_words * repl * 4 + P.nslots * (1 + 2 * (uint32_t)P.naggs) * 8 + 8 +
+                              (P.nslots + 1) * (uint32_t)P.naggs * 4 + 8
+                        : 0u);
   return SG_OK;
 }
 
@@ -1405,6 +1410,15 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.smem_bytes = q->smem_bytes;
   lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
   lp.nstage = q->nstage;
+  lp.dbg = nullptr;
+  static const bool phase_timing = getenv("SG_PHASE_TIMING") != nullptr;
+  unsigned long long* d_dbg = nullptr;
+  if (phase_timing) {
+    if (pool_alloc(c, (void**)&d_dbg, (size_t)q->grid * 16 * 8) == cudaSuccess) {
+      cudaMemsetAsync(d_dbg, 0, (size_t)q->grid * 16 * 8, c->stream);
+      lp.dbg = d_dbg;
+    }
+  }
   lp.tmaps = q->nstage ? t->d_tmaps : nullptr;
   int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(list.size(), 1));
   CUDA_TRY(c, cudaEventRecord(q->ev0, c->stream));
@@ -1419,6 +1433,23 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   CUDA_TRY(c, cudaEventElapsedTime(&ms, q->ev0, q->ev1));
   q->kernel_ms += ms;
   q->launches += 1;
+  if (d_dbg) {
+    std::vector<unsigned long long> hd((size_t)q->grid * 16);
+    cudaMemcpy(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long tot[16] = {0}, mx = 0;
+    for (int g = 0; g < q->grid; g++) {
+      unsigned long long sum = 0;
+      for (int i = 0; i < 16; i++) {
+        tot[i] += hd[(size_t)g * 16 + i];
+        if (i < 7) sum += hd[(size_t)g * 16 + i];
+      }
+      mx = std::max(mx, sum);
+    }
+    fprintf(stderr, "[sg phase cycles avg/CTA] init %llu filters %llu groups %llu time %llu aggs %llu flush %llu fetch %llu | warp0 value-pass waits: tma %llu lookback %llu | max CTA total %llu (kernel %.3f ms)\n",
+            tot[0] / q->grid, tot[1] / q->grid, tot[2] / q->grid, tot[3] / q->grid, tot[4] / q->grid, tot[5] / q->grid,
+            tot[6] / q->grid, tot[7] / q->grid, tot[8] / q->grid, mx, ms);
+    pool_release(c, d_dbg);
+  }
   return SG_OK;
 }
 
