@@ -57,9 +57,9 @@ constexpr uint32_t OFF_BINPAY = OFF_HEADPREFIX + HEAD_WORDS * 2;       // u32[SM
 constexpr uint32_t OFF_PUBA = OFF_BINPAY + SMEM_BINS * 4;              // u64[MAX_TILES]
 constexpr uint32_t OFF_PUBB = OFF_PUBA + MAX_TILES * 8;                // u64[MAX_TILES]
 constexpr uint32_t OFF_MBAR = OFF_PUBB + MAX_TILES * 8;                // u64[NWARPS][2] mbarriers
-constexpr uint32_t OFF_MISC = OFF_MBAR + NWARPS * 2 * 8;               // u32[64]
+constexpr uint32_t OFF_MISC = OFF_MBAR + NWARPS * 2 * 8;               // u32[128]
 constexpr uint32_t PL_MAX = 48;                                        // TMA-fed column passes of one block
-constexpr uint32_t OFF_PLIST = OFF_MISC + 64 * 4;                      // u32[PL_MAX][4]
+constexpr uint32_t OFF_PLIST = OFF_MISC + 128 * 4;                     // u32[PL_MAX][4]
 constexpr uint32_t OFF_PCAND = OFF_PLIST + PL_MAX * 16;                // u32[PL_MAX] candidate passes of the plan
 constexpr uint32_t OFF_PTMP = OFF_PCAND + PL_MAX * 4;                  // u32[PL_MAX][4] per-block scratch
 constexpr uint32_t FIXED_SMEM = OFF_PTMP + PL_MAX * 16;
@@ -71,7 +71,7 @@ struct Ctx {
   uint32_t* binpay_s;
   volatile unsigned long long* pubA;
   volatile unsigned long long* pubB;
-  volatile uint32_t* misc;  // [0] next block, [1] broken flag, [16..31] warp totals, [32..63] per-lane sinks
+  volatile uint32_t* misc;  // [0] next block, [1] broken flag, [16..16+NWARPS) warp totals, [64..95] per-lane sinks
   uint32_t* acc;
   int tid, lane, warp;
   uint32_t epoch;  // one per column pass; tags the published tile totals
@@ -235,8 +235,8 @@ __device__ __forceinline__ uint32_t satom_add(uint32_t addr, uint32_t v) {
 // ---------------------------------------------------------------------------
 // segmented u32 flavour: returns the running segment sum entering tile t
 __device__ __forceinline__ uint32_t lookback_seg(const Ctx& cx, uint32_t t, uint32_t prev_incl) {
-  const int tt = (int)t - 15 + cx.lane;
-  const bool valid = cx.lane < 15 && tt >= 0;
+  const int tt = (int)t - (NWARPS - 1) + cx.lane;
+  const bool valid = cx.lane < NWARPS - 1 && tt >= 0;
   uint32_t a = 0;
   if (valid) {
     unsigned long long w;
@@ -257,9 +257,9 @@ __device__ __forceinline__ uint32_t lookback_seg(const Ctx& cx, uint32_t t, uint
 }
 // plain u64 flavour: returns the sum of the totals of tiles t-15 .. t-1
 __device__ __forceinline__ unsigned long long lookback_sum(const Ctx& cx, uint32_t t) {
-  const int tt = (int)t - 15 + cx.lane;
+  const int tt = (int)t - (NWARPS - 1) + cx.lane;
   unsigned long long v = 0;
-  if (cx.lane < 15 && tt >= 0) {
+  if (cx.lane < NWARPS - 1 && tt >= 0) {
     unsigned long long lo, hi;
     do {
       lo = cx.pubA[tt];
@@ -297,8 +297,8 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     }
   }
   __syncthreads();
-  {  // exclusive prefix popcount per 32-entry word: 512 threads x 4 words
-    const uint4 w = reinterpret_cast<const uint4*>(cx.headbits)[tid];
+  {  // exclusive prefix popcount per 32-entry word: the first 512 threads x 4 words
+    const uint4 w = tid < (int)(HEAD_WORDS / 4) ? reinterpret_cast<const uint4*>(cx.headbits)[tid] : make_uint4(0, 0, 0, 0);
     const uint32_t p0 = __popc(w.x), p1 = __popc(w.y), p2 = __popc(w.z), p3 = __popc(w.w);
     const uint32_t tot = p0 + p1 + p2 + p3;
     uint32_t inc = tot;
@@ -312,10 +312,12 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     uint32_t base = 0;
     for (int i = 0; i < warp; i++) base += cx.misc[16 + i];
     const uint32_t ex = base + inc - tot;
-    cx.headprefix[tid * 4 + 0] = (uint16_t)ex;
-    cx.headprefix[tid * 4 + 1] = (uint16_t)(ex + p0);
-    cx.headprefix[tid * 4 + 2] = (uint16_t)(ex + p0 + p1);
-    cx.headprefix[tid * 4 + 3] = (uint16_t)(ex + p0 + p1 + p2);
+    if (tid < (int)(HEAD_WORDS / 4)) {
+      cx.headprefix[tid * 4 + 0] = (uint16_t)ex;
+      cx.headprefix[tid * 4 + 1] = (uint16_t)(ex + p0);
+      cx.headprefix[tid * 4 + 2] = (uint16_t)(ex + p0 + p1);
+      cx.headprefix[tid * 4 + 3] = (uint16_t)(ex + p0 + p1 + p2);
+    }
   }
   cx.epoch++;
   __syncthreads();
@@ -504,9 +506,13 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
     uint32_t a[VE];
     if (feed.on) {
       const uint32_t st = it & (cx.nstage - 1u);
+#ifdef SG_WAIT_TIMING
       const long long tw0 = cx.timing ? clock64() : 0;
+#endif
       mbar_wait(cx.mbar(st), cx.take_parity(st));
+#ifdef SG_WAIT_TIMING
       if (cx.timing) cx.t_tma += (unsigned long long)(clock64() - tw0);
+#endif
       uint32_t raw[32];
       read_staged_row(cx.buf(st), lane, raw);
       staged_reads_done();
@@ -538,10 +544,12 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
       const uint32_t tile_tot = __shfl_sync(FULL, incl, 31);
       if (lane == 0) cx.pubA[t] = (unsigned long long)tile_tot | ((unsigned long long)cx.epoch << 32);
       // totals of tiles t-15 .. t-1 (other warps) on top of this warp's previous inclusive prefix
-      const int tt = (int)t - 15 + lane;
+      const int tt = (int)t - (NWARPS - 1) + lane;
       uint32_t contrib = 0;
+#ifdef SG_WAIT_TIMING
       const long long tl0 = cx.timing ? clock64() : 0;
-      if (lane < 15 && tt >= 0) {
+#endif
+      if (lane < NWARPS - 1 && tt >= 0) {
         unsigned long long w;
         do {
           w = cx.pubA[tt];
@@ -549,7 +557,9 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
         contrib = (uint32_t)w;
       }
       const uint32_t carry = prev_incl + __reduce_add_sync(FULL, contrib);
+#ifdef SG_WAIT_TIMING
       if (cx.timing) cx.t_lb += (unsigned long long)(clock64() - tl0);
+#endif
       prev_incl = carry + tile_tot;
       const uint32_t base = incl - tot + carry;
 #pragma unroll
@@ -871,13 +881,17 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   unsigned long long matched = 0;
   // optional phase timing (thread 0 of each CTA): 0 init, 1 filters, 2 groups, 3 time, 4 count+aggs, 5 flush, 6 fetch
   unsigned long long* const dbg = lp.dbg ? lp.dbg + (size_t)blockIdx.x * 16 : nullptr;
-  long long tph = dbg ? clock64() : 0;
-  unsigned long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};  // registers of thread 0; written once at the end
+  // phase counters live in shared memory (only thread 0 touches them): no registers spent on them
+  volatile unsigned long long* const tacc = reinterpret_cast<volatile unsigned long long*>(cx.misc + 96);  // [0..6] + [7] last stamp
+  if (dbg && cx.tid == 0) {
+    for (int i = 0; i < 7; i++) tacc[i] = 0;
+    tacc[7] = (unsigned long long)clock64();
+  }
   auto phase = [&](int i) {
     if (dbg && cx.tid == 0) {
-      const long long now = clock64();
-      tacc[i] += (unsigned long long)(now - tph);
-      tph = now;
+      const unsigned long long now = (unsigned long long)clock64();
+      tacc[i] += now - tacc[7];
+      tacc[7] = now;
     }
   };
 
@@ -1119,7 +1133,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       const uint32_t gstride_b = gstride * 4u, R_b = R * 4u;
       const uint32_t cnt_s = acc_s + lane_off * 4u;            // + g*gstride_b: the slot's count word
       const uint32_t w0_s = acc_s + (w0 * R + lane_off) * 4u;  // + g*gstride_b: this aggregation's word0
-      const uint32_t dummy_s = smem_u32(const_cast<uint32_t*>(cx.misc) + 32 + cx.lane);  // per-lane sink
+      const uint32_t dummy_s = smem_u32(const_cast<uint32_t*>(cx.misc) + 64 + cx.lane);  // per-lane sink
       AggSlow AS;
       AS.info_min = KA->info_min;
       AS.info_max = KA->info_max;
