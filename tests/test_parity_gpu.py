@@ -222,3 +222,73 @@ def test_benchmark_configs_at_reduced_size(cfg, rows):
         t.close()
         ot.close()
         store.close()
+
+
+def test_tma_and_plain_load_paths_agree(monkeypatch):
+    """The TMA-staged tile feed and the plain 256-bit load path must give the same result: a table created
+    while SG_NO_TMA is set has no tensor maps, so the same kernel reads with vector loads."""
+    s = random_spec(31, nrows=9000, block_rows=4000, threshold=50, wide=True)
+    q = Q(s, int_filters=[("big", "gt", 5)], str_filters=[("state", "neq", "s3")], groups=["host"], aggs=["lat", "big"], op="hist")
+    o = run_oracle(s, q)
+    compare(run_gpu(s, q), o, q)
+    monkeypatch.setenv("SG_NO_TMA", "1")
+    compare(run_gpu(s, q), o, q)
+
+
+def test_batch_staging_restaging_and_streaming_submit():
+    """sg_table_add_blocks (batch staging), sg_table_clear + re-staging into the same arena, and
+    sg_query_submit_block (zone-map pruning before staging) all give the oracle's answer."""
+    import ctypes as C
+    from sybil_b200 import engine as E
+    from sybil_b200 import synth
+    from oracle.oracle_ffi import OracleTable
+    spec = synth.config("c3", total_rows=5 * 20000, block_rows=20000)
+    store = synth.generate(spec)
+    s = Spec(spec.key_table)
+    s.IntInfo = dict(spec.IntInfo)
+    q = Q(s, **synth.query_for(spec))
+    ot = OracleTable(spec.key_table)
+    for i in range(store.num_blocks()):
+        ot.add_block(store.block(i))
+    d, keep = q.desc()
+    o = ot.query(d, q.aggs, nthreads=2)
+    t = E.Table("b", spec.key_table)
+    t.IntInfo = dict(spec.IntInfo)
+    try:
+        ptrs, n = store.block_ptrs()
+        for _ in range(2):  # stage, query, clear, stage again into the recycled arena
+            t.add_blocks(ptrs, n)
+            compare(run_gpu(s, q, table=t), o, q)
+            t.ctx.check(t.lib.sg_table_clear(t.h))
+        # streaming: blocks submitted to a query one by one
+        qs = q.query_spec()
+        dd, keep2 = E.make_query_desc(s.KeyTable, s.KeyTypes, s.IntInfo, qs)
+        qh = t.lib.sg_query_begin(t.ctx.h, t.h, C.byref(dd))
+        assert qh
+        for i in range(n):
+            t.ctx.check(t.lib.sg_query_submit_block(qh, store.block(i)))
+        rp = C.c_void_p()
+        t.ctx.check(t.lib.sg_query_finish(qh, C.byref(rp)))
+        assert t.lib.sg_result_matched_count(rp) == o.MatchedCount
+        assert t.lib.sg_result_num_groups(rp) == len(o.Results)
+        t.lib.sg_result_free(rp)
+        t.lib.sg_query_free(qh)
+    finally:
+        t.close()
+        ot.close()
+        store.close()
+
+
+def test_staging_statistics_pick_the_right_paths():
+    """Values inside [0, 2^32) take the 32-bit scan; negative / wide values, values outside the table's
+    extents (rejected, hist_basic.go:104) and values above info_max (Max tracking) take the complete rule."""
+    rng = np.random.default_rng(33)
+    n = 6000
+    s = Spec([("g", STR), ("small", INT), ("neg", INT), ("wide", INT)])
+    s.add_rows({"g": np.array(["g%d" % v for v in rng.integers(0, 5, n)]),
+                "small": rng.integers(0, 1 << 22, n), "neg": rng.integers(-100000, 100000, n),
+                "wide": rng.integers(0, 1 << 40, n)}, threshold=10, block_rows=2500)
+    s.IntInfo["small"] = (1000, 1 << 20)  # values below Min are rejected, values up to 10*Max accepted
+    for op in ("avg", "hist"):
+        both(s, Q(s, groups=["g"], aggs=["small", "neg", "wide"], op=op))
+        both(s, Q(s, int_filters=[("small", "lt", 1 << 21), ("neg", "gt", -5)], groups=["g"], aggs=["small"], op=op))
