@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       pcand[nc++] = (uint32_t)PP->filters[fi].col | (0u << 16) | (PP->filters[fi].is_str ? 1u << 24 : 0u);
     for (int gi = 0; gi < ngroups; gi++) pcand[nc++] = (uint32_t)PP->groups[gi].col | (1u << 16);
     if (time_col >= 0) pcand[nc++] = (uint32_t)time_col | (2u << 16);
-    for (int ai = 0; ai < naggs; ai++) pcand[nc++] = (uint32_t)PP->aggs[ai].col | (3u << 16);
+    for (int ai = 0; ai < naggs; ai++) pcand[nc++] = (uint32_t)PP->aggs[ai].col | ((uint32_t)ai << 8) | (3u << 16);
     cx.misc[3] = nc;
   }
   __syncthreads();
@@ -906,6 +906,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     if (wi >= lp.nlist) break;
     phase(6);
     const uint32_t bid = lp.block_list[wi];
+    // tail blocks may be split into several work items, one per subset of the aggregations
+    const uint32_t imask = lp.item_mask ? lp.item_mask[wi] : 0x8000ffffu;
+    const uint32_t aggmask = imask & 0xffffu;
+    const bool owner = (imask >> 31) != 0;
     const uint32_t nrec = lp.blocks[bid].num_records;
     const DevCol* __restrict__ cols = lp.cols + (size_t)bid * ncolslots;
 
@@ -914,7 +918,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     if ((uint32_t)cx.tid < ncand) {
       const uint32_t pc = pcand[cx.tid];
       const uint32_t kind = (pc >> 16) & 0xffu;
-      const DevCol c = cols[pc & 0xffffu];
+      const DevCol c = cols[pc & 0xffu];
       bool on = cx.tmaps != nullptr && (c.flags & COL_TMA);
       bool bucket = c.enc == SG_ENC_BUCKET;
       if (kind == 0) {
@@ -923,6 +927,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         on = on && bucket;
       } else {
         on = on && !(c.flags & COL_IS_STR) && (bucket || c.enc == SG_ENC_VALUES);
+        if (kind == 3) on = on && ((aggmask >> ((pc >> 8) & 0xffu)) & 1u);
       }
       uint32_t n = c.nitems;
       if (!bucket && n > nrec) n = nrec;
@@ -1101,11 +1106,13 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     uint32_t agg_mode_bits = 0;  // bit a: word0 of agg a counts NON-accepted rows (value arrays)
 
     for (int ai = -1; ai < naggs; ai++) {
+      if (ai >= 0 && !((aggmask >> ai) & 1u)) continue;  // another work item of this block computes it
       if (ai < 0) {
-        // decide whether the first value-array aggregation can carry the count
+        // decide whether the first value-array aggregation (of this item) can carry the count
         bool fuse = false;
-        if (naggs > 0) {
-          const DevCol c0 = cols[PP->aggs[0].col];
+        const int ai0 = __ffs((int)(aggmask & ((naggs >= 32 ? 0xffffffffu : (1u << naggs)) - 1u))) - 1;
+        if (ai0 >= 0) {
+          const DevCol c0 = cols[PP->aggs[ai0].col];
           fuse = c0.enc == SG_ENC_VALUES && !(c0.flags & COL_IS_STR);
         }
         if (fuse) continue;
@@ -1467,7 +1474,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         gred_add(g_scalars + 1, 1ull);
       }
     } else {
-      matched += my_matched;
+      if (owner) matched += my_matched;
     }
     if (ACC_SMEM) {
       // one thread per (slot, aggregation-or-count): fold the R replicas into the CTA's running
@@ -1496,7 +1503,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         };
         const unsigned long long cnt = fold(0);
         if (a == 0) {
-          if (!broken) ctot[g * tw] += cnt;
+          if (!broken && owner) ctot[g * tw] += cnt;
         } else {
           const uint32_t w0 = 1u + 2u * (a - 1u);
           const unsigned long long word0 = fold(w0), lo = fold(w0 + 1);

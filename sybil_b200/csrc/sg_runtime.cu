@@ -984,6 +984,7 @@ struct sg_query {
   std::vector<size_t> off_hcount, off_sum, off_vmax, off_buckets;
   uint32_t* d_block_status = nullptr;
   uint32_t* d_block_list = nullptr;
+  uint32_t* d_item_mask = nullptr;
   uint32_t* d_work = nullptr;
   uint32_t* d_gslots = nullptr;
   uint32_t* d_gbinpay = nullptr;
@@ -1011,6 +1012,8 @@ void free_device(sg_query* q) {
   pool_release(c, q->d_acc);
   pool_release(c, q->d_block_status);
   pool_release(c, q->d_block_list);
+  pool_release(c, q->d_item_mask);
+  q->d_item_mask = nullptr;
   pool_release(c, q->d_work);
   pool_release(c, q->d_gslots);
   pool_release(c, q->d_gbinpay);
@@ -1337,15 +1340,18 @@ int alloc_device(sg_query* q) {
   if (!q->d_plan) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_plan, sizeof(Plan)));
   if (!q->d_work) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_work, 64));
   size_t nb = std::max<size_t>(t->blocks.size(), 1);
+  q->grid = c->sm_count > 0 ? c->sm_count : 1;
   if (nb > q->block_cap) {
     pool_release(c, q->d_block_status);
     pool_release(c, q->d_block_list);
-    q->d_block_status = q->d_block_list = nullptr;
+    pool_release(c, q->d_item_mask);
+    q->d_block_status = q->d_block_list = q->d_item_mask = nullptr;
+    const size_t items_cap = nb + (size_t)q->grid * SG_MAX_AGGS;  // tail blocks may split per aggregation
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_status, nb * 4));
-    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_list, nb * 4));
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_list, items_cap * 4));
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_item_mask, items_cap * 4));
     q->block_cap = nb;
   }
-  q->grid = c->sm_count > 0 ? c->sm_count : 1;
   if (!q->d_gbinpay) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gbinpay, (size_t)q->grid * SG_BLOCK_ROWS * 4));
   if (!q->d_gdummy) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gdummy, (size_t)q->grid * 32 * 8));
   if (q->slot_bytes == 4 && !q->d_gslots)
@@ -1390,8 +1396,33 @@ int reset_accumulators(sg_query* q) {
 int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   sg_ctx* c = q->ctx;
   sg_table* t = q->table;
-  if (!list.empty())
-    CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  // Work items.  The blocks of the last, partial wave (n mod #SMs) would leave most SMs idle for a
+  // whole block time; when the plan has several aggregations they are split into one item per subset
+  // of the aggregations (every item redoes the cheap filter/group passes, one owns the Count).
+  std::vector<uint32_t> items(list), masks(list.size(), 0x8000ffffu);
+  {
+    const size_t grid = (size_t)q->grid, n = list.size();
+    const int na = q->plan.naggs;
+    const bool force = getenv("SG_FORCE_TAIL_SPLIT") != nullptr;  // tests: split every block
+    const size_t r = force ? n : n % grid;
+    if (q->plan.acc_repl > 0 && na >= 2 && r > 0 &&
+        (force || (n > grid && r * 2 <= grid && !getenv("SG_NO_TAIL_SPLIT")))) {
+      const int k = force ? na : (int)std::min<size_t>((size_t)na, grid / r);
+      items.resize(n - r);
+      masks.resize(n - r);
+      for (size_t i = n - r; i < n; i++)
+        for (int j = 0; j < k; j++) {
+          uint32_t m = 0;
+          for (int a = j; a < na; a += k) m |= 1u << a;
+          items.push_back(list[i]);
+          masks.push_back(m | (j == 0 ? 0x80000000u : 0u));
+        }
+    }
+  }
+  if (!items.empty()) {
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, items.data(), items.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_item_mask, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  }
   CUDA_TRY(c, cudaMemsetAsync(q->d_work, 0, 64, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(q->d_block_status, 0, std::max<size_t>(t->blocks.size(), 1) * 4, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(q->d_plan, &q->plan, sizeof(Plan), cudaMemcpyHostToDevice, c->stream));
@@ -1401,7 +1432,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.blocks = t->d_blocks;
   lp.cols = t->d_cols;
   lp.block_list = q->d_block_list;
-  lp.nlist = (uint32_t)list.size();
+  lp.item_mask = q->d_item_mask;
+  lp.nlist = (uint32_t)items.size();
   lp.slot_bytes = q->slot_bytes;
   lp.work_counter = q->d_work;
   lp.gslots = q->d_gslots;
@@ -1420,7 +1452,7 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
     }
   }
   lp.tmaps = q->nstage ? t->d_tmaps : nullptr;
-  int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(list.size(), 1));
+  int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(items.size(), 1));
   CUDA_TRY(c, cudaEventRecord(q->ev0, c->stream));
   int rc = launch_scan(lp, grid, c->stream);
   if (rc != 0) {

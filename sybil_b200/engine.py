@@ -189,6 +189,31 @@ class Result:  # query_spec.go:85-93
         self.Samples = 0
 
 
+def toResultJSON(r, querySpec):
+    """Result.toResultJSON (printer.go:109-152): the dict the reference's -json output holds for one group."""
+    res = {}
+    for agg in querySpec.Aggregations:
+        h = r.Hists.get(agg.Name)
+        if FLAGS.OP == "hist":
+            inner = {}
+            res[agg.Name] = inner
+            if h is not None:
+                inner["percentiles"] = h.GetPercentiles()
+                inner["buckets"] = {str(k): v for k, v in h.GetIntBuckets().items() if v > 0}
+                inner["stddev"] = h.StdDev()
+                inner["avg"] = h.Mean()
+                inner["sum"] = h.Mean() * float(h.TotalCount())
+                inner["samples"] = h.TotalCount()
+        if FLAGS.OP == "avg":
+            res[agg.Name] = h.Mean() if h is not None else None
+    group_key = r.GroupByKey.split("\t")
+    for i, g in enumerate(querySpec.Groups):
+        res[g.Name] = group_key[i]
+    res["Count"] = r.Count
+    res["Samples"] = r.Samples
+    return res
+
+
 class _ResultHandle:
     def __init__(self, lib, h, owner=None):
         self.lib, self.h, self.owner = lib, h, owner

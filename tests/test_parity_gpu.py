@@ -292,3 +292,46 @@ def test_staging_statistics_pick_the_right_paths():
     for op in ("avg", "hist"):
         both(s, Q(s, groups=["g"], aggs=["small", "neg", "wide"], op=op))
         both(s, Q(s, int_filters=[("small", "lt", 1 << 21), ("neg", "gt", -5)], groups=["g"], aggs=["small"], op=op))
+
+
+def test_result_json_contract_like_printer_go():
+    """Result.toResultJSON (printer.go:109-152), the reference's -json output per group, rebuilt from the
+    engine's result and from the oracle's: same keys, bit-equal integers, floats within tolerance."""
+    from sybil_b200.engine import toResultJSON
+    from tests.util import close, MEAN_TOL, STD_TOL
+    s = random_spec(41, nrows=5000, block_rows=1800)
+    for op in ("hist", "avg"):
+        q = Q(s, int_filters=[("age", "gt", 11)], groups=["host", "state"], aggs=["lat", "age"], op=op)
+        g = run_gpu(s, q)
+        o = run_oracle(s, q)
+        q.set_flags()
+        qs = q.query_spec()
+        for k, r in g.Results.items():
+            j = toResultJSON(r, qs)
+            orr = o.Results[k]
+            assert j["Count"] == orr.Count and j["Samples"] == orr.Samples
+            assert (j["host"], j["state"]) == tuple(k.split("\t")[:2])
+            for a in q.aggs:
+                oh = orr.Hists.get(a)
+                if op == "avg":
+                    assert (j[a] is None) == (oh is None)
+                    if oh is not None:
+                        assert close(j[a], oh.Avg, MEAN_TOL)
+                elif oh is not None and oh.Count:
+                    assert j[a]["percentiles"] == oh.Percentiles
+                    assert j[a]["buckets"] == {str(e): c for e, c in oh.IntBuckets.items() if c > 0}
+                    assert j[a]["samples"] == oh.Count
+                    assert close(j[a]["avg"], oh.Avg, MEAN_TOL) and close(j[a]["stddev"], oh.StdDev, STD_TOL)
+                    assert close(j[a]["sum"], oh.Avg * oh.Count, 1e-9)
+
+
+def test_tail_blocks_split_per_aggregation(monkeypatch):
+    """Blocks of the last partial wave are split into one work item per subset of the aggregations;
+    SG_FORCE_TAIL_SPLIT splits every block so that small tables exercise the path."""
+    monkeypatch.setenv("SG_FORCE_TAIL_SPLIT", "1")
+    s = random_spec(51, nrows=9000, block_rows=2000, threshold=50)
+    both(s, Q(s, int_filters=[("age", "gt", 11)], groups=["host"], aggs=["age", "lat", "big"], op="avg"))
+    both(s, Q(s, groups=["host", "state"], aggs=["lat", "age"], op="hist"))
+    both(s, Q(s, groups=["host"], aggs=["lat", "big"], op="hist", time_col="time", time_bucket=600))
+    s.blocks[1].num_records = 700  # a broken block must still vanish whole
+    both(s, Q(s, groups=["host"], aggs=["age", "lat"], op="hist"))
