@@ -207,9 +207,11 @@ int sg_table_dict_get(sg_table* t, int32_t col_slot, int64_t id, const char** by
 /* value dictionary of a bucket-encoded int column (dense group-by axis) */
 int64_t sg_table_intdict_size(sg_table* t, int32_t col_slot);
 int sg_table_intdict_get(sg_table* t, int32_t col_slot, int64_t id, int64_t* value);
-/* Multi-GPU: every rank must number group keys identically before the dense
- * partials are all-reduced.  Seed the dictionaries (e.g. with rank 0's, or with the
- * table's StrInfo) BEFORE staging blocks; later strings append after the seed. */
+/* Multi-GPU fast path: when every rank numbers group keys identically the dense
+ * partials merge with two all-reduces and no dictionary exchange.  Seed the
+ * dictionaries (e.g. with the table's StrInfo) BEFORE staging blocks; later strings
+ * append after the seed.  Optional: sg_query_allreduce detects differing
+ * dictionaries and exchanges them itself. */
 int sg_table_dict_seed_str(sg_table* t, int32_t col_slot, const char* bytes, const uint32_t* offsets, int64_t n);
 int sg_table_dict_seed_int(sg_table* t, int32_t col_slot, const int64_t* values, int64_t n);
 int64_t sg_table_encoded_bytes(sg_table* t); /* bytes of encoded column arrays resident */
@@ -231,8 +233,12 @@ int sg_query_run(sg_query* q);
 /* Streaming path (end to end from host buffers): stage + scan one block; blocks
  * are batched internally, H2D overlaps the previous batch's kernel. */
 int sg_query_submit_block(sg_query* q, const sg_block_desc* block);
-/* one NCCL all-reduce of the per-group partials across ranks (CombineResults,
- * aggregate.go:414-467, across GPUs); no-op without a communicator */
+/* CombineResults (aggregate.go:414-467) across GPUs: NCCL all-reduce of the dense
+ * per-group partials (sum region + max region).  Ranks whose dictionaries / time
+ * axes differ first all-gather them and re-lay their partials by the union, after
+ * which the str ids of sg_result_group index that union (use sg_result_group_key
+ * for the strings).  Collective: every rank must call it.  No-op without a
+ * communicator. */
 int sg_query_allreduce(sg_query* q);
 /* sync, D2H, build the result (CombineResults + Cumulative + SortResults) */
 int sg_query_finish(sg_query* q, sg_result** out);

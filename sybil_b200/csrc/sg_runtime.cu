@@ -35,7 +35,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclInt64 = 4, ncclUint64 = 5 };  // nccl.h ncclDataType_t
+enum { ncclUint8 = 1, ncclInt64 = 4, ncclUint64 = 5 };  // nccl.h ncclDataType_t
 enum { ncclSum = 0, ncclMax = 2 };       // nccl.h ncclRedOp_t
 struct NcclApi {
   void* lib = nullptr;
@@ -43,6 +43,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (lib) return true;
@@ -56,8 +57,9 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
   }
 };
 NcclApi g_nccl;
@@ -1002,6 +1004,11 @@ struct sg_query {
   bool ran = false;
   std::vector<uint32_t> last_list;
   std::vector<char> hc_is_count;
+  // cross-GPU merge under differing per-rank dictionaries: the union dictionaries the merged
+  // accumulators are laid out by (per entry of dims; empty for the time axis)
+  bool merged = false;
+  std::vector<std::vector<std::string>> m_strs;
+  std::vector<std::vector<int64_t>> m_ints;
 };
 
 namespace {
@@ -1114,6 +1121,41 @@ int upload_table(sg_table* t) {
 }
 
 // Build the dense slot space and the device plan from the table's dictionaries.
+// accumulator layout for `nslots` dense slots: one SUM region (scalars | count | per agg hcount,
+// sum | per agg buckets) followed by one MAX region (per agg vmax): the cross-GPU merge is two
+// all-reduces
+int layout_accumulators(sg_query* q, uint32_t nslots) {
+  const int naggs = (int)q->layouts.size();
+  size_t words = 8;  // scalars
+  q->off_count = words;
+  words += nslots;
+  q->off_hcount.clear();
+  q->off_sum.clear();
+  q->off_vmax.clear();
+  q->off_buckets.clear();
+  for (int i = 0; i < naggs; i++) {
+    q->off_hcount.push_back(words);
+    words += nslots;
+    q->off_sum.push_back(words);
+    words += nslots;
+  }
+  for (int i = 0; i < naggs; i++) {
+    q->off_buckets.push_back(words);
+    words += (size_t)nslots * q->layouts[(size_t)i].nvals_total;
+    if (words * 8 > ((size_t)24 << 30)) {
+      q->ctx->set_err("query: accumulators exceed 24 GiB (groups x histogram buckets); needs the sparse path");
+      return SG_ERR_UNSUPPORTED;
+    }
+  }
+  q->sum_words = words;
+  for (int i = 0; i < naggs; i++) {
+    q->off_vmax.push_back(words);
+    words += nslots;
+  }
+  q->acc_words = words;
+  return SG_OK;
+}
+
 int make_plan(sg_query* q) {
   sg_ctx* c = q->ctx;
   sg_table* t = q->table;
@@ -1250,13 +1292,6 @@ int make_plan(sg_query* q) {
   // accumulator layout: one SUM region (scalars | count | per agg hcount, sum | per agg buckets)
   // followed by one MAX region (per agg vmax): the cross-GPU merge is two all-reduces
   q->layouts.clear();
-  size_t words = 8;  // scalars
-  q->off_count = words;
-  words += P.nslots;
-  q->off_hcount.clear();
-  q->off_sum.clear();
-  q->off_vmax.clear();
-  q->off_buckets.clear();
   for (int i = 0; i < P.naggs; i++) {
     const sg_agg_desc& a = q->aggs[(size_t)i];
     if (!col_ok(a.col_slot)) {
@@ -1277,25 +1312,11 @@ int make_plan(sg_query* q) {
     ka.nsub = (int32_t)L.subs.size();
     ka.nvals_total = L.nvals_total;
     for (size_t s = 0; s < L.subs.size(); s++) ka.sub[s] = L.subs[s];
-    q->off_hcount.push_back(words);
-    words += P.nslots;
-    q->off_sum.push_back(words);
-    words += P.nslots;
   }
-  for (int i = 0; i < P.naggs; i++) {
-    q->off_buckets.push_back(words);
-    words += (size_t)P.nslots * q->layouts[(size_t)i].nvals_total;
-    if (words * 8 > ((size_t)24 << 30)) {
-      c->set_err("query: accumulators exceed 24 GiB (groups x histogram buckets); needs the sparse path");
-      return SG_ERR_UNSUPPORTED;
-    }
+  {
+    int rc = layout_accumulators(q, P.nslots);
+    if (rc != SG_OK) return rc;
   }
-  q->sum_words = words;
-  for (int i = 0; i < P.naggs; i++) {
-    q->off_vmax.push_back(words);
-    words += P.nslots;
-  }
-  q->acc_words = words;
 
   // ---- shared memory budget ----------------------------------------------------------
   // TMA staging (per warp 4 KiB tiles, 1 or 2 deep) competes with the accumulator replicas:
@@ -1496,7 +1517,9 @@ std::string render_key(const sg_query* q, const std::vector<uint64_t>& key) {
       int col = q->groups[i].col_slot;
       if (t->types[(size_t)col] == SG_COL_INT)
         s += std::to_string((int64_t)v);
-      else if (v < t->sdict[(size_t)col].strs.size())
+      else if (q->merged) {
+        if (v < q->m_strs[i].size()) s += q->m_strs[i][(size_t)v];
+      } else if (v < t->sdict[(size_t)col].strs.size())
         s += t->sdict[(size_t)col].strs[(size_t)v];
     }
     s += "\t";
@@ -1566,7 +1589,8 @@ int build_result(sg_query* q, sg_result** out) {
     init_group(g, naggs);
     g.count = (int64_t)cnt[s];
     int64_t tbucket = 0;
-    for (auto& d : q->dims) {
+    for (size_t di = 0; di < q->dims.size(); di++) {
+      const GroupDim& d = q->dims[di];
       uint32_t code = (s / d.stride) % d.radix;
       if (d.is_time) {
         tbucket = (P.time_first + (int64_t)code - 1) * P.time_bucket;
@@ -1576,6 +1600,8 @@ int build_result(sg_query* q, sg_result** out) {
         g.key.push_back(SG_MISSING_KEY);
       else if (d.is_str)
         g.key.push_back((uint64_t)(code - 1));
+      else if (q->merged)
+        g.key.push_back((uint64_t)q->m_ints[di][code - 1]);
       else
         g.key.push_back((uint64_t)q->table->idict[(size_t)d.col].vals[code - 1]);
     }
@@ -1727,6 +1753,7 @@ int sg_query_run(sg_query* q) {
   if (rc != SG_OK) return rc;
   rc = upload_table(t);
   if (rc != SG_OK) return rc;
+  q->merged = false;
   rc = make_plan(q);
   if (rc != SG_OK) return rc;
   rc = alloc_device(q);
@@ -1825,29 +1852,278 @@ int sg_query_submit_block(sg_query* q, const sg_block_desc* b) {
   return sg_table_add_block(q->table, b);
 }
 
+// ---- cross-GPU merge ---------------------------------------------------------------------------
+// CombineResults across GPUs (table_query.go:155-170 across processes).  Each rank scanned its
+// shard into dense accumulators laid out by ITS dictionaries.  When every rank's dictionaries
+// (and time axis) agree — seeded tables, or shards that saw the same values in the same order —
+// the merge is two element-wise all-reduces.  Otherwise the ranks first exchange their
+// dictionaries (all-gather), build the same union dictionary in rank order, re-lay their
+// accumulators by it, and then all-reduce.
+static int nccl_fail(sg_ctx* c, const char* what, ncclResult_t r) {
+  c->set_err(std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  return SG_ERR_NCCL;
+}
+
+static int comm_allreduce_host(sg_ctx* c, uint64_t* v, size_t n, int dtype, int op) {
+  uint64_t* d = nullptr;
+  CUDA_TRY(c, pool_alloc(c, (void**)&d, n * 8));
+  CUDA_TRY(c, cudaMemcpyAsync(d, v, n * 8, cudaMemcpyHostToDevice, c->stream));
+  ncclResult_t r = g_nccl.AllReduce(d, d, n, dtype, op, c->comm, c->stream);
+  if (r != 0) return nccl_fail(c, "ncclAllReduce", r);
+  CUDA_TRY(c, cudaMemcpyAsync(v, d, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  pool_release(c, d);
+  return SG_OK;
+}
+
+// every rank contributes `each` bytes; all[r*each ...] holds rank r's
+static int comm_allgather_host(sg_ctx* c, const void* mine, size_t each, std::vector<uint8_t>& all) {
+  uint8_t *ds = nullptr, *dr = nullptr;
+  all.resize(each * (size_t)c->nranks);
+  CUDA_TRY(c, pool_alloc(c, (void**)&ds, each));
+  CUDA_TRY(c, pool_alloc(c, (void**)&dr, all.size()));
+  CUDA_TRY(c, cudaMemcpyAsync(ds, mine, each, cudaMemcpyHostToDevice, c->stream));
+  ncclResult_t r = g_nccl.AllGather(ds, dr, each, ncclUint8, c->comm, c->stream);
+  if (r != 0) return nccl_fail(c, "ncclAllGather", r);
+  CUDA_TRY(c, cudaMemcpyAsync(all.data(), dr, all.size(), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  pool_release(c, ds);
+  pool_release(c, dr);
+  return SG_OK;
+}
+
+static inline uint64_t fnv64(uint64_t h, const void* p, size_t n) {
+  const uint8_t* b = (const uint8_t*)p;
+  for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 0x100000001b3ull;
+  return h;
+}
+
+// this rank's group axes, serialised: per axis  time: [i64 first][u64 radix]
+//                                                str:  [u64 n] n x ([u32 len] bytes)
+//                                                int:  [u64 n] n x i64
+static void serialise_axes(const sg_query* q, std::vector<uint8_t>& out) {
+  auto put = [&](const void* p, size_t n) { out.insert(out.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+  const sg_table* t = q->table;
+  for (auto& d : q->dims) {
+    if (d.is_time) {
+      int64_t first = q->plan.time_first;
+      uint64_t radix = d.radix;
+      put(&first, 8);
+      put(&radix, 8);
+    } else if (d.is_str) {
+      const auto& strs = t->sdict[(size_t)d.col].strs;
+      uint64_t n = d.radix - 1;  // the entries the plan was laid out by
+      put(&n, 8);
+      for (uint64_t i = 0; i < n; i++) {
+        uint32_t len = (uint32_t)strs[(size_t)i].size();
+        put(&len, 4);
+        put(strs[(size_t)i].data(), len);
+      }
+    } else {
+      const auto& vals = t->idict[(size_t)d.col].vals;
+      uint64_t n = d.radix - 1;
+      put(&n, 8);
+      put(vals.data(), (size_t)n * 8);
+    }
+  }
+}
+
+static int remap_to_union(sg_query* q) {
+  sg_ctx* c = q->ctx;
+  Plan& P = q->plan;
+  const int nr = c->nranks;
+  std::vector<uint8_t> mine;
+  serialise_axes(q, mine);
+  uint64_t maxlen = mine.size();
+  int rc = comm_allreduce_host(c, &maxlen, 1, ncclUint64, ncclMax);
+  if (rc != SG_OK) return rc;
+  const size_t each = (size_t)((maxlen + 15) & ~7ull) + 8;
+  std::vector<uint8_t> padded(each, 0), all;
+  uint64_t mylen = mine.size();
+  memcpy(padded.data(), &mylen, 8);
+  memcpy(padded.data() + 8, mine.data(), mine.size());
+  rc = comm_allgather_host(c, padded.data(), each, all);
+  if (rc != SG_OK) return rc;
+
+  // union per axis, ranks in order; remap[axis][local code] -> union code
+  const size_t nd = q->dims.size();
+  std::vector<std::vector<std::string>> u_strs(nd);
+  std::vector<std::vector<int64_t>> u_ints(nd);
+  std::vector<std::unordered_map<std::string, uint32_t>> s_ids(nd);
+  std::vector<std::unordered_map<int64_t, uint32_t>> i_ids(nd);
+  std::vector<std::vector<uint32_t>> remap(nd);
+  int64_t g_first = 0, g_last = 0;
+  bool have_time = false;
+  for (int r = 0; r < nr; r++) {
+    const uint8_t* p = all.data() + (size_t)r * each;
+    uint64_t len;
+    memcpy(&len, p, 8);
+    p += 8;
+    const uint8_t* end = p + len;
+    auto need = [&](size_t n) { return (size_t)(end - p) >= n; };
+    for (size_t di = 0; di < nd; di++) {
+      const GroupDim& d = q->dims[di];
+      if (!need(8)) goto corrupt;
+      if (d.is_time) {
+        int64_t first;
+        uint64_t radix;
+        if (!need(16)) goto corrupt;
+        memcpy(&first, p, 8);
+        memcpy(&radix, p + 8, 8);
+        p += 16;
+        int64_t last = first + (int64_t)radix - 2;
+        if (!have_time) {
+          g_first = first;
+          g_last = last;
+          have_time = true;
+        } else {
+          g_first = std::min(g_first, first);
+          g_last = std::max(g_last, last);
+        }
+        continue;
+      }
+      uint64_t n;
+      memcpy(&n, p, 8);
+      p += 8;
+      if (r == c->rank) remap[di].assign((size_t)n + 1, 0);
+      for (uint64_t i = 0; i < n; i++) {
+        uint32_t uid;
+        if (d.is_str) {
+          uint32_t l;
+          if (!need(4)) goto corrupt;
+          memcpy(&l, p, 4);
+          p += 4;
+          if (!need(l)) goto corrupt;
+          std::string sv((const char*)p, l);
+          p += l;
+          auto it = s_ids[di].find(sv);
+          if (it == s_ids[di].end()) {
+            uid = (uint32_t)u_strs[di].size();
+            s_ids[di].emplace(sv, uid);
+            u_strs[di].push_back(std::move(sv));
+          } else {
+            uid = it->second;
+          }
+        } else {
+          int64_t v;
+          if (!need(8)) goto corrupt;
+          memcpy(&v, p, 8);
+          p += 8;
+          auto it = i_ids[di].find(v);
+          if (it == i_ids[di].end()) {
+            uid = (uint32_t)u_ints[di].size();
+            i_ids[di].emplace(v, uid);
+            u_ints[di].push_back(v);
+          } else {
+            uid = it->second;
+          }
+        }
+        if (r == c->rank) remap[di][(size_t)i + 1] = uid + 1;
+      }
+    }
+  }
+  {
+    // union slot space
+    std::vector<GroupDim> ndims = q->dims;
+    uint64_t stride = 1;
+    for (size_t di = 0; di < nd; di++) {
+      GroupDim& d = ndims[di];
+      if (d.is_time) {
+        const int64_t shift = P.time_first - g_first;
+        remap[di].assign(d.radix, 0);
+        for (uint32_t code = 1; code < d.radix; code++) remap[di][code] = (uint32_t)((int64_t)code + shift);
+        d.radix = (uint32_t)(g_last - g_first + 2);
+      } else {
+        d.radix = (uint32_t)((d.is_str ? u_strs[di].size() : u_ints[di].size()) + 1);
+      }
+      d.stride = (uint32_t)stride;
+      stride *= d.radix;
+      if (stride > (uint64_t)MAX_SLOTS) {
+        c->set_err("allreduce: union of the ranks' group keys exceeds the dense slot space");
+        return SG_ERR_UNSUPPORTED;
+      }
+    }
+    const uint32_t old_slots = P.nslots, new_slots = (uint32_t)stride;
+    // old accumulators to the host, re-laid by the union, back to the device
+    std::vector<uint64_t> h_old(q->acc_words);
+    CUDA_TRY(c, cudaMemcpy(h_old.data(), q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost));
+    q->d2h_bytes += (int64_t)q->acc_words * 8;
+    const size_t o_count = q->off_count;
+    const std::vector<size_t> o_hc = q->off_hcount, o_sum = q->off_sum, o_vmax = q->off_vmax, o_bk = q->off_buckets;
+    rc = layout_accumulators(q, new_slots);
+    if (rc != SG_OK) return rc;
+    std::vector<uint64_t> h_new(q->acc_words, 0);
+    for (size_t w = q->sum_words; w < q->acc_words; w++) h_new[w] = (uint64_t)INT64_MIN;
+    for (int w = 0; w < 8; w++) h_new[(size_t)w] = h_old[(size_t)w];
+    const int naggs = P.naggs;
+    for (uint32_t s = 0; s < old_slots; s++) {
+      if (h_old[o_count + s] == 0) continue;
+      uint64_t ns = 0;
+      for (size_t di = 0; di < nd; di++) {
+        const GroupDim& od = q->dims[di];
+        uint32_t code = (s / od.stride) % od.radix;
+        ns += (uint64_t)remap[di][code] * ndims[di].stride;
+      }
+      h_new[q->off_count + ns] = h_old[o_count + s];
+      for (int a = 0; a < naggs; a++) {
+        h_new[q->off_hcount[(size_t)a] + ns] = h_old[o_hc[(size_t)a] + s];
+        h_new[q->off_sum[(size_t)a] + ns] = h_old[o_sum[(size_t)a] + s];
+        h_new[q->off_vmax[(size_t)a] + ns] = h_old[o_vmax[(size_t)a] + s];
+        const uint32_t nv = q->layouts[(size_t)a].nvals_total;
+        if (nv)
+          memcpy(&h_new[q->off_buckets[(size_t)a] + (size_t)ns * nv], &h_old[o_bk[(size_t)a] + (size_t)s * nv], (size_t)nv * 8);
+      }
+    }
+    pool_release(c, q->d_acc);
+    q->d_acc = nullptr;
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_acc, q->acc_words * 8));
+    CUDA_TRY(c, cudaMemcpy(q->d_acc, h_new.data(), q->acc_words * 8, cudaMemcpyHostToDevice));
+    q->dims = ndims;
+    P.nslots = new_slots;
+    if (have_time) P.time_first = g_first;
+    q->m_strs = std::move(u_strs);
+    q->m_ints = std::move(u_ints);
+    q->merged = true;
+  }
+  return SG_OK;
+corrupt:
+  c->set_err("allreduce: malformed dictionary exchange");
+  return SG_ERR_NCCL;
+}
+
 int sg_query_allreduce(sg_query* q) {
   if (!q || !q->ran) return SG_ERR_STATE;
   sg_ctx* c = q->ctx;
   if (!c->comm || c->nranks <= 1) return SG_OK;
   cudaSetDevice(c->device);
-  // CombineResults across GPUs: every rank holds the same dense layout (same
-  // dictionaries, same histogram extents), so the merge is element-wise.
-  // sums: scalars, count, hcount, sum, buckets; max: vmax.
-  const Plan& P = q->plan;
+  // do the ranks agree on the slot space?  (max of sig and of ~sig: equal iff all equal)
+  std::vector<uint8_t> mine;
+  serialise_axes(q, mine);
+  const uint64_t sig = fnv64(0xcbf29ce484222325ull, mine.data(), mine.size());
+  uint64_t pr[2] = {sig, ~sig};
+  int rc = comm_allreduce_host(c, pr, 2, ncclUint64, ncclMax);
+  if (rc != SG_OK) return rc;
+  if (pr[0] != ~pr[1]) {
+    rc = remap_to_union(q);
+    if (rc != SG_OK) return rc;
+  }
+  // element-wise merge.  sums: scalars, count, hcount, sum, buckets; max: vmax.
   auto ar = [&](uint64_t* p, size_t n, int dtype, int op) -> int {
     ncclResult_t r = g_nccl.AllReduce(p, p, n, dtype, op, c->comm, c->stream);
-    if (r != 0) {
-      c->set_err(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
-      return SG_ERR_NCCL;
-    }
-    return SG_OK;
+    return r != 0 ? nccl_fail(c, "ncclAllReduce", r) : (int)SG_OK;
   };
-  (void)P;
-  int rc = ar(q->d_acc, q->sum_words, ncclUint64, ncclSum);
+  rc = ar(q->d_acc, q->sum_words, ncclUint64, ncclSum);
   if (rc == SG_OK && q->acc_words > q->sum_words)
     rc = ar(q->d_acc + q->sum_words, q->acc_words - q->sum_words, ncclInt64, ncclMax);
   if (rc != SG_OK) return rc;
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  // host-side block counters (blocks pruned by the zone maps / broken at staging) are job totals too
+  uint64_t hc[4] = {(uint64_t)q->broken_staged, (uint64_t)q->skipped, (uint64_t)q->rows_scanned, (uint64_t)q->blocks_scanned};
+  rc = comm_allreduce_host(c, hc, 4, ncclUint64, ncclSum);
+  if (rc != SG_OK) return rc;
+  q->broken_staged = (int64_t)hc[0];
+  q->skipped = (int64_t)hc[1];
+  q->rows_scanned = (int64_t)hc[2];
+  q->blocks_scanned = (int64_t)hc[3];
   return SG_OK;
 }
 

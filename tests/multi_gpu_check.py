@@ -2,8 +2,8 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 
-Every rank stages its shard of the blocks (sybil_b200.sharding.shard_range), seeds the dictionaries
-identically, scans on its GPU, merges with sg_query_allreduce (NCCL) and rank 0 compares the merged
+Every rank stages its shard of the blocks (sybil_b200.sharding.shard_range) — once with identically
+seeded dictionaries, once with per-rank dictionaries (exchanged inside sg_query_allreduce) — scans on its GPU, merges with sg_query_allreduce (NCCL) and rank 0 compares the merged
 result with the CPU oracle run over ALL blocks: the same bit-exact / tolerance contract as the
 single-GPU parity tests."""
 import os
@@ -35,6 +35,37 @@ def seed(table, spec):
     table.ctx.check(table.lib.sg_table_dict_seed_int(table.h, spec.KeyTable["age"], ages.ctypes.data, len(ages)))
 
 
+def run_mode(ctx, spec, queries, first, count, rank, world, seeded):
+    """seeded=False: every rank interns strings / int keys in the order ITS shard shows them, so the
+    ranks' slot spaces (and time axes) differ and sg_query_allreduce exchanges the dictionaries."""
+    table = E.Table("mg", spec.key_table, ctx)
+    table.IntInfo = dict(spec.IntInfo)
+    if seeded:
+        seed(table, spec)
+    for b in spec.blocks[first:first + count]:
+        table.add_block(b)
+    ok = True
+    for qi, q in enumerate(queries):
+        qs = q.query_spec()
+        ls = table.NewLoadSpec()
+        for c in ("age", "lat", "big", "time"):
+            ls.Int(c)
+        for c in ("host", "state"):
+            ls.Str(c)
+        table.LoadAndQueryRecords(ls, qs, allreduce=True)
+        if rank == 0:
+            o = run_oracle(spec, q)
+            try:
+                compare(qs, o, q)
+                print("query %d (%s dictionaries): merged result over %d GPUs == oracle over all blocks (%d groups, %d matched)" % (
+                    qi, "seeded" if seeded else "per-rank", world, len(qs.Results), qs.MatchedCount))
+            except AssertionError as e:
+                ok = False
+                print("query %d (%s dictionaries) MISMATCH: %r" % (qi, "seeded" if seeded else "per-rank", e))
+    table.close()
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ["LOCAL_RANK"])
@@ -52,30 +83,9 @@ def main():
         Q(spec, groups=["host"], aggs=["lat"], op="hist", time_col="time", time_bucket=600),
     ]
     first, count = shard_range(len(spec.blocks), rank, world)
-    table = E.Table("mg", spec.key_table, ctx)
-    table.IntInfo = dict(spec.IntInfo)
-    seed(table, spec)
-    for b in spec.blocks[first:first + count]:
-        table.add_block(b)
     ok = True
-    for qi, q in enumerate(queries):
-        qs = q.query_spec()
-        ls = table.NewLoadSpec()
-        for c in ("age", "lat", "big", "time"):
-            ls.Int(c)
-        for c in ("host", "state"):
-            ls.Str(c)
-        table.LoadAndQueryRecords(ls, qs, allreduce=True)
-        if rank == 0:
-            o = run_oracle(spec, q)
-            try:
-                compare(qs, o, q)
-                print("query %d: merged result over %d GPUs == oracle over all blocks (%d groups, %d matched)" % (
-                    qi, world, len(qs.Results), qs.MatchedCount))
-            except AssertionError as e:
-                ok = False
-                print("query %d MISMATCH: %r" % (qi, e))
-    table.close()
+    for seeded in (True, False):
+        ok &= run_mode(ctx, spec, queries, first, count, rank, world, seeded)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
