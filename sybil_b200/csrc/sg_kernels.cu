@@ -48,7 +48,8 @@ constexpr uint32_t MAX_TILES = 128;
 
 int scan_threads() { return THREADS; }
 
-// shared-memory carve-out (bytes).  The dynamic window is aligned up to 1 KiB at run time; first come
+// shared-memory carve-out (bytes).  The dynamic window is declared 1 KiB aligned (so every address
+// below is a link-time constant plus at most the staging depth); first come
 // the per-warp TMA staging tiles (128B-swizzled, must sit on 1 KiB boundaries), then the fixed part
 // below, then the slot words and the accumulators.
 constexpr uint32_t OFF_HEADBITS = 0;                                   // u32[2048]
@@ -63,7 +64,7 @@ constexpr uint32_t OFF_PLIST = OFF_MISC + 128 * 4;                     // u32[PL
 constexpr uint32_t OFF_PCAND = OFF_PLIST + PL_MAX * 16;                // u32[PL_MAX] candidate passes of the plan
 constexpr uint32_t OFF_PTMP = OFF_PCAND + PL_MAX * 4;                  // u32[PL_MAX][4] per-block scratch
 constexpr uint32_t FIXED_SMEM = OFF_PTMP + PL_MAX * 16;
-uint32_t scan_fixed_smem(uint32_t nstage) { return 1024u + NWARPS * TMA_TILE_BYTES * nstage + FIXED_SMEM; }
+uint32_t scan_fixed_smem(uint32_t nstage) { return NWARPS * TMA_TILE_BYTES * nstage + FIXED_SMEM; }
 
 struct Ctx {
   uint32_t* headbits;
@@ -84,6 +85,7 @@ struct Ctx {
   // latency at the head of a pass overlaps the tail of the previous one
   const uint32_t* plist;
   uint32_t npass, pass_idx, pref_idx;
+  uint32_t zero;  // 0 at run time, opaque to the compiler (see staged_reads_done)
   // SG_PHASE_TIMING: cycles warp 0 spent waiting for TMA tiles / for look-back totals
   bool timing;
   unsigned long long t_tma, t_lb;
@@ -145,13 +147,48 @@ __device__ __forceinline__ void read_staged_row(uint32_t buf_s, int lane, uint32
                  : "r"(addr));
   }
 }
+// The low 32-bit limbs of this lane's 16 staged int64 values.  The loads stay 16 bytes wide on
+// purpose: a lane-per-row 32-bit load of a swizzled tile is a 4-way bank conflict, and ptxas narrows
+// a vector load whose high words are dead — so the high limbs are folded into `hix`, which the
+// caller keeps alive.
+__device__ __forceinline__ void read_staged_row_lo(uint32_t buf_s, int lane, uint32_t (&lo)[16], uint32_t& hix) {
+  const uint32_t rowbase = buf_s + (uint32_t)lane * 128u;
+  const uint32_t x = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint32_t addr = rowbase + ((((uint32_t)j) ^ x) << 4);
+    asm volatile(
+        "{\n"
+        ".reg .b32 h0, h1;\n"
+        "ld.shared.v4.u32 {%0,h0,%1,h1}, [%3];\n"
+        "lop3.b32 %2, %2, h0, h1, 0x96;\n"
+        "}\n"
+        : "=r"(lo[2 * j + 0]), "=r"(lo[2 * j + 1]), "+r"(hix)
+        : "r"(addr));
+  }
+}
 // After a warp has read a staged tile with ordinary shared loads, the next TMA write into the same
-// buffer must not overtake those loads (they can sit in the load/store queue behind global
-// reductions for microseconds): every lane orders its generic-proxy reads before later async-proxy
-// accesses, then the warp converges, then lane 0 issues.
-__device__ __forceinline__ void staged_reads_done() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncwarp();
+// buffer must not overtake those loads (they can sit in the load/store queue behind reductions for
+// microseconds).  A proxy fence would do, but it compiles to MEMBAR.ALL.CTA, which also waits for
+// every reduction in flight.  Instead the re-issue is made DATA dependent on the loads: `dep` is
+// computed from a word of every load of the lane, the ballot needs every lane's `dep`, and its
+// result (always 0: cx.zero is a zero the compiler cannot see) is added to the TMA coordinate.  A
+// load whose value has reached a register has been performed; the copy cannot start before that.
+__device__ __forceinline__ uint32_t staged_reads_done(const Ctx& cx, uint32_t dep) {
+  uint32_t b;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %1, 0;\n"
+      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+      "}\n"
+      : "=r"(b)
+      : "r"(dep & cx.zero)
+      : "memory");
+  return b;
+}
+__device__ __forceinline__ uint32_t dep_of(const uint32_t (&w)[32]) {
+  return (w[0] ^ w[4] ^ w[8]) ^ (w[12] ^ w[16] ^ w[20]) ^ (w[24] ^ w[28]);
 }
 // the tile feed of one column pass: issue(tile) by lane 0, take(stage) by the whole warp
 struct Feed {
@@ -166,10 +203,10 @@ __device__ __forceinline__ Feed make_feed(const Ctx& cx, const DevCol& c) {
   f.row0 = c.data_row;
   return f;
 }
-__device__ __forceinline__ void feed_issue(const Ctx& cx, const Feed& f, uint32_t tile, uint32_t st) {
+__device__ __forceinline__ void feed_issue(const Ctx& cx, const Feed& f, uint32_t tile, uint32_t st, uint32_t after = 0u) {
   if (cx.lane == 0) {
     mbar_expect_tx(cx.mbar(st), TMA_TILE_BYTES);
-    tma_load_tile(cx.buf(st), f.tmap, f.row0 + tile * 32u, cx.mbar(st));
+    tma_load_tile(cx.buf(st), f.tmap, f.row0 + tile * 32u + after, cx.mbar(st));
   }
 }
 // start of a fed pass: request this warp's first tile(s) unless the previous pass already did
@@ -336,8 +373,8 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
       const uint32_t st = it & (cx.nstage - 1u);
       mbar_wait(cx.mbar(st), cx.take_parity(st));
       read_staged_row(cx.buf(st), lane, a);
-      staged_reads_done();
-      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st);
+      const uint32_t after = staged_reads_done(cx, dep_of(a));
+      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
       if (idx0 + BE > n) {
 #pragma unroll
         for (int k = 0; k < BE; k++)
@@ -440,8 +477,8 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
       mbar_wait(cx.mbar(st), cx.take_parity(st));
       uint32_t raw[32];
       read_staged_row(cx.buf(st), lane, raw);
-      staged_reads_done();
-      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st);
+      const uint32_t after = staged_reads_done(cx, dep_of(raw));
+      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
 #pragma unroll
       for (int k = 0; k < VE; k++)
         a[k] = (idx0 + k < n) ? ((unsigned long long)raw[2 * k] | ((unsigned long long)raw[2 * k + 1] << 32)) : 0ull;
@@ -498,6 +535,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
   cx.epoch++;
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   uint32_t prev_incl = 0;
+  uint32_t hix = 0;  // xor of the high limbs read (keeps the staged loads 16 bytes wide)
   const Feed feed = make_feed(cx, c);
   feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
@@ -513,12 +551,14 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
 #ifdef SG_WAIT_TIMING
       if (cx.timing) cx.t_tma += (unsigned long long)(clock64() - tw0);
 #endif
-      uint32_t raw[32];
-      read_staged_row(cx.buf(st), lane, raw);
-      staged_reads_done();
-      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st);
+      read_staged_row_lo(cx.buf(st), lane, a, hix);  // low limbs: exact mod 2^32
+      const uint32_t after = staged_reads_done(cx, hix);
+      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
+      if (idx0 + VE > n) {
 #pragma unroll
-      for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? raw[2 * k] : 0u;  // low limbs: exact mod 2^32
+        for (int k = 0; k < VE; k++)
+          if (idx0 + k >= n) a[k] = 0u;
+      }
     } else if (idx0 + VE <= n) {
 #pragma unroll
       for (int j = 0; j < VE / 4; j++) {
@@ -568,6 +608,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
     const uint32_t nvalid = (idx0 >= n) ? 0u : ((n - idx0 < VE) ? n - idx0 : (uint32_t)VE);
     tile_visit(idx0, a, nvalid);
   }
+  if (hix == 0x5bd1e995u) cx.misc[4] = hix;  // never read: the use that keeps hix (and the wide loads) alive
   feed_epilogue(cx, feed);
   __syncthreads();
 }
@@ -790,16 +831,18 @@ __device__ __noinline__ void agg_slow(const AggSlow* A, uint32_t g, long long v,
 // ---------------------------------------------------------------------------
 template <typename SlotT, bool ACC_SMEM>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Plan* __restrict__ PP = lp.plan;
   Ctx cx;
   cx.tid = threadIdx.x;
   cx.lane = threadIdx.x & 31;
   cx.warp = threadIdx.x >> 5;
   cx.epoch = 0;
-  // align the window to 1 KiB (the 128B swizzle pattern of the staged tiles repeats every 1 KiB)
-  unsigned char* const stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  cx.nstage = lp.tmaps ? lp.nstage : 0u;
+  // the 128B swizzle pattern of the staged tiles repeats every 1 KiB: the window must start on one
+  unsigned char* const stage_base = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();
+  cx.nstage = lp.nstage;  // 0 when the table has no tensor maps
+  cx.zero = lp.nlist >> 31;  // nlist < 2^31
   cx.tmaps = reinterpret_cast<const unsigned char*>(lp.tmaps);
   unsigned char* const smem = stage_base + NWARPS * TMA_TILE_BYTES * cx.nstage;
   cx.headbits = reinterpret_cast<uint32_t*>(smem + OFF_HEADBITS);
@@ -853,6 +896,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
 
   // replicated words of (nslots + trash) slots, then one unreplicated high limb per (slot, aggregation)
   const uint32_t acc_rep = ACC_SMEM ? (nslots + 1u) * gstride : 0u;
+  const uint32_t tw_magic = 0xffffffffu / (1u + 2u * (uint32_t)naggs) + 1u;  // x / tw == umulhi(x, magic), x * tw < 2^32
   const uint32_t acc_total = ACC_SMEM ? acc_rep + (nslots + 1u) * (uint32_t)naggs : 0u;
   for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
   // the CTA's running totals (64-bit) behind the replicated accumulators
@@ -1229,15 +1273,19 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         // every value inside the fast range and no carry possible: no per-row checks at all
         const bool allfast = nocarry && c.vmin >= fmin && c.vmax <= fmax;
         const unsigned long long magic0 = KA->sub[0].magic;
-        auto tile32 = [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid, auto do_count_tag, auto allfast_tag) {
+        auto tile32 = [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid, auto do_count_tag, auto allfast_tag,
+                          auto nofilt_tag) {
           constexpr bool DO_COUNT = decltype(do_count_tag)::value;
           constexpr bool ALLFAST = decltype(allfast_tag)::value;
+          // NOFILT: no filters, no time column, at most one group column — every slot word IS a valid
+          // slot (stored from the per-bin payload), so the pass test and the clamp to TRASH drop out
+          constexpr bool NOFILT = decltype(nofilt_tag)::value;
           uint32_t sw[VE];
           load_slots(slot, idx0, sw);
           if (nvalid < VE) {
 #pragma unroll
             for (int k = 0; k < VE; k++)
-              if (k >= nvalid) sw[k] = ~0u;  // rows past len(Values): handled by the tail loop below
+              if (k >= nvalid) sw[k] = NOFILT ? trash : ~0u;  // rows past len(Values): handled by the tail loop below
           }
           if (DO_COUNT && count_matched) {
 #pragma unroll
@@ -1247,7 +1295,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           uint32_t cmask = 0, slow_any = 0;
 #pragma unroll
           for (int k = 0; k < VE; k++) {
-            const uint32_t e = min(sw[k] ^ passbits, trash);  // passing row: its slot, else trash
+            const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);  // passing row: its slot, else trash
             if (DO_COUNT) sred_add(cnt_s + e * gstride_b, 1u);
             if (ALLFAST) {
               sred_add(w0_s + R_b + e * gstride_b, a[k]);
@@ -1262,7 +1310,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           if (!ALLFAST && (cmask | slow_any)) {  // rare
 #pragma unroll
             for (int k = 0; k < VE; k++) {
-              const uint32_t e = min(sw[k] ^ passbits, trash);
+              const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
               const bool fr = (a[k] - fmin32) <= fspan32;
               if ((cmask >> k) & 1u) sred_add(hi_s + (fr ? e : trash) * hi_stride_b, 1u);  // carry
               if (!fr && e != trash) agg_slow(&AS, e, (long long)a[k], 0);
@@ -1271,7 +1319,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           if (nsub > 0) {
 #pragma unroll
             for (int k = 0; k < VE; k++) {
-              const uint32_t e = min(sw[k] ^ passbits, trash);
+              const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
               const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
               const uint32_t e2 = fr ? e : trash;
               if (hist32) {
@@ -1285,21 +1333,26 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             }
           }
         };
-        auto run32 = [&](auto dc, auto af) {
+        auto run32 = [&](auto dc, auto af, auto nf) {
           scan_values_u32(cx, c, nrec, [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid) {
-            tile32(idx0, a, nvalid, dc, af);
+            tile32(idx0, a, nvalid, dc, af, nf);
           });
         };
+        const bool nofilt = allfast && nfilters == 0 && time_col < 0 && ngroups <= 1;
         if (do_count) {
-          if (allfast)
-            run32(std::true_type(), std::true_type());
+          if (nofilt)
+            run32(std::true_type(), std::true_type(), std::true_type());
+          else if (allfast)
+            run32(std::true_type(), std::true_type(), std::false_type());
           else
-            run32(std::true_type(), std::false_type());
+            run32(std::true_type(), std::false_type(), std::false_type());
         } else {
-          if (allfast)
-            run32(std::false_type(), std::true_type());
+          if (nofilt)
+            run32(std::false_type(), std::true_type(), std::true_type());
+          else if (allfast)
+            run32(std::false_type(), std::true_type(), std::false_type());
           else
-            run32(std::false_type(), std::false_type());
+            run32(std::false_type(), std::false_type(), std::false_type());
         }
         // rows past len(Values) are unpopulated for this column (Q6): they still count
         const uint32_t nv = c.nitems < nrec ? c.nitems : nrec;
@@ -1477,46 +1530,74 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       if (owner) matched += my_matched;
     }
     if (ACC_SMEM) {
-      // one thread per (slot, aggregation-or-count): fold the R replicas into the CTA's running
-      // 64-bit totals (shared memory, no atomics).  The totals reach the global accumulators once,
-      // when the CTA runs out of blocks: per-block global reductions from 148 CTAs in lockstep
-      // serialise on the same few hundred L2 addresses right in front of a barrier.
-      const uint32_t per_slot = 1u + (uint32_t)naggs;
-      const uint32_t tw = 1u + 2u * (uint32_t)naggs;  // totals per slot: count, then (hist count, sum) per agg
-      for (uint32_t i = cx.tid; i < nslots * per_slot; i += THREADS) {
-        const uint32_t g = i / per_slot, a = i - g * per_slot;  // a == 0: the count
-        const uint32_t* base = cx.acc + g * gstride;
-        // sum of the R replicas of word w (R is a power of two; 16-byte loads when R >= 4)
-        auto fold = [&](uint32_t w) -> unsigned long long {
-          unsigned long long t = 0;
-          if (R >= 4) {
-            const uint4* p4 = reinterpret_cast<const uint4*>(base + w * R);
-#pragma unroll 8
-            for (uint32_t j = 0; j < R / 4; j++) {
-              const uint4 q = p4[j];
-              t += (unsigned long long)q.x + q.y + q.z + q.w;
-            }
-          } else {
-            for (uint32_t r = 0; r < R; r++) t += base[w * R + r];
+      // Fold the R replicas of every accumulator word into the CTA's running 64-bit totals (shared
+      // memory, no atomics) and zero them for the next block.  A row = the R replicas of one
+      // (slot, word).  R >= 4: every lane takes 16 bytes, R/4 lanes share a row, 128/R rows per warp
+      // step — consecutive addresses across the warp (no bank conflicts) — and the lanes of a row
+      // combine with xor-shuffles.  The totals reach the global accumulators once, when the CTA runs
+      // out of blocks: per-block global reductions from 148 CTAs in lockstep serialise on the same
+      // few hundred L2 addresses right in front of a barrier.
+      const uint32_t tw = 1u + 2u * (uint32_t)naggs;  // words per slot: count, then (word0, low limb) per agg
+      const uint32_t nrows = nslots * tw, nrows_all = (nslots + 1u) * tw;  // + the trash slot (zeroed only)
+      auto fold_row = [&](uint32_t row, unsigned long long t) {
+        const uint32_t g = tw == 1u ? row : __umulhi(row, tw_magic), w = row - g * tw;  // exact: row * tw < 2^32
+        if (w == 0) {
+          // this block's count of slot g: parked in the (zeroed) row for the second step below
+          cx.acc[row * R] = (uint32_t)t;
+          if (R > 1) cx.acc[row * R + 1] = (uint32_t)(t >> 32);
+          if (!broken && owner) ctot[g * tw] += t;
+        } else if (!broken) {
+          // word0 of a value-array aggregation counts the NON-accepted rows: hist count = count - word0
+          const bool neg = (w & 1u) && ((agg_mode_bits >> ((w - 1u) >> 1)) & 1u);
+          ctot[g * tw + w] += neg ? (0ull - t) : t;
+        }
+      };
+      if (R >= 4) {
+        const uint32_t lpr = R >> 2;  // lanes per row
+        const uint32_t lg = 31u - (uint32_t)__clz(lpr);
+        const uint32_t rps = 32u >> lg;
+        const uint32_t sub = (uint32_t)cx.lane & (lpr - 1u), grp = (uint32_t)cx.lane >> lg;
+        uint4* const acc4 = reinterpret_cast<uint4*>(cx.acc);
+        for (uint32_t r0 = (uint32_t)cx.warp * rps; r0 < nrows_all; r0 += NWARPS * rps) {
+          const uint32_t row = r0 + grp;
+          uint4 q = make_uint4(0, 0, 0, 0);
+          if (row < nrows_all) {
+            q = acc4[row * lpr + sub];
+            acc4[row * lpr + sub] = make_uint4(0, 0, 0, 0);
           }
-          return t;
-        };
-        const unsigned long long cnt = fold(0);
-        if (a == 0) {
-          if (!broken && owner) ctot[g * tw] += cnt;
-        } else {
-          const uint32_t w0 = 1u + 2u * (a - 1u);
-          const unsigned long long word0 = fold(w0), lo = fold(w0 + 1);
-          const unsigned long long hi = cx.acc[acc_rep + g * (uint32_t)naggs + (a - 1u)];
-          const unsigned long long hc = ((agg_mode_bits >> (a - 1u)) & 1u) ? cnt - word0 : word0;
-          if (!broken) {
-            ctot[g * tw + 1 + 2 * (a - 1u)] += hc;
-            ctot[g * tw + 2 + 2 * (a - 1u)] += lo + (hi << 32);
+          unsigned long long t = ((unsigned long long)q.x + q.y) + ((unsigned long long)q.z + q.w);
+          for (uint32_t d = lpr >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULL, t, d);
+          if (sub == 0 && row < nrows) fold_row(row, t);
+        }
+      } else {
+        for (uint32_t row = cx.tid; row < nrows_all; row += THREADS) {
+          unsigned long long t = cx.acc[row * R];
+          cx.acc[row * R] = 0;
+          if (R == 2) {
+            t += cx.acc[row * R + 1];
+            cx.acc[row * R + 1] = 0;
           }
+          if (row < nrows) fold_row(row, t);
         }
       }
       __syncthreads();
-      for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
+      // second step, one thread per (slot, aggregation): the unreplicated high limbs and "+ count"
+      for (uint32_t i = cx.tid; i < (nslots + 1u) * (uint32_t)naggs; i += THREADS) {
+        const uint32_t g = i / (uint32_t)naggs, a = i - g * (uint32_t)naggs;
+        const unsigned long long hi = cx.acc[acc_rep + i];
+        cx.acc[acc_rep + i] = 0;
+        if (g < nslots && !broken) {
+          unsigned long long cnt = cx.acc[g * gstride];  // R == 1: a block's count fits one word
+          if (R > 1) cnt |= (unsigned long long)cx.acc[g * gstride + 1] << 32;
+          if (hi) ctot[g * tw + 2 + 2 * a] += hi << 32;
+          if ((agg_mode_bits >> a) & 1u) ctot[g * tw + 1 + 2 * a] += cnt;
+        }
+      }
+      __syncthreads();
+      for (uint32_t g = cx.tid; g < nslots; g += THREADS) {
+        cx.acc[g * gstride] = 0;
+        if (R > 1) cx.acc[g * gstride + 1] = 0;
+      }
     }
     phase(5);
   }
@@ -1571,6 +1652,7 @@ __global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const D
   cx.acc = nullptr;
   cx.tmaps = nullptr;
   cx.nstage = 0;
+  cx.zero = 0;
   cx.buf0 = cx.buf1 = cx.mbar0 = cx.mbar1 = cx.par0 = cx.par1 = 0;
   cx.plist = nullptr;
   cx.timing = false;

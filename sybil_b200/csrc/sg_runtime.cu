@@ -1462,7 +1462,7 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.gdummy = q->d_gdummy;
   lp.smem_bytes = q->smem_bytes;
   lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
-  lp.nstage = q->nstage;
+  lp.nstage = t->d_tmaps ? q->nstage : 0u;
   lp.dbg = nullptr;
   static const bool phase_timing = getenv("SG_PHASE_TIMING") != nullptr;
   unsigned long long* d_dbg = nullptr;
@@ -1472,7 +1472,7 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
       lp.dbg = d_dbg;
     }
   }
-  lp.tmaps = q->nstage ? t->d_tmaps : nullptr;
+  lp.tmaps = lp.nstage ? t->d_tmaps : nullptr;
   int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(items.size(), 1));
   CUDA_TRY(c, cudaEventRecord(q->ev0, c->stream));
   int rc = launch_scan(lp, grid, c->stream);
