@@ -25,7 +25,7 @@ def _run(cmd):
 
 def build_gpu(force=False):
     """libsybilgpu.so: hand-written sm_100a kernels + runtime, cudart linked statically."""
-    out = os.path.join(CSRC, "libsybilgpu.so")
+    out = os.environ.get("SG_LIB_OUT") or os.path.join(CSRC, "libsybilgpu.so")
     srcs = [os.path.join(CSRC, f) for f in ("sg_kernels.cu", "sg_runtime.cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("sg_internal.h", "sg_hist.h")] + [
         os.path.join(ROOT, "include", "sybilgpu.h")]
@@ -33,7 +33,7 @@ def build_gpu(force=False):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     _run([nvcc] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress",
-                               "186", "-o", out] + srcs + ["-ldl"])
+                               "186", "-o", out] + os.environ.get("SG_NVCC_FLAGS", "").split() + srcs + ["-ldl"])
     return out
 
 

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsybilgpu.so")
+# SG_LIB: an alternative build of the same library (kernel experiments: `SG_NVCC_FLAGS=... SG_LIB_OUT=... _build.build_gpu`)
+LIB_PATH = os.environ.get("SG_LIB") or os.path.join(_HERE, "csrc", "libsybilgpu.so")
 GEN_PATH = os.path.join(_HERE, "csrc", "libsybilblockgen.so")
 
 SG_ABI_VERSION = 1

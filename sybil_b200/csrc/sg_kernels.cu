@@ -36,7 +36,10 @@
 
 namespace sg {
 
-constexpr int THREADS = 512;
+#ifndef SG_THREADS
+#define SG_THREADS 512
+#endif
+constexpr int THREADS = SG_THREADS;
 constexpr int NWARPS = THREADS / 32;
 constexpr uint32_t FLAG = 0x80000000u;
 constexpr uint32_t HEAD_WORDS = SG_BLOCK_ROWS / 32;  // 2048
@@ -86,6 +89,19 @@ struct Ctx {
   const uint32_t* plist;
   uint32_t npass, pass_idx, pref_idx;
   uint32_t zero;  // 0 at run time, opaque to the compiler (see staged_reads_done)
+#ifdef SG_FINE_TIMING
+  volatile unsigned long long* tacc;  // thread 0 only: [9..15] fine-grained marks
+  bool t0;
+  __device__ __forceinline__ void tmark(int i) {
+    if (t0) {
+      const unsigned long long now = (unsigned long long)clock64();
+      tacc[i] += now - tacc[8];
+      tacc[8] = now;
+    }
+  }
+#else
+  __device__ __forceinline__ void tmark(int) {}
+#endif
   // SG_PHASE_TIMING: cycles warp 0 spent waiting for TMA tiles / for look-back totals
   bool timing;
   unsigned long long t_tma, t_lb;
@@ -133,6 +149,12 @@ __device__ __forceinline__ void tma_load_tile(uint32_t dst_s, const void* tmap, 
           dst_s),
       "l"(tmap), "r"(0), "r"(row), "r"(mbar_s)
       : "memory");
+}
+// the same tile, only as far as L2 (no shared memory, no barrier): issued a few tiles ahead of the
+// staged load so that the load finds its lines in L2 instead of waiting out the HBM latency — the
+// bytes in flight per SM are no longer capped by the staging buffers
+__device__ __forceinline__ void tma_prefetch_tile(const void* tmap, uint32_t row) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(0), "r"(row) : "memory");
 }
 // this lane's 128-byte row of a staged tile (32 words), undoing the 128B swizzle:
 // 16-byte chunk j of row r sits at chunk position j ^ (r & 7)
@@ -195,12 +217,23 @@ struct Feed {
   const void* tmap;
   uint32_t row0;
   bool on;
+  // L2 prefetch distance bookkeeping: this warp's tile count in this pass, and the next fed pass
+  uint32_t mine;
+  const void* ntmap;
+  uint32_t nrow0, nnt;
 };
+#ifndef SG_PF_AHEAD
+#define SG_PF_AHEAD 0  // measured on C2: 0 -> 0.677 ms, 2 -> 0.708 ms, 4 -> 0.731 ms (the scan is bandwidth-, not latency-bound)
+#endif
+constexpr uint32_t PF_AHEAD = SG_PF_AHEAD;  // L2 prefetch runs this many of the warp's tiles ahead of its staged loads (0: off)
 __device__ __forceinline__ Feed make_feed(const Ctx& cx, const DevCol& c) {
   Feed f;
   f.on = cx.tmaps != nullptr && (c.flags & COL_TMA) != 0;
   f.tmap = cx.tmaps + (size_t)c.data_chunk * 128;
   f.row0 = c.data_row;
+  f.mine = 0;
+  f.ntmap = nullptr;
+  f.nrow0 = f.nnt = 0;
   return f;
 }
 __device__ __forceinline__ void feed_issue(const Ctx& cx, const Feed& f, uint32_t tile, uint32_t st, uint32_t after = 0u) {
@@ -209,14 +242,34 @@ __device__ __forceinline__ void feed_issue(const Ctx& cx, const Feed& f, uint32_
     tma_load_tile(cx.buf(st), f.tmap, f.row0 + tile * 32u + after, cx.mbar(st));
   }
 }
+// L2 prefetch of this warp's v-th tile counted from the start of the pass; past the end of the pass
+// it runs on into the warp's first tiles of the next fed pass of the block
+__device__ __forceinline__ void feed_prefetch(const Ctx& cx, const Feed& f, uint32_t v) {
+  if (PF_AHEAD == 0 || cx.lane != 0) return;
+  if (v < f.mine) {
+    tma_prefetch_tile(f.tmap, f.row0 + (cx.warp + v * NWARPS) * 32u);
+  } else {
+    const uint32_t t = cx.warp + (v - f.mine) * NWARPS;
+    if (t < f.nnt) tma_prefetch_tile(f.ntmap, f.nrow0 + t * 32u);
+  }
+}
 // start of a fed pass: request this warp's first tile(s) unless the previous pass already did
-__device__ __forceinline__ void feed_prologue(Ctx& cx, const Feed& f, uint32_t ntiles) {
+__device__ __forceinline__ void feed_prologue(Ctx& cx, Feed& f, uint32_t ntiles) {
   if (!f.on) return;
   const uint32_t* e = cx.plist + 4 * cx.pass_idx;
   if (cx.pass_idx >= cx.npass || e[1] != f.row0 || e[2] != ntiles) __trap();  // pass list out of step
+  f.mine = (uint32_t)cx.warp < ntiles ? (ntiles - (uint32_t)cx.warp + NWARPS - 1u) / NWARPS : 0u;
+  if (cx.pass_idx + 1 < cx.npass) {
+    f.ntmap = cx.tmaps + (size_t)e[4] * 128;
+    f.nrow0 = e[5];
+    f.nnt = e[6];
+  }
   if (cx.pref_idx != cx.pass_idx)
     for (uint32_t st = 0; st < cx.nstage; st++)
       if (cx.warp + st * NWARPS < ntiles) feed_issue(cx, f, cx.warp + st * NWARPS, st);
+  // the first pass of a block has nobody before it to prefetch its head
+  if (cx.pass_idx == 0)
+    for (uint32_t v = cx.nstage; v < cx.nstage + PF_AHEAD; v++) feed_prefetch(cx, f, v);
 }
 // end of a fed pass (all of this warp's tiles consumed, both staging buffers free): request the
 // first tile(s) of the next fed pass of the block
@@ -312,16 +365,22 @@ __device__ __forceinline__ unsigned long long lookback_sum(const Ctx& cx, uint32
 }
 
 // ---------------------------------------------------------------------------
-// bucket-encoded column: on_bin(bin) whenever the bin of the lane's next entry
-// changes (and before its first entry), on_row(row) for every (bin,row) pair
-// ---------------------------------------------------------------------------
-template <class OnBin, class OnRow>
-__device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint32_t nrec, OnBin on_bin, OnRow on_row) {
+// bucket-encoded column: on_row(row, pay_of(bin)) for every (bin,row) pair; pay_of(bin) is
+// evaluated once per run of entries of the same bin inside a lane
+template <class PayT, class PayOf, class OnRow>
+__device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint32_t nrec, PayOf pay_of, OnRow on_row) {
   const uint32_t n = c.nitems;
   const uint32_t nbins = c.nbins;
   const uint32_t* __restrict__ ids = reinterpret_cast<const uint32_t*>(c.data);
   const bool delta = (c.flags & COL_DELTA_IDS) != 0;
   const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
+#ifndef SG_FINE_FLUSH
+  cx.tmark(9);  // since the previous mark: the caller's per-bin payload build
+#endif
+  // request this warp's first tile(s) right away: the HBM latency overlaps the head-bit build
+  const uint32_t ntiles = (n + (32 * BE - 1)) / (32 * BE);
+  Feed feed = make_feed(cx, c);
+  feed_prologue(cx, feed, ntiles);
 
   // segment heads: one bit per flat entry that starts a (non-empty) bin
   for (uint32_t i = tid; i < HEAD_WORDS; i += THREADS) cx.headbits[i] = 0;
@@ -334,35 +393,44 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     }
   }
   __syncthreads();
-  {  // exclusive prefix popcount per 32-entry word: the first 512 threads x 4 words
-    const uint4 w = tid < (int)(HEAD_WORDS / 4) ? reinterpret_cast<const uint4*>(cx.headbits)[tid] : make_uint4(0, 0, 0, 0);
-    const uint32_t p0 = __popc(w.x), p1 = __popc(w.y), p2 = __popc(w.z), p3 = __popc(w.w);
-    const uint32_t tot = p0 + p1 + p2 + p3;
-    uint32_t inc = tot;
+  {  // exclusive prefix popcount per 32-entry word: THREADS x 4 words per step
+    uint32_t running = 0;
+    for (uint32_t i0 = 0; i0 < HEAD_WORDS / 4; i0 += THREADS) {
+      const uint32_t i = i0 + (uint32_t)tid;
+      const uint4 w = i < HEAD_WORDS / 4 ? reinterpret_cast<const uint4*>(cx.headbits)[i] : make_uint4(0, 0, 0, 0);
+      const uint32_t p0 = __popc(w.x), p1 = __popc(w.y), p2 = __popc(w.z), p3 = __popc(w.w);
+      const uint32_t tot = p0 + p1 + p2 + p3;
+      uint32_t inc = tot;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, inc, d);
-      if (lane >= d) inc += t;
-    }
-    if (lane == 31) cx.misc[16 + warp] = inc;
-    __syncthreads();
-    uint32_t base = 0;
-    for (int i = 0; i < warp; i++) base += cx.misc[16 + i];
-    const uint32_t ex = base + inc - tot;
-    if (tid < (int)(HEAD_WORDS / 4)) {
-      cx.headprefix[tid * 4 + 0] = (uint16_t)ex;
-      cx.headprefix[tid * 4 + 1] = (uint16_t)(ex + p0);
-      cx.headprefix[tid * 4 + 2] = (uint16_t)(ex + p0 + p1);
-      cx.headprefix[tid * 4 + 3] = (uint16_t)(ex + p0 + p1 + p2);
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (i0) __syncthreads();  // the previous step's warp totals have been read
+      if (lane == 31) cx.misc[16 + warp] = inc;
+      __syncthreads();
+      uint32_t base = running;
+      for (int k = 0; k < NWARPS; k++) {
+        const uint32_t wt = cx.misc[16 + k];
+        if (k < warp) base += wt;
+        running += wt;
+      }
+      const uint32_t ex = base + inc - tot;
+      if (i < HEAD_WORDS / 4) {
+        cx.headprefix[i * 4 + 0] = (uint16_t)ex;
+        cx.headprefix[i * 4 + 1] = (uint16_t)(ex + p0);
+        cx.headprefix[i * 4 + 2] = (uint16_t)(ex + p0 + p1);
+        cx.headprefix[i * 4 + 3] = (uint16_t)(ex + p0 + p1 + p2);
+      }
     }
   }
   cx.epoch++;
   __syncthreads();
 
-  const uint32_t ntiles = (n + (32 * BE - 1)) / (32 * BE);
+#ifndef SG_FINE_FLUSH
+  cx.tmark(10);  // head bits + prefix popcounts
+#endif
   uint32_t prev_incl = 0;  // running segment sum through this warp's previous tile
-  const Feed feed = make_feed(cx, c);
-  feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * BE) + lane * BE;
@@ -375,6 +443,7 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
       read_staged_row(cx.buf(st), lane, a);
       const uint32_t after = staged_reads_done(cx, dep_of(a));
       if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
+      feed_prefetch(cx, feed, it + cx.nstage + PF_AHEAD);
       if (idx0 + BE > n) {
 #pragma unroll
         for (int k = 0; k < BE; k++)
@@ -401,6 +470,63 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
         for (int k = 0; k < BE; k++) a[k] &= 0xFFFFu;
       }
     }
+    const uint32_t lastrow = nrec - 1u;
+    // Fast path (warp-uniform): a full tile of delta-encoded ids in which no lane sees more than one
+    // bin head.  The lane's 32 gaps become in-place prefix sums P_k; with the head at entry h the
+    // row of entry k is P_k + carry for k < h and P_k - P_{h-1} for k >= h, the payload likewise one
+    // of two values: no per-entry head test, bin step or payload lookup.
+    if (delta && idx0 - lane * BE + 32 * BE <= n && !__any_sync(FULL, (word & (word - 1u)) != 0u)) {
+      const uint32_t below = word ? ((word & (0u - word)) - 1u) : FULL;  // entries before the head (all if none)
+#pragma unroll
+      for (int k = 1; k < BE; k++) a[k] += a[k - 1];
+      const uint32_t tot_all = a[BE - 1];
+      // pre = P_{h-1}: a 5-level select over the register array (h = 0 or no head: unused / tot_all)
+      uint32_t pre = 0;
+      {
+        const uint32_t hm1 = (uint32_t)__popc(below) - 1u;  // h - 1 (31 when there is no head)
+        uint32_t l1[16], l2[8], l3[4], l4[2];
+#pragma unroll
+        for (int j = 0; j < 16; j++) l1[j] = (hm1 & 1u) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) l2[j] = (hm1 & 2u) ? l1[2 * j + 1] : l1[2 * j];
+#pragma unroll
+        for (int j = 0; j < 4; j++) l3[j] = (hm1 & 4u) ? l2[2 * j + 1] : l2[2 * j];
+#pragma unroll
+        for (int j = 0; j < 2; j++) l4[j] = (hm1 & 8u) ? l3[2 * j + 1] : l3[2 * j];
+        pre = (hm1 & 16u) ? l4[1] : l4[0];
+        if (below == 0u) pre = 0u;  // head at entry 0
+      }
+      const uint32_t tot = word ? tot_all - pre : tot_all;
+      uint32_t incl = tot | (word ? FLAG : 0u);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d && !(incl & FLAG)) incl += v;
+      }
+      uint32_t excl = __shfl_up_sync(FULL, incl, 1);
+      if (lane == 0) excl = 0;
+      const uint32_t tile_tot = __shfl_sync(FULL, incl, 31);
+      if (lane == 0) cx.pubA[t] = (unsigned long long)tile_tot | ((unsigned long long)cx.epoch << 32);
+      const uint32_t carry = lookback_seg(cx, t, prev_incl);
+      prev_incl = (tile_tot & FLAG) ? (tile_tot & ~FLAG) : ((carry + tile_tot) & ~FLAG);
+      const uint32_t offA = (excl & FLAG) ? (excl & ~FLAG) : ((excl + carry) & ~FLAG);
+      const uint32_t offB = 0u - pre;
+      int binA = (int)cx.headprefix[idx0 >> 5] - 1, binB = binA + 1;
+      if ((binA < 0 && below != 0u) || (word && (uint32_t)binB >= nbins)) cx.misc[1] = 1;
+      if (binA < 0) binA = 0;
+      if ((uint32_t)binB >= nbins) binB = 0;
+      const PayT payA = pay_of((uint32_t)binA);
+      const PayT payB = word ? pay_of((uint32_t)binB) : payA;
+      // rows grow inside a segment: the lane's largest is the last one of either segment
+      const uint32_t lastA = (below ? pre : 0u) + offA, lastB = tot_all + (word ? offB : offA);
+      if (max(below ? lastA : 0u, lastB) > lastrow) cx.misc[1] = 1;
+#pragma unroll
+      for (int k = 0; k < BE; k++) {
+        const bool lo = (below >> k) & 1u;
+        on_row(min(a[k] + (lo ? offA : offB), lastrow), lo ? payA : payB);
+      }
+      continue;
+    }
     // pass 1: lane total since the last head in the lane
     uint32_t tot = 0;
 #pragma unroll
@@ -424,7 +550,7 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     int bin = (int)((idx0 < n) ? cx.headprefix[idx0 >> 5] : 0) - 1;
     const uint32_t cnt = (idx0 >= n) ? 0u : ((n - idx0 < BE) ? n - idx0 : BE);
     uint32_t maxrow = 0;
-    const uint32_t lastrow = nrec - 1u;
+    PayT cur = PayT();
     auto step = [&](int k) {
       const bool head = (word >> k) & 1u;
       if (head) bin++;
@@ -434,10 +560,10 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
           cx.misc[1] = 1;
           bin = 0;
         }
-        on_bin((uint32_t)bin);
+        cur = pay_of((uint32_t)bin);
       }
       maxrow = max(maxrow, run);
-      on_row(min(run, lastrow));
+      on_row(min(run, lastrow), cur);
     };
     if (cnt == BE) {
 #pragma unroll
@@ -449,8 +575,14 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     }
     if (maxrow > lastrow) cx.misc[1] = 1;
   }
+#ifndef SG_FINE_FLUSH
+  cx.tmark(11);  // this thread's tiles
+#endif
   feed_epilogue(cx, feed);
   __syncthreads();
+#ifndef SG_FINE_FLUSH
+  cx.tmark(12);  // waiting for the slowest warp
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -466,7 +598,7 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
   cx.epoch++;
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   unsigned long long prev_incl = 0;
-  const Feed feed = make_feed(cx, c);
+  Feed feed = make_feed(cx, c);
   feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
@@ -479,6 +611,7 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
       read_staged_row(cx.buf(st), lane, raw);
       const uint32_t after = staged_reads_done(cx, dep_of(raw));
       if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
+      feed_prefetch(cx, feed, it + cx.nstage + PF_AHEAD);
 #pragma unroll
       for (int k = 0; k < VE; k++)
         a[k] = (idx0 + k < n) ? ((unsigned long long)raw[2 * k] | ((unsigned long long)raw[2 * k + 1] << 32)) : 0ull;
@@ -536,7 +669,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   uint32_t prev_incl = 0;
   uint32_t hix = 0;  // xor of the high limbs read (keeps the staged loads 16 bytes wide)
-  const Feed feed = make_feed(cx, c);
+  Feed feed = make_feed(cx, c);
   feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
@@ -554,6 +687,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
       read_staged_row_lo(cx.buf(st), lane, a, hix);  // low limbs: exact mod 2^32
       const uint32_t after = staged_reads_done(cx, hix);
       if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
+      feed_prefetch(cx, feed, it + cx.nstage + PF_AHEAD);
       if (idx0 + VE > n) {
 #pragma unroll
         for (int k = 0; k < VE; k++)
@@ -937,8 +1071,26 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       tacc[i] += now - tacc[7];
       tacc[7] = now;
     }
+#ifdef SG_FINE_TIMING
+    cx.tmark(13);  // everything outside the marked regions
+#endif
   };
+#ifdef SG_FINE_TIMING
+  cx.tacc = tacc;
+  cx.t0 = dbg && cx.tid == 0;
+  if (cx.t0) {
+    for (int i = 8; i < 16; i++) tacc[i] = 0;
+    tacc[8] = (unsigned long long)clock64();
+  }
+#endif
 
+#ifdef SG_STAGGER
+  {  // experiment: desynchronise the CTAs' phases
+    const long long until = clock64() + (long long)(blockIdx.x % 16u) * SG_STAGGER;
+    while (clock64() < until) {
+    }
+  }
+#endif
   for (;;) {
     __syncthreads();
     if (cx.tid == 0) {
@@ -1028,10 +1180,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           pay[b] = F.is_str ? (sp(str_gid(c, bv)) ? 1u : 0u) : (int_pred(F.op, bv, F.ival) ? 1u : 0u);
         }
         __syncthreads();
-        SlotT cur = 0;  // finc for rows of a passing bin, else 0: the read-modify-write runs unconditionally
-        scan_bucket(
-            cx, c, nrec, [&](uint32_t bin) { cur = pay[bin] ? fincS : (SlotT)0; },
-            [&](uint32_t row) { slot[row] = (SlotT)(slot[row] + cur); });
+        // finc for rows of a passing bin, else 0: the read-modify-write runs unconditionally
+        scan_bucket<SlotT>(
+            cx, c, nrec, [&](uint32_t bin) { return pay[bin] ? fincS : (SlotT)0; },
+            [&](uint32_t row, SlotT cur) { slot[row] = (SlotT)(slot[row] + cur); });
       } else if (c.enc == SG_ENC_VALUES) {
         if (F.is_str) {
           scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
@@ -1079,15 +1231,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           pay[b] = ((uint32_t)code + 1u) * G.stride;
         }
         __syncthreads();
-        SlotT cur = 0;
         if (nfilters == 0 && gi == 0) {
           // first pass to touch the (zeroed) slot words: a store, not a read-modify-write
-          scan_bucket(
-              cx, c, nrec, [&](uint32_t bin) { cur = (SlotT)pay[bin]; }, [&](uint32_t row) { slot[row] = cur; });
+          scan_bucket<SlotT>(
+              cx, c, nrec, [&](uint32_t bin) { return (SlotT)pay[bin]; },
+              [&](uint32_t row, SlotT cur) { slot[row] = cur; });
         } else {
-          scan_bucket(
-              cx, c, nrec, [&](uint32_t bin) { cur = (SlotT)pay[bin]; },
-              [&](uint32_t row) { slot[row] = (SlotT)(slot[row] + cur); });
+          scan_bucket<SlotT>(
+              cx, c, nrec, [&](uint32_t bin) { return (SlotT)pay[bin]; },
+              [&](uint32_t row, SlotT cur) { slot[row] = (SlotT)(slot[row] + cur); });
         }
       } else if (c.enc == SG_ENC_VALUES && G.is_str) {
         const uint32_t stride = G.stride;
@@ -1109,10 +1261,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
         for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) pay[b] = time_code(c.bin_values[b], tb, tf, tr);
         __syncthreads();
-        uint32_t cur = 0;
-        scan_bucket(
-            cx, c, nrec, [&](uint32_t bin) { cur = pay[bin]; },
-            [&](uint32_t row) {
+        scan_bucket<uint32_t>(
+            cx, c, nrec, [&](uint32_t bin) { return pay[bin]; },
+            [&](uint32_t row, uint32_t cur) {
               if (cur)
                 slot[row] = (SlotT)(slot[row] + cur * ts + tok);
               else
@@ -1262,10 +1413,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       };
 
       if (c.enc == SG_ENC_BUCKET) {
-        long long curv = 0;
-        scan_bucket(
-            cx, c, nrec, [&](uint32_t bin) { curv = c.bin_values[bin]; },
-            [&](uint32_t row) { accept_one((uint32_t)slot[row], curv); });
+        scan_bucket<long long>(
+            cx, c, nrec, [&](uint32_t bin) { return (long long)c.bin_values[bin]; },
+            [&](uint32_t row, long long curv) { accept_one((uint32_t)slot[row], curv); });
       } else if (c.enc == SG_ENC_VALUES && ACC_SMEM && fast_any && (c.flags & COL_STATS) && c.vmin >= 0 &&
                  c.vmax <= 0xffffffffll) {
         // ---- value array whose decoded values provably fit 32 bits (staging statistics) ----
@@ -1519,6 +1669,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     __syncthreads();
 
     phase(4);
+    cx.tmark(15);
     // ---- end of block: publish or discard ------------------------------------------------
     const bool broken = cx.misc[1] != 0;
     if (broken) {
@@ -1559,6 +1710,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         const uint32_t sub = (uint32_t)cx.lane & (lpr - 1u), grp = (uint32_t)cx.lane >> lg;
         uint4* const acc4 = reinterpret_cast<uint4*>(cx.acc);
         for (uint32_t r0 = (uint32_t)cx.warp * rps; r0 < nrows_all; r0 += NWARPS * rps) {
+#ifdef SG_FINE_FLUSH
+          cx.tmark(12);
+#endif
           const uint32_t row = r0 + grp;
           uint4 q = make_uint4(0, 0, 0, 0);
           if (row < nrows_all) {
@@ -1566,7 +1720,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             acc4[row * lpr + sub] = make_uint4(0, 0, 0, 0);
           }
           unsigned long long t = ((unsigned long long)q.x + q.y) + ((unsigned long long)q.z + q.w);
+#ifdef SG_FINE_FLUSH
+          if (t == 0x123456789ull) cx.misc[5] = 1;
+          cx.tmark(11);
+#endif
           for (uint32_t d = lpr >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULL, t, d);
+#ifdef SG_FINE_FLUSH
+          if (t == 0x123456789ull) cx.misc[5] = 1;
+          cx.tmark(10);
+#endif
           if (sub == 0 && row < nrows) fold_row(row, t);
         }
       } else {
@@ -1580,6 +1742,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           if (row < nrows) fold_row(row, t);
         }
       }
+      cx.tmark(14);  // fold loop
       __syncthreads();
       // second step, one thread per (slot, aggregation): the unreplicated high limbs and "+ count"
       for (uint32_t i = cx.tid; i < (nslots + 1u) * (uint32_t)naggs; i += THREADS) {
@@ -1606,6 +1769,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     for (int i = 0; i < 7; i++) dbg[i] = tacc[i];
     dbg[7] = cx.t_tma;
     dbg[8] = cx.t_lb;
+#ifdef SG_FINE_TIMING
+    for (int i = 9; i < 16; i++) dbg[i] = tacc[i];
+#endif
   }
   if (ACC_SMEM) {
     __syncthreads();

@@ -1501,6 +1501,9 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
     fprintf(stderr, "[sg phase cycles avg/CTA] init %llu filters %llu groups %llu time %llu aggs %llu flush %llu fetch %llu | warp0 value-pass waits: tma %llu lookback %llu | max CTA total %llu (kernel %.3f ms)\n",
             tot[0] / q->grid, tot[1] / q->grid, tot[2] / q->grid, tot[3] / q->grid, tot[4] / q->grid, tot[5] / q->grid,
             tot[6] / q->grid, tot[7] / q->grid, tot[8] / q->grid, mx, ms);
+    if (tot[9] | tot[10] | tot[11] | tot[12] | tot[13])  // -DSG_FINE_TIMING builds: bucket-pass breakdown (thread 0)
+      fprintf(stderr, "[sg bucket passes avg/CTA] payload build %llu head bits %llu own tiles %llu wait for slowest warp %llu | elsewhere %llu | flush: fold loop %llu (rest of flush in elsewhere) pre %llu\n",
+              tot[9] / q->grid, tot[10] / q->grid, tot[11] / q->grid, tot[12] / q->grid, tot[13] / q->grid, tot[14] / q->grid, tot[15] / q->grid);
     pool_release(c, d_dbg);
   }
   return SG_OK;
