@@ -106,6 +106,21 @@ struct sg_ctx {
   // query-lifetime device buffers are recycled: cudaMalloc/cudaFree per query cost milliseconds
   std::vector<std::pair<void*, size_t>> pool_free;
   std::unordered_map<void*, size_t> pool_live;
+  // pinned host scratch for the per-query parameter uploads and the accumulator read-back: copies
+  // from/to pageable memory are staged by the driver and block the caller
+  char* hpin = nullptr;
+  size_t hpin_cap = 0;
+  char* scratch(size_t bytes) {
+    if (bytes > hpin_cap) {
+      if (hpin) cudaFreeHost(hpin);
+      hpin = nullptr;
+      hpin_cap = 0;
+      size_t cap = std::max<size_t>(bytes * 2, (size_t)1 << 20);
+      if (cudaHostAlloc((void**)&hpin, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+      hpin_cap = cap;
+    }
+    return hpin;
+  }
   void set_err(const std::string& s) { err = s; }
   bool is_pinned(const void* p, size_t n) const {
     const char* c = (const char*)p;
@@ -395,6 +410,7 @@ void sg_destroy(sg_ctx* c) {
   if (!c) return;
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& p : c->pool_free) cudaFree(p.first);
+  if (c->hpin) cudaFreeHost(c->hpin);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -1007,6 +1023,9 @@ struct sg_query {
   // cross-GPU merge under differing per-rank dictionaries: the union dictionaries the merged
   // accumulators are laid out by (per entry of dims; empty for the time axis)
   bool merged = false;
+  // accumulators as read back right behind the kernel (small plans): spares build_result a blocking copy
+  std::vector<uint64_t> h_acc;
+  bool h_acc_valid = false;
   std::vector<std::vector<std::string>> m_strs;
   std::vector<std::vector<int64_t>> m_ints;
 };
@@ -1440,13 +1459,26 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
         }
     }
   }
+  // parameters go up from pinned scratch (truly asynchronous); the same scratch later receives the
+  // accumulators when they are small
+  const size_t acc_back = q->acc_words * 8 <= ((size_t)4 << 20) ? q->acc_words * 8 : 64;
+  const size_t off_items = (sizeof(Plan) + 255) & ~(size_t)255, off_masks = off_items + ((items.size() * 4 + 255) & ~(size_t)255);
+  const size_t off_acc = off_masks + ((masks.size() * 4 + 255) & ~(size_t)255);
+  char* hp = c->scratch(off_acc + acc_back);
+  if (!hp) {
+    c->set_err("cudaHostAlloc (query scratch) failed");
+    return SG_ERR_CUDA;
+  }
+  memcpy(hp, &q->plan, sizeof(Plan));
   if (!items.empty()) {
-    CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, items.data(), items.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(q->d_item_mask, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    memcpy(hp + off_items, items.data(), items.size() * 4);
+    memcpy(hp + off_masks, masks.data(), masks.size() * 4);
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, hp + off_items, items.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_item_mask, hp + off_masks, masks.size() * 4, cudaMemcpyHostToDevice, c->stream));
   }
   CUDA_TRY(c, cudaMemsetAsync(q->d_work, 0, 64, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(q->d_block_status, 0, std::max<size_t>(t->blocks.size(), 1) * 4, c->stream));
-  CUDA_TRY(c, cudaMemcpyAsync(q->d_plan, &q->plan, sizeof(Plan), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(q->d_plan, hp, sizeof(Plan), cudaMemcpyHostToDevice, c->stream));
   LaunchParams lp;
   memset(&lp, 0, sizeof(lp));
   lp.plan = q->d_plan;
@@ -1481,7 +1513,11 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
     return SG_ERR_CUDA;
   }
   CUDA_TRY(c, cudaEventRecord(q->ev1, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(hp + off_acc, q->d_acc, acc_back, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  q->h_acc.assign((const uint64_t*)(hp + off_acc), (const uint64_t*)(hp + off_acc + acc_back));
+  q->h_acc_valid = acc_back == q->acc_words * 8;
+  q->d2h_bytes += (int64_t)acc_back;
   float ms = 0;
   CUDA_TRY(c, cudaEventElapsedTime(&ms, q->ev0, q->ev1));
   q->kernel_ms += ms;
@@ -1564,9 +1600,15 @@ void sort_groups(std::vector<ResultGroup>& v) {
 int build_result(sg_query* q, sg_result** out) {
   sg_ctx* c = q->ctx;
   const Plan& P = q->plan;
-  std::vector<uint64_t> h(q->acc_words);
-  CUDA_TRY(c, cudaMemcpy(h.data(), q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost));
-  q->d2h_bytes += (int64_t)q->acc_words * 8;
+  std::vector<uint64_t> h;
+  if (q->h_acc_valid && q->h_acc.size() == q->acc_words) {
+    h.swap(q->h_acc);
+    q->h_acc_valid = false;
+  } else {
+    h.resize(q->acc_words);
+    CUDA_TRY(c, cudaMemcpy(h.data(), q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost));
+    q->d2h_bytes += (int64_t)q->acc_words * 8;
+  }
   std::unique_ptr<sg_result> r(new sg_result());
   r->q = q;
   r->layouts = q->layouts;
@@ -1818,8 +1860,7 @@ int sg_query_run(sg_query* q) {
     if (rc != SG_OK) return rc;
     rc = run_list(q, list);
     if (rc != SG_OK) return rc;
-    uint64_t scal[8];
-    CUDA_TRY(c, cudaMemcpy(scal, q->d_acc, sizeof(scal), cudaMemcpyDeviceToHost));
+    const uint64_t* scal = q->h_acc.data();  // read back behind the kernel by run_list
     if (scal[2] != 0) {
       c->set_err("query: rows fall outside the planned time axis (time_min/time_max too narrow)");
       return SG_ERR_INVALID;
@@ -2099,6 +2140,7 @@ int sg_query_allreduce(sg_query* q) {
   sg_ctx* c = q->ctx;
   if (!c->comm || c->nranks <= 1) return SG_OK;
   cudaSetDevice(c->device);
+  q->h_acc_valid = false;  // the device copy is about to change
   // do the ranks agree on the slot space?  (max of sig and of ~sig: equal iff all equal)
   std::vector<uint8_t> mine;
   serialise_axes(q, mine);
