@@ -1143,9 +1143,12 @@ int upload_table(sg_table* t) {
 // accumulator layout for `nslots` dense slots: one SUM region (scalars | count | per agg hcount,
 // sum | per agg buckets) followed by one MAX region (per agg vmax): the cross-GPU merge is two
 // all-reduces
+// scalars: [0] matched rows, [1] broken blocks, [2] time overflow rows (kernel); [8..15] the cross-GPU
+// merge header (block counters + axes signature) written by sg_query_allreduce
+constexpr size_t SCALAR_WORDS = 16;
 int layout_accumulators(sg_query* q, uint32_t nslots) {
   const int naggs = (int)q->layouts.size();
-  size_t words = 8;  // scalars
+  size_t words = SCALAR_WORDS;  // scalars
   q->off_count = words;
   words += nslots;
   q->off_hcount.clear();
@@ -2098,7 +2101,7 @@ static int remap_to_union(sg_query* q) {
     if (rc != SG_OK) return rc;
     std::vector<uint64_t> h_new(q->acc_words, 0);
     for (size_t w = q->sum_words; w < q->acc_words; w++) h_new[w] = (uint64_t)INT64_MIN;
-    for (int w = 0; w < 8; w++) h_new[(size_t)w] = h_old[(size_t)w];
+    for (size_t w = 0; w < SCALAR_WORDS; w++) h_new[w] = h_old[w];
     const int naggs = P.naggs;
     for (uint32_t s = 0; s < old_slots; s++) {
       if (h_old[o_count + s] == 0) continue;
@@ -2141,14 +2144,102 @@ int sg_query_allreduce(sg_query* q) {
   if (!c->comm || c->nranks <= 1) return SG_OK;
   cudaSetDevice(c->device);
   q->h_acc_valid = false;  // the device copy is about to change
-  // do the ranks agree on the slot space?  (max of sig and of ~sig: equal iff all equal)
+  // Small plans (the usual case: a few hundred groups): ONE collective.  Every rank writes a header
+  // (block counters, signature of its axes) into its scalars and all-gathers its whole accumulator
+  // array; each rank then reduces the gathered copies on the host (sum region, max region) — or, if
+  // the signatures differ, falls through to the dictionary exchange below with its own copy intact.
+  if (q->acc_words * 8 * (size_t)c->nranks <= ((size_t)2 << 20)) {
+    std::vector<uint8_t> axes;
+    serialise_axes(q, axes);
+    const uint64_t sig = fnv64(0xcbf29ce484222325ull, axes.data(), axes.size());
+    const size_t aw = q->acc_words, nr = (size_t)c->nranks;
+    char* hp = c->scratch(64 + aw * 8 * nr);
+    uint64_t* d_all = nullptr;
+    if (!hp) {
+      c->set_err("cudaHostAlloc (merge scratch) failed");
+      return SG_ERR_CUDA;
+    }
+    CUDA_TRY(c, pool_alloc(c, (void**)&d_all, aw * 8 * nr));
+    uint64_t* hdr = (uint64_t*)hp;
+    hdr[0] = (uint64_t)q->broken_staged;
+    hdr[1] = (uint64_t)q->skipped;
+    hdr[2] = (uint64_t)q->rows_scanned;
+    hdr[3] = (uint64_t)q->blocks_scanned;
+    hdr[4] = sig;
+    hdr[5] = (uint64_t)axes.size();
+    hdr[6] = hdr[7] = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_acc + 8, hdr, 64, cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = g_nccl.AllGather(q->d_acc, d_all, aw * 8, ncclUint8, c->comm, c->stream);
+    if (r != 0) return nccl_fail(c, "ncclAllGather", r);
+    uint64_t* all = (uint64_t*)(hp + 64);
+    CUDA_TRY(c, cudaMemcpyAsync(all, d_all, aw * 8 * nr, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    pool_release(c, d_all);
+    q->d2h_bytes += (int64_t)(aw * 8 * nr);
+    bool agree = true;
+    for (size_t k = 0; k < nr; k++) agree = agree && all[k * aw + 12] == sig && all[k * aw + 13] == (uint64_t)axes.size();
+    // the counters are job totals on either path
+    uint64_t tot[4] = {0, 0, 0, 0};
+    for (size_t k = 0; k < nr; k++)
+      for (int j = 0; j < 4; j++) tot[j] += all[k * aw + 8 + (size_t)j];
+    if (agree) {
+      q->h_acc.assign(aw, 0);
+      uint64_t* h = q->h_acc.data();
+      for (size_t w = 0; w < q->sum_words; w++) {
+        uint64_t v = 0;
+        for (size_t k = 0; k < nr; k++) v += all[k * aw + w];
+        h[w] = v;
+      }
+      for (size_t w = q->sum_words; w < aw; w++) {
+        int64_t v = INT64_MIN;
+        for (size_t k = 0; k < nr; k++) v = std::max(v, (int64_t)all[k * aw + w]);
+        h[w] = (uint64_t)v;
+      }
+      q->h_acc_valid = true;  // build_result reads the merged host copy (the device copy stays per-rank)
+      q->broken_staged = (int64_t)tot[0];
+      q->skipped = (int64_t)tot[1];
+      q->rows_scanned = (int64_t)tot[2];
+      q->blocks_scanned = (int64_t)tot[3];
+      return SG_OK;
+    }
+    // differing axes: every rank sees that in the same gathered data and takes the exchange path
+    CUDA_TRY(c, cudaMemsetAsync(q->d_acc + 8, 0, 64, c->stream));
+  }
+  // One small all-reduce (sum) carries the job-wide block counters AND answers "do the ranks agree on
+  // the slot space?": with two independent 30-bit signatures s of the serialised axes, every rank
+  // checks  sum(s) == n*s_mine  and  sum(s^2) == n*s_mine^2  (exact in 64 bits for n <= 8); if the
+  // signatures differ, the variance is positive and the second test fails on EVERY rank, so all
+  // ranks take the same branch.
   std::vector<uint8_t> mine;
   serialise_axes(q, mine);
   const uint64_t sig = fnv64(0xcbf29ce484222325ull, mine.data(), mine.size());
-  uint64_t pr[2] = {sig, ~sig};
-  int rc = comm_allreduce_host(c, pr, 2, ncclUint64, ncclMax);
-  if (rc != SG_OK) return rc;
-  if (pr[0] != ~pr[1]) {
+  const uint64_t sa = sig & 0x3fffffffull, sb = (sig >> 32) & 0x3fffffffull;
+  uint64_t hc[8] = {(uint64_t)q->broken_staged, (uint64_t)q->skipped, (uint64_t)q->rows_scanned, (uint64_t)q->blocks_scanned,
+                    sa, sa * sa, sb, sb * sb};
+  int rc = SG_OK;
+  if (c->nranks <= 8) {
+    rc = comm_allreduce_host(c, hc, 8, ncclUint64, ncclSum);
+    if (rc != SG_OK) return rc;
+  } else {
+    // more ranks than the exact-moment test covers: max of sig and of ~sig (equal iff all equal)
+    uint64_t pr[2] = {sig, ~sig};
+    rc = comm_allreduce_host(c, pr, 2, ncclUint64, ncclMax);
+    if (rc != SG_OK) return rc;
+    rc = comm_allreduce_host(c, hc, 4, ncclUint64, ncclSum);
+    if (rc != SG_OK) return rc;
+    const bool same = pr[0] == ~pr[1];
+    hc[4] = same ? sa * (uint64_t)c->nranks : ~0ull;
+    hc[5] = sa * sa * (uint64_t)c->nranks;
+    hc[6] = sb * (uint64_t)c->nranks;
+    hc[7] = sb * sb * (uint64_t)c->nranks;
+  }
+  const uint64_t n = (uint64_t)c->nranks;
+  const bool agree = hc[4] == n * sa && hc[5] == n * sa * sa && hc[6] == n * sb && hc[7] == n * sb * sb;
+  q->broken_staged = (int64_t)hc[0];
+  q->skipped = (int64_t)hc[1];
+  q->rows_scanned = (int64_t)hc[2];
+  q->blocks_scanned = (int64_t)hc[3];
+  if (!agree) {
     rc = remap_to_union(q);
     if (rc != SG_OK) return rc;
   }
@@ -2161,14 +2252,20 @@ int sg_query_allreduce(sg_query* q) {
   if (rc == SG_OK && q->acc_words > q->sum_words)
     rc = ar(q->d_acc + q->sum_words, q->acc_words - q->sum_words, ncclInt64, ncclMax);
   if (rc != SG_OK) return rc;
-  // host-side block counters (blocks pruned by the zone maps / broken at staging) are job totals too
-  uint64_t hc[4] = {(uint64_t)q->broken_staged, (uint64_t)q->skipped, (uint64_t)q->rows_scanned, (uint64_t)q->blocks_scanned};
-  rc = comm_allreduce_host(c, hc, 4, ncclUint64, ncclSum);
-  if (rc != SG_OK) return rc;
-  q->broken_staged = (int64_t)hc[0];
-  q->skipped = (int64_t)hc[1];
-  q->rows_scanned = (int64_t)hc[2];
-  q->blocks_scanned = (int64_t)hc[3];
+  // read the merged accumulators back behind the all-reduces (small plans): build_result then needs
+  // no further copy
+  if (q->acc_words * 8 <= ((size_t)4 << 20)) {
+    char* hp = c->scratch(q->acc_words * 8);
+    if (hp) {
+      CUDA_TRY(c, cudaMemcpyAsync(hp, q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      q->h_acc.assign((const uint64_t*)hp, (const uint64_t*)hp + q->acc_words);
+      q->h_acc_valid = true;
+      q->d2h_bytes += (int64_t)q->acc_words * 8;
+      return SG_OK;
+    }
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return SG_OK;
 }
 
