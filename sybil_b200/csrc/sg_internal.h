@@ -63,6 +63,12 @@ struct KGroup {
   int32_t is_str;
   uint32_t stride;  // slot += (code + 1) * stride ; code 0 is "missing"
   uint32_t radix;
+  // value-array encoded int group column: value -> dense code through an open-addressing table
+  // (ids == 0xffffffff: empty) over the column's table-wide value dictionary
+  const long long* vh_keys;
+  const uint32_t* vh_ids;
+  uint32_t vh_mask;  // capacity - 1
+  uint32_t _pad;
 };
 
 struct KSubHist {  // one BasicHist bucket layout (hist_basic.go:34-70)
@@ -137,13 +143,28 @@ struct LaunchParams {
   const void* tmaps;          // CUtensorMap[chunks] in global memory (nullptr: plain vector loads)
   uint32_t nstage;            // TMA staging depth per warp (1 or 2)
   unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
+  uint32_t hashg;             // a group column is a value-array int column (hash lookup path; slot_bytes == 4)
 };
+
+// the hash both sides of the value -> code table use
+__host__ __device__ static inline uint32_t vh_hash(long long v) {
+  unsigned long long x = (unsigned long long)v;
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33;
+  return (uint32_t)x;
+}
 
 // host-callable launchers (sg_kernels.cu)
 int launch_scan(const LaunchParams& lp, int grid, void* stream);
 // extents of value-array int columns: items[i] = index into cols[] (block * ncolslots + slot)
 int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
                  void* stream);
+// distinct values of value-array int columns: keys[cap] (pre-filled with INT64_MIN = empty) receives every
+// distinct decoded value of the listed (block, column) items; counters[0] += new keys, counters[1] = 1 if
+// INT64_MIN itself occurred, counters[2] = 1 if the set filled up (more than cap/2 keys)
+int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
+                    long long* keys, uint32_t cap_mask, unsigned int* counters, void* stream);
 int scan_threads();
 // shared memory the kernel needs besides slots and accumulators (nstage: TMA staging depth, 0 = none)
 uint32_t scan_fixed_smem(uint32_t nstage);

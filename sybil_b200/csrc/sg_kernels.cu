@@ -963,7 +963,7 @@ __device__ __noinline__ void agg_slow(const AggSlow* A, uint32_t g, long long v,
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
-template <typename SlotT, bool ACC_SMEM>
+template <typename SlotT, bool ACC_SMEM, bool HASHG = false>
 __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Plan* __restrict__ PP = lp.plan;
@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       if (kind == 0) {
         on = on && (bucket || (c.enc == SG_ENC_VALUES && !(pc >> 24)));
       } else if (kind == 1) {
-        on = on && bucket;
+        on = on && (bucket || (HASHG && c.enc == SG_ENC_VALUES && !(c.flags & COL_IS_STR)));
       } else {
         on = on && !(c.flags & COL_IS_STR) && (bucket || c.enc == SG_ENC_VALUES);
         if (kind == 3) on = on && ((aggmask >> ((pc >> 8) & 0xffu)) & 1u);
@@ -1247,7 +1247,36 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           slot[row] = (SlotT)(slot[row] + ((uint32_t)str_gid(c, local) + 1u) * stride);
         });
       }
-      // VALUES int group columns are routed away from this kernel by the planner
+      else if (HASHG && c.enc == SG_ENC_VALUES && !G.is_str) {
+        // value-array int group column: decoded value -> dense code through the table-wide value
+        // dictionary's open-addressing table (L2-resident); a value the table does not hold can
+        // only come from a block staged after the table was built: the block is dropped
+        const uint32_t stride = G.stride, vmask = G.vh_mask;
+        const long long* __restrict__ vk = G.vh_keys;
+        const uint32_t* __restrict__ vi = G.vh_ids;
+        scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+          uint32_t inc[VE];
+#pragma unroll
+          for (int k = 0; k < VE; k++) {
+            inc[k] = 0u;
+            if (k < nvalid) {
+              const long long v = (long long)a[k];
+              uint32_t h = vh_hash(v) & vmask, id;
+              for (;;) {
+                id = vi[h];
+                if (id == 0xffffffffu || vk[h] == v) break;
+                h = (h + 1u) & vmask;
+              }
+              if (id == 0xffffffffu) {
+                cx.misc[1] = 1;
+                id = 0u;
+              }
+              inc[k] = (id + 1u) * stride;
+            }
+          }
+          add_slots(slot, idx0, inc);
+        });
+      }
     }
 
     phase(2);
@@ -1868,6 +1897,90 @@ __global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const D
   }
 }
 
+// ---------------------------------------------------------------------------
+// distinct values of value-array int columns (group-by on such a column needs a table-wide
+// value dictionary; built on demand, once per staged block)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1) distinct_kernel(const DevCol* cols, const DevBlock* blocks,
+                                                              const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
+                                                              long long* keys, uint32_t cap_mask, unsigned int* counters) {
+  __shared__ __align__(16) unsigned char smem_s[FIXED_SMEM];
+  Ctx cx;
+  cx.tid = threadIdx.x;
+  cx.lane = threadIdx.x & 31;
+  cx.warp = threadIdx.x >> 5;
+  cx.epoch = 0;
+  cx.headbits = reinterpret_cast<uint32_t*>(smem_s + OFF_HEADBITS);
+  cx.headprefix = reinterpret_cast<uint16_t*>(smem_s + OFF_HEADPREFIX);
+  cx.binpay_s = reinterpret_cast<uint32_t*>(smem_s + OFF_BINPAY);
+  cx.pubA = reinterpret_cast<volatile unsigned long long*>(smem_s + OFF_PUBA);
+  cx.pubB = reinterpret_cast<volatile unsigned long long*>(smem_s + OFF_PUBB);
+  cx.misc = reinterpret_cast<volatile uint32_t*>(smem_s + OFF_MISC);
+  cx.acc = nullptr;
+  cx.tmaps = nullptr;
+  cx.nstage = 0;
+  cx.zero = 0;
+  cx.buf0 = cx.buf1 = cx.mbar0 = cx.mbar1 = cx.par0 = cx.par1 = 0;
+  cx.plist = nullptr;
+  cx.timing = false;
+  cx.t_tma = cx.t_lb = 0;
+  cx.npass = cx.pass_idx = 0;
+  cx.pref_idx = 0xffffffffu;
+  for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
+    cx.pubA[i] = 0;
+    cx.pubB[i] = 0;
+  }
+  __syncthreads();
+  const long long EMPTY = -0x7fffffffffffffffll - 1;
+  const unsigned int limit = (cap_mask + 1u) / 2u;
+  for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const uint32_t ci = items[it];
+    const DevCol c = cols[ci];
+    const uint32_t nrec = blocks[ci / ncolslots].num_records;
+    scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+      long long prev = EMPTY;
+#pragma unroll
+      for (int k = 0; k < VE; k++)
+        if (k < nvalid) {
+          const long long v = (long long)a[k];
+          if (v == prev) continue;  // runs of equal values are common in sorted / low-entropy columns
+          prev = v;
+          if (v == EMPTY) {
+            counters[1] = 1u;
+            continue;
+          }
+          if (counters[2]) continue;  // the set is full: the host reports the overflow
+          uint32_t h = vh_hash(v) & cap_mask;
+          for (;;) {
+            const long long cur = keys[h];
+            if (cur == v) break;
+            if (cur == EMPTY) {
+              const long long old = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(keys + h),
+                                                         (unsigned long long)EMPTY, (unsigned long long)v);
+              if (old == EMPTY) {
+                if (atomicAdd(&counters[0], 1u) + 1u > limit) counters[2] = 1u;
+                break;
+              }
+              if (old == v) break;
+            }
+            h = (h + 1u) & cap_mask;
+          }
+        }
+    });
+  }
+}
+
+int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
+                    long long* keys, uint32_t cap_mask, unsigned int* counters, void* stream) {
+  if (nitems == 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t grid = nitems < (uint32_t)sms * 2 ? nitems : (uint32_t)sms * 2;
+  distinct_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(cols, blocks, items, nitems, ncolslots, keys, cap_mask, counters);
+  return (int)cudaGetLastError();
+}
+
 int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
                  void* stream) {
   if (nitems == 0) return 0;
@@ -1879,9 +1992,9 @@ int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, ui
   return (int)cudaGetLastError();
 }
 
-template <typename SlotT, bool ACC_SMEM>
+template <typename SlotT, bool ACC_SMEM, bool HASHG = false>
 static int launch_one(const LaunchParams& lp, int grid, cudaStream_t st) {
-  auto k = scan_kernel<SlotT, ACC_SMEM>;
+  auto k = scan_kernel<SlotT, ACC_SMEM, HASHG>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem_bytes);
   if (e != cudaSuccess) return (int)e;
   k<<<grid, THREADS, lp.smem_bytes, st>>>(lp);
@@ -1892,6 +2005,11 @@ int launch_scan(const LaunchParams& lp, int grid, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool acc_smem = lp.acc_smem != 0;
   const uint32_t sb = lp.slot_bytes;
+  if (lp.hashg) {
+    // the planner gives plans with a hashed group column 32-bit slot words and global accumulators
+    if (sb != 4 || acc_smem) return (int)cudaErrorInvalidValue;
+    return launch_one<uint32_t, false, true>(lp, grid, st);
+  }
   if (sb == 1) return acc_smem ? launch_one<uint8_t, true>(lp, grid, st) : launch_one<uint8_t, false>(lp, grid, st);
   if (sb == 2) return acc_smem ? launch_one<uint16_t, true>(lp, grid, st) : launch_one<uint16_t, false>(lp, grid, st);
   return acc_smem ? launch_one<uint32_t, true>(lp, grid, st) : launch_one<uint32_t, false>(lp, grid, st);

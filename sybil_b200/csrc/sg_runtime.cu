@@ -283,6 +283,16 @@ struct sg_table {
   std::vector<StrDict> sdict;
   std::vector<IntDict> idict;
   std::vector<char> has_values_int;  // an int column that is value-array encoded somewhere
+  // group-by on such a column: its value-array blocks' distinct values join the column's IntDict
+  // (on demand, kernel-side distinct set) and a device open-addressing table maps value -> code
+  struct ValueHash {
+    size_t blocks_done = 0;      // blocks [0, blocks_done) have contributed their values
+    size_t dict_size = 0;        // IntDict size the device table was built from
+    long long* d_keys = nullptr;
+    uint32_t* d_ids = nullptr;
+    uint32_t mask = 0;
+  };
+  std::vector<ValueHash> vhash;
   std::vector<uint32_t> pending_stats;  // value-array int columns whose extents are not computed yet
   std::vector<std::pair<char*, size_t>> chunks;  // device arena chunks (ptr, capacity)
   size_t chunk_idx = 0, chunk_used = 0;
@@ -497,6 +507,7 @@ sg_table* sg_table_create(sg_ctx* c, int32_t num_col_slots, const int32_t* col_t
   t->sdict.resize((size_t)num_col_slots);
   t->idict.resize((size_t)num_col_slots);
   t->has_values_int.assign((size_t)num_col_slots, 0);
+  t->vhash.assign((size_t)num_col_slots, sg_table::ValueHash());
   cudaSetDevice(c->device);
   for (int i = 0; i < 2; i++) {
     if (cudaHostAlloc((void**)&t->stage[i].host, STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess ||
@@ -520,6 +531,10 @@ void sg_table_free(sg_table* t) {
   }
   if (t->d_blocks) cudaFree(t->d_blocks);
   if (t->d_cols) cudaFree(t->d_cols);
+  for (auto& vh : t->vhash) {
+    if (vh.d_keys) cudaFree(vh.d_keys);
+    if (vh.d_ids) cudaFree(vh.d_ids);
+  }
   if (t->d_tmaps) cudaFree(t->d_tmaps);
   delete t;
 }
@@ -865,6 +880,7 @@ int sg_table_clear(sg_table* t) {
   t->blocks.clear();
   t->cols.clear();
   t->pending_stats.clear();
+  for (auto& vh : t->vhash) vh.blocks_done = 0;
   t->chunk_idx = 0;
   t->chunk_used = 0;
   t->stage[0].pending = t->stage[1].pending = false;
@@ -1023,6 +1039,7 @@ struct sg_query {
   // cross-GPU merge under differing per-rank dictionaries: the union dictionaries the merged
   // accumulators are laid out by (per entry of dims; empty for the time axis)
   bool merged = false;
+  bool hashg = false;  // a group column goes through the value -> code hash table
   // accumulators as read back right behind the kernel (small plans): spares build_result a blocking copy
   std::vector<uint64_t> h_acc;
   bool h_acc_valid = false;
@@ -1143,6 +1160,96 @@ int upload_table(sg_table* t) {
 // accumulator layout for `nslots` dense slots: one SUM region (scalars | count | per agg hcount,
 // sum | per agg buckets) followed by one MAX region (per agg vmax): the cross-GPU merge is two
 // all-reduces
+__global__ void fill_ll(long long* p, size_t n, long long v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// Group-by on an int column that is value-array encoded in some blocks (more than
+// CARDINALITY_THRESHOLD distinct values there, column_store_io.go:82-113): the dense slot space needs
+// a table-wide value dictionary.  The blocks' distinct values are collected on the GPU (one pass over
+// each such block's array, once), joined into the column's IntDict (ascending, so the numbering does
+// not depend on the hash order), and a device open-addressing table value -> code is (re)built.
+int ensure_value_dict(sg_table* t, int col) {
+  sg_ctx* c = t->ctx;
+  auto& vh = t->vhash[(size_t)col];
+  IntDict& D = t->idict[(size_t)col];
+  const size_t nb = t->blocks.size();
+  std::vector<uint32_t> items;
+  for (size_t b = vh.blocks_done; b < nb; b++) {
+    const DevCol& dc = t->cols[b * (size_t)t->ncols + (size_t)col];
+    if (dc.enc == SG_ENC_VALUES && !(dc.flags & (COL_IS_STR | COL_BROKEN))) items.push_back((uint32_t)(b * (size_t)t->ncols + (size_t)col));
+  }
+  if (!items.empty()) {
+    const uint32_t cap = (uint32_t)(INT_DICT_CAP * 2);  // load factor <= 1/2 at the dictionary's size limit
+    long long* d_keys = nullptr;
+    uint32_t* d_items = nullptr;
+    unsigned int* d_cnt = nullptr;
+    CUDA_TRY(c, pool_alloc(c, (void**)&d_keys, (size_t)cap * 8));
+    CUDA_TRY(c, pool_alloc(c, (void**)&d_items, items.size() * 4));
+    CUDA_TRY(c, pool_alloc(c, (void**)&d_cnt, 16));
+    fill_ll<<<(unsigned)(((size_t)cap + 255) / 256), 256, 0, c->stream>>>(d_keys, cap, INT64_MIN);
+    CUDA_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(d_items, items.data(), items.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_distinct(t->d_cols, t->d_blocks, d_items, (uint32_t)items.size(), (uint32_t)t->ncols, d_keys, cap - 1u, d_cnt,
+                             c->stream);
+    if (rc != 0) {
+      c->set_err(std::string("distinct kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+      return SG_ERR_CUDA;
+    }
+    unsigned int cnt[4] = {0, 0, 0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    std::vector<int64_t> found;
+    if (!cnt[2]) {
+      std::vector<long long> keys(cap);
+      CUDA_TRY(c, cudaMemcpy(keys.data(), d_keys, (size_t)cap * 8, cudaMemcpyDeviceToHost));
+      found.reserve(cnt[0] + 1);
+      for (uint32_t i = 0; i < cap; i++)
+        if (keys[i] != INT64_MIN) found.push_back(keys[i]);
+      if (cnt[1]) found.push_back(INT64_MIN);
+    }
+    pool_release(c, d_keys);
+    pool_release(c, d_items);
+    pool_release(c, d_cnt);
+    if (cnt[2]) {
+      D.overflow = true;
+    } else {
+      std::sort(found.begin(), found.end());
+      for (int64_t v : found) D.intern(v);
+    }
+    vh.blocks_done = nb;
+  }
+  if (D.overflow) {
+    c->set_err("query: group-by int column has more distinct values than the dense slot space holds");
+    return SG_ERR_UNSUPPORTED;
+  }
+  if (vh.dict_size != D.vals.size() || !vh.d_keys) {
+    uint32_t cap = 1024;
+    while ((size_t)cap < D.vals.size() * 2 + 2) cap <<= 1;
+    std::vector<long long> keys(cap, 0);
+    std::vector<uint32_t> ids(cap, 0xffffffffu);
+    for (size_t i = 0; i < D.vals.size(); i++) {
+      uint32_t h = vh_hash((long long)D.vals[i]) & (cap - 1u);
+      while (ids[h] != 0xffffffffu) h = (h + 1u) & (cap - 1u);
+      keys[h] = (long long)D.vals[i];
+      ids[h] = (uint32_t)i;
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // no query is using the old table
+    if (vh.d_keys) cudaFree(vh.d_keys);
+    if (vh.d_ids) cudaFree(vh.d_ids);
+    vh.d_keys = nullptr;
+    vh.d_ids = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&vh.d_keys, (size_t)cap * 8));
+    CUDA_TRY(c, cudaMalloc((void**)&vh.d_ids, (size_t)cap * 4));
+    CUDA_TRY(c, cudaMemcpy(vh.d_keys, keys.data(), (size_t)cap * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(vh.d_ids, ids.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
+    vh.mask = cap - 1u;
+    vh.dict_size = D.vals.size();
+  }
+  return SG_OK;
+}
+
 // scalars: [0] matched rows, [1] broken blocks, [2] time overflow rows (kernel); [8..15] the cross-GPU
 // merge header (block counters + axes signature) written by sg_query_allreduce
 constexpr size_t SCALAR_WORDS = 16;
@@ -1183,6 +1290,7 @@ int make_plan(sg_query* q) {
   sg_table* t = q->table;
   Plan& P = q->plan;
   memset(&P, 0, sizeof(P));
+  q->hashg = false;
   P.nfilters = (int32_t)q->filters.size();
   P.ngroups = (int32_t)q->groups.size();
   P.naggs = (int32_t)q->aggs.size();
@@ -1203,8 +1311,16 @@ int make_plan(sg_query* q) {
       return SG_ERR_INVALID;
     }
     gd.is_str = t->types[(size_t)gd.col] == SG_COL_STR;
-    if (!gd.is_str && (t->has_values_int[(size_t)gd.col] || t->idict[(size_t)gd.col].overflow)) {
-      c->set_err("query: group-by on a value-array encoded int column needs the hash path (not in this build)");
+    if (!gd.is_str && t->has_values_int[(size_t)gd.col]) {
+      int rc = ensure_value_dict(t, gd.col);
+      if (rc != SG_OK) return rc;
+      const auto& vh = t->vhash[(size_t)gd.col];
+      P.groups[i].vh_keys = vh.d_keys;
+      P.groups[i].vh_ids = vh.d_ids;
+      P.groups[i].vh_mask = vh.mask;
+      q->hashg = true;
+    } else if (!gd.is_str && t->idict[(size_t)gd.col].overflow) {
+      c->set_err("query: group-by int column has more distinct values than the dense slot space holds");
       return SG_ERR_UNSUPPORTED;
     }
     uint64_t card = gd.is_str ? t->sdict[(size_t)gd.col].strs.size() : t->idict[(size_t)gd.col].vals.size();
@@ -1265,6 +1381,7 @@ int make_plan(sg_query* q) {
     return SG_ERR_UNSUPPORTED;
   }
   q->slot_bytes = total_bits <= 8 ? 1u : (total_bits <= 16 ? 2u : 4u);
+  if (q->hashg) q->slot_bytes = 4;  // the hashed group pass exists for 32-bit slot words + global accumulators only
   P.finc = 1u << P.gbits;
   P.filt_mask = (1u << fbits) - 1u;
   P.filt_target = (uint32_t)P.nfilters;
@@ -1364,7 +1481,7 @@ int make_plan(sg_query* q) {
   }
   if (scan_fixed_smem(nstage) + slots_b > MAX_DYN_SMEM) nstage = 0;
   q->nstage = nstage;
-  const uint32_t repl = repl_for(nstage);
+  const uint32_t repl = q->hashg ? 0u : repl_for(nstage);
   P.acc_repl = repl;  // 0: accumulate straight into global memory
   q->smem_bytes = scan_fixed_smem(nstage) + slots_b +
                   (repl ? (P.nslots + 1) * P.acc_words * repl * 4 + P.nslots * (1 + 2 * (uint32_t)P.naggs) * 8 + 8 +
@@ -1499,6 +1616,7 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
   lp.nstage = t->d_tmaps ? q->nstage : 0u;
   lp.dbg = nullptr;
+  lp.hashg = q->hashg ? 1u : 0u;
   static const bool phase_timing = getenv("SG_PHASE_TIMING") != nullptr;
   unsigned long long* d_dbg = nullptr;
   if (phase_timing) {

@@ -335,3 +335,36 @@ def test_tail_blocks_split_per_aggregation(monkeypatch):
     both(s, Q(s, groups=["host"], aggs=["lat", "big"], op="hist", time_col="time", time_bucket=600))
     s.blocks[1].num_records = 700  # a broken block must still vanish whole
     both(s, Q(s, groups=["host"], aggs=["age", "lat"], op="hist"))
+
+
+def test_group_by_value_array_int_column():
+    """Group-by on an int column that is value-array encoded (more distinct values per block than the
+    cardinality threshold, column_store_io.go:82-113): the engine collects the blocks' distinct values on
+    the GPU, joins them into the table-wide value dictionary and maps value -> dense code through a hash
+    table.  Bit-exact against the oracle: keys, counts, sums, histogram buckets."""
+    rng = np.random.default_rng(77)
+    n = 6000
+    s = Spec([("k", INT), ("v", INT), ("host", STR), ("lat", INT), ("time", INT)])
+    keys = rng.integers(-(1 << 45), 1 << 45, 300)  # 300 distinct values, negative and above 2^32
+    keys[0] = -(1 << 63)                           # the hash set's "empty" marker is a legal value
+    s.add_rows({"k": keys[rng.integers(0, 300, n)], "v": rng.integers(0, 1000, n),
+                "host": np.array(["h%d" % x for x in rng.integers(0, 4, n)]),
+                "lat": rng.integers(0, 5000, n), "time": 1500000000 + np.sort(rng.integers(0, 7200, n))},
+               {"k": rng.random(n) > 0.05, "v": rng.random(n) > 0.05}, threshold=50, block_rows=1700)
+    both(s, Q(s, groups=["k"], aggs=["v"], op="avg"))
+    both(s, Q(s, int_filters=[("v", "gt", 100)], str_filters=[("host", "neq", "h2")], groups=["host", "k"], aggs=["lat"], op="hist"))
+    both(s, Q(s, groups=["k"], aggs=["v"], op="avg", time_col="time", time_bucket=1800))
+    both(s, Q(s, groups=["k"]))  # count only
+
+
+def test_group_by_int_column_with_mixed_encodings():
+    """The same int column bucket-encoded in one block (few distinct values there) and value-array
+    encoded in another: bin values and array values share one dictionary."""
+    rng = np.random.default_rng(78)
+    s = Spec([("k", INT), ("v", INT)])
+    s.add_rows({"k": rng.integers(0, 20, 1500), "v": rng.integers(0, 100, 1500)}, threshold=50, block_rows=1500)
+    s.add_rows({"k": rng.integers(0, 400, 1500), "v": rng.integers(0, 100, 1500)}, threshold=50, block_rows=1500)
+    s.add_rows({"k": rng.integers(10, 30, 1500), "v": rng.integers(0, 100, 1500)}, threshold=50, block_rows=1500)
+    g, o = both(s, Q(s, groups=["k"], aggs=["v"], op="avg"))
+    assert len(g.Results) == len(o.Results) and len(g.Results) > 300
+    both(s, Q(s, int_filters=[("k", "lt", 200)], groups=["k"], aggs=["v"], op="hist"))
