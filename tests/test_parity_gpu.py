@@ -368,3 +368,70 @@ def test_group_by_int_column_with_mixed_encodings():
     g, o = both(s, Q(s, groups=["k"], aggs=["v"], op="avg"))
     assert len(g.Results) == len(o.Results) and len(g.Results) > 300
     both(s, Q(s, int_filters=[("k", "lt", 200)], groups=["k"], aggs=["v"], op="hist"))
+
+
+def _splitmix64_np(x):
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def test_full_size_c2_checksums_and_block_additivity():
+    """BASELINE.json's metric configuration at FULL size (100M rows; the oracle would need minutes), through
+    size-independent properties:
+      * per-group Count and exact Sum of every aggregated column equal an independent numpy evaluation of the
+        counter-based generator (no encoder, no decoder, no block structure: a checksum of the whole decode +
+        filter-free group-by + aggregation path, bit-exact);
+      * block additivity (CombineResults): the result over all blocks equals the merge of the results over
+        the first and the second half of the blocks, staged as two separate tables."""
+    from sybil_b200 import engine as E
+    from sybil_b200 import synth
+    spec = synth.config("c2")
+    rows = spec.total_rows
+    assert rows == 100_000_000
+    store = synth.generate(spec)
+    s = Spec(spec.key_table)
+    s.IntInfo = dict(spec.IntInfo)
+    q = Q(s, **synth.query_for(spec))
+    nb = store.num_blocks()
+    tabs = [E.Table("c2_all", spec.key_table), E.Table("c2_a", spec.key_table), E.Table("c2_b", spec.key_table)]
+    try:
+        for t in tabs:
+            t.IntInfo = dict(spec.IntInfo)
+        for i in range(nb):
+            tabs[0].add_block_desc_ptr(store.block(i))
+            tabs[1 if i < nb // 2 else 2].add_block_desc_ptr(store.block(i))
+        res = [run_gpu(s, q, table=t) for t in tabs]
+        g = res[0]
+        assert g.MatchedCount == rows and sum(r.Count for r in g.Sorted) == rows and len(g.Results) == 64
+        # --- independent evaluation of the generator, 10M rows at a time
+        cnt = np.zeros(64, np.int64)
+        sums = {c.name: np.zeros(64, np.float64) for c in spec.cols[1:]}
+        gcol = spec.cols[0]
+        for lo in range(0, rows, 10_000_000):
+            r = np.arange(lo, min(lo + 10_000_000, rows), dtype=np.uint64)
+            key = (_splitmix64_np(np.uint64(spec.seed) ^ (np.uint64(gcol.col_slot) << np.uint64(40)) ^ r) % np.uint64(gcol.span)).astype(np.int64)
+            cnt += np.bincount(key, minlength=64)
+            for c in spec.cols[1:]:
+                v = (_splitmix64_np(np.uint64(spec.seed) ^ (np.uint64(c.col_slot) << np.uint64(40)) ^ r) % np.uint64(c.span)).astype(np.float64) + c.lo
+                sums[c.name] += np.bincount(key, weights=v, minlength=64)  # exact: every partial sum < 2^53
+        for k in range(64):
+            r = g.Results["k%d\t" % k]
+            assert r.Count == cnt[k]
+            for c in spec.cols[1:]:
+                assert r.Hists[c.name].Count == cnt[k]
+                assert r.Hists[c.name].Sum() == int(sums[c.name][k]), (k, c.name)
+        # --- additivity
+        a, b = res[1], res[2]
+        assert a.MatchedCount + b.MatchedCount == rows
+        for key, r in g.Results.items():
+            ra, rb = a.Results[key], b.Results[key]
+            assert r.Count == ra.Count + rb.Count
+            for c in spec.cols[1:]:
+                assert r.Hists[c.name].Sum() == ra.Hists[c.name].Sum() + rb.Hists[c.name].Sum()
+    finally:
+        for t in tabs:
+            t.close()
+        store.close()
