@@ -129,9 +129,8 @@ struct LaunchParams {
   const Plan* plan;
   const DevBlock* blocks;
   const DevCol* cols;         // [nblocks_table][ncolslots]
-  const uint32_t* block_list; // blocks to scan (work items)
-  const uint32_t* item_mask;  // per work item: bits 0..15 = aggregations this item computes, bit 31 = the
-                              // item owns the block's Count / MatchedCount (nullptr: every item does all)
+  const uint4* items;         // work items {block, mask, NumRecords, -}; mask bits 0..15 = aggregations this
+                              // item computes, bit 31 = the item owns the block's Count / MatchedCount
   uint32_t nlist;
   uint32_t slot_bytes;        // 1, 2 (shared memory) or 4 (global scratch)
   uint32_t* work_counter;

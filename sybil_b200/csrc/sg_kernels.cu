@@ -66,7 +66,8 @@ constexpr uint32_t PL_MAX = 48;                                        // TMA-fe
 constexpr uint32_t OFF_PLIST = OFF_MISC + 128 * 4;                     // u32[PL_MAX][4]
 constexpr uint32_t OFF_PCAND = OFF_PLIST + PL_MAX * 16;                // u32[PL_MAX] candidate passes of the plan
 constexpr uint32_t OFF_PTMP = OFF_PCAND + PL_MAX * 4;                  // u32[PL_MAX][4] per-block scratch
-constexpr uint32_t FIXED_SMEM = OFF_PTMP + PL_MAX * 16;
+constexpr uint32_t OFF_COLCACHE = OFF_PTMP + PL_MAX * 16;               // DevCol[PL_MAX]: the block's candidate columns
+constexpr uint32_t FIXED_SMEM = OFF_COLCACHE + PL_MAX * 80;
 uint32_t scan_fixed_smem(uint32_t nstage) { return NWARPS * TMA_TILE_BYTES * nstage + FIXED_SMEM; }
 
 struct Ctx {
@@ -1045,6 +1046,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   // 3 aggregation) | (string filter) << 24.  Built once; each block only looks its columns up.
   uint32_t* const pcand = reinterpret_cast<uint32_t*>(smem + OFF_PCAND);
   uint32_t* const ptmp = reinterpret_cast<uint32_t*>(smem + OFF_PTMP);
+  // the block's column descriptors, one per candidate pass (same order as pcand): each pass would
+  // otherwise start with two dependent global loads (plan -> column slot -> descriptor)
+  DevCol* const colcache = reinterpret_cast<DevCol*>(smem + OFF_COLCACHE);
   if (cx.tid == 0) {
     uint32_t nc = 0;
     for (int fi = 0; fi < nfilters; fi++)
@@ -1101,12 +1105,12 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     const uint32_t wi = cx.misc[0];
     if (wi >= lp.nlist) break;
     phase(6);
-    const uint32_t bid = lp.block_list[wi];
-    // tail blocks may be split into several work items, one per subset of the aggregations
-    const uint32_t imask = lp.item_mask ? lp.item_mask[wi] : 0x8000ffffu;
+    // work item = {block, aggregation mask | owner bit, NumRecords, -}: one load behind the counter.
+    // Tail blocks may be split into several items, one per subset of the aggregations
+    const uint4 item = lp.items[wi];
+    const uint32_t bid = item.x, imask = item.y, nrec = item.z;
     const uint32_t aggmask = imask & 0xffffu;
     const bool owner = (imask >> 31) != 0;
-    const uint32_t nrec = lp.blocks[bid].num_records;
     const DevCol* __restrict__ cols = lp.cols + (size_t)bid * ncolslots;
 
     // the block's TMA-fed passes in execution order (mirrors the pass sequence below): one thread
@@ -1127,6 +1131,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       }
       uint32_t n = c.nitems;
       if (!bucket && n > nrec) n = nrec;
+      colcache[cx.tid] = c;
       ptmp[4 * cx.tid + 0] = on ? 1u : 0u;
       ptmp[4 * cx.tid + 1] = c.data_chunk;
       ptmp[4 * cx.tid + 2] = c.data_row;
@@ -1166,7 +1171,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     // ---- filters (aggregate.go:105-112; unpopulated -> false, Q1) -----------------
     for (int fi = 0; fi < nfilters; fi++) {
       const KFilter F = PP->filters[fi];
-      const DevCol c = cols[F.col];
+      const DevCol c = colcache[fi];
       const SlotT fincS = (SlotT)finc;
       StrPred sp;
       sp.op = F.op;
@@ -1223,7 +1228,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     // ---- group key (aggregate.go:125-143) as a dense mixed-radix index ---------------
     for (int gi = 0; gi < ngroups; gi++) {
       const KGroup G = PP->groups[gi];
-      const DevCol c = cols[G.col];
+      const DevCol c = colcache[nfilters + gi];
       if (c.enc == SG_ENC_BUCKET) {
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
         for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) {
@@ -1282,7 +1287,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     phase(2);
     // ---- time bucket (aggregate.go:146-183) ------------------------------------------
     if (time_col >= 0) {
-      const DevCol c = cols[time_col];
+      const DevCol c = colcache[nfilters + ngroups];
       const SlotT tok = (SlotT)time_ok;
       const long long tb = PP->time_bucket, tf = PP->time_first;
       const uint32_t tr = PP->time_radix, ts = PP->time_stride;
@@ -1329,6 +1334,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     bool counted = false;
     uint32_t agg_mode_bits = 0;  // bit a: word0 of agg a counts NON-accepted rows (value arrays)
 
+    const int agg_cand0 = nfilters + ngroups + (time_col >= 0 ? 1 : 0);  // candidate index of aggregation 0
     for (int ai = -1; ai < naggs; ai++) {
       if (ai >= 0 && !((aggmask >> ai) & 1u)) continue;  // another work item of this block computes it
       if (ai < 0) {
@@ -1336,7 +1342,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         bool fuse = false;
         const int ai0 = __ffs((int)(aggmask & ((naggs >= 32 ? 0xffffffffu : (1u << naggs)) - 1u))) - 1;
         if (ai0 >= 0) {
-          const DevCol c0 = cols[PP->aggs[ai0].col];
+          const DevCol c0 = colcache[agg_cand0 + ai0];
           fuse = c0.enc == SG_ENC_VALUES && !(c0.flags & COL_IS_STR);
         }
         if (fuse) continue;
@@ -1356,7 +1362,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         continue;
       }
       const KAgg* __restrict__ KA = &PP->aggs[ai];
-      const DevCol c = cols[KA->col];
+      const DevCol c = colcache[agg_cand0 + ai];
       if (c.flags & COL_IS_STR) continue;  // Populated != INT_VAL: no update
       const uint32_t w0 = 1u + 2u * (uint32_t)ai;  // word0 of this aggregation inside a slot's replicated words
       const bool do_count = !counted;              // only reachable for ai == 0 on a value array

@@ -1508,8 +1508,7 @@ int alloc_device(sg_query* q) {
     q->d_block_status = q->d_block_list = q->d_item_mask = nullptr;
     const size_t items_cap = nb + (size_t)q->grid * SG_MAX_AGGS;  // tail blocks may split per aggregation
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_status, nb * 4));
-    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_list, items_cap * 4));
-    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_item_mask, items_cap * 4));
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_list, items_cap * 16));  // uint4 {block, mask, NumRecords, -}
     q->block_cap = nb;
   }
   if (!q->d_gbinpay) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gbinpay, (size_t)q->grid * SG_BLOCK_ROWS * 4));
@@ -1582,8 +1581,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   // parameters go up from pinned scratch (truly asynchronous); the same scratch later receives the
   // accumulators when they are small
   const size_t acc_back = q->acc_words * 8 <= ((size_t)4 << 20) ? q->acc_words * 8 : 64;
-  const size_t off_items = (sizeof(Plan) + 255) & ~(size_t)255, off_masks = off_items + ((items.size() * 4 + 255) & ~(size_t)255);
-  const size_t off_acc = off_masks + ((masks.size() * 4 + 255) & ~(size_t)255);
+  const size_t off_items = (sizeof(Plan) + 255) & ~(size_t)255;
+  const size_t off_acc = off_items + ((items.size() * 16 + 255) & ~(size_t)255);
   char* hp = c->scratch(off_acc + acc_back);
   if (!hp) {
     c->set_err("cudaHostAlloc (query scratch) failed");
@@ -1591,10 +1590,14 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   }
   memcpy(hp, &q->plan, sizeof(Plan));
   if (!items.empty()) {
-    memcpy(hp + off_items, items.data(), items.size() * 4);
-    memcpy(hp + off_masks, masks.data(), masks.size() * 4);
-    CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, hp + off_items, items.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(q->d_item_mask, hp + off_masks, masks.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t* w = (uint32_t*)(hp + off_items);
+    for (size_t i = 0; i < items.size(); i++) {
+      w[4 * i + 0] = items[i];
+      w[4 * i + 1] = masks[i];
+      w[4 * i + 2] = (uint32_t)t->blocks[items[i]].num_records;
+      w[4 * i + 3] = 0;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, hp + off_items, items.size() * 16, cudaMemcpyHostToDevice, c->stream));
   }
   CUDA_TRY(c, cudaMemsetAsync(q->d_work, 0, 64, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(q->d_block_status, 0, std::max<size_t>(t->blocks.size(), 1) * 4, c->stream));
@@ -1604,8 +1607,7 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.plan = q->d_plan;
   lp.blocks = t->d_blocks;
   lp.cols = t->d_cols;
-  lp.block_list = q->d_block_list;
-  lp.item_mask = q->d_item_mask;
+  lp.items = reinterpret_cast<const uint4*>(q->d_block_list);
   lp.nlist = (uint32_t)items.size();
   lp.slot_bytes = q->slot_bytes;
   lp.work_counter = q->d_work;
