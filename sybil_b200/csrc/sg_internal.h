@@ -142,6 +142,7 @@ struct LaunchParams {
   const void* tmaps;          // CUtensorMap[chunks] in global memory (nullptr: plain vector loads)
   uint32_t nstage;            // TMA staging depth per warp (1 or 2)
   unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
+  uint32_t fold_every;        // blocks whose shared accumulators may be folded together (>= 1)
   uint32_t hashg;             // a group column is a value-array int column (hash lookup path; slot_bytes == 4)
 };
 

@@ -1095,6 +1095,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     }
   }
 #endif
+  // pending-fold state: bits 0-7 blocks accumulated since the last fold, 8 discard, 9 fold right away
+  // (aggregation-subset item), 10 the item owns the Count, 16+ word0 semantics per aggregation
+  uint32_t fstate = 0;
   for (;;) {
     __syncthreads();
     if (cx.tid == 0) {
@@ -1103,11 +1106,106 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     }
     __syncthreads();
     const uint32_t wi = cx.misc[0];
-    if (wi >= lp.nlist) break;
-    phase(6);
+    const bool done = wi >= lp.nlist;
     // work item = {block, aggregation mask | owner bit, NumRecords, -}: one load behind the counter.
     // Tail blocks may be split into several items, one per subset of the aggregations
-    const uint4 item = lp.items[wi];
+    const uint4 item = done ? make_uint4(0u, 0x8000ffffu, 0u, 0u) : lp.items[wi];
+    const uint32_t next_imask = item.y;
+    // ---- deferred fold.  The replicated 32-bit accumulators of up to lp.fold_every consecutive blocks
+    // are folded together (the planner bounds that number so that the no-carry proof of the hot path
+    // still holds); always before an item that computes a subset of the aggregations, after one,
+    // after a broken block (whose partial sums — and the pending blocks' — are discarded: the host
+    // reruns the launch without that block) and when the CTA runs out of work.
+    if (ACC_SMEM && (fstate & 0xffu) != 0u &&
+        (done || (fstate & 0xffu) >= lp.fold_every || (fstate & 0x300u) != 0u || next_imask != 0x8000ffffu)) {
+      const bool broken = (fstate & 0x100u) != 0u, owner = (fstate & 0x400u) != 0u;
+      const uint32_t agg_mode_bits = fstate >> 16;
+      fstate = 0;
+      // Fold the R replicas of every accumulator word into the CTA's running 64-bit totals (shared
+      // memory, no atomics) and zero them for the next block.  A row = the R replicas of one
+      // (slot, word).  R >= 4: every lane takes 16 bytes, R/4 lanes share a row, 128/R rows per warp
+      // step — consecutive addresses across the warp (no bank conflicts) — and the lanes of a row
+      // combine with xor-shuffles.  The totals reach the global accumulators once, when the CTA runs
+      // out of blocks: per-block global reductions from 148 CTAs in lockstep serialise on the same
+      // few hundred L2 addresses right in front of a barrier.
+      const uint32_t tw = 1u + 2u * (uint32_t)naggs;  // words per slot: count, then (word0, low limb) per agg
+      const uint32_t nrows = nslots * tw, nrows_all = (nslots + 1u) * tw;  // + the trash slot (zeroed only)
+      auto fold_row = [&](uint32_t row, unsigned long long t) {
+        const uint32_t g = tw == 1u ? row : __umulhi(row, tw_magic), w = row - g * tw;  // exact: row * tw < 2^32
+        if (w == 0) {
+          // this block's count of slot g: parked in the (zeroed) row for the second step below
+          cx.acc[row * R] = (uint32_t)t;
+          if (R > 1) cx.acc[row * R + 1] = (uint32_t)(t >> 32);
+          if (!broken && owner) ctot[g * tw] += t;
+        } else if (!broken) {
+          // word0 of a value-array aggregation counts the NON-accepted rows: hist count = count - word0
+          const bool neg = (w & 1u) && ((agg_mode_bits >> ((w - 1u) >> 1)) & 1u);
+          ctot[g * tw + w] += neg ? (0ull - t) : t;
+        }
+      };
+      if (R >= 4) {
+        const uint32_t lpr = R >> 2;  // lanes per row
+        const uint32_t lg = 31u - (uint32_t)__clz(lpr);
+        const uint32_t rps = 32u >> lg;
+        const uint32_t sub = (uint32_t)cx.lane & (lpr - 1u), grp = (uint32_t)cx.lane >> lg;
+        uint4* const acc4 = reinterpret_cast<uint4*>(cx.acc);
+        for (uint32_t r0 = (uint32_t)cx.warp * rps; r0 < nrows_all; r0 += NWARPS * rps) {
+#ifdef SG_FINE_FLUSH
+          cx.tmark(12);
+#endif
+          const uint32_t row = r0 + grp;
+          uint4 q = make_uint4(0, 0, 0, 0);
+          if (row < nrows_all) {
+            q = acc4[row * lpr + sub];
+            acc4[row * lpr + sub] = make_uint4(0, 0, 0, 0);
+          }
+          unsigned long long t = ((unsigned long long)q.x + q.y) + ((unsigned long long)q.z + q.w);
+#ifdef SG_FINE_FLUSH
+          if (t == 0x123456789ull) cx.misc[5] = 1;
+          cx.tmark(11);
+#endif
+          for (uint32_t d = lpr >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULL, t, d);
+#ifdef SG_FINE_FLUSH
+          if (t == 0x123456789ull) cx.misc[5] = 1;
+          cx.tmark(10);
+#endif
+          if (sub == 0 && row < nrows) fold_row(row, t);
+        }
+      } else {
+        for (uint32_t row = cx.tid; row < nrows_all; row += THREADS) {
+          unsigned long long t = cx.acc[row * R];
+          cx.acc[row * R] = 0;
+          if (R == 2) {
+            t += cx.acc[row * R + 1];
+            cx.acc[row * R + 1] = 0;
+          }
+          if (row < nrows) fold_row(row, t);
+        }
+      }
+      cx.tmark(14);  // fold loop
+      __syncthreads();
+      // second step, one thread per (slot, aggregation): the unreplicated high limbs and "+ count"
+      for (uint32_t i = cx.tid; i < (nslots + 1u) * (uint32_t)naggs; i += THREADS) {
+        const uint32_t g = i / (uint32_t)naggs, a = i - g * (uint32_t)naggs;
+        const unsigned long long hi = cx.acc[acc_rep + i];
+        cx.acc[acc_rep + i] = 0;
+        if (g < nslots && !broken) {
+          unsigned long long cnt = cx.acc[g * gstride];  // R == 1: a block's count fits one word
+          if (R > 1) cnt |= (unsigned long long)cx.acc[g * gstride + 1] << 32;
+          if (hi) ctot[g * tw + 2 + 2 * a] += hi << 32;
+          if ((agg_mode_bits >> a) & 1u) ctot[g * tw + 1 + 2 * a] += cnt;
+        }
+      }
+      __syncthreads();
+      for (uint32_t g = cx.tid; g < nslots; g += THREADS) {
+        cx.acc[g * gstride] = 0;
+        if (R > 1) cx.acc[g * gstride + 1] = 0;
+      }
+    }
+    // (the block below starts behind the barrier that ends the pass-list build)
+
+    if (done) break;
+    phase(6);
     const uint32_t bid = item.x, imask = item.y, nrec = item.z;
     const uint32_t aggmask = imask & 0xffffu;
     const bool owner = (imask >> 31) != 0;
@@ -1417,7 +1515,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       const uint32_t fmin32 = (uint32_t)fmin, fspan32 = (uint32_t)fspan;
       // no carry can leave a low limb inside one block when every hot-path value is below
       // 2^32 / (rows one replica can receive per block): then the adds need no return value
-      const bool nocarry = fast_any && (unsigned long long)fmax * (unsigned long long)(SG_BLOCK_ROWS / R) < 0x100000000ull;
+      const bool nocarry = fast_any && (unsigned long long)fmax * (unsigned long long)(SG_BLOCK_ROWS / R) * lp.fold_every < 0x100000000ull;
       unsigned long long* const hdummy = lp.gdummy + (size_t)blockIdx.x * 32 + cx.lane;
 
       // one populated value of a row whose slot word is s (bucket columns: row order is scattered)
@@ -1716,86 +1814,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       if (owner) matched += my_matched;
     }
     if (ACC_SMEM) {
-      // Fold the R replicas of every accumulator word into the CTA's running 64-bit totals (shared
-      // memory, no atomics) and zero them for the next block.  A row = the R replicas of one
-      // (slot, word).  R >= 4: every lane takes 16 bytes, R/4 lanes share a row, 128/R rows per warp
-      // step — consecutive addresses across the warp (no bank conflicts) — and the lanes of a row
-      // combine with xor-shuffles.  The totals reach the global accumulators once, when the CTA runs
-      // out of blocks: per-block global reductions from 148 CTAs in lockstep serialise on the same
-      // few hundred L2 addresses right in front of a barrier.
-      const uint32_t tw = 1u + 2u * (uint32_t)naggs;  // words per slot: count, then (word0, low limb) per agg
-      const uint32_t nrows = nslots * tw, nrows_all = (nslots + 1u) * tw;  // + the trash slot (zeroed only)
-      auto fold_row = [&](uint32_t row, unsigned long long t) {
-        const uint32_t g = tw == 1u ? row : __umulhi(row, tw_magic), w = row - g * tw;  // exact: row * tw < 2^32
-        if (w == 0) {
-          // this block's count of slot g: parked in the (zeroed) row for the second step below
-          cx.acc[row * R] = (uint32_t)t;
-          if (R > 1) cx.acc[row * R + 1] = (uint32_t)(t >> 32);
-          if (!broken && owner) ctot[g * tw] += t;
-        } else if (!broken) {
-          // word0 of a value-array aggregation counts the NON-accepted rows: hist count = count - word0
-          const bool neg = (w & 1u) && ((agg_mode_bits >> ((w - 1u) >> 1)) & 1u);
-          ctot[g * tw + w] += neg ? (0ull - t) : t;
-        }
-      };
-      if (R >= 4) {
-        const uint32_t lpr = R >> 2;  // lanes per row
-        const uint32_t lg = 31u - (uint32_t)__clz(lpr);
-        const uint32_t rps = 32u >> lg;
-        const uint32_t sub = (uint32_t)cx.lane & (lpr - 1u), grp = (uint32_t)cx.lane >> lg;
-        uint4* const acc4 = reinterpret_cast<uint4*>(cx.acc);
-        for (uint32_t r0 = (uint32_t)cx.warp * rps; r0 < nrows_all; r0 += NWARPS * rps) {
-#ifdef SG_FINE_FLUSH
-          cx.tmark(12);
-#endif
-          const uint32_t row = r0 + grp;
-          uint4 q = make_uint4(0, 0, 0, 0);
-          if (row < nrows_all) {
-            q = acc4[row * lpr + sub];
-            acc4[row * lpr + sub] = make_uint4(0, 0, 0, 0);
-          }
-          unsigned long long t = ((unsigned long long)q.x + q.y) + ((unsigned long long)q.z + q.w);
-#ifdef SG_FINE_FLUSH
-          if (t == 0x123456789ull) cx.misc[5] = 1;
-          cx.tmark(11);
-#endif
-          for (uint32_t d = lpr >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULL, t, d);
-#ifdef SG_FINE_FLUSH
-          if (t == 0x123456789ull) cx.misc[5] = 1;
-          cx.tmark(10);
-#endif
-          if (sub == 0 && row < nrows) fold_row(row, t);
-        }
-      } else {
-        for (uint32_t row = cx.tid; row < nrows_all; row += THREADS) {
-          unsigned long long t = cx.acc[row * R];
-          cx.acc[row * R] = 0;
-          if (R == 2) {
-            t += cx.acc[row * R + 1];
-            cx.acc[row * R + 1] = 0;
-          }
-          if (row < nrows) fold_row(row, t);
-        }
-      }
-      cx.tmark(14);  // fold loop
-      __syncthreads();
-      // second step, one thread per (slot, aggregation): the unreplicated high limbs and "+ count"
-      for (uint32_t i = cx.tid; i < (nslots + 1u) * (uint32_t)naggs; i += THREADS) {
-        const uint32_t g = i / (uint32_t)naggs, a = i - g * (uint32_t)naggs;
-        const unsigned long long hi = cx.acc[acc_rep + i];
-        cx.acc[acc_rep + i] = 0;
-        if (g < nslots && !broken) {
-          unsigned long long cnt = cx.acc[g * gstride];  // R == 1: a block's count fits one word
-          if (R > 1) cnt |= (unsigned long long)cx.acc[g * gstride + 1] << 32;
-          if (hi) ctot[g * tw + 2 + 2 * a] += hi << 32;
-          if ((agg_mode_bits >> a) & 1u) ctot[g * tw + 1 + 2 * a] += cnt;
-        }
-      }
-      __syncthreads();
-      for (uint32_t g = cx.tid; g < nslots; g += THREADS) {
-        cx.acc[g * gstride] = 0;
-        if (R > 1) cx.acc[g * gstride + 1] = 0;
-      }
+      // the replicated accumulators are folded at the top of a later iteration (see there): remember
+      // what that fold must know about the blocks it covers
+      fstate = ((fstate & 0xffu) + 1u) | (broken || (fstate & 0x100u) ? 0x100u : 0u) |
+               (imask != 0x8000ffffu ? 0x200u : 0u) | (owner ? 0x400u : 0u) | (agg_mode_bits << 16);
     }
     phase(5);
   }

@@ -1619,6 +1619,38 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.nstage = t->d_tmaps ? q->nstage : 0u;
   lp.dbg = nullptr;
   lp.hashg = q->hashg ? 1u : 0u;
+  // Deferred fold: the replicated 32-bit accumulators of up to fold_every consecutive blocks are
+  // folded together.  Needs one encoding per aggregation column across the listed blocks (word0
+  // counts accepted rows for bucket columns, rejected ones for value arrays) and keeps the hot
+  // path's no-carry proof: fast-range max x rows one replica can receive x fold_every < 2^32.
+  lp.fold_every = 1;
+  if (q->plan.acc_repl > 0 && !list.empty() && !getenv("SG_NO_DEFER_FOLD")) {
+    bool uniform = true;
+    for (int a = 0; a < q->plan.naggs && uniform; a++) {
+      const size_t col = (size_t)q->plan.aggs[a].col;
+      const uint32_t enc0 = t->cols[(size_t)list[0] * (size_t)t->ncols + col].enc;
+      for (uint32_t b : list)
+        if (t->cols[(size_t)b * (size_t)t->ncols + col].enc != enc0) {
+          uniform = false;
+          break;
+        }
+    }
+    if (uniform) {
+      const unsigned long long rows = (unsigned long long)SG_BLOCK_ROWS / q->plan.acc_repl;
+      unsigned long long k = 4;
+      for (int a = 0; a < q->plan.naggs; a++) {
+        const KAgg& ka = q->plan.aggs[a];
+        const long long fmin = ka.info_min > 0 ? ka.info_min : 0;
+        long long fmax = ka.info_max < 0xffffffffll ? ka.info_max : 0xffffffffll;
+        if (ka.reject_hi < fmax) fmax = ka.reject_hi;
+        if (fmax < fmin || fmax <= 0) continue;
+        const unsigned long long per_block = (unsigned long long)fmax * rows;
+        if (per_block >= 0x100000000ull) continue;  // never carry-free: the carry path is exact for any k
+        k = std::min<unsigned long long>(k, 0xffffffffull / per_block);
+      }
+      lp.fold_every = (uint32_t)std::max<unsigned long long>(k, 1);
+    }
+  }
   static const bool phase_timing = getenv("SG_PHASE_TIMING") != nullptr;
   unsigned long long* d_dbg = nullptr;
   if (phase_timing) {
