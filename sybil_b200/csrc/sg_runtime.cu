@@ -142,6 +142,18 @@ static void pool_release(sg_ctx* c, void* p);
     }                                                                                         \
   } while (0)
 
+// a temporary pool buffer that goes back to the pool on every exit path
+struct PoolTmp {
+  sg_ctx* c;
+  void* p = nullptr;
+  explicit PoolTmp(sg_ctx* ctx) : c(ctx) {}
+  ~PoolTmp() {
+    if (p) pool_release(c, p);
+  }
+  PoolTmp(const PoolTmp&) = delete;
+  PoolTmp& operator=(const PoolTmp&) = delete;
+};
+
 static cudaError_t pool_alloc(sg_ctx* c, void** out, size_t bytes) {
   std::lock_guard<std::mutex> lk(c->mu);
   size_t best = (size_t)-1;
@@ -420,6 +432,7 @@ void sg_destroy(sg_ctx* c) {
   if (!c) return;
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& p : c->pool_free) cudaFree(p.first);
+  for (auto& p : c->pool_live) cudaFree(p.first);  // buffers an error path did not hand back
   if (c->hpin) cudaFreeHost(c->hpin);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1182,12 +1195,13 @@ int ensure_value_dict(sg_table* t, int col) {
   }
   if (!items.empty()) {
     const uint32_t cap = (uint32_t)(INT_DICT_CAP * 2);  // load factor <= 1/2 at the dictionary's size limit
-    long long* d_keys = nullptr;
-    uint32_t* d_items = nullptr;
-    unsigned int* d_cnt = nullptr;
-    CUDA_TRY(c, pool_alloc(c, (void**)&d_keys, (size_t)cap * 8));
-    CUDA_TRY(c, pool_alloc(c, (void**)&d_items, items.size() * 4));
-    CUDA_TRY(c, pool_alloc(c, (void**)&d_cnt, 16));
+    PoolTmp tk(c), ti(c), tc(c);
+    CUDA_TRY(c, pool_alloc(c, &tk.p, (size_t)cap * 8));
+    CUDA_TRY(c, pool_alloc(c, &ti.p, items.size() * 4));
+    CUDA_TRY(c, pool_alloc(c, &tc.p, 16));
+    long long* d_keys = (long long*)tk.p;
+    uint32_t* d_items = (uint32_t*)ti.p;
+    unsigned int* d_cnt = (unsigned int*)tc.p;
     fill_ll<<<(unsigned)(((size_t)cap + 255) / 256), 256, 0, c->stream>>>(d_keys, cap, INT64_MIN);
     CUDA_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(d_items, items.data(), items.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1209,9 +1223,6 @@ int ensure_value_dict(sg_table* t, int col) {
         if (keys[i] != INT64_MIN) found.push_back(keys[i]);
       if (cnt[1]) found.push_back(INT64_MIN);
     }
-    pool_release(c, d_keys);
-    pool_release(c, d_items);
-    pool_release(c, d_cnt);
     if (cnt[2]) {
       D.overflow = true;
     } else {
