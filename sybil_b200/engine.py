@@ -346,6 +346,17 @@ class Table:
         d = blk.desc() if hasattr(blk, "desc") else blk
         self.ctx.check(self.lib.sg_table_add_block(self.h, C.byref(d) if not isinstance(d, C._Pointer) else d))
 
+    def LoadBlockFromDir(self, dirname, loadSpec=None):
+        """Table.LoadBlockFromDir (table_block_io.go:225-310) for a sybil block directory on disk: gob-decode
+        `info.db` and the `int_*.db` / `str_*.db` files the LoadSpec names (all, when None) and stage the
+        still-encoded arrays (sybil_b200/blockdir.py; no Go involved).  Returns the SavedBlock."""
+        from . import blockdir
+        cols = set(loadSpec.columns) if loadSpec is not None else None
+        key_table = [(n, self.KeyTypes[s]) for n, s in sorted(self.KeyTable.items(), key=lambda kv: kv[1])]
+        blk = blockdir.read_block_dir(dirname, key_table, cols, block_index=int(self.lib.sg_table_num_blocks(self.h)))
+        self.add_block(blk)
+        return blk
+
     def add_block_desc_ptr(self, p):
         self.ctx.check(self.lib.sg_table_add_block(self.h, p))
 

@@ -10,11 +10,16 @@ tests/golden/node_results_rows.json: one representative row per counted value
 (floor of the bucket's running average, which lies inside the bucket), so that the
 whole pipeline can be driven to reproduce the golden bucket counters.
 
+Also copies the reference's gob fixtures (`node_results.golden.gob`, `flag_defs.golden.gob` and the JSON
+rendering of the latter) next to them: test DATA of `decoding_test.go:20-74`, used by tests/test_gob.py to pin
+the gob reader to Go's own output.
+
 Run in the build container only (the GPU box has no /root/reference).
 """
 import json
 import math
 import os
+import shutil
 
 SRC = "/root/reference/src/lib/testdata/TestDecodeGoldenFiles/node_results.golden.json"
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -56,6 +61,8 @@ def main():
                     assert lo <= v < lo + h["BucketSize"], (k, b, v, lo)
                 rows.append([browser, device, v, c])
     json.dump(out, open(os.path.join(HERE, "node_results_hist.json"), "w"), separators=(",", ":"))
+    for f in ("node_results.golden.gob", "flag_defs.golden.gob", "flag_defs.golden.json"):
+        shutil.copyfile(os.path.join(os.path.dirname(SRC), f), os.path.join(HERE, f))
     json.dump({"columns": ["browser", "device", "pageload", "repeat"], "rows": rows},
               open(os.path.join(HERE, "node_results_rows.json"), "w"), separators=(",", ":"))
     print("groups", len(out["Results"]), "row classes", len(rows), "rows", sum(r[3] for r in rows))
