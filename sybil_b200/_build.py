@@ -57,5 +57,15 @@ def build_oracle(force=False):
     return out
 
 
+def build_gobread(force=False):
+    """libsybilgob.so: sybil block directory (gob column files) -> sg_block_desc, host-side C++ (include/sybilgob.h)."""
+    out = os.path.join(CSRC, "libsybilgob.so")
+    src = os.path.join(CSRC, "gobread.cpp")
+    if not force and not _newer(out, [src, os.path.join(ROOT, "include", "sybilgob.h"), os.path.join(ROOT, "include", "sybilgpu.h")]):
+        return out
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src, "-lz"])
+    return out
+
+
 def build_all(force=False):
-    return [build_gpu(force), build_blockgen(force), build_oracle(force)]
+    return [build_gpu(force), build_blockgen(force), build_gobread(force), build_oracle(force)]

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SG_LIB: an alternative build of the same library (kernel experiments: `SG_NVCC_FLAGS=... SG_LIB_OUT=... _build.build_gpu`)
 LIB_PATH = os.environ.get("SG_LIB") or os.path.join(_HERE, "csrc", "libsybilgpu.so")
 GEN_PATH = os.path.join(_HERE, "csrc", "libsybilblockgen.so")
+GOB_PATH = os.path.join(_HERE, "csrc", "libsybilgob.so")
 
 SG_ABI_VERSION = 1
 SG_MAX_FILTERS, SG_MAX_GROUPS, SG_MAX_AGGS, SG_MAX_COLS = 15, 8, 16, 64
@@ -194,3 +195,23 @@ def gen():
             raise RuntimeError("libsybilblockgen.so is not built (%s)" % GEN_PATH)
         _gen = bind(C.CDLL(GEN_PATH), GEN_SYMBOLS)
     return _gen
+
+
+# ---- include/sybilgob.h: sybil block directory -> sg_block_desc (host side, C++) -------------------
+GOB_SYMBOLS = {
+    "sgob_read_block_dir": (P, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8),
+                                C.c_int64, C.c_char_p, C.c_size_t]),
+    "sgob_block_desc": (C.POINTER(sg_block_desc), [P]),
+    "sgob_block_free": (None, [P]),
+    "sgob_block_bytes": (C.c_int64, [P]),
+}
+_gob = None
+
+
+def gobread():
+    global _gob
+    if _gob is None:
+        if not os.path.exists(GOB_PATH):
+            raise RuntimeError("libsybilgob.so is not built (%s)" % GOB_PATH)
+        _gob = bind(C.CDLL(GOB_PATH), GOB_SYMBOLS)
+    return _gob

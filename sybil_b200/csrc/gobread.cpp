@@ -1,0 +1,387 @@
+// gobread.cpp — sybil block directory -> sg_block_desc, without Go (include/sybilgob.h).
+//
+// A small Go `encoding/gob` reader: it parses the type definitions that precede the values in the
+// stream and binds struct fields BY NAME (a receiver must not rely on field positions), then pulls out
+// the fields of SavedIntColumn / SavedStrColumn / SavedColumnInfo (src/lib/column_store.go:39-64) and
+// skips everything else.  Wire format: Go's encoding/gob documentation; SURVEY.md appendix A.
+// The Python reader (sybil_b200/gob.py) is pinned to Go's own output by the reference's golden gob
+// files; tests/test_gobread.py checks this reader against it on block directories.
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sybilgob.h"
+
+namespace {
+
+enum { T_BOOL = 1, T_INT = 2, T_UINT = 3, T_FLOAT = 4, T_BYTES = 5, T_STRING = 6, T_COMPLEX = 7, T_INTERFACE = 8,
+       T_WIRETYPE = 16, T_ARRAYTYPE = 17, T_COMMONTYPE = 18, T_SLICETYPE = 19, T_STRUCTTYPE = 20, T_FIELDTYPE = 21,
+       T_FIELDTYPE_SLICE = 22, T_MAPTYPE = 23, T_GOBENC = 24, T_BINMARSH = 25, T_TEXTMARSH = 26 };
+
+struct Err : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+struct TypeDef {
+  enum Kind { NONE, STRUCT, SLICE, ARRAY, MAP, OPAQUE } kind = NONE;
+  std::vector<std::pair<std::string, int64_t>> fields;  // STRUCT
+  int64_t elem = 0, key = 0;
+};
+
+struct Reader {
+  const uint8_t* p;
+  const uint8_t* end;
+  std::map<int64_t, TypeDef> types;
+
+  Reader(const uint8_t* b, size_t n) : p(b), end(b + n) {
+    auto st = [&](int64_t id, std::initializer_list<std::pair<const char*, int64_t>> f) {
+      TypeDef t;
+      t.kind = TypeDef::STRUCT;
+      for (auto& x : f) t.fields.emplace_back(x.first, x.second);
+      types[id] = t;
+    };
+    st(T_WIRETYPE, {{"ArrayT", T_ARRAYTYPE}, {"SliceT", T_SLICETYPE}, {"StructT", T_STRUCTTYPE}, {"MapT", T_MAPTYPE},
+                    {"GobEncoderT", T_GOBENC}, {"BinaryMarshalerT", T_BINMARSH}, {"TextMarshalerT", T_TEXTMARSH}});
+    st(T_ARRAYTYPE, {{"CommonType", T_COMMONTYPE}, {"Elem", T_INT}, {"Len", T_INT}});
+    st(T_COMMONTYPE, {{"Name", T_STRING}, {"Id", T_INT}});
+    st(T_SLICETYPE, {{"CommonType", T_COMMONTYPE}, {"Elem", T_INT}});
+    st(T_STRUCTTYPE, {{"CommonType", T_COMMONTYPE}, {"Field", T_FIELDTYPE_SLICE}});
+    st(T_FIELDTYPE, {{"Name", T_STRING}, {"Id", T_INT}});
+    st(T_MAPTYPE, {{"CommonType", T_COMMONTYPE}, {"Key", T_INT}, {"Elem", T_INT}});
+    st(T_GOBENC, {{"CommonType", T_COMMONTYPE}});
+    st(T_BINMARSH, {{"CommonType", T_COMMONTYPE}});
+    st(T_TEXTMARSH, {{"CommonType", T_COMMONTYPE}});
+    TypeDef fs;
+    fs.kind = TypeDef::SLICE;
+    fs.elem = T_FIELDTYPE;
+    types[T_FIELDTYPE_SLICE] = fs;
+  }
+
+  bool eof() const { return p >= end; }
+  uint64_t u() {
+    if (p >= end) throw Err("gob: unexpected end of stream");
+    uint8_t c = *p++;
+    if (c < 128) return c;
+    unsigned n = 256u - c;
+    if (n > 8 || p + n > end) throw Err("gob: bad uint");
+    uint64_t v = 0;
+    for (unsigned i = 0; i < n; i++) v = (v << 8) | *p++;
+    return v;
+  }
+  int64_t i() {
+    uint64_t x = u();
+    return (x & 1) ? (int64_t)~(x >> 1) : (int64_t)(x >> 1);
+  }
+  std::string str() {
+    uint64_t n = u();
+    if ((uint64_t)(end - p) < n) throw Err("gob: bad length");
+    std::string s((const char*)p, (size_t)n);
+    p += n;
+    return s;
+  }
+  const TypeDef& def(int64_t tid) {
+    auto it = types.find(tid);
+    if (it == types.end()) throw Err("gob: value of undefined type " + std::to_string(tid));
+    return it->second;
+  }
+  // struct: f(field name, field type id) must consume the value (or call skip)
+  template <class F>
+  void structure(int64_t tid, F f) {
+    const TypeDef& t = def(tid);
+    if (t.kind != TypeDef::STRUCT) throw Err("gob: expected a struct");
+    int64_t idx = -1;
+    for (;;) {
+      uint64_t d = u();
+      if (d == 0) return;
+      idx += (int64_t)d;
+      if (idx >= (int64_t)t.fields.size()) throw Err("gob: field number out of range");
+      f(t.fields[(size_t)idx].first, t.fields[(size_t)idx].second);
+    }
+  }
+  void skip(int64_t tid) {
+    switch (tid) {
+      case T_BOOL: case T_INT: case T_UINT: case T_FLOAT: u(); return;
+      case T_BYTES: case T_STRING: str(); return;
+      case T_COMPLEX: u(); u(); return;
+      case T_INTERFACE: throw Err("gob: interface values are not expected in column files");
+      default: break;
+    }
+    const TypeDef& t = def(tid);
+    if (t.kind == TypeDef::STRUCT) {
+      structure(tid, [&](const std::string&, int64_t ft) { skip(ft); });
+    } else if (t.kind == TypeDef::SLICE || t.kind == TypeDef::ARRAY) {
+      uint64_t n = u();
+      for (uint64_t k = 0; k < n; k++) skip(t.elem);
+    } else if (t.kind == TypeDef::MAP) {
+      uint64_t n = u();
+      for (uint64_t k = 0; k < n; k++) {
+        skip(t.key);
+        skip(t.elem);
+      }
+    } else if (t.kind == TypeDef::OPAQUE) {
+      str();
+    } else {
+      throw Err("gob: unknown type kind");
+    }
+  }
+  void define(int64_t tid) {
+    TypeDef nt;
+    structure(T_WIRETYPE, [&](const std::string& which, int64_t wt) {
+      if (which == "GobEncoderT" || which == "BinaryMarshalerT" || which == "TextMarshalerT") {
+        nt.kind = TypeDef::OPAQUE;
+        skip(wt);
+        return;
+      }
+      nt.kind = which == "StructT" ? TypeDef::STRUCT : which == "SliceT" ? TypeDef::SLICE : which == "ArrayT" ? TypeDef::ARRAY : TypeDef::MAP;
+      structure(wt, [&](const std::string& fn, int64_t ft) {
+        if (fn == "Elem") nt.elem = i();
+        else if (fn == "Key") nt.key = i();
+        else if (fn == "Field") {
+          uint64_t n = u();
+          for (uint64_t k = 0; k < n; k++) {
+            std::string name;
+            int64_t id = 0;
+            structure(T_FIELDTYPE, [&](const std::string& a, int64_t at) {
+              if (a == "Name") name = str();
+              else if (a == "Id") id = i();
+              else skip(at);
+            });
+            nt.fields.emplace_back(name, id);
+          }
+        } else {
+          skip(ft);
+        }
+      });
+    });
+    if (nt.kind == TypeDef::NONE) throw Err("gob: empty wireType");
+    types[tid] = nt;
+  }
+  // positions the reader at the first top-level value; returns its type id
+  int64_t next_value() {
+    for (;;) {
+      u();  // message length
+      int64_t tid = i();
+      if (tid < 0) {
+        define(-tid);
+        continue;
+      }
+      if (def_kind(tid) != TypeDef::STRUCT && u() != 0) throw Err("gob: expected the 0 marker of a non-struct value");
+      return tid;
+    }
+  }
+  TypeDef::Kind def_kind(int64_t tid) {
+    auto it = types.find(tid);
+    return it == types.end() ? TypeDef::NONE : it->second.kind;
+  }
+  template <class T>
+  void ints(int64_t tid, std::vector<T>& out, bool is_unsigned) {
+    const TypeDef& t = def(tid);
+    if (t.kind != TypeDef::SLICE && t.kind != TypeDef::ARRAY) throw Err("gob: expected a slice");
+    uint64_t n = u();
+    if (n > ((uint64_t)1 << 28)) throw Err("gob: slice too long");
+    out.reserve(out.size() + (size_t)n);
+    if (t.elem == T_UINT || (is_unsigned && t.elem != T_INT))
+      for (uint64_t k = 0; k < n; k++) out.push_back((T)u());
+    else
+      for (uint64_t k = 0; k < n; k++) out.push_back((T)i());
+  }
+};
+
+bool read_file(const std::string& path, std::vector<uint8_t>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (f) {
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize((size_t)std::max(n, 0l));
+    size_t got = n > 0 ? fread(out.data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    out.resize(got);
+    return true;
+  }
+  gzFile g = gzopen((path + ".gz").c_str(), "rb");
+  if (!g) return false;
+  out.clear();
+  uint8_t buf[1 << 16];
+  int n;
+  while ((n = gzread(g, buf, sizeof(buf))) > 0) out.insert(out.end(), buf, buf + n);
+  gzclose(g);
+  return n == 0;
+}
+
+struct Column {
+  int32_t slot = 0, type = 0, encoding = SG_ENC_ABSENT;
+  bool delta_ids = false, delta_values = false;
+  std::vector<int64_t> bin_values;
+  std::vector<uint32_t> bin_offsets{0};
+  std::vector<uint32_t> record_ids;
+  std::vector<int64_t> values_i64;
+  std::vector<int32_t> values_i32;
+  std::string dict_bytes;
+  std::vector<uint32_t> dict_offsets{0};
+  uint32_t ndict = 0;
+};
+
+void read_column(const std::vector<uint8_t>& raw, Column& c) {
+  Reader r(raw.data(), raw.size());
+  const int64_t tid = r.next_value();
+  bool bucket = false;
+  r.structure(tid, [&](const std::string& f, int64_t ft) {
+    if (f == "DeltaEncodedIDs") c.delta_ids = r.u() != 0;
+    else if (f == "ValueEncoded") c.delta_values = r.u() != 0;
+    else if (f == "BucketEncoded") bucket = r.u() != 0;
+    else if (f == "Bins") {
+      const TypeDef& st = r.def(ft);
+      uint64_t n = r.u();
+      for (uint64_t k = 0; k < n; k++) {
+        int64_t value = 0;
+        r.structure(st.elem, [&](const std::string& bf, int64_t bt) {
+          if (bf == "Value") value = r.i();
+          else if (bf == "Records") r.ints(bt, c.record_ids, true);
+          else r.skip(bt);
+        });
+        c.bin_values.push_back(value);
+        c.bin_offsets.push_back((uint32_t)c.record_ids.size());
+      }
+    } else if (f == "Values") {
+      if (c.type == SG_COL_INT) r.ints(ft, c.values_i64, false);
+      else r.ints(ft, c.values_i32, false);
+    } else if (f == "StringTable") {
+      uint64_t n = r.u();
+      for (uint64_t k = 0; k < n; k++) {
+        c.dict_bytes += r.str();
+        c.dict_offsets.push_back((uint32_t)c.dict_bytes.size());
+      }
+      c.ndict = (uint32_t)n;
+    } else {
+      r.skip(ft);
+    }
+  });
+  c.encoding = bucket ? SG_ENC_BUCKET : SG_ENC_VALUES;
+  if (!bucket) {
+    c.bin_values.clear();
+    c.bin_offsets.assign(1, 0);
+    c.record_ids.clear();
+  }
+}
+
+}  // namespace
+
+struct sgob_block {
+  std::vector<Column> cols;
+  std::vector<sg_column_desc> descs;
+  std::vector<sg_int_info> info;
+  sg_block_desc desc;
+  int64_t bytes = 0;
+};
+
+extern "C" {
+
+sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, const int32_t* col_types, int32_t ncols,
+                                const uint8_t* load_mask, int64_t block_index, char* err, size_t errlen) {
+  auto fail = [&](const std::string& m) -> sgob_block* {
+    if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
+    return nullptr;
+  };
+  if (!dir || ncols < 0 || (ncols > 0 && (!col_names || !col_types))) return fail("sgob_read_block_dir: bad arguments");
+  std::unique_ptr<sgob_block> b(new sgob_block());
+  try {
+    std::vector<uint8_t> raw;
+    const std::string d(dir);
+    if (!read_file(d + "/info.db", raw)) return fail(d + "/info.db: cannot be read");
+    int64_t num_records = 0;
+    {
+      Reader r(raw.data(), raw.size());
+      const int64_t tid = r.next_value();
+      r.structure(tid, [&](const std::string& f, int64_t ft) {
+        if (f == "NumRecords") num_records = r.i();
+        else if (f == "IntInfoMap") {
+          const TypeDef& mt = r.def(ft);
+          uint64_t n = r.u();
+          for (uint64_t k = 0; k < n; k++) {
+            if (mt.key != T_STRING) throw Err("info.db: IntInfoMap key is not a string");
+            const std::string name = r.str();
+            sg_int_info ii;
+            memset(&ii, 0, sizeof(ii));
+            ii.col_slot = -1;
+            r.structure(mt.elem, [&](const std::string& a, int64_t at) {
+              if (a == "Min") ii.min = r.i();
+              else if (a == "Max") ii.max = r.i();
+              else r.skip(at);
+            });
+            for (int32_t s = 0; s < ncols; s++)
+              if (name == col_names[s]) ii.col_slot = s;
+            if (ii.col_slot >= 0) b->info.push_back(ii);
+          }
+        } else {
+          r.skip(ft);
+        }
+      });
+    }
+    for (int32_t s = 0; s < ncols; s++) {
+      if (load_mask && !load_mask[s]) continue;
+      if (col_types[s] != SG_COL_INT && col_types[s] != SG_COL_STR) continue;
+      const std::string path = d + "/" + (col_types[s] == SG_COL_INT ? "int_" : "str_") + col_names[s] + ".db";
+      if (!read_file(path, raw)) continue;  // the block does not hold that column
+      Column c;
+      c.slot = s;
+      c.type = col_types[s];
+      read_column(raw, c);
+      b->cols.push_back(std::move(c));
+    }
+    b->descs.resize(b->cols.size());
+    for (size_t k = 0; k < b->cols.size(); k++) {
+      const Column& c = b->cols[k];
+      sg_column_desc& cd = b->descs[k];
+      memset(&cd, 0, sizeof(cd));
+      cd.col_slot = c.slot;
+      cd.col_type = c.type;
+      cd.encoding = c.encoding;
+      cd.delta_ids = c.delta_ids ? 1 : 0;
+      cd.delta_values = c.delta_values ? 1 : 0;
+      if (c.encoding == SG_ENC_BUCKET) {
+        cd.nbins = (uint32_t)c.bin_values.size();
+        cd.nrecord_ids = (uint32_t)c.record_ids.size();
+        cd.bin_values = c.bin_values.data();
+        cd.bin_offsets = c.bin_offsets.data();
+        cd.record_ids = c.record_ids.data();
+        b->bytes += (int64_t)c.record_ids.size() * 4 + (int64_t)c.bin_values.size() * 12;
+      } else if (c.type == SG_COL_INT) {
+        cd.nvalues = (uint32_t)c.values_i64.size();
+        cd.values_i64 = c.values_i64.data();
+        b->bytes += (int64_t)c.values_i64.size() * 8;
+      } else {
+        cd.nvalues = (uint32_t)c.values_i32.size();
+        cd.values_i32 = c.values_i32.data();
+        b->bytes += (int64_t)c.values_i32.size() * 4;
+      }
+      if (c.type == SG_COL_STR) {
+        cd.ndict = c.ndict;
+        cd.dict_bytes = c.dict_bytes.empty() ? "" : c.dict_bytes.data();
+        cd.dict_offsets = c.dict_offsets.data();
+      }
+    }
+    memset(&b->desc, 0, sizeof(b->desc));
+    b->desc.block_index = block_index;
+    b->desc.num_records = (int32_t)num_records;
+    b->desc.ncols = (int32_t)b->descs.size();
+    b->desc.cols = b->descs.data();
+    b->desc.ninfo = (int32_t)b->info.size();
+    b->desc.info = b->info.data();
+  } catch (const std::exception& e) {
+    return fail(std::string(dir) + ": " + e.what());
+  }
+  return b.release();
+}
+
+const sg_block_desc* sgob_block_desc(const sgob_block* b) { return b ? &b->desc : nullptr; }
+int64_t sgob_block_bytes(const sgob_block* b) { return b ? b->bytes : 0; }
+void sgob_block_free(sgob_block* b) { delete b; }
+
+}  // extern "C"

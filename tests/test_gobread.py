@@ -1,0 +1,117 @@
+"""The native (C++) block-directory reader, include/sybilgob.h: the same decode the Python reader does
+(sybil_b200/gob.py, pinned to Go's output by the reference's golden gob files), producing the sg_block_desc
+the C ABI takes.  Checked array for array against the Python reader and through the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from sybil_b200 import _ffi as F
+from sybil_b200 import blockdir
+from tests.util import INT, STR, Q, Spec, run_oracle
+
+
+def _read_native(d, key_table, mask=None, block_index=0):
+    g = F.gobread()
+    names = (C.c_char_p * len(key_table))(*[n.encode() for n, _ in key_table])
+    types = (C.c_int32 * len(key_table))(*[t for _, t in key_table])
+    m = (C.c_uint8 * len(key_table))(*mask) if mask is not None else None
+    err = C.create_string_buffer(512)
+    h = g.sgob_read_block_dir(d.encode(), names, types, len(key_table), m, block_index, err, len(err))
+    return g, h, err.value.decode()
+
+
+def _arr(ptr, n, dtype):
+    """numpy copy of n items at a raw address (the descriptor's pointer fields are void*)."""
+    if not n:
+        return np.zeros(0, dtype)
+    ct = {np.int64: C.c_int64, np.uint32: C.c_uint32, np.int32: C.c_int32}[dtype]
+    return np.frombuffer((ct * int(n)).from_address(int(ptr)), dtype=dtype).copy()
+
+
+@pytest.mark.parametrize("compress", [False, True])
+def test_native_reader_matches_python_reader_and_oracle(tmp_path, compress):
+    rng = np.random.default_rng(21)
+    n = 4000
+    s = Spec([("age", INT), ("big", INT), ("host", STR), ("uid", STR), ("never", INT)])
+    s.add_rows({"age": rng.integers(10, 30, n), "big": rng.integers(-(1 << 40), 1 << 45, n),
+                "host": np.array(["h%d" % x for x in rng.integers(0, 5, n)]),
+                "uid": np.array(["u%d" % x for x in rng.integers(0, 4 * n, n)])},
+               {"age": rng.random(n) > 0.1, "host": rng.random(n) > 0.1}, threshold=50, block_rows=1500)
+    from oracle.oracle_ffi import OracleTable
+    ot = OracleTable(s.key_table)
+    keep = []
+    try:
+        for i, b in enumerate(s.blocks):
+            d = str(tmp_path / ("block%d" % i))
+            blockdir.write_block_dir(d, b, s.key_table, compress=compress)
+            want = blockdir.read_block_dir(d, s.key_table, block_index=b.block_index)
+            g, h, err = _read_native(d, s.key_table, block_index=b.block_index)
+            assert h, err
+            keep.append((g, h))
+            assert g.sgob_block_bytes(h) > 0
+            desc = g.sgob_block_desc(h).contents
+            assert desc.num_records == b.num_records and desc.block_index == b.block_index
+            assert desc.ncols == len(want.cols)
+            assert {desc.info[k].col_slot: (desc.info[k].min, desc.info[k].max) for k in range(desc.ninfo)} == want.info
+            for k, wc in enumerate(want.cols):
+                cd = desc.cols[k]
+                assert (cd.col_slot, cd.col_type, cd.encoding, bool(cd.delta_ids), bool(cd.delta_values)) == (
+                    wc.col_slot, wc.col_type, wc.encoding, wc.delta_ids, wc.delta_values)
+                if wc.encoding == F.SG_ENC_BUCKET:
+                    assert np.array_equal(_arr(cd.bin_values, cd.nbins, np.int64), wc.bin_values)
+                    assert np.array_equal(_arr(cd.bin_offsets, cd.nbins + 1, np.uint32), wc.bin_offsets)
+                    assert np.array_equal(_arr(cd.record_ids, cd.nrecord_ids, np.uint32), wc.record_ids)
+                elif wc.col_type == F.SG_COL_INT:
+                    assert np.array_equal(_arr(cd.values_i64, cd.nvalues, np.int64), wc.values_i64)
+                else:
+                    assert np.array_equal(_arr(cd.values_i32, cd.nvalues, np.int32), wc.values_i32)
+                if wc.col_type == F.SG_COL_STR:
+                    offs = _arr(cd.dict_offsets, cd.ndict + 1, np.uint32)
+                    blob = C.string_at(cd.dict_bytes, int(offs[-1])) if cd.ndict else b""
+                    assert [blob[offs[j]:offs[j + 1]] for j in range(cd.ndict)] == wc.string_table
+            ot.add_block(g.sgob_block_desc(h))
+        # the oracle over the natively decoded descriptors == the oracle over the in-memory blocks
+        q = Q(s, int_filters=[("age", "gt", 12)], groups=["host"], aggs=["big", "age"], op="hist")
+        d, _keep = q.desc()
+        o2 = ot.query(d, q.aggs, nthreads=2)
+        o1 = run_oracle(s, q)
+        assert o1.MatchedCount == o2.MatchedCount and set(o1.Results) == set(o2.Results)
+        for k in o1.Results:
+            assert o1.Results[k].Count == o2.Results[k].Count
+            for name in ("big", "age"):
+                assert o1.Results[k].Hists[name].ExactSum == o2.Results[k].Hists[name].ExactSum
+                assert np.array_equal(o1.Results[k].Hists[name].Values, o2.Results[k].Hists[name].Values)
+    finally:
+        for g, h in keep:
+            g.sgob_block_free(h)
+        ot.close()
+
+
+def test_native_reader_load_mask_and_errors(tmp_path):
+    rng = np.random.default_rng(22)
+    s = Spec([("a", INT), ("b", STR)])
+    s.add_rows({"a": rng.integers(0, 9, 500), "b": np.array(["x%d" % v for v in rng.integers(0, 3, 500)])}, block_rows=500)
+    d = str(tmp_path / "blk")
+    blockdir.write_block_dir(d, s.blocks[0], s.key_table)
+    g, h, err = _read_native(d, s.key_table, mask=[0, 1])
+    assert h and g.sgob_block_desc(h).contents.ncols == 1 and g.sgob_block_desc(h).contents.cols[0].col_slot == 1
+    g.sgob_block_free(h)
+    g, h, err = _read_native(str(tmp_path / "nope"), s.key_table)
+    assert not h and "info.db" in err
+    raw = open(os.path.join(d, "int_a.db"), "rb").read()
+    open(os.path.join(d, "int_a.db"), "wb").write(raw[:len(raw) // 2])  # truncated column file
+    g, h, err = _read_native(d, s.key_table)
+    assert not h and "gob" in err
+
+
+def test_native_reader_exports_every_declared_symbol():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "sybilgob.h")).read()
+    declared = set(re.findall(r"\b(sgob_[a-z_]+)\s*\(", hdr))
+    assert declared == set(F.GOB_SYMBOLS), (declared, set(F.GOB_SYMBOLS))
+    lib = C.CDLL(F.GOB_PATH)
+    for name in declared:
+        getattr(lib, name)
