@@ -210,8 +210,13 @@ def decode(data):
 # writer: values described by explicit Go-like type descriptors
 #   "bool" "int" "uint" "float" "string" "bytes"
 #   ("slice", elem)  ("map", key, elem)  ("struct", GoTypeName, [(FieldName, type), ...])
+#   "interface": the value is (registered name, concrete type descriptor, concrete value) or None.
+#       The concrete types' definitions are sent ahead of the value message (Encoder.encode collects
+#       them from the value), so an interface value is name, type id, byte count, value — the form
+#       Go's decodeTypeSequence accepts when it has nothing to define in line.
 # ---------------------------------------------------------------------------------------------
-_BASIC = {"bool": T_BOOL, "int": T_INT, "uint": T_UINT, "float": T_FLOAT, "bytes": T_BYTES, "string": T_STRING}
+_BASIC = {"bool": T_BOOL, "int": T_INT, "uint": T_UINT, "float": T_FLOAT, "bytes": T_BYTES, "string": T_STRING,
+          "interface": T_INTERFACE}
 
 
 def _enc_uint(v):
@@ -275,7 +280,7 @@ class Encoder:
 
     def _name(self, t):
         if isinstance(t, str):
-            return {"bytes": "[]uint8", "float": "float64"}.get(t, t)
+            return {"bytes": "[]uint8", "float": "float64", "interface": "interface {}"}.get(t, t)
         if t[0] == "struct":
             return t[1]
         if t[0] == "slice":
@@ -289,6 +294,8 @@ class Encoder:
         return _enc_uint(1) + _enc_uint(1) + _enc_uint(len(nb)) + nb + _enc_uint(1) + _enc_int(tid) + b"\x00"
 
     def _zero(self, v, t):
+        if t == "interface":
+            return v is None
         if isinstance(t, str):
             return v in (0, 0.0, False, "", b"", None)
         if t[0] == "struct":
@@ -309,6 +316,15 @@ class Encoder:
             return _enc_uint(len(b)) + b
         if t == "bytes":
             return _enc_uint(len(v)) + bytes(v)
+        if t == "interface":
+            if v is None:
+                return _enc_uint(0)
+            name, ct, cv = v
+            nb = name.encode()
+            body = self._val(cv, ct)
+            if isinstance(ct, str) or ct[0] != "struct":
+                body = b"\x00" + body
+            return _enc_uint(len(nb)) + nb + _enc_int(self._type_id(ct)) + _enc_uint(len(body)) + body
         if t[0] == "slice":
             et = t[1]
             if et == "uint":
@@ -329,8 +345,30 @@ class Encoder:
             return out + b"\x00"
         raise GobError("unknown descriptor %r" % (t,))
 
+    def _register_concrete(self, v, t):
+        """Assign ids to (and queue the definitions of) the concrete types inside interface values."""
+        if t == "interface":
+            if v is not None:
+                self._type_id(v[1])
+                self._register_concrete(v[2], v[1])
+        elif isinstance(t, str) or v is None:
+            return
+        elif t[0] == "slice":
+            if not isinstance(t[1], str) or t[1] == "interface":
+                for x in v:
+                    self._register_concrete(x, t[1])
+        elif t[0] == "map":
+            if not isinstance(t[2], str) or t[2] == "interface":
+                for x in v.values():
+                    self._register_concrete(x, t[2])
+        elif t[0] == "struct":
+            for fname, ft in t[2]:
+                if fname in v:
+                    self._register_concrete(v[fname], ft)
+
     def encode(self, value, t):
         tid = self._type_id(t)
+        self._register_concrete(value, t)
         out = b""
         for did, body in self.defs:
             msg = _enc_int(-did) + body

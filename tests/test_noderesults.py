@@ -1,0 +1,85 @@
+"""NodeResults emitter: what the engine hands to an unmodified `sybil aggregate`."""
+import os
+
+import numpy as np
+
+from sybil_b200 import gob, noderesults as NR
+from tests.util import INT, STR, Q, Spec, run_oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _covered(v, t):
+    """v restricted to the fields descriptor t names (what this module emits), recursively."""
+    if isinstance(t, str) or v is None:
+        return v
+    if t[0] == "struct":
+        return {n: _covered(v[n], ft) for n, ft in t[2] if n in v}
+    if t[0] == "slice":
+        return [_covered(x, t[1]) for x in v]
+    if t[0] == "map":
+        return {k: _covered(x, t[2]) for k, x in v.items()}
+    raise AssertionError(t)
+
+
+def _as_interfaces(v):
+    """decoded tree -> encoder input: interface values become (name, descriptor, value)."""
+    if isinstance(v, dict):
+        if v.get("__type__") == NR.HIST_NAME:
+            return (NR.HIST_NAME, NR.HIST_COMPAT, _covered({k: x for k, x in v.items() if k != "__type__"}, NR.HIST_COMPAT))
+        return {k: _as_interfaces(x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_as_interfaces(x) for x in v]
+    return v
+
+
+def _strip(v):
+    """Drop the decoder's type tags and every zero / empty field (gob does not send those)."""
+    if isinstance(v, dict):
+        out = {k: _strip(x) for k, x in v.items() if k != "__type__"}
+        return {k: x for k, x in out.items() if x not in (0, 0.0, False, "", None) and x != {} and x != []}
+    if isinstance(v, list):
+        return [_strip(x) for x in v]
+    return v
+
+
+def test_reemitting_the_golden_node_results_preserves_every_covered_value():
+    """Go's own NodeResults stream, decoded, re-emitted with this module's type layouts and decoded again:
+    groups, keys, counts, all 1002 bucket counters, Avg (bit-equal), extents — identical."""
+    gold = gob.decode(open(os.path.join(GOLD, "node_results.golden.gob"), "rb").read())
+    want = _covered(gold, NR.NODE_RESULTS)
+    raw = gob.encode(_as_interfaces(want), NR.NODE_RESULTS) + b"\n"
+    back = gob.decode(raw)
+    res = back["QuerySpec"]["QueryResults"]["Results"]
+    assert len(res) == 12
+    h = res["edge\tdesktop\t"]["Hists"]["pageload"]
+    assert h["__type__"] == NR.HIST_NAME and len(h["BasicHist"]["BasicHistCachedInfo"]["Values"]) == 1002
+    gold_h = gold["QuerySpec"]["QueryResults"]["Results"]["edge\tdesktop\t"]["Hists"]["pageload"]["BasicHist"]["BasicHistCachedInfo"]
+    assert h["BasicHist"]["BasicHistCachedInfo"]["Avg"] == gold_h["Avg"]
+    assert _strip(back) == _strip(want)
+
+
+def test_oracle_results_round_trip_as_node_results():
+    rng = np.random.default_rng(3)
+    n = 3000
+    s = Spec([("lat", INT), ("host", STR), ("dc", STR)])
+    s.add_rows({"lat": rng.integers(30, 5000, n), "host": np.array(["h%d" % x for x in rng.integers(0, 4, n)]),
+                "dc": np.array(["d%d" % x for x in rng.integers(0, 3, n)])}, block_rows=1000)
+    q = Q(s, groups=["host", "dc"], aggs=["lat"], op="hist")
+    o = run_oracle(s, q)
+    raw = NR.encode_node_results(o, "t", ["host", "dc"], ["lat"], {"lat": s.IntInfo["lat"]})
+    assert raw.endswith(b"\n")
+    back = gob.decode(raw)
+    qr = back["QuerySpec"]["QueryResults"]
+    assert qr["MatchedCount"] == o.MatchedCount and set(qr["Results"]) == set(o.Results)
+    assert [r["GroupByKey"] for r in qr["Sorted"]] == [r.GroupByKey for r in o.Sorted]
+    assert [g["Name"] for g in back["QuerySpec"]["QueryParams"]["Groups"]] == ["host", "dc"]
+    for k, r in o.Results.items():
+        b = qr["Results"][k]
+        assert b["Count"] == r.Count and b.get("Samples", 0) == r.Samples
+        c = b["Hists"]["lat"]["BasicHist"]["BasicHistCachedInfo"]
+        h = r.Hists["lat"]
+        assert c["Count"] == h.Count and c["Avg"] == h.Avg and c["NumBuckets"] == h.NumBuckets and c["BucketSize"] == h.BucketSize
+        assert c["Values"] == [int(v) for v in h.Values] and c["PercentileMode"] is True
+        assert (c["Info"].get("Min", 0), c["Info"].get("Max", 0)) == tuple(s.IntInfo["lat"])
+    assert qr["Cumulative"]["Count"] == o.Cumulative.Count
