@@ -37,6 +37,21 @@ void sgob_block_free(sgob_block* b);
 /* bytes of column data decoded (sum over the arrays of the descriptor) */
 int64_t sgob_block_bytes(const sgob_block* b);
 
+/* ---- the table directory: <dbdir>/<table>/info.db + one sub-directory per block ----------------
+ * info.db = gob(Table{Name, KeyTable, KeyTypes, IntInfo, StrInfo}) (src/lib/table_io.go:66-78,128-175);
+ * blocks = the sub-directories file_looks_like_block accepts (table_io.go:213-239), in name order
+ * (LoadAndQueryRecords walks ioutil.ReadDir, table_query.go:22,96-111). */
+typedef struct sgob_table sgob_table;
+sgob_table* sgob_table_open(const char* dbdir, const char* table, char* err, size_t errlen);
+void sgob_table_free(sgob_table* t);
+int32_t sgob_table_num_cols(const sgob_table* t);                 /* key slots: max slot + 1 */
+const char* sgob_table_col_name(const sgob_table* t, int32_t slot); /* "" for an unused slot */
+int32_t sgob_table_col_type(const sgob_table* t, int32_t slot);   /* KeyTypes: 1 int, 2 str, else 0 */
+/* table-level IntInfo{Min,Max} of a column (the histogram extents, hist.go:27-38); 1 if present */
+int32_t sgob_table_int_info(const sgob_table* t, int32_t slot, int64_t* min_out, int64_t* max_out);
+int64_t sgob_table_num_blocks(const sgob_table* t);
+const char* sgob_table_block_dir(const sgob_table* t, int64_t i);
+
 #ifdef __cplusplus
 }
 #endif

@@ -204,6 +204,14 @@ GOB_SYMBOLS = {
     "sgob_block_desc": (C.POINTER(sg_block_desc), [P]),
     "sgob_block_free": (None, [P]),
     "sgob_block_bytes": (C.c_int64, [P]),
+    "sgob_table_open": (P, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    "sgob_table_free": (None, [P]),
+    "sgob_table_num_cols": (C.c_int32, [P]),
+    "sgob_table_col_name": (C.c_char_p, [P, C.c_int32]),
+    "sgob_table_col_type": (C.c_int32, [P, C.c_int32]),
+    "sgob_table_int_info": (C.c_int32, [P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sgob_table_num_blocks": (C.c_int64, [P]),
+    "sgob_table_block_dir": (C.c_char_p, [P, C.c_int64]),
 }
 _gob = None
 

@@ -6,7 +6,11 @@
 // skips everything else.  Wire format: Go's encoding/gob documentation; SURVEY.md appendix A.
 // The Python reader (sybil_b200/gob.py) is pinned to Go's own output by the reference's golden gob
 // files; tests/test_gobread.py checks this reader against it on block directories.
+#include <dirent.h>
+#include <sys/stat.h>
 #include <zlib.h>
+
+#include <algorithm>
 
 #include <cstdio>
 #include <cstring>
@@ -281,6 +285,14 @@ struct sgob_block {
   int64_t bytes = 0;
 };
 
+struct sgob_table {
+  std::vector<std::string> names;
+  std::vector<int32_t> types;
+  std::vector<char> has_info;
+  std::vector<std::pair<int64_t, int64_t>> info;
+  std::vector<std::string> blocks;
+};
+
 extern "C" {
 
 sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, const int32_t* col_types, int32_t ncols,
@@ -379,6 +391,105 @@ sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, c
   }
   return b.release();
 }
+
+sgob_table* sgob_table_open(const char* dbdir, const char* table, char* err, size_t errlen) {
+  auto fail = [&](const std::string& m) -> sgob_table* {
+    if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
+    return nullptr;
+  };
+  if (!dbdir || !table) return fail("sgob_table_open: bad arguments");
+  std::unique_ptr<sgob_table> t(new sgob_table());
+  const std::string tdir = std::string(dbdir) + "/" + table;
+  try {
+    std::vector<uint8_t> raw;
+    if (!read_file(tdir + "/info.db", raw)) return fail(tdir + "/info.db: cannot be read");
+    std::map<int64_t, std::string> by_slot;
+    std::map<int64_t, int64_t> types;
+    std::map<int64_t, std::pair<int64_t, int64_t>> info;
+    Reader r(raw.data(), raw.size());
+    const int64_t tid = r.next_value();
+    r.structure(tid, [&](const std::string& f, int64_t ft) {
+      if (f == "KeyTable") {
+        const TypeDef& mt = r.def(ft);
+        if (mt.key != T_STRING) throw Err("info.db: KeyTable key is not a string");
+        uint64_t n = r.u();
+        for (uint64_t k = 0; k < n; k++) {
+          std::string name = r.str();
+          by_slot[r.i()] = name;
+        }
+      } else if (f == "KeyTypes") {
+        uint64_t n = r.u();
+        for (uint64_t k = 0; k < n; k++) {
+          int64_t slot = r.i();
+          types[slot] = r.i();
+        }
+      } else if (f == "IntInfo") {
+        const TypeDef& mt = r.def(ft);
+        uint64_t n = r.u();
+        for (uint64_t k = 0; k < n; k++) {
+          int64_t slot = r.i();
+          std::pair<int64_t, int64_t> mm(0, 0);
+          r.structure(mt.elem, [&](const std::string& a, int64_t at) {
+            if (a == "Min") mm.first = r.i();
+            else if (a == "Max") mm.second = r.i();
+            else r.skip(at);
+          });
+          info[slot] = mm;
+        }
+      } else {
+        r.skip(ft);
+      }
+    });
+    int64_t nslots = by_slot.empty() ? 0 : by_slot.rbegin()->first + 1;
+    if (nslots < 0 || nslots > 32768) return fail(tdir + "/info.db: key slots out of range");
+    t->names.assign((size_t)nslots, "");
+    t->types.assign((size_t)nslots, 0);
+    t->has_info.assign((size_t)nslots, 0);
+    t->info.assign((size_t)nslots, {0, 0});
+    for (auto& kv : by_slot)
+      if (kv.first >= 0) t->names[(size_t)kv.first] = kv.second;
+    for (auto& kv : types)
+      if (kv.first >= 0 && kv.first < nslots && (kv.second == SG_COL_INT || kv.second == SG_COL_STR)) t->types[(size_t)kv.first] = (int32_t)kv.second;
+    for (auto& kv : info)
+      if (kv.first >= 0 && kv.first < nslots) {
+        t->has_info[(size_t)kv.first] = 1;
+        t->info[(size_t)kv.first] = kv.second;
+      }
+  } catch (const std::exception& e) {
+    return fail(tdir + "/info.db: " + e.what());
+  }
+  DIR* d = opendir(tdir.c_str());
+  if (!d) return fail(tdir + ": cannot be listed");
+  auto ends_with = [](const std::string& s, const char* suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+  };
+  while (dirent* e = readdir(d)) {
+    const std::string n = e->d_name;
+    if (n == "." || n == ".." || n == "ingest" || n == ".ingest.temp" || n == "cache" || n.rfind("stomache", 0) == 0) continue;
+    bool bad = false;
+    for (const char* suf : {"info.db", "old", "broken", "lock", "export", "partial"}) bad = bad || ends_with(n, suf);
+    if (bad) continue;
+    struct stat st;
+    if (stat((tdir + "/" + n).c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) continue;
+    t->blocks.push_back(tdir + "/" + n);
+  }
+  closedir(d);
+  std::sort(t->blocks.begin(), t->blocks.end());
+  return t.release();
+}
+void sgob_table_free(sgob_table* t) { delete t; }
+int32_t sgob_table_num_cols(const sgob_table* t) { return t ? (int32_t)t->names.size() : 0; }
+const char* sgob_table_col_name(const sgob_table* t, int32_t s) { return t && s >= 0 && (size_t)s < t->names.size() ? t->names[(size_t)s].c_str() : ""; }
+int32_t sgob_table_col_type(const sgob_table* t, int32_t s) { return t && s >= 0 && (size_t)s < t->types.size() ? t->types[(size_t)s] : 0; }
+int32_t sgob_table_int_info(const sgob_table* t, int32_t s, int64_t* mn, int64_t* mx) {
+  if (!t || s < 0 || (size_t)s >= t->has_info.size() || !t->has_info[(size_t)s]) return 0;
+  if (mn) *mn = t->info[(size_t)s].first;
+  if (mx) *mx = t->info[(size_t)s].second;
+  return 1;
+}
+int64_t sgob_table_num_blocks(const sgob_table* t) { return t ? (int64_t)t->blocks.size() : 0; }
+const char* sgob_table_block_dir(const sgob_table* t, int64_t i) { return t && i >= 0 && (size_t)i < t->blocks.size() ? t->blocks[(size_t)i].c_str() : ""; }
 
 const sg_block_desc* sgob_block_desc(const sgob_block* b) { return b ? &b->desc : nullptr; }
 int64_t sgob_block_bytes(const sgob_block* b) { return b ? b->bytes : 0; }

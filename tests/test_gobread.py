@@ -115,3 +115,33 @@ def test_native_reader_exports_every_declared_symbol():
     lib = C.CDLL(F.GOB_PATH)
     for name in declared:
         getattr(lib, name)
+
+
+def test_native_table_directory_matches_python_reader(tmp_path):
+    from sybil_b200 import tabledir
+    rng = np.random.default_rng(41)
+    n = 3000
+    s = Spec([("age", INT), ("lat", INT), ("host", STR)])
+    s.add_rows({"age": rng.integers(10, 30, n), "lat": rng.integers(30, 9000, n),
+                "host": np.array(["h%d" % x for x in rng.integers(0, 6, n)])}, block_rows=1000)
+    tdir = tabledir.write_table(str(tmp_path), "tbl", s.key_table, s.blocks, s.IntInfo)
+    for junk in ("ingest", "cache", "stomache9", "b.partial", "c.broken"):
+        os.makedirs(os.path.join(tdir, junk))
+    want = tabledir.read_table(str(tmp_path), "tbl")
+    g = F.gobread()
+    err = C.create_string_buffer(256)
+    t = g.sgob_table_open(str(tmp_path).encode(), b"tbl", err, len(err))
+    assert t, err.value
+    try:
+        nc = g.sgob_table_num_cols(t)
+        assert [(g.sgob_table_col_name(t, i).decode(), g.sgob_table_col_type(t, i)) for i in range(nc)] == want.key_table
+        for i, (name, _) in enumerate(want.key_table):
+            mn, mx = C.c_int64(), C.c_int64()
+            has = g.sgob_table_int_info(t, i, C.byref(mn), C.byref(mx))
+            assert (has == 1) == (name in want.IntInfo)
+            if has:
+                assert (mn.value, mx.value) == want.IntInfo[name]
+        assert [g.sgob_table_block_dir(t, i).decode() for i in range(g.sgob_table_num_blocks(t))] == want.block_dirs
+    finally:
+        g.sgob_table_free(t)
+    assert not g.sgob_table_open(str(tmp_path).encode(), b"missing", err, len(err)) and b"info.db" in err.value
