@@ -145,3 +145,18 @@ def test_native_table_directory_matches_python_reader(tmp_path):
     finally:
         g.sgob_table_free(t)
     assert not g.sgob_table_open(str(tmp_path).encode(), b"missing", err, len(err)) and b"info.db" in err.value
+
+
+def test_native_example_host_compiles_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/query_dir.cpp (table dir -> gob decode -> stage -> query, no Go) builds against both headers;
+    on a machine without a CUDA device it must stop at sg_create with an error, never fall back."""
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "query_dir")
+    csrc = os.path.join(root, "sybil_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "query_dir.cpp"),
+                           "-L", csrc, "-lsybilgob", "-lsybilgpu", "-lz", "-Wl,-rpath," + csrc, "-o", exe])
+    if not torch.cuda.is_available():
+        p = subprocess.run([exe, str(tmp_path), "nosuchtable", "g", "a"], capture_output=True, text=True)
+        assert p.returncode != 0 and "info.db" in p.stderr
