@@ -149,3 +149,40 @@ def test_block_directory_round_trip_and_query(tmp_path, compress):
         for name in ("big", "age"):
             assert a.Results[k].Hists[name].Count == b.Results[k].Hists[name].Count
             assert a.Results[k].Hists[name].ExactSum == b.Results[k].Hists[name].ExactSum
+
+
+def test_writer_reader_round_trip_property():
+    """Random values of random shapes survive encode -> decode (zero / empty fields excepted: gob drops them)."""
+    from hypothesis import given, settings, strategies as st
+
+    ints = st.integers(min_value=-(1 << 63), max_value=(1 << 63) - 1)
+    inner_t = ("struct", "In", [("A", "int"), ("U", "uint"), ("S", "string"), ("F", "float"), ("L", ("slice", "int"))])
+    outer_t = ("struct", "Out", [("I", inner_t), ("Items", ("slice", inner_t)), ("M", ("map", "string", inner_t)),
+                                 ("K", ("map", "int", ("slice", "uint"))), ("B", "bool"), ("Raw", "bytes")])
+    inner = st.fixed_dictionaries({"A": ints, "U": st.integers(0, (1 << 64) - 1), "S": st.text(max_size=12),
+                                   "F": st.floats(allow_nan=False), "L": st.lists(ints, max_size=6)})
+    outer = st.fixed_dictionaries({"I": inner, "Items": st.lists(inner, max_size=4), "M": st.dictionaries(st.text(max_size=5), inner, max_size=3),
+                                   "K": st.dictionaries(ints, st.lists(st.integers(0, 1 << 40), min_size=1, max_size=4), max_size=3),
+                                   "B": st.booleans(), "Raw": st.binary(max_size=9)})
+
+    def drop_zero_fields(v, t):
+        if isinstance(t, str):
+            return v
+        if t[0] == "struct":
+            out = {}
+            for n, ft in t[2]:
+                x = drop_zero_fields(v[n], ft)
+                zero = (x in (0, 0.0, False, "", b"") and isinstance(ft, str)) or (not isinstance(ft, str) and ft[0] != "struct" and len(x) == 0)
+                if not zero:
+                    out[n] = x
+            return out
+        if t[0] == "slice":
+            return [drop_zero_fields(x, t[1]) for x in v]
+        return {k: drop_zero_fields(x, t[2]) for k, x in v.items()}
+
+    @settings(max_examples=150, deadline=None)
+    @given(outer)
+    def check(v):
+        assert gob.decode(gob.encode(v, outer_t)) == drop_zero_fields(v, outer_t)
+
+    check()
