@@ -175,7 +175,16 @@ class sbg_spec(C.Structure):
                 ("cardinality_threshold", C.c_int32), ("num_col_slots", C.c_int32), ("cols", C.POINTER(sbg_col))]
 
 
+class sbg_eval_spec(C.Structure):
+    _fields_ = [("nfilters", C.c_int32), ("filter_col", C.c_int32 * 8), ("filter_op", C.c_int32 * 8),
+                ("filter_val", C.c_int64 * 8), ("ngroups", C.c_int32), ("group_col", C.c_int32 * 4),
+                ("time_col", C.c_int32), ("naggs", C.c_int32), ("time_bucket", C.c_int64), ("time_first", C.c_int64),
+                ("time_n", C.c_int32), ("nvals", C.c_int32), ("agg_col", C.c_int32 * 16), ("info_min", C.c_int64 * 16),
+                ("info_max", C.c_int64 * 16), ("bsize", C.c_int64 * 16)]
+
+
 GEN_SYMBOLS = {
+    "sbg_eval": (C.c_int64, [C.POINTER(sbg_spec), C.POINTER(sbg_eval_spec), C.c_int64, C.c_int64, C.c_int, P, P, P, P]),
     "sbg_generate": (P, [C.POINTER(sbg_spec), C.c_int64, C.c_int64, C.c_int, P, C.c_size_t]),
     "sbg_free": (None, [P]),
     "sbg_num_blocks": (C.c_int64, [P]),

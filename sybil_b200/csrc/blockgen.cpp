@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -377,6 +378,141 @@ int64_t sbg_cell(const sbg_spec* spec, int32_t col_index, int64_t row, int32_t* 
   uint64_t u = splitmix64(spec->seed ^ ((uint64_t)c.col_slot << 40) ^ (uint64_t)row);
   if (valid_out) *valid_out = c.null_per_1024 > 0 ? ((splitmix64(u) & 1023) >= (uint64_t)c.null_per_1024) : 1;
   return col_value(c, u, row);
+}
+
+
+/* ---- direct evaluation of a query on the generator's ROW VALUES ---------------------------------
+ * Independent of the block encoding, of the GPU decode and of the oracle: every row's cells are
+ * recomputed from (seed, column, row) and filtered / grouped / aggregated with plain loops.  bench.py
+ * and the full-size GPU tests compare the engine's merged result with these arrays (per group: Count;
+ * per aggregation: hist Count, exact sum, every bucket counter).  Columns must be null-free.
+ * Semantics: IntFilter gt/lt/eq/neq on the cell value (filter.go:177-189; for a string
+ * key column the value is the key's number, so eq/neq on "v3" is value 3); group slot = mixed radix
+ * over (value - lo) of the group columns, then the time bucket index v / bucket - time_first
+ * (aggregate.go:146-183); BasicHist.AddWeightedValue (hist_basic.go:101-151): reject v > max*10 or
+ * v < min, bucket (v - min) / bsize clamped into [0, nvals-1]. */
+typedef struct sbg_eval_spec {
+  int32_t nfilters;
+  int32_t filter_col[8]; /* index into spec->cols */
+  int32_t filter_op[8];  /* sg_filter_op: GT, LT, EQ, NEQ */
+  int64_t filter_val[8];
+  int32_t ngroups;
+  int32_t group_col[4];
+  int32_t time_col; /* -1: none */
+  int32_t naggs;
+  int64_t time_bucket, time_first;
+  int32_t time_n; /* number of time buckets on the axis */
+  int32_t nvals;  /* bucket counters per (slot, aggregation); 0: no buckets (avg mode) */
+  int32_t agg_col[16];
+  int64_t info_min[16], info_max[16], bsize[16];
+} sbg_eval_spec;
+
+/* slots = prod(span of group cols) * (time_n or 1).  out_count[slots]; out_hcount, out_sum [naggs][slots];
+ * out_buckets [naggs][slots][nvals].  Returns the number of rows that passed the filters, -1 on bad input. */
+int64_t sbg_eval(const sbg_spec* spec, const sbg_eval_spec* ev, int64_t row0, int64_t row1, int nthreads, uint64_t* out_count,
+                 uint64_t* out_hcount, uint64_t* out_sum, uint64_t* out_buckets) {
+  const sbg_col* cols = spec->cols;
+  uint64_t slots = 1;
+  uint64_t gstride[4] = {0, 0, 0, 0};
+  for (int g = 0; g < ev->ngroups; g++) {
+    const sbg_col& c = cols[ev->group_col[g]];
+    if (c.kind != SBG_UNIFORM && c.kind != SBG_STRKEY) return -1;
+    gstride[g] = slots;
+    slots *= (uint64_t)c.span;
+  }
+  const uint64_t tstride = slots;
+  if (ev->time_col >= 0) slots *= (uint64_t)ev->time_n;
+  const int na = ev->naggs;
+  const uint64_t nv = (uint64_t)ev->nvals;
+  const uint64_t words = slots * (1 + (uint64_t)na * (2 + nv));
+  const bool priv = words <= ((uint64_t)4 << 20);
+  if (nthreads < 1) nthreads = 1;
+  memset(out_count, 0, slots * 8);
+  if (na) {
+    memset(out_hcount, 0, slots * (uint64_t)na * 8);
+    memset(out_sum, 0, slots * (uint64_t)na * 8);
+    if (nv) memset(out_buckets, 0, slots * (uint64_t)na * nv * 8);
+  }
+  std::atomic<int64_t> matched(0);
+  std::atomic<int> bad(0);
+  auto cell = [&](int ci, int64_t row) {
+    const sbg_col& c = cols[ci];
+    return col_value(c, splitmix64(spec->seed ^ ((uint64_t)c.col_slot << 40) ^ (uint64_t)row), row);
+  };
+  auto worker = [&](int tix) {
+    const int64_t n = row1 - row0, per = (n + nthreads - 1) / nthreads;
+    const int64_t a = row0 + per * tix, b = std::min<int64_t>(row1, a + per);
+    std::vector<uint64_t> loc;
+    uint64_t *cnt = out_count, *hc = out_hcount, *sm = out_sum, *bk = out_buckets;
+    if (priv) {
+      loc.assign(words, 0);
+      cnt = loc.data();
+      hc = cnt + slots;
+      sm = hc + slots * (uint64_t)na;
+      bk = sm + slots * (uint64_t)na;
+    }
+    auto add = [&](uint64_t* p, uint64_t v) {
+      if (priv)
+        *p += v;
+      else
+        __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+    };
+    int64_t m = 0;
+    for (int64_t row = a; row < b; row++) {
+      bool pass = true;
+      for (int f = 0; f < ev->nfilters && pass; f++) {
+        const int64_t v = cell(ev->filter_col[f], row), lit = ev->filter_val[f];
+        switch (ev->filter_op[f]) {
+          case SG_OP_GT: pass = v > lit; break;
+          case SG_OP_LT: pass = v < lit; break;
+          case SG_OP_EQ: pass = v == lit; break;
+          case SG_OP_NEQ: pass = v != lit; break;
+          default: pass = false;
+        }
+      }
+      if (!pass) continue;
+      m++;
+      uint64_t slot = 0;
+      for (int g = 0; g < ev->ngroups; g++) slot += (uint64_t)(cell(ev->group_col[g], row) - cols[ev->group_col[g]].lo) * gstride[g];
+      if (ev->time_col >= 0) {
+        const int64_t q = cell(ev->time_col, row) / ev->time_bucket - ev->time_first;
+        if (q < 0 || q >= ev->time_n) {
+          bad = 1;
+          continue;
+        }
+        slot += (uint64_t)q * tstride;
+      }
+      add(cnt + slot, 1);
+      for (int ai = 0; ai < na; ai++) {
+        const int64_t v = cell(ev->agg_col[ai], row);
+        if (v > ev->info_max[ai] * 10 || v < ev->info_min[ai]) continue;
+        add(hc + (uint64_t)ai * slots + slot, 1);
+        add(sm + (uint64_t)ai * slots + slot, (uint64_t)v);
+        if (nv) {
+          int64_t bi = (v - ev->info_min[ai]) / ev->bsize[ai];
+          if (bi >= (int64_t)nv) bi = (int64_t)nv - 1;
+          if (bi < 0) bi = 0;
+          add(bk + ((uint64_t)ai * slots + slot) * nv + (uint64_t)bi, 1);
+        }
+      }
+    }
+    matched += m;
+    if (priv) {
+      static std::mutex mu;
+      std::lock_guard<std::mutex> lk(mu);
+      for (uint64_t i = 0; i < slots; i++) out_count[i] += cnt[i];
+      for (uint64_t i = 0; i < slots * (uint64_t)na; i++) {
+        out_hcount[i] += hc[i];
+        out_sum[i] += sm[i];
+      }
+      for (uint64_t i = 0; i < slots * (uint64_t)na * nv; i++) out_buckets[i] += bk[i];
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < nthreads; i++) th.emplace_back(worker, i);
+  worker(0);
+  for (auto& x : th) x.join();
+  return bad.load() ? -1 : matched.load();
 }
 
 }  // extern "C"

@@ -18,6 +18,8 @@ enum : uint32_t {
   COL_BROKEN = 8u,        // "BLOCK SIZE CHANGED DURING QUERY" found at staging
   COL_STATS = 16u,        // vmin/vmax hold the exact extents of the decoded int values
   COL_TMA = 32u,          // data_chunk/data_row locate `data` inside an arena tensor map
+  COL_FULL = 64u,         // bucket column: the bins list every row of [0, NumRecords) exactly once (checked by
+                          // the staging statistics kernel), so no row is unpopulated for this column
 };
 
 struct DevCol {
@@ -89,6 +91,9 @@ struct KAgg {
   uint32_t nvals_total;
   uint32_t _pad;      // bit 0: the plan proved hist Count == Count for every scanned block (the
                       // kernel then skips the hist-Count reductions; accumulators-in-global plans only)
+  uint32_t hrow_off;  // offset of this aggregation's counters inside a slot's row of the shared-memory
+                      // histogram cache (HROW_NONE: its buckets go straight to L2)
+  uint32_t _pad2;
   uint64_t* buckets;  // [nslots][nvals_total]
   uint64_t* hcount;   // [nslots]
   uint64_t* sum;      // [nslots]
@@ -116,7 +121,21 @@ struct Plan {
   uint32_t acc_words;   // replicated smem words per slot: 1 + 2*naggs (count; per agg word0, sum low limb);
                         // the sum high limbs (rarely touched) follow unreplicated
   uint32_t acc_repl;    // replication (power of two, <= 32); 0 = accumulate in global memory
-  uint32_t _pad;
+  uint32_t fail_mode;   // filters set a sticky FAIL bit (finc) instead of counting passes: every filter column
+                        // of every listed block populates every row (value array, or a bucket column with
+                        // COL_FULL), so only the FAILING bins of a bucket column need to be walked
+  // ---- slot window.  The slot words, the replicated accumulators and the histogram cache index a
+  // LOCAL slot space: the group part plus a block-relative time code (1..time_win; 0 = no time).  The
+  // global slot of local slot l is l + tbase, tbase = (first time code of the block - 1) * time_stride
+  // from the time column's exact extents (staging statistics).  Without a time column, or when some
+  // listed block has no extents, the window is the whole axis and tbase = 0.
+  uint32_t lslots;      // local slots (== nslots when the window is the whole axis)
+  uint32_t time_win;    // time codes a block may span (== time_radix - 1 for the whole axis)
+  uint64_t time_magic;  // floor(2^64 / time_bucket) + 1 when time_bucket < 2^32 (0: none); see div_magic
+  // ---- shared-memory histogram cache: hist_rows local slots x hist_row_words 32-bit counters, flushed
+  // to the 64-bit bucket arrays in L2 when the window moves and when the CTA runs out of work
+  uint32_t hist_rows;
+  uint32_t hist_row_words;
   uint64_t* count;      // [nslots]
   uint64_t* scalars;    // [0] matched rows, [1] broken blocks, [2] time overflow rows, [3] blocks done
   uint32_t* block_status;  // per table block: 1 = broken in this query
@@ -168,6 +187,7 @@ int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* 
 int scan_threads();
 // shared memory the kernel needs besides slots and accumulators (nstage: TMA staging depth, 0 = none)
 uint32_t scan_fixed_smem(uint32_t nstage);
+constexpr uint32_t HROW_NONE = 0xffffffffu;
 constexpr uint32_t SMEM_BINS = 1024;  // per-bin payload entries kept in shared memory (more: global scratch)
 constexpr uint32_t TMA_TILE_BYTES = 4096;  // one warp tile: 32 rows of 128 bytes
 

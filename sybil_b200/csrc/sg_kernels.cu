@@ -368,8 +368,14 @@ __device__ __forceinline__ unsigned long long lookback_sum(const Ctx& cx, uint32
 // ---------------------------------------------------------------------------
 // bucket-encoded column: on_row(row, pay_of(bin)) for every (bin,row) pair; pay_of(bin) is
 // evaluated once per run of entries of the same bin inside a lane
+// `need`: bit t set = warp tile t (1024 flat entries) holds entries of a bin the caller cares about; the
+// other tiles are not read at all (predicate push-down into the inverted index: a filter in fail mode
+// only has to mark the rows of the FAILING bins).  A skipped tile publishes "segment restarts here": a
+// needed tile that starts inside a bin has that bin's head in an earlier, therefore also needed, tile.
+// Passes with skipped tiles use plain loads (`use_tma` false): their tiles are not in the block's pass list.
 template <class PayT, class PayOf, class OnRow>
-__device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint32_t nrec, PayOf pay_of, OnRow on_row) {
+__device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint32_t nrec, PayOf pay_of, OnRow on_row,
+                                            const unsigned long long need = ~0ull, const bool use_tma = true) {
   const uint32_t n = c.nitems;
   const uint32_t nbins = c.nbins;
   const uint32_t* __restrict__ ids = reinterpret_cast<const uint32_t*>(c.data);
@@ -381,6 +387,7 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
   // request this warp's first tile(s) right away: the HBM latency overlaps the head-bit build
   const uint32_t ntiles = (n + (32 * BE - 1)) / (32 * BE);
   Feed feed = make_feed(cx, c);
+  if (!use_tma) feed.on = false;
   feed_prologue(cx, feed, ntiles);
 
   // segment heads: one bit per flat entry that starts a (non-empty) bin
@@ -426,6 +433,9 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     }
   }
   cx.epoch++;
+  if (need != ~0ull)
+    for (uint32_t t = tid; t < ntiles; t += THREADS)
+      if (!((need >> t) & 1ull)) cx.pubA[t] = (unsigned long long)FLAG | ((unsigned long long)cx.epoch << 32);
   __syncthreads();
 
 #ifndef SG_FINE_FLUSH
@@ -434,6 +444,7 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
   uint32_t prev_incl = 0;  // running segment sum through this warp's previous tile
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
+    if (!((need >> t) & 1ull)) continue;  // (65,536 ids = at most 64 tiles)
     const uint32_t idx0 = t * (32 * BE) + lane * BE;
     uint32_t a[BE];
     if (feed.on) {
@@ -797,6 +808,30 @@ __device__ __forceinline__ void add_slots(SlotT* slot, uint32_t idx0, const uint
   }
 }
 
+// OR inc[k] (already positioned in the slot word's field) into the slot words of VE consecutive rows
+template <typename SlotT>
+__device__ __forceinline__ void or_slots(SlotT* slot, uint32_t idx0, const uint32_t (&inc)[VE]) {
+  if (sizeof(SlotT) == 1) {
+    uint4* p = reinterpret_cast<uint4*>(slot + idx0);
+    uint4 q = *p;
+    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < VE; k++) w[k >> 2] |= inc[k] << (8 * (k & 3));
+    *p = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if (sizeof(SlotT) == 2) {
+    uint4* p = reinterpret_cast<uint4*>(slot + idx0);
+    uint4 q0 = p[0], q1 = p[1];
+    uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int k = 0; k < VE; k++) w[k >> 1] |= inc[k] << (16 * (k & 1));
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VE; k++) slot[idx0 + k] = (SlotT)(slot[idx0 + k] | inc[k]);
+  }
+}
+
 // value-array str column (raw int32 local ids): visit(row, local_id)
 template <class Visit>
 __device__ __forceinline__ void scan_values_i32(Ctx& cx, const DevCol& c, const uint32_t nrec, Visit visit) {
@@ -919,6 +954,7 @@ struct AggSlow {  // what the out-of-line paths need (lives in local memory)
   uint32_t gstride_b;  // bytes between two slots' accumulators
   uint32_t R_b;        // bytes between two words' replicas
   int acc_smem;
+  uint32_t tb;         // global slot of local slot 0 (slot window of the block; 0 without a time window)
 };
 
 // BasicHist with a 64-bit bucket size, or MultiHist: first sub-range containing v (hist_multi.go:81-86)
@@ -932,7 +968,7 @@ __device__ __noinline__ void hist_bucket_general(const AggSlow* A, uint32_t g, l
     long long b = (long long)((unsigned long long)v - (unsigned long long)S.lo) / S.bsize;
     if (b >= (long long)S.nvals) b = (long long)S.nvals - 1;  // outlier: last slot (hist_basic.go:134-137)
     if (b < 0) b = 0;
-    gred_add(A->buckets + ((size_t)g * A->nvals_total + S.base + (uint32_t)b), 1ull);
+    gred_add(A->buckets + ((size_t)(g + A->tb) * A->nvals_total + S.base + (uint32_t)b), 1ull);
     break;
   }
 }
@@ -954,10 +990,10 @@ __device__ __noinline__ void agg_slow(const AggSlow* A, uint32_t g, long long v,
     if (old > ~lo) hi += 1u;  // carry out of the low limb
     if (hi) sred_add(A->hi_s + g * A->hi_stride_b, hi);
   } else {
-    gred_add(A->hcount + g, 1ull);
-    gred_add(A->sum + g, (unsigned long long)v);
+    gred_add(A->hcount + g + A->tb, 1ull);
+    gred_add(A->sum + g + A->tb, (unsigned long long)v);
   }
-  if (v > A->info_max) gred_max(A->vmax + g, v);
+  if (v > A->info_max) gred_max(A->vmax + g + A->tb, v);
   if (A->nsub > 0) hist_bucket_general(A, g, v);
 }
 
@@ -1022,6 +1058,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   const int time_col = PP->time_col;
   const uint32_t gbits = PP->gbits, pass_target = PP->pass_target, finc = PP->finc, time_ok = PP->time_ok;
   const uint32_t filt_target = PP->filt_target, filt_mask = PP->filt_mask, nslots = PP->nslots;
+  // local slot space (see Plan): slot words, replicated accumulators and the histogram cache index it
+  const uint32_t lslots = PP->lslots;
+  const bool fail_mode = PP->fail_mode != 0;
   const uint32_t acc_words = PP->acc_words, R = ACC_SMEM ? PP->acc_repl : 1u;
   const uint32_t gmask = (1u << gbits) - 1u;
   const uint32_t gstride = acc_words * R;       // words between two slots' accumulators
@@ -1029,15 +1068,43 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   unsigned long long* const g_count = reinterpret_cast<unsigned long long*>(PP->count);
   unsigned long long* const g_scalars = reinterpret_cast<unsigned long long*>(PP->scalars);
 
-  // replicated words of (nslots + trash) slots, then one unreplicated high limb per (slot, aggregation)
-  const uint32_t acc_rep = ACC_SMEM ? (nslots + 1u) * gstride : 0u;
+  // replicated words of (lslots + trash) local slots, then one unreplicated high limb per (slot, aggregation)
+  const uint32_t acc_rep = ACC_SMEM ? (lslots + 1u) * gstride : 0u;
   const uint32_t tw_magic = 0xffffffffu / (1u + 2u * (uint32_t)naggs) + 1u;  // x / tw == umulhi(x, magic), x * tw < 2^32
-  const uint32_t acc_total = ACC_SMEM ? acc_rep + (nslots + 1u) * (uint32_t)naggs : 0u;
+  const uint32_t acc_total = ACC_SMEM ? acc_rep + (lslots + 1u) * (uint32_t)naggs : 0u;
   for (uint32_t i = cx.tid; i < acc_total; i += THREADS) cx.acc[i] = 0;
-  // the CTA's running totals (64-bit) behind the replicated accumulators
+  // the CTA's running totals (64-bit, one per GLOBAL slot) behind the replicated accumulators
   unsigned long long* const ctot = reinterpret_cast<unsigned long long*>(cx.acc + ((acc_total + 1u) & ~1u));
   const uint32_t ctot_n = ACC_SMEM ? nslots * (1u + 2u * (uint32_t)naggs) : 0u;
   for (uint32_t i = cx.tid; i < ctot_n; i += THREADS) ctot[i] = 0;
+  // the histogram cache: 32-bit bucket counters of the first hist_rows local slots.  A
+  // row in the cache costs one shared reduction instead of one 64-bit reduction to L2.
+  const uint32_t hist_rows = ACC_SMEM ? PP->hist_rows : 0u, hrw = PP->hist_row_words;
+  uint32_t* const hist = reinterpret_cast<uint32_t*>(ctot + ((ctot_n + 1u) & ~1u));
+  const uint32_t hist_s = smem_u32(hist);
+  for (uint32_t i = cx.tid; i < hist_rows * hrw; i += THREADS) hist[i] = 0;
+  uint32_t hist_tb = 0;      // global slot of the cache's row 0
+  uint32_t hist_blocks = 0;  // blocks counted into the cache since its last flush (32-bit counters: < 65,536)
+  auto hist_flush = [&]() {
+    __syncthreads();
+    const uint32_t nw = hist_rows * hrw;
+    for (uint32_t i = cx.tid; i < nw; i += THREADS) {
+      const uint32_t v = hist[i];
+      if (!v) continue;
+      hist[i] = 0;
+      const uint32_t row = i / hrw, off = i - row * hrw;
+      for (int a = 0; a < naggs; a++) {
+        const uint32_t ho = PP->aggs[a].hrow_off, nv = PP->aggs[a].nvals_total;
+        if (ho != HROW_NONE && off >= ho && off - ho < nv) {
+          gred_add(reinterpret_cast<unsigned long long*>(PP->aggs[a].buckets) + ((size_t)(row + hist_tb) * nv + (off - ho)),
+                   (unsigned long long)v);
+          break;
+        }
+      }
+    }
+    hist_blocks = 0;
+    __syncthreads();
+  };
   for (uint32_t i = cx.tid; i < MAX_TILES; i += THREADS) {
     cx.pubA[i] = 0;
     cx.pubB[i] = 0;
@@ -1098,6 +1165,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   // pending-fold state: bits 0-7 blocks accumulated since the last fold, 8 discard, 9 fold right away
   // (aggregation-subset item), 10 the item owns the Count, 16+ word0 semantics per aggregation
   uint32_t fstate = 0;
+  uint32_t fold_tb = 0;  // slot window base of the block(s) waiting to be folded
   for (;;) {
     __syncthreads();
     if (cx.tid == 0) {
@@ -1129,18 +1197,18 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       // out of blocks: per-block global reductions from 148 CTAs in lockstep serialise on the same
       // few hundred L2 addresses right in front of a barrier.
       const uint32_t tw = 1u + 2u * (uint32_t)naggs;  // words per slot: count, then (word0, low limb) per agg
-      const uint32_t nrows = nslots * tw, nrows_all = (nslots + 1u) * tw;  // + the trash slot (zeroed only)
+      const uint32_t nrows = lslots * tw, nrows_all = (lslots + 1u) * tw;  // + the trash slot (zeroed only)
       auto fold_row = [&](uint32_t row, unsigned long long t) {
         const uint32_t g = tw == 1u ? row : __umulhi(row, tw_magic), w = row - g * tw;  // exact: row * tw < 2^32
         if (w == 0) {
           // this block's count of slot g: parked in the (zeroed) row for the second step below
           cx.acc[row * R] = (uint32_t)t;
           if (R > 1) cx.acc[row * R + 1] = (uint32_t)(t >> 32);
-          if (!broken && owner) ctot[g * tw] += t;
+          if (!broken && owner) ctot[(g + fold_tb) * tw] += t;
         } else if (!broken) {
           // word0 of a value-array aggregation counts the NON-accepted rows: hist count = count - word0
           const bool neg = (w & 1u) && ((agg_mode_bits >> ((w - 1u) >> 1)) & 1u);
-          ctot[g * tw + w] += neg ? (0ull - t) : t;
+          ctot[(g + fold_tb) * tw + w] += neg ? (0ull - t) : t;
         }
       };
       if (R >= 4) {
@@ -1185,19 +1253,19 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       cx.tmark(14);  // fold loop
       __syncthreads();
       // second step, one thread per (slot, aggregation): the unreplicated high limbs and "+ count"
-      for (uint32_t i = cx.tid; i < (nslots + 1u) * (uint32_t)naggs; i += THREADS) {
+      for (uint32_t i = cx.tid; i < (lslots + 1u) * (uint32_t)naggs; i += THREADS) {
         const uint32_t g = i / (uint32_t)naggs, a = i - g * (uint32_t)naggs;
         const unsigned long long hi = cx.acc[acc_rep + i];
         cx.acc[acc_rep + i] = 0;
-        if (g < nslots && !broken) {
+        if (g < lslots && !broken) {
           unsigned long long cnt = cx.acc[g * gstride];  // R == 1: a block's count fits one word
           if (R > 1) cnt |= (unsigned long long)cx.acc[g * gstride + 1] << 32;
-          if (hi) ctot[g * tw + 2 + 2 * a] += hi << 32;
-          if ((agg_mode_bits >> a) & 1u) ctot[g * tw + 1 + 2 * a] += cnt;
+          if (hi) ctot[(g + fold_tb) * tw + 2 + 2 * a] += hi << 32;
+          if ((agg_mode_bits >> a) & 1u) ctot[(g + fold_tb) * tw + 1 + 2 * a] += cnt;
         }
       }
       __syncthreads();
-      for (uint32_t g = cx.tid; g < nslots; g += THREADS) {
+      for (uint32_t g = cx.tid; g < lslots; g += THREADS) {
         cx.acc[g * gstride] = 0;
         if (R > 1) cx.acc[g * gstride + 1] = 0;
       }
@@ -1220,12 +1288,18 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       bool on = cx.tmaps != nullptr && (c.flags & COL_TMA);
       bool bucket = c.enc == SG_ENC_BUCKET;
       if (kind == 0) {
-        on = on && (bucket || (c.enc == SG_ENC_VALUES && !(pc >> 24)));
+        // (a bucket filter in fail mode walks only the tiles of its failing bins, with plain loads)
+        on = on && ((bucket && !fail_mode) || (c.enc == SG_ENC_VALUES && !(pc >> 24)));
       } else if (kind == 1) {
         on = on && (bucket || (HASHG && c.enc == SG_ENC_VALUES && !(c.flags & COL_IS_STR)));
       } else {
         on = on && !(c.flags & COL_IS_STR) && (bucket || c.enc == SG_ENC_VALUES);
         if (kind == 3) on = on && ((aggmask >> ((pc >> 8) & 0xffu)) & 1u);
+        if (kind == 2 && on && (c.enc == SG_ENC_VALUES || (bucket && (c.flags & COL_FULL))) && (c.flags & COL_STATS)) {
+          // a fully populated time column whose extents fall into one time bucket is not read at all
+          const uint32_t clo = time_code(c.vmin, PP->time_bucket, PP->time_first, PP->time_radix);
+          if (clo != 0u && clo == time_code(c.vmax, PP->time_bucket, PP->time_first, PP->time_radix)) on = false;
+        }
       }
       uint32_t n = c.nitems;
       if (!bucket && n > nrec) n = nrec;
@@ -1264,9 +1338,30 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     cx.npass = cx.misc[2];
     cx.pass_idx = 0;
     cx.pref_idx = 0xffffffffu;
+    // ---- slot window of this block: first time code from the time column's exact extents -------------
+    const long long tbk = PP->time_bucket, tfirst = PP->time_first;
+    const uint32_t tradix = PP->time_radix, tstride = PP->time_stride, twin = PP->time_win;
+    uint32_t tcode0 = 1u;
+    if (time_col >= 0 && twin + 1u < tradix) {
+      const DevCol& tc = colcache[nfilters + ngroups];
+      if (tc.enc != SG_ENC_ABSENT && !(tc.flags & COL_IS_STR) && (tc.flags & COL_STATS)) {
+        const uint32_t c0 = time_code(tc.vmin, tbk, tfirst, tradix);
+        if (c0) tcode0 = min(c0, tradix - twin);  // the window stays inside the axis
+      }
+    }
+    const uint32_t tb = (tcode0 - 1u) * tstride;
+    if (hist_rows && (tb != hist_tb || hist_blocks >= 65535u)) {
+      hist_flush();
+      hist_tb = tb;
+    }
+    hist_blocks++;
     phase(0);
 
     // ---- filters (aggregate.go:105-112; unpopulated -> false, Q1) -----------------
+    // Count mode: a row collects finc per filter it passes (an unpopulated row passes none).  Fail mode
+    // (the plan proved every filter column populates every row of every listed block): a row that fails
+    // a filter gets the sticky FAIL bit (finc) OR-ed in — a bucket column then only walks the tiles
+    // that hold entries of its FAILING bins.
     for (int fi = 0; fi < nfilters; fi++) {
       const KFilter F = PP->filters[fi];
       const DevCol c = colcache[fi];
@@ -1278,19 +1373,51 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       sp.lut_bits = F.lut_bits;
       if (c.enc == SG_ENC_BUCKET) {
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
+        const bool push_down = PP->fail_mode == 1u;
+        if (push_down) {
+          if (!(c.flags & COL_FULL)) __trap();  // the planner only picks fail mode over fully populated columns
+          if (cx.tid < 2) cx.misc[6 + cx.tid] = 0;
+          __syncthreads();
+        }
         for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) {
           const long long bv = c.bin_values[b];
-          pay[b] = F.is_str ? (sp(str_gid(c, bv)) ? 1u : 0u) : (int_pred(F.op, bv, F.ival) ? 1u : 0u);
+          const bool pass = F.is_str ? sp(str_gid(c, bv)) : int_pred(F.op, bv, F.ival);
+          pay[b] = (pass != fail_mode) ? 1u : 0u;  // count mode: 1 = passes; fail mode: 1 = fails
+          if (push_down && !pass) {
+            const uint32_t o0 = c.bin_offsets[b], o1 = c.bin_offsets[b + 1];
+            for (uint32_t t = o0 >> 10; t <= ((o1 - 1u) >> 10) && t < 64u; t++)
+              atomicOr(const_cast<uint32_t*>(&cx.misc[6 + (t >> 5)]), 1u << (t & 31));
+          }
         }
         __syncthreads();
-        // finc for rows of a passing bin, else 0: the read-modify-write runs unconditionally
-        scan_bucket<SlotT>(
-            cx, c, nrec, [&](uint32_t bin) { return pay[bin] ? fincS : (SlotT)0; },
-            [&](uint32_t row, SlotT cur) { slot[row] = (SlotT)(slot[row] + cur); });
+        if (fail_mode) {
+          const unsigned long long need =
+              push_down ? ((unsigned long long)cx.misc[6] | ((unsigned long long)cx.misc[7] << 32)) : ~0ull;
+          scan_bucket<SlotT>(
+              cx, c, nrec, [&](uint32_t bin) { return pay[bin] ? fincS : (SlotT)0; },
+              // (only rows of failing bins are written: with skipped tiles the entries of a PASSING bin may
+              // decode to rows that are not theirs, and a read-modify-write there could undo another
+              // thread's FAIL bit)
+              [&](uint32_t row, SlotT cur) {
+                if (cur) slot[row] = (SlotT)(slot[row] | cur);
+              },
+              need, false);
+        } else {
+          // finc for rows of a passing bin, else 0: the read-modify-write runs unconditionally
+          scan_bucket<SlotT>(
+              cx, c, nrec, [&](uint32_t bin) { return pay[bin] ? fincS : (SlotT)0; },
+              [&](uint32_t row, SlotT cur) { slot[row] = (SlotT)(slot[row] + cur); });
+        }
       } else if (c.enc == SG_ENC_VALUES) {
+        uint32_t nval = c.nitems < nrec ? c.nitems : nrec;
         if (F.is_str) {
           scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
-            if (sp(str_gid(c, local))) slot[row] = (SlotT)(slot[row] + fincS);
+            const bool pass = sp(str_gid(c, local));
+            if (fail_mode) {
+              if (!pass) slot[row] = (SlotT)(slot[row] | fincS);
+            } else if (pass) {
+              slot[row] = (SlotT)(slot[row] + fincS);
+            }
           });
         } else {
           const IntRange rg = int_range(F.op, F.ival);
@@ -1302,23 +1429,38 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           const bool none32 = rg.none || rhi < 0 || rlo > 0xffffffffll;
           const uint32_t lo32 = rlo < 0 ? 0u : (uint32_t)rlo;
           const uint32_t span32 = none32 ? 0u : ((rhi > 0xffffffffll ? 0xffffffffu : (uint32_t)rhi) - lo32);
+          // the word a row gets: count mode finc when it passes, fail mode finc when it fails
+          const uint32_t on_pass = fail_mode ? 0u : finc, on_fail = fail_mode ? finc : 0u;
           if (u32ok) {
             scan_values_u32(cx, c, nrec, [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid) {
               uint32_t inc[VE];
 #pragma unroll
               for (int k = 0; k < VE; k++)
-                inc[k] = (k < nvalid && !rg.none && ((!none32 && (a[k] - lo32) <= span32) != rg.inv)) ? finc : 0u;
-              add_slots(slot, idx0, inc);
+                inc[k] = k < nvalid ? ((!rg.none && ((!none32 && (a[k] - lo32) <= span32) != rg.inv)) ? on_pass : on_fail) : 0u;
+              if (fail_mode)
+                or_slots(slot, idx0, inc);
+              else
+                add_slots(slot, idx0, inc);
             });
           } else {
             scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
               uint32_t inc[VE];
 #pragma unroll
-              for (int k = 0; k < VE; k++) inc[k] = (k < nvalid && rg((long long)a[k])) ? finc : 0u;
-              add_slots(slot, idx0, inc);
+              for (int k = 0; k < VE; k++) inc[k] = k < nvalid ? (rg((long long)a[k]) ? on_pass : on_fail) : 0u;
+              if (fail_mode)
+                or_slots(slot, idx0, inc);
+              else
+                add_slots(slot, idx0, inc);
             });
           }
         }
+        if (fail_mode && nval < nrec) {  // rows past len(Values) are unpopulated: they fail (Q1)
+          for (uint32_t r = nval + cx.tid; r < nrec; r += THREADS) slot[r] = (SlotT)(slot[r] | fincS);
+          __syncthreads();
+        }
+      } else if (fail_mode) {  // column absent from the block: no row passes
+        for (uint32_t r = cx.tid; r < nrec; r += THREADS) slot[r] = (SlotT)(slot[r] | fincS);
+        __syncthreads();
       }
     }
 
@@ -1384,14 +1526,52 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
 
     phase(2);
     // ---- time bucket (aggregate.go:146-183) ------------------------------------------
+    // The slot word takes the code relative to the block's window (1..twin; see Plan).  A row outside
+    // the planned axis — or outside the window, which the exact extents rule out — is counted in
+    // scalars[2] and fails the query on the host.
     if (time_col >= 0) {
       const DevCol c = colcache[nfilters + ngroups];
       const SlotT tok = (SlotT)time_ok;
-      const long long tb = PP->time_bucket, tf = PP->time_first;
-      const uint32_t tr = PP->time_radix, ts = PP->time_stride;
-      if (c.enc == SG_ENC_BUCKET && !(c.flags & COL_IS_STR)) {
+      const long long tb64 = tbk, tf = tfirst;
+      const uint32_t tr = tradix, ts = tstride;
+      auto rel_of = [&](uint32_t code) -> uint32_t {  // global code (0 = off the axis) -> window-relative, 0 = bad
+        const uint32_t r = code - tcode0 + 1u;
+        return (code != 0u && r >= 1u && r <= twin) ? r : 0u;
+      };
+      // every populated row of the block in ONE time bucket (exact extents): the column is not read
+      const bool all_rows = c.enc == SG_ENC_VALUES || (c.enc == SG_ENC_BUCKET && (c.flags & COL_FULL));
+      uint32_t cconst = 0;
+      if (all_rows && !(c.flags & COL_IS_STR) && (c.flags & COL_STATS)) {
+        const uint32_t clo = time_code(c.vmin, tb64, tf, tr);
+        if (clo != 0u && clo == time_code(c.vmax, tb64, tf, tr)) cconst = clo;
+      }
+      if (cconst) {
+        const uint32_t nval = c.enc == SG_ENC_VALUES ? (c.nitems < nrec ? c.nitems : nrec) : nrec;
+        const uint32_t w = rel_of(cconst) * ts + time_ok;
+        if (sizeof(SlotT) < 4) {
+          const uint32_t per = 16u / (uint32_t)sizeof(SlotT);
+          uint32_t rep = w;
+          if (sizeof(SlotT) == 1) rep = w * 0x01010101u;
+          if (sizeof(SlotT) == 2) rep = w * 0x00010001u;
+          uint4* s4 = reinterpret_cast<uint4*>(slot);
+          const uint32_t nfull = nval / per;
+          for (uint32_t i = cx.tid; i < nfull; i += THREADS) {
+            uint4 q = s4[i];
+            q.x += rep;
+            q.y += rep;
+            q.z += rep;
+            q.w += rep;
+            s4[i] = q;
+          }
+          for (uint32_t r = nfull * per + cx.tid; r < nval; r += THREADS) slot[r] = (SlotT)(slot[r] + w);
+        } else {
+          for (uint32_t r = cx.tid; r < nval; r += THREADS) slot[r] = (SlotT)(slot[r] + w);
+        }
+        // (the pass list built at block start leaves this pass out: same test there)
+        __syncthreads();
+      } else if (c.enc == SG_ENC_BUCKET && !(c.flags & COL_IS_STR)) {
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
-        for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) pay[b] = time_code(c.bin_values[b], tb, tf, tr);
+        for (uint32_t b = cx.tid; b < c.nbins; b += THREADS) pay[b] = rel_of(time_code(c.bin_values[b], tb64, tf, tr));
         __syncthreads();
         scan_bucket<uint32_t>(
             cx, c, nrec, [&](uint32_t bin) { return pay[bin]; },
@@ -1402,21 +1582,44 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                 gred_add(g_scalars + 2, 1ull);
             });
       } else if (c.enc == SG_ENC_VALUES && !(c.flags & COL_IS_STR)) {
-        scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
-          uint32_t inc[VE];
+        const bool stats = (c.flags & COL_STATS) != 0;
+        const unsigned long long tmagic = PP->time_magic;
+        if (stats && c.vmin >= 0 && c.vmax <= 0xffffffffll && tmagic != 0ull && tf >= 0) {
+          // 32-bit scan; v / bucket by multiply-high (exact for v < 2^32, see div_magic)
+          scan_values_u32(cx, c, nrec, [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid) {
+            uint32_t inc[VE];
 #pragma unroll
-          for (int k = 0; k < VE; k++) {
-            inc[k] = 0u;
-            if (k < nvalid) {
-              const uint32_t tc = time_code((long long)a[k], tb, tf, tr);
-              if (tc)
-                inc[k] = tc * ts + time_ok;
-              else
-                gred_add(g_scalars + 2, 1ull);
+            for (int k = 0; k < VE; k++) {
+              inc[k] = 0u;
+              if (k < nvalid) {
+                const long long q = (long long)div_magic(a[k], tmagic) - tf;
+                const uint32_t code = (q < 0 || q >= (long long)(tr - 1u)) ? 0u : (uint32_t)q + 1u;
+                const uint32_t rc = rel_of(code);
+                if (rc)
+                  inc[k] = rc * ts + time_ok;
+                else
+                  gred_add(g_scalars + 2, 1ull);
+              }
             }
-          }
-          add_slots(slot, idx0, inc);
-        });
+            add_slots(slot, idx0, inc);
+          });
+        } else {
+          scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
+            uint32_t inc[VE];
+#pragma unroll
+            for (int k = 0; k < VE; k++) {
+              inc[k] = 0u;
+              if (k < nvalid) {
+                const uint32_t rc = rel_of(time_code((long long)a[k], tb64, tf, tr));
+                if (rc)
+                  inc[k] = rc * ts + time_ok;
+                else
+                  gred_add(g_scalars + 2, 1ull);
+              }
+            }
+            add_slots(slot, idx0, inc);
+          });
+        }
       }
     }
     __syncthreads();
@@ -1453,7 +1656,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             if (ACC_SMEM)
               sred_add(smem_u32(cx.acc + g * gstride + lane_off), 1u);
             else
-              gred_add(g_count + g, 1ull);
+              gred_add(g_count + g + tb, 1ull);
           }
         }
         counted = true;
@@ -1488,6 +1691,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       AS.gstride_b = gstride_b;
       AS.R_b = R_b;
       AS.acc_smem = ACC_SMEM ? 1 : 0;
+      AS.tb = tb;
       // fast range: values the hot path takes — accepted (>= info_min, <= info_max <= reject_hi),
       // not above the table's max, and with a zero high limb
       const long long fmin = AS.info_min > 0 ? AS.info_min : 0;
@@ -1500,7 +1704,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                           KA->sub[0].lo == AS.info_min && fast_any &&
                           (unsigned long long)fmax - (unsigned long long)AS.info_min < 0x100000000ull;
       const uint32_t bsize0 = (uint32_t)KA->sub[0].bsize, nvals0 = KA->sub[0].nvals;
-      const uint32_t hoff = (uint32_t)(fmin - AS.info_min);  // fast values: v - info_min = (v - fmin) + hoff
+      const uint32_t hdelta = (uint32_t)(fmin - AS.info_min);  // fast values: v - info_min = (v - fmin) + hdelta
       unsigned long long* const bkt = AS.buckets;
       const uint32_t nvt = AS.nvals_total;
       const int nsub = AS.nsub;
@@ -1510,13 +1714,24 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       // shared atomics run unconditionally: no branch per row.  Carries out of the low limb and
       // values that need the complete rule are collected in per-lane bit masks and handled
       // after the tile.
-      const uint32_t trash = nslots;
+      const uint32_t trash = lslots;
       const uint32_t passbits = pass_target << gbits;
       const uint32_t fmin32 = (uint32_t)fmin, fspan32 = (uint32_t)fspan;
       // no carry can leave a low limb inside one block when every hot-path value is below
       // 2^32 / (rows one replica can receive per block): then the adds need no return value
       const bool nocarry = fast_any && (unsigned long long)fmax * (unsigned long long)(SG_BLOCK_ROWS / R) * lp.fold_every < 0x100000000ull;
-      unsigned long long* const hdummy = lp.gdummy + (size_t)blockIdx.x * 32 + cx.lane;
+      // one bucket increment of local slot e (may be TRASH): into the shared-memory histogram cache when
+      // the slot's row lives there, else a 64-bit reduction to L2
+      const uint32_t hoff = KA->hrow_off;
+      const uint32_t hrows = (hist32 && hoff != HROW_NONE) ? hist_rows : 0u;
+      const uint32_t hcache_s = hist_s + hoff * 4u, hrw_b = hrw * 4u;
+      unsigned long long* const bkt_w = bkt + (size_t)tb * nvt;  // the window's first row of bucket counters
+      auto hist_add = [&](uint32_t e, uint32_t b) {
+        if (e < hrows)
+          sred_add(hcache_s + e * hrw_b + b * 4u, 1u);
+        else if (e != trash)
+          gred_add(bkt_w + ((size_t)e * nvt + b), 1ull);
+      };
 
       // one populated value of a row whose slot word is s (bucket columns: row order is scattered)
       auto accept_one = [&](uint32_t s, long long v) {
@@ -1532,9 +1747,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             if (old > ~vlo) sred_add(hi_s + e * hi_stride_b, 1u);
             if (nsub > 0) {
               if (hist32) {
-                uint32_t b = (vlo - fmin32 + hoff) / bsize0;
+                uint32_t b = (vlo - fmin32 + hdelta) / bsize0;
                 if (b >= nvals0) b = nvals0 - 1;
-                gred_add(bkt + ((size_t)e * nvt + b), 1ull);
+                hist_add(e, b);
               } else {
                 hist_bucket_general(&AS, e, v);
               }
@@ -1606,10 +1821,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
               const uint32_t e2 = fr ? e : trash;
               if (hist32) {
-                const uint32_t x = a[k] - fmin32 + hoff;
+                const uint32_t x = a[k] - fmin32 + hdelta;
                 uint32_t b = magic0 ? div_magic(x, magic0) : x / bsize0;
                 b = min(b, nvals0 - 1);  // outlier: clamped into the last slot (hist_basic.go:134-137)
-                gred_add(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
+                hist_add(e2, b);
               } else if (e2 != trash) {
                 hist_bucket_general(&AS, e2, (long long)a[k]);
               }
@@ -1668,11 +1883,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             const uint32_t e = min(sw[k] ^ passbits, trash);
             if (do_count && count_matched && ((sw[k] >> gbits) & filt_mask) == filt_target) my_matched++;
             if (e == trash) continue;
-            if (do_count) gred_add(g_count + e, 1ull);
+            if (do_count) gred_add(g_count + e + tb, 1ull);
             const long long v = (long long)a[k];
             if (allin || (v >= amin && v <= amax)) {
-              if (!skip_hc) gred_add(g_hc + e, 1ull);
-              gred_add(g_sum + e, (unsigned long long)a[k]);
+              if (!skip_hc) gred_add(g_hc + e + tb, 1ull);
+              gred_add(g_sum + e + tb, (unsigned long long)a[k]);
               if (nsub > 0) hist_bucket_general(&AS, e, v);
             } else {
               agg_slow(&AS, e, v, 0);
@@ -1685,7 +1900,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           const uint32_t s = (uint32_t)slot[r];
           const uint32_t hi = s >> gbits;
           if (do_count && count_matched && (hi & filt_mask) == filt_target) my_matched++;
-          if (hi == pass_target && do_count) gred_add(g_count + (s & gmask), 1ull);
+          if (hi == pass_target && do_count) gred_add(g_count + (s & gmask) + tb, 1ull);
         }
         counted = true;
       } else if (c.enc == SG_ENC_VALUES) {
@@ -1723,9 +1938,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                 cmask |= (old > ~vlo) ? (1u << k) : 0u;
               }
               if (hist32) {
-                uint32_t b = (vlo - fmin32 + hoff) / bsize0;
+                uint32_t b = (vlo - fmin32 + hdelta) / bsize0;
                 if (b >= nvals0) b = nvals0 - 1;  // outlier: clamped into the last slot (hist_basic.go:134-137)
-                gred_add(e2 != trash ? bkt + ((size_t)e2 * nvt + b) : hdummy, 1ull);
+                hist_add(e2, b);
               }
             }
             if (cmask | slow_any) {  // rare
@@ -1756,7 +1971,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
                   if (ACC_SMEM)
                     sred_add(cnt_s + e * gstride_b, 1u);
                   else
-                    gred_add(g_count + e, 1ull);
+                    gred_add(g_count + e + tb, 1ull);
                 }
                 agg_slow(&AS, e, (long long)a[k], 0);
               }
@@ -1791,7 +2006,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               if (ACC_SMEM)
                 sred_add(cnt_s + g * gstride_b, 1u);
               else
-                gred_add(g_count + g, 1ull);
+                gred_add(g_count + g + tb, 1ull);
             }
             if (ACC_SMEM) sred_add(w0_s + g * gstride_b, 1u);
           }
@@ -1818,6 +2033,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       // what that fold must know about the blocks it covers
       fstate = ((fstate & 0xffu) + 1u) | (broken || (fstate & 0x100u) ? 0x100u : 0u) |
                (imask != 0x8000ffffu ? 0x200u : 0u) | (owner ? 0x400u : 0u) | (agg_mode_bits << 16);
+      // a moving slot window: fold before the next block (the runtime launches such plans with fold_every 1)
+      if (twin + 1u < tradix) fstate |= 0x200u;
+      fold_tb = tb;
     }
     phase(5);
   }
@@ -1830,6 +2048,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     for (int i = 9; i < 16; i++) dbg[i] = tacc[i];
 #endif
   }
+  if (hist_rows) hist_flush();
   if (ACC_SMEM) {
     __syncthreads();
     const uint32_t tw = 1u + 2u * (uint32_t)naggs;
@@ -1861,6 +2080,7 @@ __global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const D
                                                            uint32_t ncolslots) {
   __shared__ __align__(16) unsigned char smem_s[FIXED_SMEM];
   __shared__ long long red_min[NWARPS], red_max[NWARPS];
+  __shared__ uint32_t rowbits[HEAD_WORDS];  // bucket columns: one bit per listed row
   Ctx cx;
   cx.tid = threadIdx.x;
   cx.lane = threadIdx.x & 31;
@@ -1891,6 +2111,31 @@ __global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const D
     const uint32_t ci = items[it];
     const DevCol c = cols[ci];
     const uint32_t nrec = blocks[ci / ncolslots].num_records;
+    if (c.enc == SG_ENC_BUCKET) {
+      // COL_FULL: the bins list every row of [0, NumRecords) exactly once — as many entries as rows,
+      // every decoded id in range, no id twice.  Then no row is unpopulated for this column and a
+      // filter may reason about the complement of a set of bins.
+      if (c.nitems != nrec) continue;
+      for (uint32_t i = cx.tid; i < HEAD_WORDS; i += THREADS) rowbits[i] = 0;
+      if (cx.tid == 0) cx.misc[1] = 0;
+      __syncthreads();
+      scan_bucket<uint32_t>(
+          cx, c, nrec, [&](uint32_t) { return 0u; },
+          [&](uint32_t row, uint32_t) { atomicOr(&rowbits[row >> 5], 1u << (row & 31)); });
+      uint32_t pc = 0;
+      for (uint32_t i = cx.tid; i < HEAD_WORDS; i += THREADS) pc += (uint32_t)__popc(rowbits[i]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) pc += __shfl_xor_sync(FULL, pc, d);
+      if (cx.lane == 0) red_min[cx.warp] = (long long)pc;
+      __syncthreads();
+      if (cx.tid == 0) {
+        long long tot = 0;
+        for (int w = 0; w < NWARPS; w++) tot += red_min[w];
+        if (tot == (long long)nrec && cx.misc[1] == 0) cols[ci].flags = c.flags | COL_FULL;
+      }
+      __syncthreads();
+      continue;
+    }
     long long mn = 0x7fffffffffffffffll, mx = -0x7fffffffffffffffll - 1;
     scan_values_i64(cx, c, nrec, [&](uint32_t idx0, const unsigned long long(&a)[VE], uint32_t nvalid) {
 #pragma unroll

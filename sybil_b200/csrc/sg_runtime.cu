@@ -705,6 +705,7 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
         tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * 4, c->is_pinned(cd.record_ids, (size_t)cd.nrecord_ids * 4));
       tm.has_bv = tm.has_bo = tm.has_data = true;
       enc_bytes += (int64_t)(tm.bin_values.size() * 8 + tm.bin_offsets.size() * 4 + (size_t)cd.nrecord_ids * 4);
+      if (cd.nrecord_ids == nrec) stats_slots.push_back((uint32_t)cd.col_slot);  // candidate for COL_FULL
     } else if (cd.encoding == SG_ENC_VALUES) {
       dc.nitems = cd.nvalues;
       if (cd.nvalues > nrec) {
@@ -1296,7 +1297,16 @@ int layout_accumulators(sg_query* q, uint32_t nslots) {
   return SG_OK;
 }
 
-int make_plan(sg_query* q) {
+// time bucket code of the kernel (sg_kernels.cu time_code): 1.. dense index, 0 = off the planned axis
+static uint32_t host_time_code(const Plan& P, int64_t v) {
+  const int64_t qv = v / P.time_bucket - P.time_first;
+  if (qv < 0 || qv >= (int64_t)(P.time_radix - 1)) return 0u;
+  return (uint32_t)qv + 1u;
+}
+
+// `list`: the blocks the launch will scan (zone-map pruned); the slot window, the filters' fail mode
+// and the histogram cache are chosen from their column descriptors
+int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   sg_ctx* c = q->ctx;
   sg_table* t = q->table;
   Plan& P = q->plan;
@@ -1383,21 +1393,75 @@ int make_plan(sg_query* q) {
     stride *= P.time_radix;
   }
   P.nslots = (uint32_t)stride;
-  P.gbits = bits_for(stride);
-  const uint32_t fbits = bits_for((uint64_t)P.nfilters + 1);
-  const uint32_t tbit = time_mode ? 1u : 0u;
-  const uint32_t total_bits = P.gbits + fbits + tbit;
-  if (total_bits > 32) {
-    c->set_err("query: slot word wider than 32 bits");
-    return SG_ERR_UNSUPPORTED;
+  // ---- fail mode: every filter column populates every row of every listed block (value array, or a
+  // bucket column whose bins were checked to list each row once) -> one sticky FAIL bit instead of a
+  // pass count, and bucket filters walk the failing bins only
+  bool fail_mode = P.nfilters > 0 && !getenv("SG_NO_FAIL_MODE");
+  for (size_t i = 0; i < q->filters.size() && fail_mode; i++) {
+    const int col = q->filters[i].col_slot;
+    if (!col_ok(col)) break;  // reported below
+    for (uint32_t b : list) {
+      const DevCol& dc = t->cols[(size_t)b * (size_t)t->ncols + (size_t)col];
+      if (dc.enc == SG_ENC_BUCKET && !(dc.flags & COL_FULL)) {
+        fail_mode = false;
+        break;
+      }
+    }
   }
-  q->slot_bytes = total_bits <= 8 ? 1u : (total_bits <= 16 ? 2u : 4u);
-  if (q->hashg) q->slot_bytes = 4;  // the hashed group pass exists for 32-bit slot words + global accumulators only
-  P.finc = 1u << P.gbits;
-  P.filt_mask = (1u << fbits) - 1u;
-  P.filt_target = (uint32_t)P.nfilters;
-  P.time_ok = time_mode ? (1u << (P.gbits + fbits)) : 0u;
-  P.pass_target = (uint32_t)P.nfilters | (time_mode ? (1u << fbits) : 0u);
+  P.fail_mode = fail_mode ? (getenv("SG_NO_PUSHDOWN") ? 2u : 1u) : 0u;  // 2: fail bits, but every tile is walked (A/B)
+  // ---- slot window over the time axis (see Plan): widest span of time codes inside one listed block
+  const uint32_t group_slots = time_mode ? P.time_stride : P.nslots;
+  auto window_for = [&](bool windowed) {
+    uint32_t win = time_mode ? P.time_radix - 1u : 0u;
+    if (time_mode && windowed && !getenv("SG_NO_TIME_WINDOW")) {
+      bool ok = true;
+      uint32_t w = 1;
+      for (uint32_t b : list) {
+        const DevCol& dc = t->cols[(size_t)b * (size_t)t->ncols + (size_t)P.time_col];
+        if (dc.enc == SG_ENC_ABSENT) continue;
+        if (!(dc.flags & COL_STATS) || (dc.flags & COL_IS_STR)) {
+          ok = false;
+          break;
+        }
+        const uint32_t c0 = host_time_code(P, dc.vmin), c1 = host_time_code(P, dc.vmax);
+        if (!c0 || !c1) {  // rows off the planned axis: the query fails in the kernel's own check
+          ok = false;
+          break;
+        }
+        w = std::max(w, c1 - c0 + 1u);
+      }
+      if (ok && w < win) win = w;
+    }
+    P.time_win = win;
+    P.lslots = time_mode ? group_slots * (win + 1u) : P.nslots;
+    P.gbits = bits_for(P.lslots);
+  };
+  window_for(true);
+  P.time_magic = 0;
+  if (time_mode && P.time_bucket >= 2 && P.time_bucket < 0x100000000ll)
+    P.time_magic = (uint64_t)(((unsigned __int128)1 << 64) / (unsigned __int128)P.time_bucket) + 1u;
+  uint32_t fbits = 0;
+  auto slot_layout = [&]() -> int {
+    fbits = fail_mode ? 1u : bits_for((uint64_t)P.nfilters + 1);
+    const uint32_t tbit = time_mode ? 1u : 0u;
+    const uint32_t total_bits = P.gbits + fbits + tbit;
+    if (total_bits > 32) {
+      c->set_err("query: slot word wider than 32 bits");
+      return SG_ERR_UNSUPPORTED;
+    }
+    q->slot_bytes = total_bits <= 8 ? 1u : (total_bits <= 16 ? 2u : 4u);
+    if (q->hashg) q->slot_bytes = 4;  // the hashed group pass exists for 32-bit slot words + global accumulators only
+    P.finc = 1u << P.gbits;
+    P.filt_mask = (1u << fbits) - 1u;
+    P.filt_target = fail_mode ? 0u : (uint32_t)P.nfilters;
+    P.time_ok = time_mode ? (1u << (P.gbits + fbits)) : 0u;
+    P.pass_target = P.filt_target | (time_mode ? (1u << fbits) : 0u);
+    return SG_OK;
+  };
+  {
+    int rc = slot_layout();
+    if (rc != SG_OK) return rc;
+  }
 
   // ---- filters -----------------------------------------------------------------
   for (int i = 0; i < P.nfilters; i++) {
@@ -1468,36 +1532,81 @@ int make_plan(sg_query* q) {
     if (rc != SG_OK) return rc;
   }
 
+  // ---- histogram cache candidates: BasicHist aggregations the kernel's 32-bit bucket path serves
+  // (same test as `hist32` in scan_kernel)
+  uint32_t hrow_words = 0;
+  for (int i = 0; i < P.naggs; i++) {
+    KAgg& ka = P.aggs[i];
+    ka.hrow_off = HROW_NONE;
+    ka._pad2 = 0;
+    if (!P.hist_mode || ka.nsub != 1 || getenv("SG_NO_HIST_CACHE")) continue;
+    const long long fmin = ka.info_min > 0 ? ka.info_min : 0;
+    long long fmax = ka.info_max < 0xffffffffll ? ka.info_max : 0xffffffffll;
+    if (ka.reject_hi < fmax) fmax = ka.reject_hi;
+    const KSubHist& S = ka.sub[0];
+    if (fmax < fmin || S.bsize <= 0 || S.bsize >= 0x100000000ll || S.lo != ka.info_min ||
+        (unsigned long long)fmax - (unsigned long long)ka.info_min >= 0x100000000ull)
+      continue;
+    ka.hrow_off = hrow_words;
+    hrow_words += ka.nvals_total;
+  }
+  P.hist_row_words = hrow_words;
+
   // ---- shared memory budget ----------------------------------------------------------
-  // TMA staging (per warp 4 KiB tiles, 1 or 2 deep) competes with the accumulator replicas:
-  // take two stages while at least 8 replicas still fit, else one, else plain loads
+  // TMA staging (per warp 4 KiB tiles, 1 or 2 deep) competes with the accumulator replicas and the
+  // histogram cache: two stages while 32 replicas and every cache row still fit, else one, else plain loads
   P.acc_words = 1 + 2 * (uint32_t)P.naggs;
-  const uint32_t slots_b = q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u;
+  uint32_t slots_b = 0;
+  auto acc_bytes = [&](uint32_t repl) -> uint64_t {  // replicas (+ trash slot), high limbs, CTA totals (global slots)
+    return ((uint64_t)P.lslots + 1) * P.acc_words * repl * 4 + ((uint64_t)P.lslots + 1) * (uint64_t)P.naggs * 4 + 8 +
+           (uint64_t)P.nslots * (1 + 2 * (uint64_t)P.naggs) * 8 + 16;
+  };
   auto repl_for = [&](uint32_t nstage) -> uint32_t {
     const uint32_t fixed = scan_fixed_smem(nstage) + slots_b;
     if (fixed > MAX_DYN_SMEM) return 0;
     const uint32_t avail = MAX_DYN_SMEM - fixed;
     uint32_t repl = 32;
-    const uint64_t ctot_b = (uint64_t)P.nslots * (1 + 2 * (uint64_t)P.naggs) * 8 + 8 +  // CTA-resident 64-bit totals
-                            ((uint64_t)P.nslots + 1) * (uint64_t)P.naggs * 4 + 8;      // unreplicated high limbs
-    while (repl >= 1 && ((uint64_t)P.nslots + 1) * P.acc_words * repl * 4 + ctot_b > avail) repl >>= 1;  // + trash slot
+    while (repl >= 1 && acc_bytes(repl) > avail) repl >>= 1;
     return repl;
   };
-  uint32_t nstage = 0;
-  if (t->tma_ok && t->d_tmaps) {
-    if (repl_for(2) >= 32)
-      nstage = 2;
-    else if (repl_for(1) >= 2 || (repl_for(1) >= 1 && repl_for(0) <= 1))
-      nstage = 1;
+  auto hist_rows_for = [&](uint32_t nstage, uint32_t repl) -> uint32_t {
+    if (!hrow_words || !repl) return 0;
+    const uint64_t used = (uint64_t)scan_fixed_smem(nstage) + slots_b + acc_bytes(repl);
+    if (used >= MAX_DYN_SMEM) return 0;
+    return (uint32_t)std::min<uint64_t>(P.lslots, (MAX_DYN_SMEM - used) / ((uint64_t)hrow_words * 4));
+  };
+  uint32_t nstage = 0, repl = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    slots_b = q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u;
+    nstage = 0;
+    if (t->tma_ok && t->d_tmaps) {
+      if (repl_for(2) >= 32 && hist_rows_for(2, 32) >= std::min<uint32_t>(P.lslots, hrow_words ? P.lslots : 0u))
+        nstage = 2;
+      else if (repl_for(1) >= 2 || (repl_for(1) >= 1 && repl_for(0) <= 1))
+        nstage = 1;
+    }
+    if (scan_fixed_smem(nstage) + slots_b > MAX_DYN_SMEM) nstage = 0;
+    repl = q->hashg ? 0u : repl_for(nstage);
+    if (repl == 0 && time_mode && P.lslots != P.nslots) {
+      // accumulators in global memory: no slot window (the kernel's global paths index whole-axis slots)
+      window_for(false);
+      int rc = slot_layout();
+      if (rc != SG_OK) return rc;
+      continue;
+    }
+    break;
   }
-  if (scan_fixed_smem(nstage) + slots_b > MAX_DYN_SMEM) nstage = 0;
+  // cache rows are worth more than replicas beyond 4 (a shared reduction costs 2-3 cycles per warp
+  // instruction at any replication; a bucket increment that misses the cache costs ~45)
+  uint32_t hrows = hist_rows_for(nstage, repl);
+  while (hrow_words && repl > 4 && hrows < P.lslots) {
+    repl >>= 1;
+    hrows = hist_rows_for(nstage, repl);
+  }
   q->nstage = nstage;
-  const uint32_t repl = q->hashg ? 0u : repl_for(nstage);
   P.acc_repl = repl;  // 0: accumulate straight into global memory
-  q->smem_bytes = scan_fixed_smem(nstage) + slots_b +
-                  (repl ? (P.nslots + 1) * P.acc_words * repl * 4 + P.nslots * (1 + 2 * (uint32_t)P.naggs) * 8 + 8 +
-                              (P.nslots + 1) * (uint32_t)P.naggs * 4 + 8
-                        : 0u);
+  P.hist_rows = hrows;
+  q->smem_bytes = scan_fixed_smem(nstage) + slots_b + (repl ? (uint32_t)acc_bytes(repl) + hrows * hrow_words * 4 + 16 : 0u);
   return SG_OK;
 }
 
@@ -1646,6 +1755,7 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
           break;
         }
     }
+    if (q->plan.lslots != q->plan.nslots) uniform = false;  // a moving slot window folds block by block
     if (uniform) {
       const unsigned long long rows = (unsigned long long)SG_BLOCK_ROWS / q->plan.acc_repl;
       unsigned long long k = 4;
@@ -1965,18 +2075,16 @@ int sg_query_run(sg_query* q) {
   rc = upload_table(t);
   if (rc != SG_OK) return rc;
   q->merged = false;
-  rc = make_plan(q);
-  if (rc != SG_OK) return rc;
-  rc = alloc_device(q);
-  if (rc != SG_OK) return rc;
-  q->planned = true;
 
   // block list: zone-map pruning + blocks already known broken for a referenced column
   std::vector<char> wanted((size_t)t->ncols, 0);
-  for (auto& f : q->filters) wanted[(size_t)f.col_slot] = 1;
-  for (auto& g : q->groups) wanted[(size_t)g.col_slot] = 1;
-  for (auto& a : q->aggs) wanted[(size_t)a.col_slot] = 1;
-  if (q->plan.time_col >= 0) wanted[(size_t)q->plan.time_col] = 1;
+  auto want = [&](int col) {
+    if (col >= 0 && col < t->ncols) wanted[(size_t)col] = 1;  // (make_plan reports columns out of range)
+  };
+  for (auto& f : q->filters) want(f.col_slot);
+  for (auto& g : q->groups) want(g.col_slot);
+  for (auto& a : q->aggs) want(a.col_slot);
+  if (q->d.time_col_slot >= 0 && q->d.time_bucket > 0) want(q->d.time_col_slot);
   std::vector<uint32_t> list;
   q->skipped = q->stream_skipped;
   q->broken_staged = 0;
@@ -1997,6 +2105,11 @@ int sg_query_run(sg_query* q) {
     q->rows_scanned += t->blocks[i].num_records;
   }
   q->blocks_scanned = (int64_t)list.size();
+  rc = make_plan(q, list);
+  if (rc != SG_OK) return rc;
+  rc = alloc_device(q);
+  if (rc != SG_OK) return rc;
+  q->planned = true;
   // hist Count == Count for an aggregation when, in every scanned block, its column is a value
   // array covering every row whose exact extents lie inside the accepted range: the kernel then
   // skips that reduction (accumulators-in-global plans) and the result takes Count

@@ -10,9 +10,9 @@ a gloo all_reduce over the same dense layout.
 
 def shard_range(nblocks, rank, world):
     """[first, first+count) of the blocks rank scans: contiguous, sizes differ by at most one block."""
-    per = (nblocks + world - 1) // world
-    first = min(rank * per, nblocks)
-    return first, max(0, min(per, nblocks - first))
+    base, extra = divmod(nblocks, world)  # the first `extra` ranks take one block more
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
 
 
 def dense_layout(all_keys, naggs, nvalues):

@@ -186,3 +186,128 @@ def generate(spec, first_block=0, nblocks=None, nthreads=None, arena_ptr=None, a
     if not h:
         raise MemoryError("block generator arena too small")
     return Store(spec, h, arena_ptr)
+
+
+# ---- ground truth straight from the row values (csrc/blockgen.cpp sbg_eval) --------------------------
+class Expected:
+    """The config's query evaluated on the generator's row values with plain loops: no block encoding,
+    no decode, no oracle.  `groups`: {GroupByKey: slot}; `times`: list of time bucket starts (time mode);
+    arrays indexed [slot] / [agg][slot] / [agg][slot][bucket] with slot = group slot + time index * ngroup_slots."""
+
+    def __init__(self, spec, row0=0, row1=None, nthreads=None):
+        q = query_for(spec)
+        ci = {c.name: i for i, c in enumerate(spec.cols)}
+        ev = F.sbg_eval_spec()
+        fl = [(c, op, v) for c, op, v in q.get("int_filters", [])]
+        for c, op, v in q.get("str_filters", []):
+            col = spec.cols[ci[c]]
+            assert v.startswith(col.prefix)
+            fl.append((c, op, int(v[len(col.prefix):])))
+        ev.nfilters = len(fl)
+        for i, (c, op, v) in enumerate(fl):
+            ev.filter_col[i], ev.filter_op[i], ev.filter_val[i] = ci[c], F.OPS[op], v
+        gcols = [spec.cols[ci[g]] for g in q.get("groups", [])]
+        ev.ngroups = len(gcols)
+        for i, c in enumerate(gcols):
+            ev.group_col[i] = ci[c.name]
+        self.aggs = list(q.get("aggs", []))
+        ev.naggs = len(self.aggs)
+        self.hist = q.get("op") == "hist"
+        self.nvals = 0
+        for i, a in enumerate(self.aggs):
+            ev.agg_col[i] = ci[a]
+            mn, mx = spec.IntInfo[a]
+            ev.info_min[i], ev.info_max[i] = mn, mx
+            if self.hist:  # BasicHist.SetupBuckets (hist_basic.go:34-70), default bucket count
+                size = mx - mn
+                bs, nb = size // 1000, 1000  # NumBuckets stays 1000 unless the bucket size came out 0
+                if bs == 0:
+                    bs, nb = (1, size) if size < 100 else (size // 100, size // (size // 100))
+                ev.bsize[i] = bs
+                assert self.nvals in (0, nb + 2), "one bucket layout per query in this checker"
+                self.nvals = nb + 2  # len(Values) = NumBuckets + 1 + 1
+        ev.nvals = self.nvals
+        ev.time_col = -1
+        self.times = [None]
+        if q.get("time_col"):
+            tb = q["time_bucket"]
+            mn, mx = spec.IntInfo[q["time_col"]]
+            ev.time_col, ev.time_bucket, ev.time_first, ev.time_n = ci[q["time_col"]], tb, mn // tb, mx // tb - mn // tb + 1
+            self.times = [(mn // tb + k) * tb for k in range(ev.time_n)]
+        gslots = 1
+        for c in gcols:
+            gslots *= c.span
+        self.gslots = gslots
+        slots = gslots * len(self.times)
+        na = max(len(self.aggs), 1)
+        self.count = np.zeros(slots, np.uint64)
+        self.hcount = np.zeros((na, slots), np.uint64)
+        self.sum = np.zeros((na, slots), np.uint64)
+        self.buckets = np.zeros((na, slots, max(self.nvals, 1)), np.uint64)
+        cs = spec.c_spec()
+        row1 = spec.total_rows if row1 is None else row1
+        self.matched = F.gen().sbg_eval(C.byref(cs), C.byref(ev), row0, row1, nthreads or (os.cpu_count() or 1),
+                                        self.count.ctypes.data, self.hcount.ctypes.data, self.sum.ctypes.data,
+                                        self.buckets.ctypes.data)
+        if self.matched < 0:
+            raise ValueError("sbg_eval: row outside the time axis / unsupported column kind")
+        self.gcols = gcols
+
+    def key_of(self, gslot):
+        """GroupByKey the engine renders for a group slot (translate_group_by, aggregate.go:284-324)."""
+        if not self.gcols:
+            return "total"
+        parts = []
+        for c in self.gcols:
+            v = c.lo + gslot % c.span
+            gslot //= c.span
+            parts.append((c.prefix + str(v)) if c.col_type == STR else str(v))
+        return "\t".join(parts) + "\t"
+
+    def check(self, qs, max_groups=None):
+        """Compare a filled QuerySpec (engine result) with the row-value evaluation: MatchedCount, the set of
+        groups, every Count, hist Count, exact sum and bucket counter.  Returns the number of values compared."""
+        n = 0
+        assert qs.MatchedCount == self.matched, ("MatchedCount", qs.MatchedCount, self.matched)
+        n += 1
+        time_mode = self.times[0] is not None
+        per_key = self.count.reshape(len(self.times), self.gslots).sum(0)
+        live = [g for g in range(self.gslots) if per_key[g]]
+        assert len(qs.Results) == len(live), ("number of groups", len(qs.Results), len(live))
+        for g in live[:max_groups]:
+            k = self.key_of(g)
+            r = qs.Results.get(k)
+            assert r is not None, ("missing group", k)
+            assert r.Count == int(per_key[g]), ("Count", k, r.Count, int(per_key[g]))
+            n += 1
+            if not time_mode:
+                n += self._check_hists(r, g, k)
+        if time_mode:
+            live_t = [ti for ti in range(len(self.times)) if self.count[ti * self.gslots:(ti + 1) * self.gslots].any()]
+            assert sorted(qs.TimeResults) == [self.times[ti] for ti in live_t], "time buckets"
+            for ti in live_t:
+                m = qs.TimeResults[self.times[ti]]
+                for g in range(self.gslots):
+                    s = ti * self.gslots + g
+                    if not self.count[s]:
+                        continue
+                    r = m.get(self.key_of(g))
+                    assert r is not None and r.Count == int(self.count[s]), ("time Count", self.times[ti], g)
+                    n += 1 + self._check_hists(r, s, (self.times[ti], g))
+        return n
+
+    def _check_hists(self, r, s, where):
+        n = 0
+        for ai, a in enumerate(self.aggs):
+            h = r.Hists.get(a)
+            if not self.hcount[ai, s]:
+                assert h is None or h.TotalCount() == 0, ("unexpected hist", where, a)
+                continue
+            assert h is not None, ("missing hist", where, a)
+            assert h.TotalCount() == int(self.hcount[ai, s]), ("hist Count", where, a)
+            assert h.Sum() == int(self.sum[ai, s].astype(np.int64)), ("sum", where, a)
+            n += 2
+            if self.hist:
+                assert np.array_equal(np.asarray(h.Values, np.uint64), self.buckets[ai, s]), ("bucket counters", where, a)
+                n += self.nvals
+        return n

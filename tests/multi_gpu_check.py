@@ -35,7 +35,7 @@ def seed(table, spec):
     table.ctx.check(table.lib.sg_table_dict_seed_int(table.h, spec.KeyTable["age"], ages.ctypes.data, len(ages)))
 
 
-def run_mode(ctx, spec, queries, first, count, rank, world, seeded):
+def run_mode(ctx, spec, queries, first, count, rank, world, seeded, quiet=False):
     """seeded=False: every rank interns strings / int keys in the order ITS shard shows them, so the
     ranks' slot spaces (and time axes) differ and sg_query_allreduce exchanges the dictionaries."""
     table = E.Table("mg", spec.key_table, ctx)
@@ -57,11 +57,12 @@ def run_mode(ctx, spec, queries, first, count, rank, world, seeded):
             o = run_oracle(spec, q)
             try:
                 compare(qs, o, q)
-                print("query %d (%s dictionaries): merged result over %d GPUs == oracle over all blocks (%d groups, %d matched)" % (
-                    qi, "seeded" if seeded else "per-rank", world, len(qs.Results), qs.MatchedCount))
+                if not quiet:
+                    print("query %d (%s dictionaries): merged result over %d GPUs == oracle over all blocks (%d groups, %d matched)" % (
+                        qi, "seeded" if seeded else "per-rank", world, len(qs.Results), qs.MatchedCount))
             except AssertionError as e:
                 ok = False
-                print("query %d (%s dictionaries) MISMATCH: %r" % (qi, "seeded" if seeded else "per-rank", e))
+                print("query %d (%s dictionaries) MISMATCH: %r" % (qi, "seeded" if seeded else "per-rank", e), file=sys.stderr)
     table.close()
     return ok
 

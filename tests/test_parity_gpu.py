@@ -435,3 +435,143 @@ def test_full_size_c2_checksums_and_block_additivity():
         for t in tabs:
             t.close()
         store.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: predicate push-down into the inverted index (fail mode), slot windows over the time axis,
+# the shared-memory histogram cache, full-size parity against the generator's row values
+# ---------------------------------------------------------------------------------------------------
+def _shuffle_bins(spec, seed):
+    """Go writes a column's bins in map-iteration order: permute the bins of every bucket column (the id
+    lists move with their bins) so that failing and passing bins interleave inside the warp tiles."""
+    rng = np.random.default_rng(seed)
+    for blk in spec.blocks:
+        for col in blk.cols:
+            if col.encoding != F.SG_ENC_BUCKET or len(col.bin_values) < 2:
+                continue
+            perm = rng.permutation(len(col.bin_values))
+            offs = np.asarray(col.bin_offsets, np.int64)
+            ids = [np.asarray(col.record_ids[offs[b]:offs[b + 1]]) for b in perm]
+            col.bin_values = np.asarray(col.bin_values)[perm]
+            col.record_ids = np.concatenate(ids).astype(np.uint32)
+            col.bin_offsets = np.concatenate([[0], np.cumsum([len(x) for x in ids])]).astype(np.uint32)
+
+
+def _wide_spec(seed, nrows, block_rows, nulls=False, shuffle=True):
+    rng = np.random.default_rng(seed)
+    s = Spec([("f0", INT), ("f1", INT), ("s0", STR), ("s1", STR), ("d", INT), ("lat", INT), ("time", INT)])
+    cols = {
+        "f0": rng.integers(0, 1000, nrows), "f1": rng.integers(0, 1000000, nrows),
+        "s0": np.array(["v%d" % v for v in rng.integers(0, 16, nrows)]),
+        "s1": np.array(["g%d" % v for v in rng.integers(0, 12, nrows)]),
+        "d": rng.integers(0, 8, nrows),
+        "lat": (rng.integers(0, 65536, (nrows, 4)).sum(1) * 23470 // (4 * 65535) + 30),
+        "time": 1500000000 + np.sort(rng.integers(0, 40 * 3600, nrows)),
+    }
+    valid = {"f0": rng.random(nrows) > 0.01} if nulls else None
+    s.add_rows(cols, valid, block_rows=block_rows)
+    if shuffle:
+        _shuffle_bins(s, seed + 1)
+    return s
+
+
+@pytest.mark.parametrize("nulls", [False, True])
+def test_filter_push_down_on_fully_populated_columns(nulls, monkeypatch):
+    """Filters over bucket columns that list every row (COL_FULL) run in fail mode and walk only the tiles of
+    their failing bins; bins in arbitrary (Go map) order; full 65,536-row blocks so a column spans 64 tiles.
+    With nulls in a filter column the plan falls back to counting passes.  Both must equal the oracle, and
+    fail mode with every tile walked (SG_NO_PUSHDOWN) must agree too."""
+    s = _wide_spec(41, 3 * 65536 + 12345, 65536, nulls=nulls)
+    qs_ = [
+        Q(s, int_filters=[("f0", "gt", 100), ("f1", "lt", 900000)], str_filters=[("s0", "neq", "v3")], groups=["s1", "d"], aggs=["lat"], op="hist"),
+        Q(s, int_filters=[("f0", "eq", 7)], groups=["s1"], aggs=["lat"], op="avg"),
+        Q(s, int_filters=[("f0", "neq", 7), ("d", "lt", 5)], str_filters=[("s1", "eq", "g4")], groups=["s0"], aggs=["f1"], op="avg"),
+        Q(s, int_filters=[("f0", "lt", 0)], groups=["s1"], aggs=["lat"], op="avg"),   # every bin fails
+        Q(s, int_filters=[("f0", "gt", -1)], groups=["s1"], aggs=["lat"], op="avg"),  # no bin fails: no tile is read
+    ]
+    for q in qs_:
+        o = run_oracle(s, q, nthreads=4)
+        compare(run_gpu(s, q), o, q)
+        monkeypatch.setenv("SG_NO_PUSHDOWN", "1")
+        compare(run_gpu(s, q), o, q)
+        monkeypatch.delenv("SG_NO_PUSHDOWN")
+
+
+def test_time_window_and_histogram_cache(monkeypatch):
+    """Time rollup over a sorted time column: slot words hold block-relative time codes (the window comes
+    from the column's exact extents), blocks inside one bucket do not read the column, the bucket counters
+    live in the shared-memory cache and are flushed when the window moves.  Same answer with the window,
+    the cache and both switched off."""
+    s = _wide_spec(43, 4 * 65536 + 999, 65536, shuffle=False)
+    for q in (Q(s, aggs=["lat"], op="hist", time_col="time", time_bucket=3600),
+              Q(s, groups=["d"], aggs=["lat", "f1"], op="hist", time_col="time", time_bucket=7200),
+              Q(s, int_filters=[("f0", "gt", 500)], groups=["s1"], aggs=["lat"], op="avg", time_col="time", time_bucket=600)):
+        o = run_oracle(s, q, nthreads=4)
+        compare(run_gpu(s, q), o, q)
+        for env in ("SG_NO_TIME_WINDOW", "SG_NO_HIST_CACHE"):
+            monkeypatch.setenv(env, "1")
+            compare(run_gpu(s, q), o, q)
+            monkeypatch.delenv(env)
+
+
+@pytest.mark.parametrize("cfg,rows", [("c3", 100_000_000), ("c4", 100_000_000)])
+def test_full_size_against_row_values(cfg, rows):
+    """The histogram configs at a size where tail splitting, deferred folds, window moves and cache flushes
+    all engage (1,526 blocks): every group's Count, hist Count, exact sum and every bucket counter equal
+    the query evaluated directly on the generator's row values (synth.Expected: no encoder, no decoder)."""
+    from sybil_b200 import engine as E
+    from sybil_b200 import synth
+    spec = synth.config(cfg, total_rows=rows)
+    store = synth.generate(spec)
+    s = Spec(spec.key_table)
+    s.IntInfo = dict(spec.IntInfo)
+    q = Q(s, **synth.query_for(spec))
+    t = E.Table(cfg, spec.key_table)
+    t.IntInfo = dict(spec.IntInfo)
+    try:
+        ptrs, n = store.block_ptrs()
+        t.add_blocks(ptrs, n)
+        g = run_gpu(s, q, table=t)
+        exp = synth.Expected(spec)
+        assert exp.check(g) > 1000
+        assert g.MatchedCount > rows // 2
+    finally:
+        t.close()
+        store.close()
+
+
+def test_streaming_submit_gives_the_full_result():
+    """sg_query_submit_block + sg_query_finish: the complete result (not only the counts) equals the oracle's."""
+    import ctypes as C
+    from sybil_b200 import engine as E
+    from sybil_b200 import synth
+    from oracle.oracle_ffi import OracleTable
+    spec = synth.config("c3", total_rows=4 * 30000, block_rows=30000)
+    store = synth.generate(spec)
+    s = Spec(spec.key_table)
+    s.IntInfo = dict(spec.IntInfo)
+    q = Q(s, **synth.query_for(spec))
+    ot = OracleTable(spec.key_table)
+    for i in range(store.num_blocks()):
+        ot.add_block(store.block(i))
+    d, keep = q.desc()
+    o = ot.query(d, q.aggs, nthreads=2)
+    t = E.Table("stream", spec.key_table)
+    t.IntInfo = dict(spec.IntInfo)
+    try:
+        qs = q.query_spec()
+        dd, keep2 = E.make_query_desc(s.KeyTable, s.KeyTypes, s.IntInfo, qs)
+        qh = t.lib.sg_query_begin(t.ctx.h, t.h, C.byref(dd))
+        assert qh
+        for i in range(store.num_blocks()):
+            t.ctx.check(t.lib.sg_query_submit_block(qh, store.block(i)))
+        rp = C.c_void_p()
+        t.ctx.check(t.lib.sg_query_finish(qh, C.byref(rp)))
+        t._fill(qs, rp)
+        t.lib.sg_result_free(rp)
+        t.lib.sg_query_free(qh)
+        compare(qs, o, q)
+    finally:
+        t.close()
+        ot.close()
+        store.close()
