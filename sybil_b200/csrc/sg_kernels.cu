@@ -315,6 +315,15 @@ __device__ __forceinline__ void gred_add(unsigned long long* p, unsigned long lo
 __device__ __forceinline__ void gred_max(long long* p, long long v) {
   asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// a 64-bit constant parked in shared memory, re-read once per tile: under register pressure the
+// compiler otherwise keeps such a constant in local memory or re-reads it from the plan in global
+// memory, a long-scoreboard wait per use (the multiply-high of the bucket division showed 10% of all
+// stall samples of the C3 kernel waiting for its magic constant)
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t satom_add(uint32_t addr, uint32_t v) {
   uint32_t o;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
@@ -832,6 +841,30 @@ __device__ __forceinline__ void or_slots(SlotT* slot, uint32_t idx0, const uint3
   }
 }
 
+// One row's slot word += v / |= v from the scattered (bucket) passes.  In shared memory the update is a
+// 32-bit reduction on the word that holds the row's byte / halfword (v shifted into its lane; a slot word
+// never overflows its field, so nothing carries into the neighbour): no load, hence no dependent
+// shared-memory round trip per row (the read-modify-write version spent its time in short-scoreboard
+// stalls, profiles/r02_c3.md).  32-bit slot words live in L2: plain read-modify-write there.
+template <typename SlotT>
+__device__ __forceinline__ void slot_add(SlotT* slot, uint32_t slot_s, uint32_t row, uint32_t v) {
+  if (sizeof(SlotT) == 1)
+    sred_add(slot_s + (row & ~3u), v << ((row & 3u) << 3));
+  else if (sizeof(SlotT) == 2)
+    sred_add(slot_s + ((row & ~1u) << 1), v << ((row & 1u) << 4));
+  else
+    slot[row] = (SlotT)(slot[row] + v);
+}
+template <typename SlotT>
+__device__ __forceinline__ void slot_or(SlotT* slot, uint32_t slot_s, uint32_t row, uint32_t v) {
+  if (sizeof(SlotT) == 1)
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(slot_s + (row & ~3u)), "r"(v << ((row & 3u) << 3)) : "memory");
+  else if (sizeof(SlotT) == 2)
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(slot_s + ((row & ~1u) << 1)), "r"(v << ((row & 1u) << 4)) : "memory");
+  else
+    slot[row] = (SlotT)(slot[row] | v);
+}
+
 // value-array str column (raw int32 local ids): visit(row, local_id)
 template <class Visit>
 __device__ __forceinline__ void scan_values_i32(Ctx& cx, const DevCol& c, const uint32_t nrec, Visit visit) {
@@ -1050,6 +1083,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     acc_off = FIXED_SMEM + SG_BLOCK_ROWS * sizeof(SlotT);
   }
   cx.acc = reinterpret_cast<uint32_t*>(smem + acc_off);
+  const uint32_t slot_s = sizeof(SlotT) < 4 ? smem_u32(smem + FIXED_SMEM) : 0u;  // slot words in the shared window
   uint32_t* const gbinpay = lp.gbinpay + (size_t)blockIdx.x * SG_BLOCK_ROWS;
 
   // ---- plan scalars into registers (the plan lives in global memory; every shared
@@ -1133,9 +1167,21 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
   // phase counters live in shared memory (only thread 0 touches them): no registers spent on them
   volatile unsigned long long* const tacc = reinterpret_cast<volatile unsigned long long*>(cx.misc + 96);  // [0..6] + [7] last stamp
   if (dbg && cx.tid == 0) {
-    for (int i = 0; i < 7; i++) tacc[i] = 0;
+    for (int i = 0; i < 16; i++) tacc[i] = 0;
     tacc[7] = (unsigned long long)clock64();
   }
+#ifndef SG_FINE_TIMING
+  // SG_PHASE_TIMING also splits the block by column pass: dbg[9 + p] for the p-th pass of the plan (first 7)
+  auto pass_mark = [&](int p) {
+    if (dbg && cx.tid == 0) {
+      const unsigned long long now = (unsigned long long)clock64();
+      if (p >= 0 && p < 7) tacc[9 + p] += now - tacc[8];
+      tacc[8] = now;
+    }
+  };
+#else
+  auto pass_mark = [&](int) {};
+#endif
   auto phase = [&](int i) {
     if (dbg && cx.tid == 0) {
       const unsigned long long now = (unsigned long long)clock64();
@@ -1356,6 +1402,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     }
     hist_blocks++;
     phase(0);
+    pass_mark(-1);
+    int pass_no = 0;
 
     // ---- filters (aggregate.go:105-112; unpopulated -> false, Q1) -----------------
     // Count mode: a row collects finc per filter it passes (an unpopulated row passes none).  Fail mode
@@ -1390,23 +1438,25 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           }
         }
         __syncthreads();
-        if (fail_mode) {
+        // (a warp-per-failing-bin walk without head bits was tried here: 2.4x slower — every bin costs its
+        // warp a round trip to HBM, and one long bin serialises on a single warp)
+        {
+          // one instantiation serves both modes: rows of bins with a zero payload are left alone (with skipped
+          // tiles the entries of such a bin may decode to rows that are not theirs); count mode adds finc to
+          // the rows of passing bins, fail mode ORs it into the rows of failing bins
           const unsigned long long need =
               push_down ? ((unsigned long long)cx.misc[6] | ((unsigned long long)cx.misc[7] << 32)) : ~0ull;
           scan_bucket<SlotT>(
               cx, c, nrec, [&](uint32_t bin) { return pay[bin] ? fincS : (SlotT)0; },
-              // (only rows of failing bins are written: with skipped tiles the entries of a PASSING bin may
-              // decode to rows that are not theirs, and a read-modify-write there could undo another
-              // thread's FAIL bit)
               [&](uint32_t row, SlotT cur) {
-                if (cur) slot[row] = (SlotT)(slot[row] | cur);
+                if (cur) {
+                  if (fail_mode)
+                    slot_or(slot, slot_s, row, (uint32_t)cur);
+                  else
+                    slot_add(slot, slot_s, row, (uint32_t)cur);
+                }
               },
-              need, false);
-        } else {
-          // finc for rows of a passing bin, else 0: the read-modify-write runs unconditionally
-          scan_bucket<SlotT>(
-              cx, c, nrec, [&](uint32_t bin) { return pay[bin] ? fincS : (SlotT)0; },
-              [&](uint32_t row, SlotT cur) { slot[row] = (SlotT)(slot[row] + cur); });
+              need, !fail_mode);
         }
       } else if (c.enc == SG_ENC_VALUES) {
         uint32_t nval = c.nitems < nrec ? c.nitems : nrec;
@@ -1462,6 +1512,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         for (uint32_t r = cx.tid; r < nrec; r += THREADS) slot[r] = (SlotT)(slot[r] | fincS);
         __syncthreads();
       }
+      pass_mark(pass_no++);
     }
 
     phase(1);
@@ -1477,14 +1528,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         }
         __syncthreads();
         if (nfilters == 0 && gi == 0) {
-          // first pass to touch the (zeroed) slot words: a store, not a read-modify-write
+          // first pass to touch the (zeroed) slot words: a plain store (measured on C2: 20% faster than the
+          // reduction for this pass)
           scan_bucket<SlotT>(
               cx, c, nrec, [&](uint32_t bin) { return (SlotT)pay[bin]; },
               [&](uint32_t row, SlotT cur) { slot[row] = cur; });
         } else {
           scan_bucket<SlotT>(
               cx, c, nrec, [&](uint32_t bin) { return (SlotT)pay[bin]; },
-              [&](uint32_t row, SlotT cur) { slot[row] = (SlotT)(slot[row] + cur); });
+              [&](uint32_t row, SlotT cur) { slot_add(slot, slot_s, row, (uint32_t)cur); });
         }
       } else if (c.enc == SG_ENC_VALUES && G.is_str) {
         const uint32_t stride = G.stride;
@@ -1522,6 +1574,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           add_slots(slot, idx0, inc);
         });
       }
+      pass_mark(pass_no++);
     }
 
     phase(2);
@@ -1577,17 +1630,21 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
             cx, c, nrec, [&](uint32_t bin) { return pay[bin]; },
             [&](uint32_t row, uint32_t cur) {
               if (cur)
-                slot[row] = (SlotT)(slot[row] + cur * ts + tok);
+                slot_add(slot, slot_s, row, cur * ts + (uint32_t)tok);
               else
                 gred_add(g_scalars + 2, 1ull);
             });
       } else if (c.enc == SG_ENC_VALUES && !(c.flags & COL_IS_STR)) {
         const bool stats = (c.flags & COL_STATS) != 0;
-        const unsigned long long tmagic = PP->time_magic;
-        if (stats && c.vmin >= 0 && c.vmax <= 0xffffffffll && tmagic != 0ull && tf >= 0) {
+        const unsigned long long tmagic_p = PP->time_magic;
+        const uint32_t magic_s = smem_u32(const_cast<uint32_t*>(cx.misc) + 8);
+        if (cx.tid == 0) *reinterpret_cast<volatile unsigned long long*>(cx.misc + 8) = tmagic_p;
+        __syncthreads();
+        if (stats && c.vmin >= 0 && c.vmax <= 0xffffffffll && tmagic_p != 0ull && tf >= 0) {
           // 32-bit scan; v / bucket by multiply-high (exact for v < 2^32, see div_magic)
           scan_values_u32(cx, c, nrec, [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid) {
             uint32_t inc[VE];
+            const unsigned long long tmagic = lds_u64(magic_s);
 #pragma unroll
             for (int k = 0; k < VE; k++) {
               inc[k] = 0u;
@@ -1623,6 +1680,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       }
     }
     __syncthreads();
+    if (time_col >= 0) pass_mark(pass_no++);
 
     phase(3);
     // ---- Count / Samples (aggregate.go:202-203), MatchedCount (:117), aggregations
@@ -1726,6 +1784,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       const uint32_t hrows = (hist32 && hoff != HROW_NONE) ? hist_rows : 0u;
       const uint32_t hcache_s = hist_s + hoff * 4u, hrw_b = hrw * 4u;
       unsigned long long* const bkt_w = bkt + (size_t)tb * nvt;  // the window's first row of bucket counters
+      // deferred histogram: where this aggregation's cache misses of value tile t of this block go
+      const uint32_t sp_idx = KA->spill_idx;
+      const bool spill_on = hrows != 0u && hrows < lslots && PP->spill_naggs != 0u && sp_idx != HROW_NONE && lp.spill != nullptr;
+      const size_t sp_tile0 = ((size_t)bid * PP->spill_naggs + sp_idx) * SPILL_TILES;
       auto hist_add = [&](uint32_t e, uint32_t b) {
         if (e < hrows)
           sred_add(hcache_s + e * hrw_b + b * 4u, 1u);
@@ -1770,7 +1832,9 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         agg_mode_bits |= 1u << ai;
         // every value inside the fast range and no carry possible: no per-row checks at all
         const bool allfast = nocarry && c.vmin >= fmin && c.vmax <= fmax;
-        const unsigned long long magic0 = KA->sub[0].magic;
+        const uint32_t magic_s = smem_u32(const_cast<uint32_t*>(cx.misc) + 8);  // misc[8..9]: this aggregation's division magic
+        if (cx.tid == 0) *reinterpret_cast<volatile unsigned long long*>(cx.misc + 8) = KA->sub[0].magic;
+        __syncthreads();
         auto tile32 = [&](uint32_t idx0, const uint32_t(&a)[VE], uint32_t nvalid, auto do_count_tag, auto allfast_tag,
                           auto nofilt_tag) {
           constexpr bool DO_COUNT = decltype(do_count_tag)::value;
@@ -1780,6 +1844,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
           constexpr bool NOFILT = decltype(nofilt_tag)::value;
           uint32_t sw[VE];
           load_slots(slot, idx0, sw);
+          const unsigned long long magic0 = nsub > 0 ? lds_u64(magic_s) : 0ull;
           if (nvalid < VE) {
 #pragma unroll
             for (int k = 0; k < VE; k++)
@@ -1814,7 +1879,30 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               if (!fr && e != trash) agg_slow(&AS, e, (long long)a[k], 0);
             }
           }
-          if (nsub > 0) {
+          if (nsub > 0 && hist32 && spill_on) {
+            // cache hit: shared reduction; miss: one record, written with the other lanes' records of the
+            // same step to consecutive words of the tile's region (rank = lanes below with a record)
+            const uint32_t t = idx0 >> 9;
+            uint32_t* const rec = lp.spill + (sp_tile0 + t) * SPILL_TILE_RECS;
+            const uint32_t ltmask = (1u << cx.lane) - 1u;
+            uint32_t off = 0;
+#pragma unroll
+            for (int k = 0; k < VE; k++) {
+              const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
+              const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
+              const uint32_t e2 = fr ? e : trash;
+              const uint32_t x = a[k] - fmin32 + hdelta;
+              uint32_t b = magic0 ? div_magic(x, magic0) : x / bsize0;
+              b = min(b, nvals0 - 1);
+              const bool miss = e2 >= hrows && e2 != trash;
+              if (e2 < hrows) sred_add(hcache_s + e2 * hrw_b + b * 4u, 1u);
+              const uint32_t m = __ballot_sync(FULL, miss);
+              if (miss)  // streaming store: the records are read once, much later — keep them out of the way in L2
+                asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(rec + off + __popc(m & ltmask)), "r"(e2 * hrw + hoff + b) : "memory");
+              off += __popc(m);
+            }
+            if (cx.lane == 0) lp.spill_counts[sp_tile0 + t] = (uint16_t)off;
+          } else if (nsub > 0) {
 #pragma unroll
             for (int k = 0; k < VE; k++) {
               const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
@@ -2013,6 +2101,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
         }
         counted = true;
       }
+      if (ai >= 0) pass_mark(pass_no++);
     }
     __syncthreads();
 
@@ -2044,9 +2133,7 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
     for (int i = 0; i < 7; i++) dbg[i] = tacc[i];
     dbg[7] = cx.t_tma;
     dbg[8] = cx.t_lb;
-#ifdef SG_FINE_TIMING
-    for (int i = 9; i < 16; i++) dbg[i] = tacc[i];
-#endif
+    for (int i = 9; i < 16; i++) dbg[i] = tacc[i];  // per column pass (or the -DSG_FINE_TIMING marks)
   }
   if (hist_rows) hist_flush();
   if (ACC_SMEM) {
@@ -2241,6 +2328,116 @@ __global__ void __launch_bounds__(THREADS, 1) distinct_kernel(const DevCol* cols
         }
     });
   }
+}
+
+// ---------------------------------------------------------------------------
+// deferred histogram: add the spilled records up.  Every CTA takes a contiguous range of table blocks and
+// counts their records in 16-bit shared-memory counters (two per word; a half that reaches 2^15 sends the
+// increment straight to L2 instead, so no half can wrap: at most THREADS * 16 increments are in flight
+// between the add and its check); the counters are flushed once per pass with 64-bit reductions.  The
+// counter space [hist_rows * hrw, lslots * hrw) is covered in as many passes as 16-bit counters fit.
+// ---------------------------------------------------------------------------
+constexpr uint32_t APPLY_SMEM = 224u * 1024u;
+// one bucket counter's 64-bit home in L2, from its index in the [local slot][hist_row_words] space
+__device__ __forceinline__ unsigned long long* bucket_home(const Plan* __restrict__ PP, uint32_t idx, uint32_t hrw) {
+  const uint32_t row = idx / hrw, off = idx - row * hrw;
+  for (int a = 0; a < PP->naggs; a++) {
+    const uint32_t ho = PP->aggs[a].hrow_off, nv = PP->aggs[a].nvals_total;
+    if (ho != HROW_NONE && off >= ho && off - ho < nv)
+      return reinterpret_cast<unsigned long long*>(PP->aggs[a].buckets) + ((size_t)row * nv + (off - ho));
+  }
+  return nullptr;
+}
+__global__ void __launch_bounds__(THREADS, 1) hist_apply_kernel(const Plan* __restrict__ PP, const uint32_t* __restrict__ spill,
+                                                                const uint16_t* __restrict__ counts, uint32_t nblocks,
+                                                                uint32_t naggs_spill, uint32_t lslots, uint32_t hist_rows,
+                                                                uint32_t hrw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* const cnt = reinterpret_cast<uint32_t*>(smem_raw);
+  const uint32_t cnt_s = smem_u32(cnt);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t first = hist_rows * hrw, total = lslots * hrw - first;  // counters the records can name
+  const uint32_t cap = APPLY_SMEM / 2u;                                  // 16-bit counters per pass
+  const uint32_t per = (nblocks + gridDim.x - 1) / gridDim.x;
+  const uint32_t b0 = min(blockIdx.x * per, nblocks), b1 = min(b0 + per, nblocks);
+  const size_t ntile = (size_t)(b1 - b0) * naggs_spill * SPILL_TILES;
+  const size_t tile0 = (size_t)b0 * naggs_spill * SPILL_TILES;
+  for (uint32_t lo = 0; lo < total; lo += cap) {
+    const uint32_t n = min(cap, total - lo), base = first + lo;
+    for (uint32_t i = tid; i < (n + 1u) / 2u; i += THREADS) cnt[i] = 0;
+    __syncthreads();
+    // a warp's tiles, one ahead: the next tile's count and records (all 2 KiB of its region — what lies past
+    // the count is masked) are in flight while the current tile's 512 candidates are counted
+    size_t ti = warp;
+    uint32_t nrec_n = 0;
+    uint4 qn[4];
+    auto fetch = [&](size_t t) {
+      nrec_n = counts[tile0 + t];
+      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(spill + (tile0 + t) * SPILL_TILE_RECS);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(qn[j].x), "=r"(qn[j].y), "=r"(qn[j].z), "=r"(qn[j].w)
+                     : "l"(src + j * 32 + lane));
+    };
+    if (ti < ntile) fetch(ti);
+    while (ti < ntile) {
+      const uint32_t nrec = nrec_n;
+      uint4 q[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) q[j] = qn[j];
+      const size_t tn = ti + NWARPS;
+      if (tn < ntile) fetch(tn);
+      uint32_t hot = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t r[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t pos = (uint32_t)(j * 32 + lane) * 4u + (uint32_t)i;
+          const uint32_t c = r[i] - base;  // counter inside this pass (unsigned: the others land far out of range)
+          if (pos < nrec && c < n) {
+            const uint32_t sh = (c & 1u) << 4;
+            const uint32_t old = satom_add(cnt_s + (c >> 1) * 4u, 1u << sh);
+            hot |= ((old >> sh) & 0x8000u) ? (1u << (j * 4 + i)) : 0u;
+          }
+        }
+      }
+      if (hot) {  // rare: a half at 2^15 or above keeps its value, the increment goes straight to L2
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t r[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if ((hot >> (j * 4 + i)) & 1u) {
+              const uint32_t c = r[i] - base;
+              sred_add(cnt_s + (c >> 1) * 4u, 0u - (1u << ((c & 1u) << 4)));
+              unsigned long long* const home = bucket_home(PP, r[i], hrw);
+              if (home) gred_add(home, 1ull);
+            }
+        }
+      }
+      ti = tn;
+    }
+    __syncthreads();
+    for (uint32_t w = tid; w < (n + 1u) / 2u; w += THREADS) {
+      const uint32_t v = cnt[w];
+      if (!v) continue;
+      if (v & 0xffffu) gred_add(bucket_home(PP, base + 2u * w, hrw), (unsigned long long)(v & 0xffffu));
+      if (v >> 16) gred_add(bucket_home(PP, base + 2u * w + 1u, hrw), (unsigned long long)(v >> 16));
+    }
+    __syncthreads();
+  }
+}
+
+int launch_hist_apply(const Plan* plan, const uint32_t* spill, const uint16_t* counts, uint32_t nblocks, uint32_t naggs_spill,
+                      uint32_t lslots, uint32_t hist_rows, uint32_t hrw, int grid, void* stream) {
+  if (nblocks == 0 || naggs_spill == 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(hist_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  hist_apply_kernel<<<grid, THREADS, APPLY_SMEM, (cudaStream_t)stream>>>(plan, spill, counts, nblocks, naggs_spill, lslots,
+                                                                        hist_rows, hrw);
+  return (int)cudaGetLastError();
 }
 
 int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,

@@ -1037,6 +1037,9 @@ struct sg_query {
   uint32_t* d_gslots = nullptr;
   uint32_t* d_gbinpay = nullptr;
   unsigned long long* d_gdummy = nullptr;
+  uint32_t* d_spill = nullptr;         // deferred-histogram records (Plan::spill_naggs)
+  uint16_t* d_spill_counts = nullptr;
+  size_t spill_cap = 0;                // table blocks x spill aggregations the buffers hold
   std::vector<uint32_t*> d_luts;
   size_t block_cap = 0;
   int grid = 0;
@@ -1075,6 +1078,11 @@ void free_device(sg_query* q) {
   pool_release(c, q->d_gslots);
   pool_release(c, q->d_gbinpay);
   pool_release(c, q->d_gdummy);
+  pool_release(c, q->d_spill);
+  pool_release(c, q->d_spill_counts);
+  q->d_spill = nullptr;
+  q->d_spill_counts = nullptr;
+  q->spill_cap = 0;
   for (auto p : q->d_luts) pool_release(c, p);
   q->d_luts.clear();
   q->d_plan = nullptr;
@@ -1538,7 +1546,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   for (int i = 0; i < P.naggs; i++) {
     KAgg& ka = P.aggs[i];
     ka.hrow_off = HROW_NONE;
-    ka._pad2 = 0;
+    ka.spill_idx = HROW_NONE;
     if (!P.hist_mode || ka.nsub != 1 || getenv("SG_NO_HIST_CACHE")) continue;
     const long long fmin = ka.info_min > 0 ? ka.info_min : 0;
     long long fmax = ka.info_max < 0xffffffffll ? ka.info_max : 0xffffffffll;
@@ -1606,6 +1614,17 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   q->nstage = nstage;
   P.acc_repl = repl;  // 0: accumulate straight into global memory
   P.hist_rows = hrows;
+  // deferred histogram for the rows the cache cannot hold (whole-axis plans only: records carry local slots)
+  P.spill_naggs = 0;
+  for (int i = 0; i < P.naggs; i++) P.aggs[i].spill_idx = HROW_NONE;
+  // Off unless SG_SPILL=1: measured on C3 (profiles/r02_c3.md) the scan kernel gets 9% faster, but the
+  // records' extra HBM traffic slows the bandwidth-bound value passes of the other CTAs and the apply kernel
+  // takes the rest: no net gain at 117 slots x 1,002 buckets.
+  if (hrow_words && repl && hrows > 0 && hrows < P.lslots && P.lslots == P.nslots && getenv("SG_SPILL") && !getenv("SG_NO_SPILL") &&
+      (uint64_t)P.lslots * hrow_words < 0xffffffffull) {
+    for (int i = 0; i < P.naggs; i++)
+      if (P.aggs[i].hrow_off != HROW_NONE) P.aggs[i].spill_idx = P.spill_naggs++;
+  }
   q->smem_bytes = scan_fixed_smem(nstage) + slots_b + (repl ? (uint32_t)acc_bytes(repl) + hrows * hrow_words * 4 + 16 : 0u);
   return SG_OK;
 }
@@ -1635,6 +1654,27 @@ int alloc_device(sg_query* q) {
   if (!q->d_gdummy) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gdummy, (size_t)q->grid * 32 * 8));
   if (q->slot_bytes == 4 && !q->d_gslots)
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gslots, (size_t)q->grid * SG_BLOCK_ROWS * 4));
+  if (q->plan.spill_naggs) {
+    const size_t need = nb * (size_t)q->plan.spill_naggs;
+    if (need > q->spill_cap) {
+      pool_release(c, q->d_spill);
+      pool_release(c, q->d_spill_counts);
+      q->d_spill = nullptr;
+      q->d_spill_counts = nullptr;
+      q->spill_cap = 0;
+      if (pool_alloc(c, (void**)&q->d_spill, need * SPILL_TILES * SPILL_TILE_RECS * 4) != cudaSuccess ||
+          pool_alloc(c, (void**)&q->d_spill_counts, need * SPILL_TILES * 2) != cudaSuccess) {
+        // no room for the record buffers: cache misses go straight to L2 as before
+        cudaGetLastError();
+        pool_release(c, q->d_spill);
+        q->d_spill = nullptr;
+        q->plan.spill_naggs = 0;
+        for (int i = 0; i < q->plan.naggs; i++) q->plan.aggs[i].spill_idx = HROW_NONE;
+      } else {
+        q->spill_cap = need;
+      }
+    }
+  }
   if (!q->ev0) {
     CUDA_TRY(c, cudaEventCreate(&q->ev0));
     CUDA_TRY(c, cudaEventCreate(&q->ev1));
@@ -1739,6 +1779,11 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.nstage = t->d_tmaps ? q->nstage : 0u;
   lp.dbg = nullptr;
   lp.hashg = q->hashg ? 1u : 0u;
+  lp.spill = q->plan.spill_naggs ? q->d_spill : nullptr;
+  lp.spill_counts = q->plan.spill_naggs ? q->d_spill_counts : nullptr;
+  if (q->plan.spill_naggs)
+    CUDA_TRY(c, cudaMemsetAsync(q->d_spill_counts, 0, std::max<size_t>(t->blocks.size(), 1) * q->plan.spill_naggs * SPILL_TILES * 2,
+                                c->stream));
   // Deferred fold: the replicated 32-bit accumulators of up to fold_every consecutive blocks are
   // folded together.  Needs one encoding per aggregation column across the listed blocks (word0
   // counts accepted rows for bucket columns, rejected ones for value arrays) and keeps the hot
@@ -1788,6 +1833,15 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
     c->set_err(std::string("scan kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     return SG_ERR_CUDA;
   }
+  if (q->plan.spill_naggs) {
+    rc = launch_hist_apply(q->d_plan, q->d_spill, q->d_spill_counts, (uint32_t)t->blocks.size(), q->plan.spill_naggs,
+                           q->plan.lslots, q->plan.hist_rows, q->plan.hist_row_words, q->grid, c->stream);
+    if (rc != 0) {
+      c->set_err(std::string("hist_apply kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+      return SG_ERR_CUDA;
+    }
+    q->launches += 1;
+  }
   CUDA_TRY(c, cudaEventRecord(q->ev1, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(hp + off_acc, q->d_acc, acc_back, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1813,9 +1867,9 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
     fprintf(stderr, "[sg phase cycles avg/CTA] init %llu filters %llu groups %llu time %llu aggs %llu flush %llu fetch %llu | warp0 value-pass waits: tma %llu lookback %llu | max CTA total %llu (kernel %.3f ms)\n",
             tot[0] / q->grid, tot[1] / q->grid, tot[2] / q->grid, tot[3] / q->grid, tot[4] / q->grid, tot[5] / q->grid,
             tot[6] / q->grid, tot[7] / q->grid, tot[8] / q->grid, mx, ms);
-    if (tot[9] | tot[10] | tot[11] | tot[12] | tot[13])  // -DSG_FINE_TIMING builds: bucket-pass breakdown (thread 0)
-      fprintf(stderr, "[sg bucket passes avg/CTA] payload build %llu head bits %llu own tiles %llu wait for slowest warp %llu | elsewhere %llu | flush: fold loop %llu (rest of flush in elsewhere) pre %llu\n",
-              tot[9] / q->grid, tot[10] / q->grid, tot[11] / q->grid, tot[12] / q->grid, tot[13] / q->grid, tot[14] / q->grid, tot[15] / q->grid);
+    if (tot[9] | tot[10] | tot[11] | tot[12] | tot[13])  // per column pass in plan order (filters, groups, time, aggregations)
+      fprintf(stderr, "[sg pass cycles avg/CTA] %llu %llu %llu %llu %llu %llu %llu\n", tot[9] / q->grid, tot[10] / q->grid,
+              tot[11] / q->grid, tot[12] / q->grid, tot[13] / q->grid, tot[14] / q->grid, tot[15] / q->grid);
     pool_release(c, d_dbg);
   }
   return SG_OK;
