@@ -234,6 +234,21 @@ func (t *Table) Run(q *Query, allreduce bool) (*C.sg_result, error) {
 	d.time_col_slot, d.time_bucket = C.int32_t(q.TimeSlot), C.int64_t(q.TimeBucket)
 	d.time_min, d.time_max = C.int64_t(q.TimeMin), C.int64_t(q.TimeMax)
 	d.weight_col_slot = -1
+	// SortResults(OrderBy, OrderAsc) and FLAGS.LIMIT (ABI v2)
+	d.order_by_agg = C.SG_ORDER_COUNT
+	if spec.OrderBy == "" {
+		d.order_by_agg = C.SG_ORDER_NONE
+	} else if spec.OrderBy != "$COUNT" {
+		for i, a := range spec.Aggregations {
+			if a.Name == spec.OrderBy {
+				d.order_by_agg = C.int32_t(i)
+			}
+		}
+	}
+	if spec.OrderAsc {
+		d.order_asc = 1
+	}
+	d.limit = C.int64_t(spec.Limit)
 	h := C.sg_query_begin(t.c.h, t.h, &d)
 	if h == nil {
 		return nil, t.c.err()

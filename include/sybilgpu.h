@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 1
+#define SG_ABI_VERSION 2 /* 2: order_by_agg / order_asc / limit in sg_query_desc */
 
 /* limits of one query (reference has none; beyond these -> SG_ERR_UNSUPPORTED) */
 #define SG_MAX_FILTERS 15
@@ -72,6 +72,9 @@ typedef enum sg_filter_op {
 /* FLAGS.OP (hist_basic.go:79) and FLAGS.LOG_HIST (hist.go:29) */
 typedef enum sg_op_mode { SG_MODE_AVG = 0, SG_MODE_HIST = 1 } sg_op_mode;
 typedef enum sg_hist_kind { SG_HIST_BASIC = 0, SG_HIST_MULTI = 1 } sg_hist_kind;
+/* sg_query_desc.order_by_agg */
+#define SG_ORDER_COUNT (-1)
+#define SG_ORDER_NONE (-2)
 
 typedef struct sg_ctx sg_ctx;
 typedef struct sg_table sg_table;
@@ -120,7 +123,16 @@ typedef struct sg_query_desc {
   int64_t time_min;        /* table IntInfo of the time column: bounds the */
   int64_t time_max;        /*   dense time-bucket axis (rows outside are counted in overflow) */
   int32_t weight_col_slot; /* OPTS.WEIGHT_COL_ID, -1 = unweighted (v1 rejects others) */
+  /* SortResults (aggregate.go:43-54,497-525): QuerySpec.OrderBy = "$COUNT" (SG_ORDER_COUNT), the name of an
+   * aggregation (its index: groups ordered by Hists[col].Mean(), descending) or "" (SG_ORDER_NONE: no sort,
+   * groups come in slot order); OrderAsc reverses the sorted list.  Ties (Go's sort is unstable): GroupByKey
+   * ascending before the reversal.  A group without the histogram sorts as mean = -inf (Go would panic). */
+  int32_t order_by_agg;
+  int32_t order_asc;
   int32_t _pad;
+  /* FLAGS.LIMIT (printer.go): > 0 = only the first `limit` groups of the sorted list are materialised
+   * (sg_result_num_groups); Cumulative and sg_result_num_groups_total still cover every group.  0 = all. */
+  int64_t limit;
   const sg_filter_desc* filters;
   const sg_group_desc* groups;
   const sg_agg_desc* aggs;
@@ -252,12 +264,12 @@ int sg_comm_unique_id(sg_ctx* ctx, char id_out[128]);
 int sg_comm_init(sg_ctx* ctx, const char id[128], int rank, int nranks);
 
 /* ---- result --------------------------------------------------------------
- * QueryResults (query_spec.go:14-22).  Groups are sorted by Count descending
- * (ties: key ascending), which is SortResults with OrderBy=$COUNT made
- * deterministic (aggregate.go:43-54,497-525). */
+ * QueryResults (query_spec.go:14-22).  Groups come sorted as sg_query_desc.order_by_agg / order_asc say
+ * (SortResults made deterministic, aggregate.go:43-54,497-525). */
 void sg_result_free(sg_result* r);
 int64_t sg_result_matched_count(sg_result* r); /* QueryResults.MatchedCount */
-int64_t sg_result_num_groups(sg_result* r);    /* len(Results) */
+int64_t sg_result_num_groups(sg_result* r);    /* groups materialised: min(len(Results), limit) */
+int64_t sg_result_num_groups_total(sg_result* r); /* len(Results) */
 int64_t sg_result_num_broken(sg_result* r);    /* blocks dropped: "BLOCK SIZE CHANGED" */
 int64_t sg_result_num_skipped(sg_result* r);   /* blocks pruned by the zone map */
 /* i-th group (0-based, sorted).  key_out: ngroups u64 (ints two's complement,

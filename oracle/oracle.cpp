@@ -75,6 +75,8 @@ struct Flags {  // the globals of config.go the hot path reads
   bool weight_col = false;  // OPTS.WEIGHT_COL
   int weight_col_id = 0;    // OPTS.WEIGHT_COL_ID
   int time_col_id = -1;     // OPTS.TIME_COL_ID
+  int order_by = -1;        // QuerySpec.OrderBy: -1 "$COUNT", -2 "" (no sort), >= 0 index of the aggregation
+  bool order_asc = false;   // QuerySpec.OrderAsc
 };
 
 struct IntInfo {  // table_column_info.go:18-24 (Min/Max are all the path reads)
@@ -836,13 +838,27 @@ struct Combined {  // resultSpec of CombineResults
   std::map<int64_t, std::vector<ResultP>> TimeSorted;
 };
 
-static void sort_results(std::vector<ResultP>& v) {
-  // SortResultsByCol.Less with Col == "$COUNT" (aggregate.go:43-54); sort.Sort is
-  // unstable in Go, ties are broken here by GroupByKey ascending
-  std::sort(v.begin(), v.end(), [](const ResultP& a, const ResultP& b) {
-    if (a->Count != b->Count) return a->Count > b->Count;
+static void sort_results(const Flags* f, std::vector<ResultP>& v) {
+  // QuerySpec.SortResults (aggregate.go:497-525): no sort for OrderBy == ""; SortResultsByCol.Less (:43-54)
+  // orders descending by Count ("$COUNT") or by Hists[col].Mean(); sort.Sort is unstable in Go, ties are
+  // broken here by GroupByKey ascending; orderAsc then reverses the whole list (:516-520).  A group without
+  // the histogram (Go: nil map entry, Mean() would panic) sorts as mean = -inf.
+  if (f->order_by == -2) return;
+  const int col = f->order_by;
+  auto mean = [col](const ResultP& r) {
+    auto it = r->Hists.find(col);
+    return it == r->Hists.end() || it->second.TotalCount() == 0 ? -INFINITY : it->second.Mean();
+  };
+  std::sort(v.begin(), v.end(), [&](const ResultP& a, const ResultP& b) {
+    if (col < 0) {
+      if (a->Count != b->Count) return a->Count > b->Count;
+    } else {
+      const double ma = mean(a), mb = mean(b);
+      if (ma != mb) return ma > mb;
+    }
     return a->GroupByKey < b->GroupByKey;
   });
+  if (f->order_asc) std::reverse(v.begin(), v.end());
 }
 
 // aggregate.go:414-467; block_specs iterated in ascending block order
@@ -874,11 +890,11 @@ static void CombineResults(const QuerySpec& proto, std::vector<std::unique_ptr<Q
     }
   }
   for (auto& k : out.Results.order) out.Sorted.push_back(out.Results.idx.at(k));
-  sort_results(out.Sorted);
+  sort_results(f, out.Sorted);
   for (auto& tv : out.TimeResults) {
     auto& v = out.TimeSorted[tv.first];
     for (auto& k : tv.second.order) v.push_back(tv.second.idx.at(k));
-    sort_results(v);
+    sort_results(f, v);
   }
 }
 
@@ -956,6 +972,8 @@ orc_result* orc_query(orc_table* tab, const sg_query_desc* d, int nthreads, int6
   r->flags.weight_col = d->weight_col_slot >= 0;
   r->flags.weight_col_id = d->weight_col_slot >= 0 ? d->weight_col_slot : 0;
   r->flags.time_col_id = d->time_col_slot;
+  r->flags.order_by = d->order_by_agg;
+  r->flags.order_asc = d->order_asc != 0;
   QuerySpec proto;
   proto.fp = &r->flags;
   proto.TimeBucket = d->time_col_slot >= 0 ? d->time_bucket : 0;

@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("SG_LIB") or os.path.join(_HERE, "csrc", "libsybilgpu.
 GEN_PATH = os.path.join(_HERE, "csrc", "libsybilblockgen.so")
 GOB_PATH = os.path.join(_HERE, "csrc", "libsybilgob.so")
 
-SG_ABI_VERSION = 1
+SG_ABI_VERSION = 2
+SG_ORDER_COUNT, SG_ORDER_NONE = -1, -2
 SG_MAX_FILTERS, SG_MAX_GROUPS, SG_MAX_AGGS, SG_MAX_COLS = 15, 8, 16, 64
 SG_BLOCK_ROWS = 65536
 SG_MISSING_KEY = 0xFFFFFFFFFFFFFFFF
@@ -46,7 +47,8 @@ class sg_query_desc(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("op_mode", C.c_int32), ("hist_kind", C.c_int32),
                 ("hist_bucket", C.c_int32), ("nfilters", C.c_int32), ("ngroups", C.c_int32), ("naggs", C.c_int32),
                 ("time_col_slot", C.c_int32), ("time_bucket", C.c_int64), ("time_min", C.c_int64),
-                ("time_max", C.c_int64), ("weight_col_slot", C.c_int32), ("_pad", C.c_int32),
+                ("time_max", C.c_int64), ("weight_col_slot", C.c_int32), ("order_by_agg", C.c_int32),
+                ("order_asc", C.c_int32), ("_pad", C.c_int32), ("limit", C.c_int64),
                 ("filters", C.POINTER(sg_filter_desc)), ("groups", C.POINTER(sg_group_desc)),
                 ("aggs", C.POINTER(sg_agg_desc))]
 
@@ -124,6 +126,7 @@ SYMBOLS = {
     "sg_result_free": (None, [P]),
     "sg_result_matched_count": (C.c_int64, [P]),
     "sg_result_num_groups": (C.c_int64, [P]),
+    "sg_result_num_groups_total": (C.c_int64, [P]),
     "sg_result_num_broken": (C.c_int64, [P]),
     "sg_result_num_skipped": (C.c_int64, [P]),
     "sg_result_group": (C.c_int, [P, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -13,6 +13,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +22,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -120,6 +123,34 @@ struct sg_ctx {
       hpin_cap = cap;
     }
     return hpin;
+  }
+  // pinned buffers large results are read back into (and read from: no copy to pageable memory); recycled,
+  // because cudaHostAlloc of tens of megabytes costs milliseconds
+  std::vector<std::pair<char*, size_t>> pin_free;
+  char* pin_get(size_t bytes, size_t* got) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < pin_free.size(); i++)
+        if (pin_free[i].second >= bytes && pin_free[i].second <= bytes * 2 + ((size_t)1 << 20)) {
+          char* p = pin_free[i].first;
+          *got = pin_free[i].second;
+          pin_free.erase(pin_free.begin() + (long)i);
+          return p;
+        }
+    }
+    char* p = nullptr;
+    if (cudaHostAlloc((void**)&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    *got = bytes;
+    return p;
+  }
+  void pin_put(char* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (pin_free.size() >= 4) {
+      cudaFreeHost(pin_free.front().first);
+      pin_free.erase(pin_free.begin());
+    }
+    pin_free.emplace_back(p, bytes);
   }
   void set_err(const std::string& s) { err = s; }
   bool is_pinned(const void* p, size_t n) const {
@@ -306,6 +337,10 @@ struct sg_table {
   };
   std::vector<ValueHash> vhash;
   std::vector<uint32_t> pending_stats;  // value-array int columns whose extents are not computed yet
+  // sort ranks of the dictionaries' rendered fields (ties of SortResults break by GroupByKey ascending):
+  // rank[id] over the strings (resp. the decimal renderings of the int values) + '\t'; rebuilt when a
+  // dictionary has grown
+  std::vector<std::vector<uint32_t>> srank, irank;
   std::vector<std::pair<char*, size_t>> chunks;  // device arena chunks (ptr, capacity)
   size_t chunk_idx = 0, chunk_used = 0;
   Stage stage[2];
@@ -326,6 +361,7 @@ struct sg_table {
   DevCol* d_cols = nullptr;
   size_t d_blocks_cap = 0;
   bool dirty = true;
+  uint64_t version = 1;  // bumped whenever blocks or dictionaries change: a query's plan is reused while it stands
 };
 
 namespace {
@@ -434,6 +470,7 @@ void sg_destroy(sg_ctx* c) {
   for (auto& p : c->pool_free) cudaFree(p.first);
   for (auto& p : c->pool_live) cudaFree(p.first);  // buffers an error path did not hand back
   if (c->hpin) cudaFreeHost(c->hpin);
+  for (auto& p : c->pin_free) cudaFreeHost(p.first);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -521,6 +558,8 @@ sg_table* sg_table_create(sg_ctx* c, int32_t num_col_slots, const int32_t* col_t
   t->idict.resize((size_t)num_col_slots);
   t->has_values_int.assign((size_t)num_col_slots, 0);
   t->vhash.assign((size_t)num_col_slots, sg_table::ValueHash());
+  t->srank.assign((size_t)num_col_slots, std::vector<uint32_t>());
+  t->irank.assign((size_t)num_col_slots, std::vector<uint32_t>());
   cudaSetDevice(c->device);
   for (int i = 0; i < 2; i++) {
     if (cudaHostAlloc((void**)&t->stage[i].host, STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess ||
@@ -820,6 +859,7 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
   t->total_rows += nrec;
   t->encoded_bytes += enc_bytes;
   t->dirty = true;
+  t->version++;
   return SG_OK;
 }
 
@@ -903,6 +943,7 @@ int sg_table_clear(sg_table* t) {
   t->encoded_bytes = 0;
   t->h2d_bytes = 0;
   t->dirty = true;
+  t->version++;
   return SG_OK;
 }
 
@@ -933,11 +974,13 @@ int sg_table_dict_get(sg_table* t, int32_t col, int64_t id, const char** bytes, 
 int sg_table_dict_seed_str(sg_table* t, int32_t col, const char* bytes, const uint32_t* offsets, int64_t n) {
   if (!t || col < 0 || col >= t->ncols || n < 0 || (n > 0 && (!bytes || !offsets))) return SG_ERR_INVALID;
   for (int64_t i = 0; i < n; i++) t->sdict[(size_t)col].intern(bytes + offsets[i], offsets[i + 1] - offsets[i]);
+  t->version++;
   return SG_OK;
 }
 int sg_table_dict_seed_int(sg_table* t, int32_t col, const int64_t* values, int64_t n) {
   if (!t || col < 0 || col >= t->ncols || n < 0 || (n > 0 && !values)) return SG_ERR_INVALID;
   for (int64_t i = 0; i < n; i++) t->idict[(size_t)col].intern(values[i]);
+  t->version++;
   return SG_OK;
 }
 int64_t sg_table_intdict_size(sg_table* t, int32_t col) {
@@ -1001,6 +1044,19 @@ struct sg_result {
   std::vector<int64_t> time_keys;
   std::vector<std::unique_ptr<sg_result>> time_slices;
   bool has_total_hists = true;
+  // Results without a time axis are materialised on demand: the accumulators stay as read back, `order`
+  // lists the (limit) slots in sorted order and a ResultGroup is built the first time it is asked for — a
+  // 1M-group result no longer renders and sorts a million keys on the host per query
+  bool lazy = false;
+  std::vector<uint64_t> acc;  // accumulator words [0, acc_have): small results
+  char* pin = nullptr;        // ... large results: a pinned buffer of the context's pool
+  size_t pin_bytes = 0;
+  const uint64_t* accp = nullptr;
+  size_t acc_have = 0;
+  ~sg_result();
+  std::vector<uint32_t> order;
+  int64_t ngroups_total = 0;
+  std::unordered_map<int64_t, std::unique_ptr<ResultGroup>> cache;
 };
 
 struct sg_query {
@@ -1028,6 +1084,7 @@ struct sg_query {
   uint64_t* d_acc = nullptr;  // one allocation: scalars | count | per agg hcount,sum,vmax | buckets
   size_t acc_words = 0;
   size_t sum_words = 0;  // leading words merged by SUM; the rest (vmax) by MAX
+  size_t prefix_words = 0;  // scalars | count | sums
   size_t off_count = 0;
   std::vector<size_t> off_hcount, off_sum, off_vmax, off_buckets;
   uint32_t* d_block_status = nullptr;
@@ -1051,6 +1108,14 @@ struct sg_query {
   int64_t rows_scanned = 0, blocks_scanned = 0;
   int64_t d2h_bytes = 0;
   bool ran = false;
+  double host_plan_ms = 0, host_run_ms = 0;  // SG_HOST_TIMING
+  // a prepared query run again over an unchanged table keeps its block list, plan and uploaded work items
+  uint64_t plan_version = 0;
+  std::vector<uint32_t> plan_list;
+  int64_t plan_skipped = 0, plan_broken = 0, plan_rows = 0;
+  std::vector<uint32_t> items_up, masks_up;  // work items as they sit in d_block_list
+  uint64_t fold_version = 0;
+  uint32_t fold_every = 1;
   std::vector<uint32_t> last_list;
   std::vector<char> hc_is_count;
   // cross-GPU merge under differing per-rank dictionaries: the union dictionaries the merged
@@ -1063,6 +1128,10 @@ struct sg_query {
   std::vector<std::vector<std::string>> m_strs;
   std::vector<std::vector<int64_t>> m_ints;
 };
+
+sg_result::~sg_result() {
+  if (pin && q) q->ctx->pin_put(pin, pin_bytes);
+}
 
 namespace {
 
@@ -1282,10 +1351,15 @@ int layout_accumulators(sg_query* q, uint32_t nslots) {
   q->off_sum.clear();
   q->off_vmax.clear();
   q->off_buckets.clear();
+  // all sums, then all hist Counts: when every hist Count equals Count (hc_is_count) and no buckets exist,
+  // scalars | count | sums is all a result needs and it is one contiguous prefix of the array
+  for (int i = 0; i < naggs; i++) {
+    q->off_sum.push_back(words);
+    words += nslots;
+  }
+  q->prefix_words = words;
   for (int i = 0; i < naggs; i++) {
     q->off_hcount.push_back(words);
-    words += nslots;
-    q->off_sum.push_back(words);
     words += nslots;
   }
   for (int i = 0; i < naggs; i++) {
@@ -1749,7 +1823,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
     return SG_ERR_CUDA;
   }
   memcpy(hp, &q->plan, sizeof(Plan));
-  if (!items.empty()) {
+  const bool items_same = items == q->items_up && masks == q->masks_up && q->fold_version == t->version;
+  if (!items.empty() && !items_same) {
     uint32_t* w = (uint32_t*)(hp + off_items);
     for (size_t i = 0; i < items.size(); i++) {
       w[4 * i + 0] = items[i];
@@ -1758,6 +1833,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
       w[4 * i + 3] = 0;
     }
     CUDA_TRY(c, cudaMemcpyAsync(q->d_block_list, hp + off_items, items.size() * 16, cudaMemcpyHostToDevice, c->stream));
+    q->items_up = items;
+    q->masks_up = masks;
   }
   CUDA_TRY(c, cudaMemsetAsync(q->d_work, 0, 64, c->stream));
   CUDA_TRY(c, cudaMemsetAsync(q->d_block_status, 0, std::max<size_t>(t->blocks.size(), 1) * 4, c->stream));
@@ -1789,7 +1866,9 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   // counts accepted rows for bucket columns, rejected ones for value arrays) and keeps the hot
   // path's no-carry proof: fast-range max x rows one replica can receive x fold_every < 2^32.
   lp.fold_every = 1;
-  if (q->plan.acc_repl > 0 && !list.empty() && !getenv("SG_NO_DEFER_FOLD")) {
+  if (items_same) {
+    lp.fold_every = q->fold_every;
+  } else if (q->plan.acc_repl > 0 && !list.empty() && !getenv("SG_NO_DEFER_FOLD")) {
     bool uniform = true;
     for (int a = 0; a < q->plan.naggs && uniform; a++) {
       const size_t col = (size_t)q->plan.aggs[a].col;
@@ -1817,6 +1896,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
       lp.fold_every = (uint32_t)std::max<unsigned long long>(k, 1);
     }
   }
+  q->fold_every = lp.fold_every;
+  q->fold_version = t->version;
   static const bool phase_timing = getenv("SG_PHASE_TIMING") != nullptr;
   unsigned long long* d_dbg = nullptr;
   if (phase_timing) {
@@ -1918,121 +1999,341 @@ void init_group(ResultGroup& g, int naggs) {
   for (int a = 0; a < naggs; a++) g.vx(a) = INT64_MIN;
 }
 
-void sort_groups(std::vector<ResultGroup>& v) {
-  // SortResults with OrderBy = $COUNT (aggregate.go:43-54,497-525); Go's sort is
-  // unstable, ties are broken by the rendered key ascending
-  std::sort(v.begin(), v.end(), [](const ResultGroup& a, const ResultGroup& b) {
-    if (a.count != b.count) return a.count > b.count;
+// ---- SortResults (aggregate.go:43-54,497-525) -------------------------------------------------------
+// the value groups are ordered by: Count, or the mean of one aggregation (-inf without its histogram)
+static inline double order_value(const sg_query* q, int64_t count, int64_t hc, int64_t sum) {
+  const int ob = q->d.order_by_agg;
+  if (ob < 0) return (double)count;
+  return hc == 0 ? -INFINITY : (double)sum / (double)hc;
+}
+void sort_groups(const sg_query* q, std::vector<ResultGroup>& v) {
+  // descending by the order value; Go's sort is unstable, ties are broken by the rendered key ascending;
+  // OrderAsc reverses the sorted list; OrderBy == "" leaves the groups in slot order
+  const int ob = q->d.order_by_agg;
+  if (ob == SG_ORDER_NONE) return;
+  auto val = [&](const ResultGroup& g) { return ob < 0 ? (double)g.count : order_value(q, g.count, g.hc(ob), g.sm(ob)); };
+  std::sort(v.begin(), v.end(), [&](const ResultGroup& a, const ResultGroup& b) {
+    const double va = val(a), vb = val(b);
+    if (va != vb) return va > vb;
     return a.skey < b.skey;
   });
+  if (q->d.order_asc) std::reverse(v.begin(), v.end());
+}
+
+// a < b for the rendered fields a + '\t', b + '\t'
+static inline bool tab_less(const std::string& a, const std::string& b) {
+  const size_t n = std::min(a.size(), b.size());
+  const int c = memcmp(a.data(), b.data(), n);
+  if (c != 0) return c < 0;
+  if (a.size() == b.size()) return false;
+  return a.size() < b.size() ? (unsigned char)'\t' < (unsigned char)b[n] : (unsigned char)a[n] < (unsigned char)'\t';
+}
+static void ranks_of(const std::vector<std::string>& strs, std::vector<uint32_t>& rank) {
+  std::vector<uint32_t> idx(strs.size());
+  for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
+  std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return tab_less(strs[x], strs[y]); });
+  rank.resize(strs.size());
+  for (size_t i = 0; i < idx.size(); i++) rank[idx[i]] = (uint32_t)i;
+}
+// rank of every code of one slot-space axis in the order of its rendered field (code 0 = missing = "" first)
+static const std::vector<uint32_t>& axis_ranks(sg_query* q, size_t di, std::vector<uint32_t>& scratch) {
+  const GroupDim& d = q->dims[di];
+  sg_table* t = q->table;
+  if (q->merged) {  // union dictionaries of a cross-GPU merge: per query
+    if (d.is_str) {
+      ranks_of(q->m_strs[di], scratch);
+    } else {
+      std::vector<std::string> r;
+      for (int64_t v : q->m_ints[di]) r.push_back(std::to_string(v));
+      ranks_of(r, scratch);
+    }
+    return scratch;
+  }
+  if (d.is_str) {
+    auto& cache = t->srank[(size_t)d.col];
+    if (cache.size() != t->sdict[(size_t)d.col].strs.size()) ranks_of(t->sdict[(size_t)d.col].strs, cache);
+    return cache;
+  }
+  auto& cache = t->irank[(size_t)d.col];
+  const auto& vals = t->idict[(size_t)d.col].vals;
+  if (cache.size() != vals.size()) {
+    std::vector<std::string> r;
+    r.reserve(vals.size());
+    for (int64_t v : vals) r.push_back(std::to_string(v));
+    ranks_of(r, cache);
+  }
+  return cache;
+}
+
+// one group's ResultGroup from the accumulators of dense slot s (h: words [0, have))
+static void make_group(const sg_query* q, const uint64_t* h, uint32_t s, ResultGroup& g, int64_t* tbucket) {
+  const Plan& P = q->plan;
+  const int naggs = P.naggs;
+  init_group(g, naggs);
+  g.count = (int64_t)h[q->off_count + s];
+  for (size_t di = 0; di < q->dims.size(); di++) {
+    const GroupDim& d = q->dims[di];
+    uint32_t code = (s / d.stride) % d.radix;
+    if (d.is_time) {
+      if (tbucket) *tbucket = (P.time_first + (int64_t)code - 1) * P.time_bucket;
+      continue;
+    }
+    if (code == 0)
+      g.key.push_back(SG_MISSING_KEY);
+    else if (d.is_str)
+      g.key.push_back((uint64_t)(code - 1));
+    else if (q->merged)
+      g.key.push_back((uint64_t)q->m_ints[di][code - 1]);
+    else
+      g.key.push_back((uint64_t)q->table->idict[(size_t)d.col].vals[code - 1]);
+  }
+  g.skey = render_key(q, g.key);
+  const bool want_max = P.hist_mode || q->d.hist_kind == SG_HIST_MULTI;
+  for (int a = 0; a < naggs; a++) {
+    g.hc(a) = (size_t)a < q->hc_is_count.size() && q->hc_is_count[(size_t)a] ? g.count : (int64_t)h[q->off_hcount[(size_t)a] + s];
+    g.sm(a) = (int64_t)h[q->off_sum[(size_t)a] + s];
+    g.vx(a) = want_max ? (int64_t)h[q->off_vmax[(size_t)a] + s] : INT64_MIN;
+    uint32_t nv = q->layouts[(size_t)a].nvals_total;
+    if (nv && g.hc(a)) {
+      const uint64_t* src = h + q->off_buckets[(size_t)a] + (size_t)s * nv;
+      if (g.values.size() < (size_t)naggs) g.values.resize((size_t)naggs);
+      g.values[(size_t)a].assign(src, src + nv);
+    }
+  }
+}
+
+// run fn(thread index, first slot, end slot) over [0, n) on up to `want` host threads
+template <class Fn>
+static void parallel_slots(uint32_t n, int want, Fn fn) {
+  int nt = n >= (1u << 17) ? want : 1;
+  if (nt <= 1) {
+    fn(0, 0u, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const uint32_t per = (n + (uint32_t)nt - 1) / (uint32_t)nt;
+  for (int i = 0; i < nt; i++) {
+    const uint32_t a = std::min(n, per * (uint32_t)i), b = std::min(n, a + per);
+    th.emplace_back(fn, i, a, b);
+  }
+  for (auto& x : th) x.join();
 }
 
 int build_result(sg_query* q, sg_result** out) {
   sg_ctx* c = q->ctx;
   const Plan& P = q->plan;
-  std::vector<uint64_t> h;
-  if (q->h_acc_valid && q->h_acc.size() == q->acc_words) {
-    h.swap(q->h_acc);
-    q->h_acc_valid = false;
-  } else {
-    h.resize(q->acc_words);
-    CUDA_TRY(c, cudaMemcpy(h.data(), q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost));
-    q->d2h_bytes += (int64_t)q->acc_words * 8;
-  }
+  const bool time_mode = P.time_col >= 0;
+  const int naggs = P.naggs;
+  // what the result reads: without bucket counters, without hist Min/Max tracking and with every hist Count
+  // equal to Count, the contiguous prefix scalars | count | sums is enough
+  bool all_hc = true;
+  for (int a = 0; a < naggs; a++) all_hc = all_hc && (size_t)a < q->hc_is_count.size() && q->hc_is_count[(size_t)a];
+  const bool want_max = P.hist_mode || q->d.hist_kind == SG_HIST_MULTI;
+  size_t have = q->acc_words;
+  if (!want_max) have = q->sum_words;
+  if (!want_max && !P.hist_mode && all_hc) have = q->prefix_words;
   std::unique_ptr<sg_result> r(new sg_result());
   r->q = q;
+  std::vector<uint64_t> hv;
+  const uint64_t* h = nullptr;
+  if (q->h_acc_valid && q->h_acc.size() == q->acc_words) {
+    hv.swap(q->h_acc);
+    q->h_acc_valid = false;
+    have = q->acc_words;
+    h = hv.data();
+  } else {
+    // large results are read back into a pinned buffer the result keeps (a pageable destination is staged by
+    // the driver at a fraction of the PCIe rate, and a second copy would cost as much again)
+    r->pin = c->pin_get(have * 8, &r->pin_bytes);
+    if (!r->pin) {
+      c->set_err("cudaHostAlloc (result buffer) failed");
+      return SG_ERR_CUDA;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(r->pin, q->d_acc, have * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    q->d2h_bytes += (int64_t)have * 8;
+    h = (const uint64_t*)r->pin;
+  }
   r->layouts = q->layouts;
   r->hist_mode = P.hist_mode != 0;
   r->ngroups_cols = P.ngroups;
-  r->naggs = P.naggs;
+  r->naggs = naggs;
   r->matched = (int64_t)h[0];
   r->broken = q->broken_staged + (int64_t)h[1];
   r->skipped = q->skipped;
-  const bool time_mode = P.time_col >= 0;
-  const int naggs = P.naggs;
   init_group(r->total, naggs);
   r->total.skey = "TOTAL";
   for (int i = 1; i < P.ngroups; i++) r->total.skey += "\t";
   r->has_total_hists = !time_mode;
+  const uint64_t* cnt = h + q->off_count;
 
+  if (!time_mode) {
+    // ---- lazy result: live slots, Cumulative, order -------------------------------------------------
+    const uint32_t ns = P.nslots;
+    const int ob = q->d.order_by_agg;
+    const int64_t limit = q->d.limit;
+    int hw = (int)std::thread::hardware_concurrency();
+    const int nt = std::max(1, std::min(hw > 0 ? hw : 1, 16));
+    // tie-break ranks: GroupByKey ascending == lexicographic over the axes' rendered fields
+    std::vector<std::vector<uint32_t>> scratch(q->dims.size());
+    std::vector<const std::vector<uint32_t>*> ranks(q->dims.size(), nullptr);
+    if (ob != SG_ORDER_NONE)
+      for (size_t di = 0; di < q->dims.size(); di++) ranks[di] = &axis_ranks(q, di, scratch[di]);
+    auto tie_of = [&](uint32_t s) {
+      uint64_t tie = 0;
+      for (size_t di = 0; di < q->dims.size(); di++) {
+        const GroupDim& d = q->dims[di];
+        const uint32_t code = (s / d.stride) % d.radix;
+        tie = tie * d.radix + (code ? (uint64_t)(*ranks[di])[code - 1] + 1u : 0u);
+      }
+      return tie;
+    };
+    struct Ent {
+      double v;
+      uint64_t tie;
+      uint32_t slot;
+    };
+    auto before = [](const Ent& a, const Ent& b) { return a.v != b.v ? a.v > b.v : a.tie < b.tie; };
+    struct Part {
+      std::vector<Ent> ents;
+      ResultGroup tot;
+      int64_t live = 0;
+    };
+    std::vector<Part> parts((size_t)nt);
+    for (auto& p : parts) init_group(p.tot, naggs);
+    const bool keep_all = ob == SG_ORDER_NONE || limit <= 0 || q->d.order_asc;  // ascending: the END of the list
+    parallel_slots(ns, nt, [&](int ti, uint32_t s0, uint32_t s1) {
+      Part& p = parts[(size_t)ti];
+      double thr = -INFINITY;  // top-`limit` only: order values below the part's limit-th best cannot make the list
+      const size_t trim_at = keep_all ? (size_t)-1 : (size_t)limit * 4 + 64;
+      if (P.hist_mode) {
+        p.tot.values.resize((size_t)naggs);
+        for (int a = 0; a < naggs; a++) p.tot.values[(size_t)a].assign(q->layouts[(size_t)a].nvals_total, 0);
+      }
+      for (uint32_t s = s0; s < s1; s++) {
+        const int64_t n = (int64_t)cnt[s];
+        if (n == 0) continue;
+        p.live++;
+        p.tot.count += n;
+        int64_t hc_o = 0, sm_o = 0;
+        for (int a = 0; a < naggs; a++) {
+          const int64_t hc = q->hc_is_count[(size_t)a] ? n : (int64_t)h[q->off_hcount[(size_t)a] + s];
+          if (hc == 0) continue;
+          const int64_t sm = (int64_t)h[q->off_sum[(size_t)a] + s];
+          p.tot.hc(a) += hc;
+          p.tot.sm(a) = (int64_t)((uint64_t)p.tot.sm(a) + (uint64_t)sm);
+          if (want_max) p.tot.vx(a) = std::max(p.tot.vx(a), (int64_t)h[q->off_vmax[(size_t)a] + s]);
+          const uint32_t nv = q->layouts[(size_t)a].nvals_total;
+          if (nv) {
+            const uint64_t* src = h + q->off_buckets[(size_t)a] + (size_t)s * nv;
+            int64_t* dst = p.tot.values[(size_t)a].data();
+            for (uint32_t k = 0; k < nv; k++) dst[k] += (int64_t)src[k];
+          }
+          if (a == ob) {
+            hc_o = hc;
+            sm_o = sm;
+          }
+        }
+        Ent e;
+        e.slot = s;
+        e.v = ob == SG_ORDER_NONE ? 0.0 : order_value(q, n, hc_o, sm_o);
+        if (e.v < thr) continue;
+        e.tie = ob == SG_ORDER_NONE ? 0 : tie_of(s);
+        p.ents.push_back(e);
+        if (p.ents.size() >= trim_at) {
+          std::nth_element(p.ents.begin(), p.ents.begin() + limit, p.ents.end(), before);
+          p.ents.resize((size_t)limit);
+          thr = p.ents[0].v;
+          for (auto& x : p.ents) thr = std::min(thr, x.v);
+        }
+      }
+      if (!keep_all && (int64_t)p.ents.size() > limit) {  // only this part's best `limit` can make the list
+        std::nth_element(p.ents.begin(), p.ents.begin() + limit, p.ents.end(), before);
+        p.ents.resize((size_t)limit);
+      }
+    });
+    std::vector<Ent> all;
+    int64_t live = 0;
+    for (auto& p : parts) {
+      live += p.live;
+      all.insert(all.end(), p.ents.begin(), p.ents.end());
+      // Cumulative (aggregate.go:422-436): every group combined
+      r->total.count += p.tot.count;
+      for (int a = 0; a < naggs; a++) {
+        if (p.tot.hc(a) == 0) continue;
+        r->total.hc(a) += p.tot.hc(a);
+        r->total.sm(a) = (int64_t)((uint64_t)r->total.sm(a) + (uint64_t)p.tot.sm(a));
+        r->total.vx(a) = std::max(r->total.vx(a), p.tot.vx(a));
+        const uint32_t nv = q->layouts[(size_t)a].nvals_total;
+        if (nv && p.tot.values.size() > (size_t)a && !p.tot.values[(size_t)a].empty()) {
+          if (r->total.values.size() < (size_t)naggs) r->total.values.resize((size_t)naggs);
+          if (r->total.values[(size_t)a].empty()) r->total.values[(size_t)a].assign(nv, 0);
+          for (uint32_t k = 0; k < nv; k++) r->total.values[(size_t)a][k] += p.tot.values[(size_t)a][k];
+        }
+      }
+    }
+    if (ob != SG_ORDER_NONE) {
+      std::sort(all.begin(), all.end(), before);
+      if (q->d.order_asc) std::reverse(all.begin(), all.end());
+    }
+    if (limit > 0 && (int64_t)all.size() > limit) all.resize((size_t)limit);
+    r->order.reserve(all.size());
+    for (auto& e : all) r->order.push_back(e.slot);
+    r->ngroups_total = live;
+    // without a time column every matched row is counted in exactly one group, so the kernel does not
+    // count matches separately (MatchedCount, aggregate.go:117)
+    r->matched = r->total.count;
+    r->lazy = true;
+    r->acc_have = have;
+    if (!r->pin) {
+      r->acc.swap(hv);
+      r->accp = r->acc.data();
+    } else {
+      r->accp = h;
+    }
+    *out = r.release();
+    return SG_OK;
+  }
+
+  // ---- time mode: Results[key] (counts), TimeResults[bucket][key] ----------------------------------
   std::map<std::vector<uint64_t>, size_t> by_key;                    // Results in time mode
   std::map<int64_t, std::unique_ptr<sg_result>> slices;              // TimeResults
-  const uint64_t* cnt = h.data() + q->off_count;
   for (uint32_t s = 0; s < P.nslots; s++) {
     if (cnt[s] == 0) continue;
     ResultGroup g;
-    init_group(g, naggs);
-    g.count = (int64_t)cnt[s];
     int64_t tbucket = 0;
-    for (size_t di = 0; di < q->dims.size(); di++) {
-      const GroupDim& d = q->dims[di];
-      uint32_t code = (s / d.stride) % d.radix;
-      if (d.is_time) {
-        tbucket = (P.time_first + (int64_t)code - 1) * P.time_bucket;
-        continue;
-      }
-      if (code == 0)
-        g.key.push_back(SG_MISSING_KEY);
-      else if (d.is_str)
-        g.key.push_back((uint64_t)(code - 1));
-      else if (q->merged)
-        g.key.push_back((uint64_t)q->m_ints[di][code - 1]);
-      else
-        g.key.push_back((uint64_t)q->table->idict[(size_t)d.col].vals[code - 1]);
+    make_group(q, h, s, g, &tbucket);
+    // Results[key]: Count/Samples only (aggregate.go:156-171); hists live per bucket
+    auto it = by_key.find(g.key);
+    if (it == by_key.end()) {
+      ResultGroup base;
+      init_group(base, naggs);
+      base.key = g.key;
+      base.skey = g.skey;
+      by_key[g.key] = r->groups.size();
+      r->groups.push_back(std::move(base));
+      it = by_key.find(g.key);
     }
-    g.skey = render_key(q, g.key);
-    for (int a = 0; a < naggs; a++) {
-      g.hc(a) = (size_t)a < q->hc_is_count.size() && q->hc_is_count[(size_t)a] ? (int64_t)cnt[s]
-                                                                               : (int64_t)h[q->off_hcount[(size_t)a] + s];
-      g.sm(a) = (int64_t)h[q->off_sum[(size_t)a] + s];
-      g.vx(a) = (int64_t)h[q->off_vmax[(size_t)a] + s];
-      uint32_t nv = q->layouts[(size_t)a].nvals_total;
-      if (nv && g.hc(a)) {
-        const uint64_t* src = h.data() + q->off_buckets[(size_t)a] + (size_t)s * nv;
-        if (g.values.size() < (size_t)naggs) g.values.resize((size_t)naggs);
-        g.values[(size_t)a].assign(src, src + nv);
-      }
+    r->groups[it->second].count += g.count;
+    r->total.count += g.count;
+    auto& sl = slices[tbucket];
+    if (!sl) {
+      sl.reset(new sg_result());
+      sl->q = q;
+      sl->layouts = q->layouts;
+      sl->hist_mode = r->hist_mode;
+      sl->ngroups_cols = P.ngroups;
+      sl->naggs = naggs;
+      init_group(sl->total, naggs);
     }
-    if (!time_mode) {
-      merge_group(r->total, g, naggs, q->layouts, true);
-      r->groups.push_back(std::move(g));
-    } else {
-      // Results[key]: Count/Samples only (aggregate.go:156-171); hists live per bucket
-      auto it = by_key.find(g.key);
-      if (it == by_key.end()) {
-        ResultGroup base;
-        init_group(base, naggs);
-        base.key = g.key;
-        base.skey = g.skey;
-        by_key[g.key] = r->groups.size();
-        r->groups.push_back(std::move(base));
-        it = by_key.find(g.key);
-      }
-      r->groups[it->second].count += g.count;
-      r->total.count += g.count;
-      auto& sl = slices[tbucket];
-      if (!sl) {
-        sl.reset(new sg_result());
-        sl->q = q;
-        sl->layouts = q->layouts;
-        sl->hist_mode = r->hist_mode;
-        sl->ngroups_cols = P.ngroups;
-        sl->naggs = naggs;
-        init_group(sl->total, naggs);
-      }
-      sl->groups.push_back(std::move(g));
-    }
+    sl->groups.push_back(std::move(g));
   }
-  if (!time_mode) {
-    // without a time column every matched row is counted in exactly one group, so the kernel
-    // does not count matches separately (MatchedCount, aggregate.go:117)
-    int64_t m = 0;
-    for (uint32_t s = 0; s < P.nslots; s++) m += (int64_t)cnt[s];
-    r->matched = m;
-  }
-  sort_groups(r->groups);
+  sort_groups(q, r->groups);
+  r->ngroups_total = (int64_t)r->groups.size();
+  if (q->d.limit > 0 && (int64_t)r->groups.size() > q->d.limit) r->groups.resize((size_t)q->d.limit);
   for (auto& kv : slices) {
-    sort_groups(kv.second->groups);
+    sort_groups(q, kv.second->groups);
+    kv.second->ngroups_total = (int64_t)kv.second->groups.size();
     r->time_keys.push_back(kv.first);
     r->time_slices.push_back(std::move(kv.second));
   }
@@ -2124,12 +2425,23 @@ int sg_query_run(sg_query* q) {
   sg_ctx* c = q->ctx;
   sg_table* t = q->table;
   cudaSetDevice(c->device);
+  const auto t_begin = std::chrono::steady_clock::now();
   int rc = sg_table_sync(t);
   if (rc != SG_OK) return rc;
   rc = upload_table(t);
   if (rc != SG_OK) return rc;
+  const bool reuse = q->planned && q->plan_version == t->version && !q->merged && !getenv("SG_NO_PLAN_REUSE");
   q->merged = false;
-
+  q->kernel_ms = 0;  // statistics are per run
+  q->launches = 0;
+  q->d2h_bytes = 0;
+  std::vector<uint32_t> list;
+  if (reuse) {
+    list = q->plan_list;
+    q->skipped = q->plan_skipped;
+    q->broken_staged = q->plan_broken;
+    q->rows_scanned = q->plan_rows;
+  } else {
   // block list: zone-map pruning + blocks already known broken for a referenced column
   std::vector<char> wanted((size_t)t->ncols, 0);
   auto want = [&](int col) {
@@ -2139,7 +2451,6 @@ int sg_query_run(sg_query* q) {
   for (auto& g : q->groups) want(g.col_slot);
   for (auto& a : q->aggs) want(a.col_slot);
   if (q->d.time_col_slot >= 0 && q->d.time_bucket > 0) want(q->d.time_col_slot);
-  std::vector<uint32_t> list;
   q->skipped = q->stream_skipped;
   q->broken_staged = 0;
   q->rows_scanned = 0;
@@ -2185,7 +2496,15 @@ int sg_query_run(sg_query* q) {
       q->plan.aggs[a]._pad = ok ? 1u : 0u;
     }
   }
+  q->plan_version = t->version;
+  q->plan_list = list;
+  q->plan_skipped = q->skipped;
+  q->plan_broken = q->broken_staged;
+  q->plan_rows = q->rows_scanned;
+  }  // !reuse
 
+  const auto t_planned = std::chrono::steady_clock::now();
+  q->host_plan_ms = std::chrono::duration<double, std::milli>(t_planned - t_begin).count();
   // a block found broken by the kernel ("BLOCK SIZE CHANGED", row id >= NumRecords)
   // must contribute nothing: rerun without it (rare path)
   for (int attempt = 0; attempt < 8; attempt++) {
@@ -2214,6 +2533,7 @@ int sg_query_run(sg_query* q) {
   }
   q->last_list = list;
   q->ran = true;
+  q->host_run_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_planned).count();
   return SG_OK;
 }
 
@@ -2606,7 +2926,13 @@ int sg_query_finish(sg_query* q, sg_result** out) {
     if (rc != SG_OK) return rc;
   }
   cudaSetDevice(q->ctx->device);
-  return build_result(q, out);
+  static const bool host_timing = getenv("SG_HOST_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = build_result(q, out);
+  if (host_timing)
+    fprintf(stderr, "[sg host] build_result %.3f ms (run: plan+list %.3f, launch+wait %.3f)\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), q->host_plan_ms, q->host_run_ms);
+  return rc;
 }
 
 double sg_query_kernel_ms(sg_query* q) { return q ? q->kernel_ms : 0; }
@@ -2630,13 +2956,24 @@ int sg_query_stats(sg_query* q, sg_stats* s) {
 // ===========================================================================
 void sg_result_free(sg_result* r) { delete r; }
 int64_t sg_result_matched_count(sg_result* r) { return r ? r->matched : 0; }
-int64_t sg_result_num_groups(sg_result* r) { return r ? (int64_t)r->groups.size() : 0; }
+int64_t sg_result_num_groups(sg_result* r) { return r ? (int64_t)(r->lazy ? r->order.size() : r->groups.size()) : 0; }
+int64_t sg_result_num_groups_total(sg_result* r) { return r ? r->ngroups_total : 0; }
 int64_t sg_result_num_broken(sg_result* r) { return r ? r->broken : 0; }
 int64_t sg_result_num_skipped(sg_result* r) { return r ? r->skipped : 0; }
 
 static ResultGroup* pick_group(sg_result* r, int64_t i) {
   if (!r) return nullptr;
   if (i == -1) return &r->total;
+  if (r->lazy) {
+    if (i < 0 || (size_t)i >= r->order.size()) return nullptr;
+    auto it = r->cache.find(i);
+    if (it == r->cache.end()) {
+      std::unique_ptr<ResultGroup> g(new ResultGroup());
+      make_group(r->q, r->accp, r->order[(size_t)i], *g, nullptr);
+      it = r->cache.emplace(i, std::move(g)).first;
+    }
+    return it->second.get();
+  }
   if (i < 0 || (size_t)i >= r->groups.size()) return nullptr;
   return &r->groups[(size_t)i];
 }

@@ -242,19 +242,20 @@ class _ResultHandle:
 
 
 class QueryParams:  # query_spec.go:25-41
-    def __init__(self, Filters=None, Groups=None, Aggregations=None, TimeBucket=0, OrderBy="$COUNT", Limit=100):
+    def __init__(self, Filters=None, Groups=None, Aggregations=None, TimeBucket=0, OrderBy="$COUNT", OrderAsc=False, Limit=0):
         self.Filters = Filters or []
         self.Groups = Groups or []
         self.Aggregations = Aggregations or []
         self.TimeBucket = TimeBucket
-        self.OrderBy = OrderBy
-        self.Limit = Limit
+        self.OrderBy = OrderBy    # "$COUNT" (SORT_COUNT), an aggregation's name, or "" (no sort)
+        self.OrderAsc = OrderAsc  # query_spec.go:33
+        self.Limit = Limit        # FLAGS.LIMIT (the CLI's default is 100); 0 = every group is materialised
 
 
 class QuerySpec:  # query_spec.go:60-67
     def __init__(self, params=None, **kw):
         self.QueryParams = params or QueryParams(**kw)
-        for k in ("Filters", "Groups", "Aggregations", "TimeBucket", "OrderBy", "Limit"):
+        for k in ("Filters", "Groups", "Aggregations", "TimeBucket", "OrderBy", "OrderAsc", "Limit"):
             setattr(self, k, getattr(self.QueryParams, k))
         self.Results = {}
         self.TimeResults = {}
@@ -303,6 +304,19 @@ def make_query_desc(KeyTable, KeyTypes, IntInfo, qs):
     d.groups = C.cast(gr, C.POINTER(F.sg_group_desc))
     d.aggs = C.cast(ag, C.POINTER(F.sg_agg_desc))
     d.weight_col_slot = -1
+    # SortResults(OrderBy, OrderAsc) (aggregate.go:497-525)
+    order = getattr(qs, "OrderBy", "$COUNT")
+    if order == "$COUNT":
+        d.order_by_agg = F.SG_ORDER_COUNT
+    elif not order:
+        d.order_by_agg = F.SG_ORDER_NONE
+    else:
+        names = [a.Name for a in qs.Aggregations]
+        if order not in names:
+            raise ValueError("OrderBy %r is not one of the query's aggregations" % order)
+        d.order_by_agg = names.index(order)
+    d.order_asc = 1 if getattr(qs, "OrderAsc", False) else 0
+    d.limit = int(getattr(qs, "Limit", 0) or 0)
     d.time_col_slot = -1
     if qs.TimeBucket and FLAGS.TIME_COL:
         d.time_col_slot = KeyTable[FLAGS.TIME_COL]
@@ -402,41 +416,16 @@ class Table:
     def LoadAndQueryRecords(self, loadSpec, querySpec, allreduce=False):
         """Table.LoadAndQueryRecords (table_query.go:18-422).  Returns the matched row count and
         fills querySpec.{Results, TimeResults, Cumulative, MatchedCount, Sorted}."""
-        qs = querySpec
-        if loadSpec is not None:
-            for what, name in ([("filter", f.Field) for f in qs.Filters] + [("group", g.Name) for g in qs.Groups] +
-                               [("aggregation", a.Name) for a in qs.Aggregations]):
-                if name not in loadSpec.columns:
-                    raise ValueError("%s column %r is not in the LoadSpec: sybil would not load it" % (what, name))
-        d, keep = self._desc(qs)
-        q = self.lib.sg_query_begin(self.ctx.h, self.h, C.byref(d))
-        if not q:
-            raise SybilGpuError(F.SG_ERR_INVALID, self.ctx.err())
+        pq = self.Prepare(loadSpec, querySpec)
         try:
-            for i, f in enumerate(qs.Filters):
-                if isinstance(f, StrFilter) and f.regex is not None:
-                    # the host evaluates the regexp once per distinct string (filter.go:215-237)
-                    strs = self.dict_strings(f.Field)
-                    bits = np.zeros((len(strs) + 31) // 32 + 1, np.uint32)
-                    for gid, s in enumerate(strs):
-                        if f.regex.search(s.decode("utf-8", "replace")):
-                            bits[gid >> 5] |= np.uint32(1 << (gid & 31))
-                    self.ctx.check(self.lib.sg_query_set_str_lut(q, i, bits.ctypes.data, len(strs)))
-            self.ctx.check(self.lib.sg_query_run(q))
-            if allreduce:
-                self.ctx.check(self.lib.sg_query_allreduce(q))
-            rp = C.c_void_p()
-            self.ctx.check(self.lib.sg_query_finish(q, C.byref(rp)))
-            st = F.sg_stats()
-            self.lib.sg_query_stats(q, C.byref(st))
-            qs.stats = st
-            try:
-                self._fill(qs, rp)
-            finally:
-                self.lib.sg_result_free(rp)
+            return pq.Run(querySpec, allreduce=allreduce)
         finally:
-            self.lib.sg_query_free(q)
-        return qs.MatchedCount
+            pq.Close()
+
+    def Prepare(self, loadSpec, querySpec):
+        """The same query as a prepared handle (sg_query_begin once, sg_query_run per Run()): a host that
+        repeats a query over an unchanged table keeps the block list, the plan and the uploaded work items."""
+        return PreparedQuery(self, loadSpec, querySpec)
 
     def _fill(self, qs, rp):
         lib = self.lib
@@ -444,7 +433,7 @@ class Table:
         qs.MatchedCount = lib.sg_result_matched_count(rp)
         qs.BrokenBlocks = lib.sg_result_num_broken(rp)
         qs.SkippedBlocks = lib.sg_result_num_skipped(rp)
-        qs.NumGroups = lib.sg_result_num_groups(rp)
+        qs.NumGroups = lib.sg_result_num_groups_total(rp)
         if not getattr(qs, "materialize", True):
             # counts only: the full result exists in the library (sg_result); building one
             # Python object per group is harness work the caller asked to skip
@@ -459,3 +448,57 @@ class Table:
             tb = lib.sg_result_time_bucket(rp, b)
             sl = _ResultHandle(lib, lib.sg_result_time_slice(rp, b))
             qs.TimeResults[tb] = {r.GroupByKey: r for r in sl.groups(qs.Aggregations, False)}
+
+
+class PreparedQuery:
+    """sg_query handle kept across runs (see Table.Prepare)."""
+
+    def __init__(self, table, loadSpec, qs):
+        self.table = table
+        lib, ctx = table.lib, table.ctx
+        if loadSpec is not None:
+            for what, name in ([("filter", f.Field) for f in qs.Filters] + [("group", g.Name) for g in qs.Groups] +
+                               [("aggregation", a.Name) for a in qs.Aggregations]):
+                if name not in loadSpec.columns:
+                    raise ValueError("%s column %r is not in the LoadSpec: sybil would not load it" % (what, name))
+        d, self._keep = table._desc(qs)
+        self.q = lib.sg_query_begin(ctx.h, table.h, C.byref(d))
+        if not self.q:
+            raise SybilGpuError(F.SG_ERR_INVALID, ctx.err())
+        try:
+            for i, f in enumerate(qs.Filters):
+                if isinstance(f, StrFilter) and f.regex is not None:
+                    # the host evaluates the regexp once per distinct string (filter.go:215-237)
+                    strs = table.dict_strings(f.Field)
+                    bits = np.zeros((len(strs) + 31) // 32 + 1, np.uint32)
+                    for gid, s in enumerate(strs):
+                        if f.regex.search(s.decode("utf-8", "replace")):
+                            bits[gid >> 5] |= np.uint32(1 << (gid & 31))
+                    ctx.check(lib.sg_query_set_str_lut(self.q, i, bits.ctypes.data, len(strs)))
+        except Exception:
+            self.Close()
+            raise
+
+    def Run(self, qs, allreduce=False):
+        """One pass of the hot path; fills qs like LoadAndQueryRecords.  The result object is freed before
+        the call returns (the Python mirror copies what it exposes)."""
+        t = self.table
+        lib, ctx = t.lib, t.ctx
+        ctx.check(lib.sg_query_run(self.q))
+        if allreduce:
+            ctx.check(lib.sg_query_allreduce(self.q))
+        rp = C.c_void_p()
+        ctx.check(lib.sg_query_finish(self.q, C.byref(rp)))
+        st = F.sg_stats()
+        lib.sg_query_stats(self.q, C.byref(st))
+        qs.stats = st
+        try:
+            t._fill(qs, rp)
+        finally:
+            lib.sg_result_free(rp)
+        return qs.MatchedCount
+
+    def Close(self):
+        if self.q:
+            self.table.lib.sg_query_free(self.q)
+            self.q = None

@@ -597,3 +597,45 @@ def test_deferred_histogram_records_and_hot_counters(monkeypatch):
         monkeypatch.setenv("SG_SPILL", "1")
         compare(run_gpu(s, q), o, q)  # ... written as records and added up by hist_apply_kernel
         monkeypatch.delenv("SG_SPILL")
+
+
+def _age_spec(seed, n=6000):
+    rng = np.random.default_rng(seed)
+    age = rng.integers(10, 30, n)
+    s = Spec([("id", INT), ("age", INT), ("age_str", STR), ("w", INT)])
+    s.add_rows({"id": np.arange(n), "age": age, "age_str": np.array([str(a) for a in age]), "w": rng.integers(0, 1000, n)},
+               block_rows=n // 3 + 1)
+    return s
+
+
+def test_order_by_like_aggregate_test_go():
+    """aggregate_test.go:281-413 (TestOrderBy / TestOrderByDesc): OrderBy = an aggregation's name sorts the
+    groups by Hists[col].Mean() descending, OrderAsc reverses the list; also $COUNT ascending, Limit, and
+    OrderBy == "" (no sort).  The CUDA path's Sorted list equals the oracle's, group for group."""
+    s = _age_spec(51)
+    for kw in (dict(order_by="age"), dict(order_by="age", order_asc=True), dict(order_by="$COUNT", order_asc=True),
+               dict(order_by="w"), dict(order_by="age", limit=5), dict(order_by="$COUNT", limit=7),
+               dict(order_by="$COUNT", order_asc=True, limit=4), dict(order_by="")):
+        q = Q(s, groups=["age_str"], aggs=["age", "w"], op="avg", **kw)
+        g, o = both(s, q)
+        if kw.get("order_by") == "age":
+            means = [r.Hists["age"].Mean() for r in g.Sorted]
+            assert means == sorted(means, reverse=not kw.get("order_asc", False))  # the reference test's own check
+        if kw.get("limit"):
+            assert len(g.Sorted) == kw["limit"] and g.NumGroups == 20
+            assert g.Cumulative.Count == 6000  # Cumulative still covers every group
+    # hist mode, two group columns, mean order with ties broken by the rendered key
+    q = Q(s, groups=["age_str", "age"], aggs=["w"], op="hist", order_by="w", limit=10)
+    both(s, q)
+
+
+def test_top_groups_of_a_high_cardinality_result():
+    """300k distinct keys (accumulators in global memory), Limit = 100: the materialised top of the sorted list,
+    NumGroups and Cumulative equal the oracle's full result; with ties broken by the rendered key."""
+    rng = np.random.default_rng(53)
+    n = 400_000
+    s = Spec([("k", STR), ("m", INT)])
+    s.add_rows({"k": np.array(["key%d" % v for v in rng.integers(0, 300_000, n)]), "m": rng.integers(0, 10000, n)},
+               block_rows=65536)
+    for kw in (dict(limit=100), dict(limit=100, order_by="m"), dict(limit=50, order_asc=True)):
+        both(s, Q(s, groups=["k"], aggs=["m"], op="avg", **kw))

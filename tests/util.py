@@ -58,8 +58,9 @@ class Q:
     """A query in the reference's vocabulary, buildable without a GPU."""
 
     def __init__(self, spec, int_filters=(), str_filters=(), groups=(), aggs=(), op="avg", loghist=False,
-                 time_col=None, time_bucket=0, hist_bucket=0):
+                 time_col=None, time_bucket=0, hist_bucket=0, order_by="$COUNT", order_asc=False, limit=0):
         self.spec = spec
+        self.order_by, self.order_asc, self.limit = order_by, order_asc, limit
         self.int_filters, self.str_filters = list(int_filters), list(str_filters)
         self.groups, self.aggs = list(groups), list(aggs)
         self.op, self.loghist, self.time_col, self.time_bucket, self.hist_bucket = op, loghist, time_col, time_bucket, hist_bucket
@@ -80,7 +81,8 @@ class Q:
         filters += [E.StrFilter(c, s.KeyTable[c], op, v) for c, op, v in self.str_filters]
         groups = [E.Grouping(c, s.KeyTable[c]) for c in self.groups]
         aggs = [E.Aggregation(c, s.KeyTable[c], self.op) for c in self.aggs]
-        return E.QuerySpec(Filters=filters, Groups=groups, Aggregations=aggs, TimeBucket=self.time_bucket if self.time_col else 0)
+        return E.QuerySpec(Filters=filters, Groups=groups, Aggregations=aggs, TimeBucket=self.time_bucket if self.time_col else 0,
+                           OrderBy=self.order_by, OrderAsc=self.order_asc, Limit=self.limit)
 
     def desc(self):
         qs = self.query_spec()
@@ -162,10 +164,17 @@ def compare(qs, oq, q):
     assert qs.MatchedCount == oq.MatchedCount, "MatchedCount"
     assert qs.BrokenBlocks == oq.BrokenBlocks, "broken blocks"
     assert qs.SkippedBlocks == oq.SkippedBlocks, "skipped blocks"
-    assert set(qs.Results) == set(oq.Results), "group keys"
-    assert [r.GroupByKey for r in qs.Sorted] == [r.GroupByKey for r in oq.Sorted], "Sorted order"
-    for k, o in oq.Results.items():
-        compare_group(qs.Results[k], o, q.aggs if not q.time_col else [], op_hist, ("Results", k), q.loghist)
+    assert qs.NumGroups == len(oq.Results), "number of groups"
+    want = list(oq.Sorted)
+    if q.limit:  # only the first `limit` groups of the sorted list are materialised (FLAGS.LIMIT)
+        want = want[:q.limit]
+    if q.order_by:
+        assert [r.GroupByKey for r in qs.Sorted] == [r.GroupByKey for r in want], "Sorted order"
+    else:  # OrderBy == "": no sort (aggregate.go:499) — the same groups in whatever order
+        assert sorted(r.GroupByKey for r in qs.Sorted) == sorted(r.GroupByKey for r in want), "groups"
+    assert set(qs.Results) == set(r.GroupByKey for r in want), "group keys"
+    for k in qs.Results:
+        compare_group(qs.Results[k], oq.Results[k], q.aggs if not q.time_col else [], op_hist, ("Results", k), q.loghist)
     c, oc = qs.Cumulative, oq.Cumulative
     assert c.GroupByKey == oc.GroupByKey
     assert c.Count == oc.Count and c.Samples == oc.Samples, "Cumulative counts"
