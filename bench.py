@@ -148,6 +148,11 @@ def make_query(spec, synth):
     s = Spec(spec.key_table)
     s.IntInfo = dict(spec.IntInfo)
     kw = dict(synth.query_for(spec))
+    # diagnostics only (scripts/gpu_ab.sh): SG_BENCH_OP=avg|hist, SG_BENCH_GROUPS=a,b override the config's query
+    if os.environ.get("SG_BENCH_OP"):
+        kw["op"] = os.environ["SG_BENCH_OP"]
+    if os.environ.get("SG_BENCH_GROUPS") is not None:
+        kw["groups"] = [g for g in os.environ["SG_BENCH_GROUPS"].split(",") if g]
     if spec.name == "c5":
         kw["limit"] = 100  # the reference CLI's default -limit (FLAGS.LIMIT): the top 100 of the 1M groups are materialised
     return Q(s, **kw)

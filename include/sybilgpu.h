@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 2 /* 2: order_by_agg / order_asc / limit in sg_query_desc */
+#define SG_ABI_VERSION 3 /* 2: order_by_agg / order_asc / limit in sg_query_desc; 3: narrow arrays (id_bits / value_bits) */
 
 /* limits of one query (reference has none; beyond these -> SG_ERR_UNSUPPORTED) */
 #define SG_MAX_FILTERS 15
@@ -138,7 +138,18 @@ typedef struct sg_query_desc {
   const sg_agg_desc* aggs;
 } sg_query_desc;
 
-/* One column of one block: the post-gob form of SavedIntColumn / SavedStrColumn. */
+/* One column of one block: the post-gob form of SavedIntColumn / SavedStrColumn.
+ *
+ * Narrow arrays.  On disk the arrays are gob varints (1-3 bytes per small gap); a decoder
+ * that keeps them narrow instead of widening every element to Go's uint32 / int64 moves 2-3x fewer bytes
+ * over PCIe and HBM.  The library takes them as they are and widens in the scan kernel:
+ *   id_bits    0 / 32: record_ids is uint32_t[];  16: it points to uint16_t[] (a row id or gap is < 65,536 in
+ *              every valid block, so this form always exists);
+ *   value_bits 0 / 64 (int) or 0 / 32 (str): values_i64 is int64_t[] / values_i32 is int32_t[];
+ *              int, 32 or 16: values_i64 points to int32_t[] / int16_t[] DELTAS (delta_values must be 1):
+ *              decoded value k = value_base + deltas[0] + ... + deltas[k] (wrapping int64 arithmetic, like the
+ *              reference's running sum, column_store_io.go:760-767);
+ *              str, 16: values_i32 points to uint16_t[] local string ids (ids < len(StringTable) <= 65,536). */
 typedef struct sg_column_desc {
   int32_t col_slot;
   int32_t col_type;     /* sg_coltype */
@@ -155,9 +166,12 @@ typedef struct sg_column_desc {
   const int32_t* values_i32;   /* str VALUES (local string ids) */
   /* SavedStrColumn.StringTable as one byte buffer + ndict+1 offsets */
   uint32_t ndict;
-  uint32_t _pad;
+  int32_t id_bits;
   const char* dict_bytes;
   const uint32_t* dict_offsets;
+  int32_t value_bits;
+  int32_t _pad;
+  int64_t value_base;
 } sg_column_desc;
 
 /* Block info.db IntInfoMap entry (column_store.go:39-44) for zone-map pruning */

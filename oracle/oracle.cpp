@@ -944,12 +944,32 @@ int orc_table_add_block(orc_table* t, const sg_block_desc* d) {
     if (c.encoding == SG_ENC_BUCKET) {
       sc.bin_values.assign(c.bin_values, c.bin_values + c.nbins);
       sc.bin_offsets.assign(c.bin_offsets, c.bin_offsets + c.nbins + 1);
-      sc.record_ids.assign(c.record_ids, c.record_ids + c.nrecord_ids);
+      // narrow arrays (sybilgpu.h): the oracle widens them to the post-gob form the reference decodes
+      if (c.id_bits == 16) {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(c.record_ids);
+        sc.record_ids.assign(p, p + c.nrecord_ids);
+      } else {
+        sc.record_ids.assign(c.record_ids, c.record_ids + c.nrecord_ids);
+      }
     } else if (c.encoding == SG_ENC_VALUES) {
-      if (c.col_type == SG_COL_INT)
-        sc.values_i64.assign(c.values_i64, c.values_i64 + c.nvalues);
-      else
+      if (c.col_type == SG_COL_INT) {
+        if (c.value_bits == 32 || c.value_bits == 16) {
+          // deltas relative to value_base -> Go's delta form: Values[0] absolute, then gaps
+          sc.values_i64.resize(c.nvalues);
+          for (uint32_t k = 0; k < c.nvalues; k++) {
+            const int64_t dlt = c.value_bits == 32 ? (int64_t) reinterpret_cast<const int32_t*>(c.values_i64)[k]
+                                                   : (int64_t) reinterpret_cast<const int16_t*>(c.values_i64)[k];
+            sc.values_i64[k] = k == 0 ? (int64_t)((uint64_t)c.value_base + (uint64_t)dlt) : dlt;
+          }
+        } else {
+          sc.values_i64.assign(c.values_i64, c.values_i64 + c.nvalues);
+        }
+      } else if (c.value_bits == 16) {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(c.values_i32);
+        sc.values_i32.assign(p, p + c.nvalues);
+      } else {
         sc.values_i32.assign(c.values_i32, c.values_i32 + c.nvalues);
+      }
     }
     if (c.col_type == SG_COL_STR)
       for (uint32_t k = 0; k < c.ndict; k++)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SG_LIB") or os.path.join(_HERE, "csrc", "libsybilgpu.
 GEN_PATH = os.path.join(_HERE, "csrc", "libsybilblockgen.so")
 GOB_PATH = os.path.join(_HERE, "csrc", "libsybilgob.so")
 
-SG_ABI_VERSION = 2
+SG_ABI_VERSION = 3
 SG_ORDER_COUNT, SG_ORDER_NONE = -1, -2
 SG_MAX_FILTERS, SG_MAX_GROUPS, SG_MAX_AGGS, SG_MAX_COLS = 15, 8, 16, 64
 SG_BLOCK_ROWS = 65536
@@ -58,8 +58,9 @@ class sg_column_desc(C.Structure):
                 ("delta_values", C.c_int32), ("nbins", C.c_uint32), ("nrecord_ids", C.c_uint32),
                 ("nvalues", C.c_uint32), ("bin_values", C.c_void_p), ("bin_offsets", C.c_void_p),
                 ("record_ids", C.c_void_p), ("values_i64", C.c_void_p), ("values_i32", C.c_void_p),
-                ("ndict", C.c_uint32), ("_pad", C.c_uint32), ("dict_bytes", C.c_void_p),
-                ("dict_offsets", C.c_void_p)]
+                ("ndict", C.c_uint32), ("id_bits", C.c_int32), ("dict_bytes", C.c_void_p),
+                ("dict_offsets", C.c_void_p), ("value_bits", C.c_int32), ("_pad", C.c_int32),
+                ("value_base", C.c_int64)]
 
 
 class sg_int_info(C.Structure):
@@ -175,7 +176,8 @@ class sbg_col(C.Structure):
 
 class sbg_spec(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("total_rows", C.c_int64), ("block_rows", C.c_int32), ("ncols", C.c_int32),
-                ("cardinality_threshold", C.c_int32), ("num_col_slots", C.c_int32), ("cols", C.POINTER(sbg_col))]
+                ("cardinality_threshold", C.c_int32), ("num_col_slots", C.c_int32), ("cols", C.POINTER(sbg_col)),
+                ("narrow", C.c_int32), ("_pad", C.c_int32)]
 
 
 class sbg_eval_spec(C.Structure):

@@ -43,7 +43,12 @@ class SavedColumn:
         if self.encoding == F.SG_ENC_BUCKET:
             self.bin_values = np.ascontiguousarray(self.bin_values, np.int64)
             self.bin_offsets = np.ascontiguousarray(self.bin_offsets, np.uint32)
-            self.record_ids = np.ascontiguousarray(self.record_ids, np.uint32)
+            # narrow arrays (sybilgpu.h): a uint16 id array is passed as it is (id_bits = 16)
+            if np.asarray(self.record_ids).dtype == np.uint16:
+                self.record_ids = np.ascontiguousarray(self.record_ids)
+                d.id_bits = 16
+            else:
+                self.record_ids = np.ascontiguousarray(self.record_ids, np.uint32)
             d.nbins = len(self.bin_values)
             d.nrecord_ids = len(self.record_ids)
             d.bin_values = _ptr(self.bin_values)
@@ -51,11 +56,22 @@ class SavedColumn:
             d.record_ids = _ptr(self.record_ids)
         elif self.encoding == F.SG_ENC_VALUES:
             if self.col_type == F.SG_COL_INT:
-                self.values_i64 = np.ascontiguousarray(self.values_i64, np.int64)
+                # int32 / int16 arrays hold deltas relative to value_base (value_bits = 32 / 16)
+                dt = np.asarray(self.values_i64).dtype
+                if dt == np.int32 or dt == np.int16:
+                    self.values_i64 = np.ascontiguousarray(self.values_i64)
+                    d.value_bits = 32 if dt == np.int32 else 16
+                    d.value_base = int(getattr(self, "value_base", 0))
+                else:
+                    self.values_i64 = np.ascontiguousarray(self.values_i64, np.int64)
                 d.nvalues = len(self.values_i64)
                 d.values_i64 = _ptr(self.values_i64)
             else:
-                self.values_i32 = np.ascontiguousarray(self.values_i32, np.int32)
+                if np.asarray(self.values_i32).dtype == np.uint16:
+                    self.values_i32 = np.ascontiguousarray(self.values_i32)
+                    d.value_bits = 16
+                else:
+                    self.values_i32 = np.ascontiguousarray(self.values_i32, np.int32)
                 d.nvalues = len(self.values_i32)
                 d.values_i32 = _ptr(self.values_i32)
         if self.col_type == F.SG_COL_STR:
@@ -188,10 +204,48 @@ def decode_column(col, num_records):
             pop[rows] = True
     elif col.encoding == F.SG_ENC_VALUES:
         if col.col_type == F.SG_COL_INT:
-            v = col.values_i64.astype(np.uint64)
+            v = np.asarray(col.values_i64).astype(np.int64).astype(np.uint64)  # (narrow deltas sign-extend)
+            if len(v) and np.asarray(col.values_i64).dtype != np.int64:
+                v[0] += np.uint64(int(getattr(col, "value_base", 0)) & 0xFFFFFFFFFFFFFFFF)
             v = np.cumsum(v, dtype=np.uint64).astype(np.int64) if col.delta_values else v.astype(np.int64)
         else:
             v = col.values_i32.astype(np.int64)
         vals[:len(v)] = v
         pop[:len(v)] = True
     return vals, pop
+
+
+def narrow_column(col):
+    """The same column with its arrays as narrow as their values allow — what a decoder that keeps gob's
+    varints narrow hands over (include/sybilgpu.h, sg_column_desc::id_bits / value_bits): uint16 record ids,
+    int16 / int32 value deltas on top of value_base, uint16 local string ids."""
+    import copy
+    c = copy.copy(col)
+    if c.encoding == F.SG_ENC_BUCKET:
+        ids = np.asarray(c.record_ids)
+        if len(ids) == 0 or int(ids.max()) < 65536:
+            c.record_ids = ids.astype(np.uint16)
+    elif c.encoding == F.SG_ENC_VALUES:
+        if c.col_type == F.SG_COL_INT:
+            d = np.asarray(c.values_i64, np.int64)
+            if c.delta_values and len(d):
+                rest = d[1:]
+                lo, hi = (int(rest.min()), int(rest.max())) if len(rest) else (0, 0)
+                dt = np.int16 if -32768 <= lo and hi <= 32767 else (np.int32 if -2**31 <= lo and hi < 2**31 else None)
+                if dt is not None:
+                    nd = np.zeros(len(d), dt)
+                    nd[1:] = rest
+                    c.values_i64, c.value_base = nd, int(d[0])
+        else:
+            ids = np.asarray(c.values_i32)
+            if len(ids) == 0 or (int(ids.min()) >= 0 and int(ids.max()) < 65536):
+                c.values_i32 = ids.astype(np.uint16)
+    return c
+
+
+def narrow_block(blk):
+    """A SavedBlock with every column in its narrow form (see narrow_column)."""
+    nb = SavedBlock(blk.block_index, blk.num_records)
+    nb.info = dict(blk.info)
+    nb.cols = [narrow_column(c) for c in blk.cols]
+    return nb

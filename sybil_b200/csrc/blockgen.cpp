@@ -20,6 +20,7 @@
  */
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -59,6 +60,11 @@ typedef struct sbg_spec {
   int32_t cardinality_threshold; /* CARDINALITY_THRESHOLD */
   int32_t num_col_slots;
   const sbg_col* cols;
+  /* 1: arrays as narrow as their values allow, the way a decoder that does not widen gob's varints hands them
+   * over (sybilgpu.h, sg_column_desc::id_bits / value_bits): uint16 record ids, int32 / int16 value deltas on
+   * top of value_base, uint16 local string ids.  0: Go's decoded types (uint32 / int64 / int32). */
+  int32_t narrow;
+  int32_t _pad;
 } sbg_spec;
 
 }  // extern "C"
@@ -207,8 +213,15 @@ void encode_column(sbg_store& st, const sbg_col& c, int32_t n, const std::vector
     out.nrecord_ids = (uint32_t)npop;
     out.bin_values = arena_copy(st.arena, keys, ovf);
     out.bin_offsets = arena_copy(st.arena, offsets, ovf);
-    out.record_ids = arena_copy(st.arena, ids, ovf);
-    bytes += (int64_t)(keys.size() * 8 + offsets.size() * 4 + ids.size() * 4);
+    if (st.spec.narrow) {  // a row id / gap inside a block is < 65,536
+      std::vector<uint16_t> ids16(ids.begin(), ids.end());
+      out.record_ids = reinterpret_cast<const uint32_t*>(arena_copy(st.arena, ids16, ovf));
+      out.id_bits = 16;
+      bytes += (int64_t)(keys.size() * 8 + offsets.size() * 4 + ids.size() * 2);
+    } else {
+      out.record_ids = arena_copy(st.arena, ids, ovf);
+      bytes += (int64_t)(keys.size() * 8 + offsets.size() * 4 + ids.size() * 4);
+    }
   } else {
     out.encoding = SG_ENC_VALUES;
     out.nvalues = (uint32_t)max_r;
@@ -223,8 +236,37 @@ void encode_column(sbg_store& st, const sbg_col& c, int32_t n, const std::vector
         prev = val;
       }
       out.delta_values = 1;
-      out.values_i64 = arena_copy(st.arena, vals, ovf);
-      bytes += (int64_t)vals.size() * 8;
+      // narrow form: the gaps as int16 / int32 when every one of them fits, on top of value_base = Values[0]
+      int64_t dmin = 0, dmax = 0;
+      for (int32_t i = 1; i < max_r; i++) {
+        dmin = std::min(dmin, vals[(size_t)i]);
+        dmax = std::max(dmax, vals[(size_t)i]);
+      }
+      if (st.spec.narrow && dmin >= INT16_MIN && dmax <= INT16_MAX) {
+        std::vector<int16_t> d16((size_t)max_r, 0);
+        for (int32_t i = 1; i < max_r; i++) d16[(size_t)i] = (int16_t)vals[(size_t)i];
+        out.value_base = vals[0];
+        out.value_bits = 16;
+        out.values_i64 = reinterpret_cast<const int64_t*>(arena_copy(st.arena, d16, ovf));
+        bytes += (int64_t)vals.size() * 2;
+      } else if (st.spec.narrow && dmin >= INT32_MIN && dmax <= INT32_MAX) {
+        std::vector<int32_t> d32((size_t)max_r, 0);
+        for (int32_t i = 1; i < max_r; i++) d32[(size_t)i] = (int32_t)vals[(size_t)i];
+        out.value_base = vals[0];
+        out.value_bits = 32;
+        out.values_i64 = reinterpret_cast<const int64_t*>(arena_copy(st.arena, d32, ovf));
+        bytes += (int64_t)vals.size() * 4;
+      } else {
+        out.values_i64 = arena_copy(st.arena, vals, ovf);
+        bytes += (int64_t)vals.size() * 8;
+      }
+    } else if (st.spec.narrow) {  // local string ids < len(StringTable) <= 65,536
+      std::vector<uint16_t> vals((size_t)max_r, 0);
+      for (int32_t i = 0; i < max_r; i++)
+        if (valid[(size_t)i]) vals[(size_t)i] = (uint16_t)codes[(size_t)i];
+      out.values_i32 = reinterpret_cast<const int32_t*>(arena_copy(st.arena, vals, ovf));
+      out.value_bits = 16;
+      bytes += (int64_t)vals.size() * 2;
     } else {
       std::vector<int32_t> vals((size_t)max_r, 0);
       for (int32_t i = 0; i < max_r; i++)

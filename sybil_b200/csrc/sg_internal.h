@@ -20,7 +20,16 @@ enum : uint32_t {
   COL_TMA = 32u,          // data_chunk/data_row locate `data` inside an arena tensor map
   COL_FULL = 64u,         // bucket column: the bins list every row of [0, NumRecords) exactly once (checked by
                           // the staging statistics kernel), so no row is unpopulated for this column
+  // narrow arrays (sybilgpu.h, sg_column_desc::id_bits / value_bits): `data` holds
+  COL_ID16 = 128u,        //   uint16 record ids / gaps
+  COL_VAL32 = 256u,       //   int32 deltas relative to vbase (int VALUES)
+  COL_VAL16 = 512u,       //   int16 deltas relative to vbase (int VALUES) / uint16 local string ids (str VALUES)
 };
+// log2(4-byte-id or 8-byte-value width / stored width): the row pitch of the arena view a column's tiles are
+// fetched through is 128 >> shift bytes, so a warp tile always holds 1024 ids / 512 values
+__host__ __device__ static inline uint32_t col_shift(uint32_t flags) {
+  return (flags & (COL_ID16 | COL_VAL32)) ? 1u : ((flags & COL_VAL16) ? 2u : 0u);
+}
 
 struct DevCol {
   uint32_t enc;     // sg_encoding
@@ -29,7 +38,10 @@ struct DevCol {
   uint32_t nitems;  // record ids (BUCKET) or values (VALUES)
   uint32_t nremap;  // str: dictionary size; int BUCKET: nbins
   int32_t oob_gid;  // str: global id used for a local id outside the dictionary
-  const int64_t* bin_values;    // [nbins] int value, or local string id widened
+  union {
+    const int64_t* bin_values;  // BUCKET: [nbins] int value, or local string id widened
+    int64_t vbase;              // VALUES with narrow deltas: decoded value k = vbase + deltas[0..k] (0 otherwise)
+  };
   const uint32_t* bin_offsets;  // [nbins+1]
   const void* data;             // record ids u32[] | values i64[] | values i32[]
   const int32_t* remap;         // str: local id -> global id; int BUCKET: bin -> value-dict code
@@ -165,7 +177,8 @@ struct LaunchParams {
   unsigned long long* gdummy; // [grid][32] sink for histogram reductions of rows that did not pass
   uint32_t smem_bytes;
   uint32_t acc_smem;          // accumulators replicated in shared memory (plan.acc_repl > 0)
-  const void* tmaps;          // CUtensorMap[chunks] in global memory (nullptr: plain vector loads)
+  const void* tmaps;          // CUtensorMap[chunks][3] in global memory: row pitch 128 / 64 / 32 bytes (nullptr: plain
+                              // vector loads)
   uint32_t nstage;            // TMA staging depth per warp (1 or 2)
   unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
   uint32_t fold_every;        // blocks whose shared accumulators may be folded together (>= 1)

@@ -107,6 +107,12 @@ struct Ctx {
   bool timing;
   unsigned long long t_tma, t_lb;
   __device__ __forceinline__ uint32_t buf(uint32_t st) const { return st ? buf1 : buf0; }
+  // narrow arrays (col_shift > 0): a tile is 2 KiB or 1 KiB, so even a one-deep staging buffer of 4 KiB holds
+  // two of them — such passes always run two stages deep
+  __device__ __forceinline__ uint32_t stages(uint32_t shift) const { return (nstage == 2u || shift != 0u) ? 2u : 1u; }
+  __device__ __forceinline__ uint32_t bufx(uint32_t st, uint32_t shift) const {
+    return nstage == 2u ? (st ? buf1 : buf0) : buf0 + st * (TMA_TILE_BYTES >> 1);  // (st == 1 only when shift > 0)
+  }
   __device__ __forceinline__ uint32_t mbar(uint32_t st) const { return st ? mbar1 : mbar0; }
   __device__ __forceinline__ uint32_t take_parity(uint32_t st) {
     const uint32_t p = st ? par1 : par0;
@@ -190,6 +196,31 @@ __device__ __forceinline__ void read_staged_row_lo(uint32_t buf_s, int lane, uin
         : "r"(addr));
   }
 }
+// The same for the narrow views (64 / 32 byte rows, 64B / 32B swizzle): chunk j of row r sits at
+// j ^ ((r >> 1) & 3) resp. j ^ ((r >> 2) & 1) — the address bits the hardware XORs are bits 7.. of the shared
+// address, i.e. the 128-byte line the row lies in.  A quarter warp's 16-byte loads still cover all 32 banks.
+__device__ __forceinline__ void read_staged_row64(uint32_t buf_s, int lane, uint32_t (&w)[16]) {
+  const uint32_t rowbase = buf_s + (uint32_t)lane * 64u;
+  const uint32_t x = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t addr = rowbase + ((((uint32_t)j) ^ x) << 4);
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w[4 * j + 0]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                 : "r"(addr));
+  }
+}
+__device__ __forceinline__ void read_staged_row32(uint32_t buf_s, int lane, uint32_t (&w)[8]) {
+  const uint32_t rowbase = buf_s + (uint32_t)lane * 32u;
+  const uint32_t x = (uint32_t)(lane >> 2) & 1u;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const uint32_t addr = rowbase + ((((uint32_t)j) ^ x) << 4);
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w[4 * j + 0]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                 : "r"(addr));
+  }
+}
 // After a warp has read a staged tile with ordinary shared loads, the next TMA write into the same
 // buffer must not overtake those loads (they can sit in the load/store queue behind reductions for
 // microseconds).  A proxy fence would do, but it compiles to MEMBAR.ALL.CTA, which also waits for
@@ -216,7 +247,9 @@ __device__ __forceinline__ uint32_t dep_of(const uint32_t (&w)[32]) {
 // the tile feed of one column pass: issue(tile) by lane 0, take(stage) by the whole warp
 struct Feed {
   const void* tmap;
-  uint32_t row0;
+  uint32_t row0;   // first row of the column's data in the view `tmap` describes (rows of 128 >> shift bytes)
+  uint32_t shift;  // col_shift of the column
+  uint32_t ns;     // stages this pass runs with
   bool on;
   // L2 prefetch distance bookkeeping: this warp's tile count in this pass, and the next fed pass
   uint32_t mine;
@@ -230,8 +263,10 @@ constexpr uint32_t PF_AHEAD = SG_PF_AHEAD;  // L2 prefetch runs this many of the
 __device__ __forceinline__ Feed make_feed(const Ctx& cx, const DevCol& c) {
   Feed f;
   f.on = cx.tmaps != nullptr && (c.flags & COL_TMA) != 0;
-  f.tmap = cx.tmaps + (size_t)c.data_chunk * 128;
-  f.row0 = c.data_row;
+  f.shift = col_shift(c.flags);
+  f.ns = cx.stages(f.shift);
+  f.tmap = cx.tmaps + ((size_t)c.data_chunk * 3u + f.shift) * 128;
+  f.row0 = c.data_row << f.shift;
   f.mine = 0;
   f.ntmap = nullptr;
   f.nrow0 = f.nnt = 0;
@@ -239,8 +274,8 @@ __device__ __forceinline__ Feed make_feed(const Ctx& cx, const DevCol& c) {
 }
 __device__ __forceinline__ void feed_issue(const Ctx& cx, const Feed& f, uint32_t tile, uint32_t st, uint32_t after = 0u) {
   if (cx.lane == 0) {
-    mbar_expect_tx(cx.mbar(st), TMA_TILE_BYTES);
-    tma_load_tile(cx.buf(st), f.tmap, f.row0 + tile * 32u + after, cx.mbar(st));
+    mbar_expect_tx(cx.mbar(st), TMA_TILE_BYTES >> f.shift);
+    tma_load_tile(cx.bufx(st, f.shift), f.tmap, f.row0 + tile * 32u + after, cx.mbar(st));
   }
 }
 // L2 prefetch of this warp's v-th tile counted from the start of the pass; past the end of the pass
@@ -266,11 +301,11 @@ __device__ __forceinline__ void feed_prologue(Ctx& cx, Feed& f, uint32_t ntiles)
     f.nnt = e[6];
   }
   if (cx.pref_idx != cx.pass_idx)
-    for (uint32_t st = 0; st < cx.nstage; st++)
+    for (uint32_t st = 0; st < f.ns; st++)
       if (cx.warp + st * NWARPS < ntiles) feed_issue(cx, f, cx.warp + st * NWARPS, st);
   // the first pass of a block has nobody before it to prefetch its head
   if (cx.pass_idx == 0)
-    for (uint32_t v = cx.nstage; v < cx.nstage + PF_AHEAD; v++) feed_prefetch(cx, f, v);
+    for (uint32_t v = f.ns; v < f.ns + PF_AHEAD; v++) feed_prefetch(cx, f, v);
 }
 // end of a fed pass (all of this warp's tiles consumed, both staging buffers free): request the
 // first tile(s) of the next fed pass of the block
@@ -281,10 +316,12 @@ __device__ __forceinline__ void feed_epilogue(Ctx& cx, const Feed& f) {
     const uint32_t* e = cx.plist + 4 * cx.pass_idx;
     Feed nf;
     nf.on = true;
-    nf.tmap = cx.tmaps + (size_t)e[0] * 128;
+    nf.tmap = cx.tmaps + (size_t)e[0] * 128;  // e[0] = chunk * 3 + shift: the view's index
     nf.row0 = e[1];
+    nf.shift = e[0] % 3u;
+    nf.ns = cx.stages(nf.shift);
     const uint32_t nt = e[2];
-    for (uint32_t st = 0; st < cx.nstage; st++)
+    for (uint32_t st = 0; st < nf.ns; st++)
       if (cx.warp + st * NWARPS < nt) feed_issue(cx, nf, cx.warp + st * NWARPS, st);
     cx.pref_idx = cx.pass_idx;
   }
@@ -311,6 +348,27 @@ __device__ __forceinline__ void sred_add(uint32_t addr, uint32_t v) {
 // compiler cannot prove global becomes a generic ATOM that returns a predicate (round trip to L2)
 __device__ __forceinline__ void gred_add(unsigned long long* p, unsigned long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// predicated forms (one instruction each, no branch): the bucket step of the histogram hot path
+__device__ __forceinline__ void sred_inc_if(uint32_t pred, uint32_t addr) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %0, 0;\n"
+      "@p red.shared.add.u32 [%1], 1;\n"
+      "}\n" ::"r"(pred),
+      "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void gred_inc_if(uint32_t pred, unsigned long long* p) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %0, 0;\n"
+      "@p red.global.add.u64 [%1], 1;\n"
+      "}\n" ::"r"(pred),
+      "l"(p)
+      : "memory");
 }
 __device__ __forceinline__ void gred_max(long long* p, long long v) {
   asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -389,6 +447,7 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
   const uint32_t nbins = c.nbins;
   const uint32_t* __restrict__ ids = reinterpret_cast<const uint32_t*>(c.data);
   const bool delta = (c.flags & COL_DELTA_IDS) != 0;
+  const bool ids16 = (c.flags & COL_ID16) != 0;  // narrow ids: 1024 of them are 2 KiB (64-byte rows)
   const int tid = cx.tid, lane = cx.lane, warp = cx.warp;
 #ifndef SG_FINE_FLUSH
   cx.tmark(9);  // since the previous mark: the caller's per-bin payload build
@@ -459,16 +518,44 @@ __device__ __forceinline__ void scan_bucket(Ctx& cx, const DevCol& c, const uint
     if (feed.on) {
       // the tile was requested one (or two) iterations ago: TMA wrote it into this warp's staging
       // buffer while the previous tile was being processed
-      const uint32_t st = it & (cx.nstage - 1u);
+      const uint32_t st = it & (feed.ns - 1u);
       mbar_wait(cx.mbar(st), cx.take_parity(st));
-      read_staged_row(cx.buf(st), lane, a);
-      const uint32_t after = staged_reads_done(cx, dep_of(a));
-      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
-      feed_prefetch(cx, feed, it + cx.nstage + PF_AHEAD);
+      uint32_t dep;
+      if (ids16) {
+        uint32_t h[BE / 2];
+        read_staged_row64(cx.bufx(st, 1u), lane, h);
+        dep = (h[0] ^ h[4]) ^ (h[8] ^ h[12]);
+#pragma unroll
+        for (int k = 0; k < BE / 2; k++) {
+          a[2 * k] = h[k] & 0xffffu;
+          a[2 * k + 1] = h[k] >> 16;
+        }
+      } else {
+        read_staged_row(cx.bufx(st, 0u), lane, a);
+        dep = dep_of(a);
+      }
+      const uint32_t after = staged_reads_done(cx, dep);
+      if (t + feed.ns * NWARPS < ntiles) feed_issue(cx, feed, t + feed.ns * NWARPS, st, after);
+      feed_prefetch(cx, feed, it + feed.ns + PF_AHEAD);
       if (idx0 + BE > n) {
 #pragma unroll
         for (int k = 0; k < BE; k++)
           if (idx0 + k >= n) a[k] = 0u;
+      }
+    } else if (ids16) {
+      const uint16_t* __restrict__ ids_h = reinterpret_cast<const uint16_t*>(c.data);
+      if (idx0 + BE <= n) {
+        uint32_t h[BE / 2];
+#pragma unroll
+        for (int j = 0; j < BE / 16; j++) ldg256(ids_h + idx0 + 16 * j, h + 8 * j);
+#pragma unroll
+        for (int k = 0; k < BE / 2; k++) {
+          a[2 * k] = h[k] & 0xffffu;
+          a[2 * k + 1] = h[k] >> 16;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < BE; k++) a[k] = (idx0 + k < n) ? (uint32_t)ids_h[idx0 + k] : 0u;
       }
     } else if (idx0 + BE <= n) {
 #pragma unroll
@@ -615,10 +702,11 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
   if (n > nrec) n = nrec;  // staging already flags len(Values) > NumRecords as broken
   const unsigned long long* __restrict__ vals = reinterpret_cast<const unsigned long long*>(c.data);
   const bool delta = (c.flags & COL_DELTA_VALUES) != 0;
+  const uint32_t vw = col_shift(c.flags);  // 0: int64 values; 1 / 2: int32 / int16 deltas on top of c.vbase
   const int lane = cx.lane, warp = cx.warp;
   cx.epoch++;
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
-  unsigned long long prev_incl = 0;
+  unsigned long long prev_incl = vw ? (unsigned long long)c.vbase : 0ull;
   Feed feed = make_feed(cx, c);
   feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
@@ -626,16 +714,65 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
     unsigned long long a[VE];
     if (feed.on) {
-      const uint32_t st = it & (cx.nstage - 1u);
+      const uint32_t st = it & (feed.ns - 1u);
       mbar_wait(cx.mbar(st), cx.take_parity(st));
-      uint32_t raw[32];
-      read_staged_row(cx.buf(st), lane, raw);
-      const uint32_t after = staged_reads_done(cx, dep_of(raw));
-      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
-      feed_prefetch(cx, feed, it + cx.nstage + PF_AHEAD);
+      uint32_t dep;
+      if (vw == 0u) {
+        uint32_t raw[32];
+        read_staged_row(cx.bufx(st, 0u), lane, raw);
+        dep = dep_of(raw);
 #pragma unroll
-      for (int k = 0; k < VE; k++)
-        a[k] = (idx0 + k < n) ? ((unsigned long long)raw[2 * k] | ((unsigned long long)raw[2 * k + 1] << 32)) : 0ull;
+        for (int k = 0; k < VE; k++) a[k] = (unsigned long long)raw[2 * k] | ((unsigned long long)raw[2 * k + 1] << 32);
+      } else if (vw == 1u) {
+        uint32_t raw[16];
+        read_staged_row64(cx.bufx(st, 1u), lane, raw);
+        dep = (raw[0] ^ raw[4]) ^ (raw[8] ^ raw[12]);
+#pragma unroll
+        for (int k = 0; k < VE; k++) a[k] = (unsigned long long)(long long)(int32_t)raw[k];
+      } else {
+        uint32_t raw[8];
+        read_staged_row32(cx.bufx(st, 2u), lane, raw);
+        dep = raw[0] ^ raw[4];
+#pragma unroll
+        for (int k = 0; k < VE / 2; k++) {
+          a[2 * k] = (unsigned long long)(long long)(int16_t)(raw[k] & 0xffffu);
+          a[2 * k + 1] = (unsigned long long)(long long)((int32_t)raw[k] >> 16);
+        }
+      }
+      const uint32_t after = staged_reads_done(cx, dep);
+      if (t + feed.ns * NWARPS < ntiles) feed_issue(cx, feed, t + feed.ns * NWARPS, st, after);
+      feed_prefetch(cx, feed, it + feed.ns + PF_AHEAD);
+      if (idx0 + VE > n) {
+#pragma unroll
+        for (int k = 0; k < VE; k++)
+          if (idx0 + k >= n) a[k] = 0ull;
+      }
+    } else if (vw == 1u) {
+      const int32_t* __restrict__ v32 = reinterpret_cast<const int32_t*>(c.data);
+      if (idx0 + VE <= n) {
+        uint32_t raw[16];
+        ldg256(v32 + idx0, raw);
+        ldg256(v32 + idx0 + 8, raw + 8);
+#pragma unroll
+        for (int k = 0; k < VE; k++) a[k] = (unsigned long long)(long long)(int32_t)raw[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? (unsigned long long)(long long)v32[idx0 + k] : 0ull;
+      }
+    } else if (vw == 2u) {
+      const int16_t* __restrict__ v16 = reinterpret_cast<const int16_t*>(c.data);
+      if (idx0 + VE <= n) {
+        uint32_t raw[8];
+        ldg256(v16 + idx0, raw);
+#pragma unroll
+        for (int k = 0; k < VE / 2; k++) {
+          a[2 * k] = (unsigned long long)(long long)(int16_t)(raw[k] & 0xffffu);
+          a[2 * k + 1] = (unsigned long long)(long long)((int32_t)raw[k] >> 16);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? (unsigned long long)(long long)v16[idx0 + k] : 0ull;
+      }
     } else if (idx0 + VE <= n) {
 #pragma unroll
       for (int j = 0; j < VE / 4; j++) ldg256(vals + idx0 + 4 * j, a + 4 * j);
@@ -685,10 +822,11 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
   if (n > nrec) n = nrec;
   const unsigned long long* __restrict__ vals = reinterpret_cast<const unsigned long long*>(c.data);
   const bool delta = (c.flags & COL_DELTA_VALUES) != 0;
+  const uint32_t vw = col_shift(c.flags);  // 0: int64 values; 1 / 2: int32 / int16 deltas on top of c.vbase
   const int lane = cx.lane, warp = cx.warp;
   cx.epoch++;
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
-  uint32_t prev_incl = 0;
+  uint32_t prev_incl = vw ? (uint32_t)(unsigned long long)c.vbase : 0u;  // decoded values are exact mod 2^32
   uint32_t hix = 0;  // xor of the high limbs read (keeps the staged loads 16 bytes wide)
   Feed feed = make_feed(cx, c);
   feed_prologue(cx, feed, ntiles);
@@ -697,7 +835,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
     uint32_t a[VE];
     if (feed.on) {
-      const uint32_t st = it & (cx.nstage - 1u);
+      const uint32_t st = it & (feed.ns - 1u);
 #ifdef SG_WAIT_TIMING
       const long long tw0 = cx.timing ? clock64() : 0;
 #endif
@@ -705,14 +843,53 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
 #ifdef SG_WAIT_TIMING
       if (cx.timing) cx.t_tma += (unsigned long long)(clock64() - tw0);
 #endif
-      read_staged_row_lo(cx.buf(st), lane, a, hix);  // low limbs: exact mod 2^32
-      const uint32_t after = staged_reads_done(cx, hix);
-      if (t + cx.nstage * NWARPS < ntiles) feed_issue(cx, feed, t + cx.nstage * NWARPS, st, after);
-      feed_prefetch(cx, feed, it + cx.nstage + PF_AHEAD);
+      uint32_t dep;
+      if (vw == 0u) {
+        read_staged_row_lo(cx.bufx(st, 0u), lane, a, hix);  // low limbs: exact mod 2^32
+        dep = hix;
+      } else if (vw == 1u) {
+        read_staged_row64(cx.bufx(st, 1u), lane, a);  // int32 deltas: as they are (mod 2^32)
+        dep = (a[0] ^ a[4]) ^ (a[8] ^ a[12]);
+      } else {
+        uint32_t raw[8];
+        read_staged_row32(cx.bufx(st, 2u), lane, raw);
+        dep = raw[0] ^ raw[4];
+#pragma unroll
+        for (int k = 0; k < VE / 2; k++) {
+          a[2 * k] = (uint32_t)(int32_t)(int16_t)(raw[k] & 0xffffu);
+          a[2 * k + 1] = (uint32_t)((int32_t)raw[k] >> 16);
+        }
+      }
+      const uint32_t after = staged_reads_done(cx, dep);
+      if (t + feed.ns * NWARPS < ntiles) feed_issue(cx, feed, t + feed.ns * NWARPS, st, after);
+      feed_prefetch(cx, feed, it + feed.ns + PF_AHEAD);
       if (idx0 + VE > n) {
 #pragma unroll
         for (int k = 0; k < VE; k++)
           if (idx0 + k >= n) a[k] = 0u;
+      }
+    } else if (vw == 1u) {
+      const uint32_t* __restrict__ v32 = reinterpret_cast<const uint32_t*>(c.data);
+      if (idx0 + VE <= n) {
+        ldg256(v32 + idx0, a);
+        ldg256(v32 + idx0 + 8, a + 8);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? v32[idx0 + k] : 0u;
+      }
+    } else if (vw == 2u) {
+      const int16_t* __restrict__ v16 = reinterpret_cast<const int16_t*>(c.data);
+      if (idx0 + VE <= n) {
+        uint32_t raw[8];
+        ldg256(v16 + idx0, raw);
+#pragma unroll
+        for (int k = 0; k < VE / 2; k++) {
+          a[2 * k] = (uint32_t)(int32_t)(int16_t)(raw[k] & 0xffffu);
+          a[2 * k + 1] = (uint32_t)((int32_t)raw[k] >> 16);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VE; k++) a[k] = (idx0 + k < n) ? (uint32_t)(int32_t)v16[idx0 + k] : 0u;
       }
     } else if (idx0 + VE <= n) {
 #pragma unroll
@@ -871,6 +1048,26 @@ __device__ __forceinline__ void scan_values_i32(Ctx& cx, const DevCol& c, const 
   uint32_t n = c.nitems;
   if (n > nrec) n = nrec;
   const uint32_t* __restrict__ vals = reinterpret_cast<const uint32_t*>(c.data);
+  if (c.flags & COL_VAL16) {  // narrow form: uint16 local ids, 16 per lane and step
+    const uint16_t* __restrict__ v16 = reinterpret_cast<const uint16_t*>(c.data);
+    for (uint32_t idx0 = cx.tid * 2 * SE; idx0 < n; idx0 += THREADS * 2 * SE) {
+      if (idx0 + 2 * SE <= n) {
+        uint32_t a[SE];
+        ldg256(v16 + idx0, a);
+#pragma unroll
+        for (int k = 0; k < SE; k++) {
+          visit(idx0 + 2 * k, (int32_t)(a[k] & 0xffffu));
+          visit(idx0 + 2 * k + 1, (int32_t)(a[k] >> 16));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2 * SE; k++)
+          if (idx0 + k < n) visit(idx0 + k, (int32_t)v16[idx0 + k]);
+      }
+    }
+    __syncthreads();
+    return;
+  }
   for (uint32_t idx0 = cx.tid * SE; idx0 < n; idx0 += THREADS * SE) {
     uint32_t a[SE];
     if (idx0 + SE <= n) {
@@ -1351,8 +1548,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
       if (!bucket && n > nrec) n = nrec;
       colcache[cx.tid] = c;
       ptmp[4 * cx.tid + 0] = on ? 1u : 0u;
-      ptmp[4 * cx.tid + 1] = c.data_chunk;
-      ptmp[4 * cx.tid + 2] = c.data_row;
+      ptmp[4 * cx.tid + 1] = c.data_chunk * 3u + col_shift(c.flags);  // which view of the chunk (see make_feed)
+      ptmp[4 * cx.tid + 2] = c.data_row << col_shift(c.flags);
       ptmp[4 * cx.tid + 3] = bucket ? (n + (32 * BE - 1)) / (32 * BE) : (n + (32 * VE - 1)) / (32 * VE);
     }
     // every row starts as: group slot 0, no filter passed
@@ -1902,20 +2099,44 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const LaunchParams lp)
               off += __popc(m);
             }
             if (cx.lane == 0) lp.spill_counts[sp_tile0 + t] = (uint16_t)off;
+          } else if (nsub > 0 && hist32) {
+            // Straight-line bucket step: x / BucketSize by multiply-high (BucketSize 1 has no magic: b = x), then
+            // ONE predicated shared reduction (the slot's row is in the cache) and, unless every row is, ONE
+            // predicated 64-bit reduction to L2.  (With `magic ? mulhi : x / bsize` and if / else-if the compiler
+            // kept a software division and five branches per row: the loop was branch- and fetch-bound.)
+            const bool unit = bsize0 == 1u;
+            const uint32_t nv1 = nvals0 - 1u;
+            if (hrows >= lslots) {
+#pragma unroll
+              for (int k = 0; k < VE; k++) {
+                const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
+                const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
+                const uint32_t e2 = fr ? e : trash;
+                const uint32_t x = a[k] - fmin32 + hdelta;
+                const uint32_t q = div_magic(x, magic0);
+                const uint32_t b = min(unit ? x : q, nv1);  // outlier: clamped into the last slot (hist_basic.go:134-137)
+                sred_inc_if(e2 < hrows ? 1u : 0u, hcache_s + e2 * hrw_b + b * 4u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < VE; k++) {
+                const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
+                const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
+                const uint32_t e2 = fr ? e : trash;
+                const uint32_t x = a[k] - fmin32 + hdelta;
+                const uint32_t q = div_magic(x, magic0);
+                const uint32_t b = min(unit ? x : q, nv1);
+                sred_inc_if(e2 < hrows ? 1u : 0u, hcache_s + e2 * hrw_b + b * 4u);
+                gred_inc_if((e2 >= hrows && e2 != trash) ? 1u : 0u, bkt_w + ((size_t)e2 * nvt + b));
+              }
+            }
           } else if (nsub > 0) {
 #pragma unroll
             for (int k = 0; k < VE; k++) {
               const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
               const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
               const uint32_t e2 = fr ? e : trash;
-              if (hist32) {
-                const uint32_t x = a[k] - fmin32 + hdelta;
-                uint32_t b = magic0 ? div_magic(x, magic0) : x / bsize0;
-                b = min(b, nvals0 - 1);  // outlier: clamped into the last slot (hist_basic.go:134-137)
-                hist_add(e2, b);
-              } else if (e2 != trash) {
-                hist_bucket_general(&AS, e2, (long long)a[k]);
-              }
+              if (e2 != trash) hist_bucket_general(&AS, e2, (long long)a[k]);
             }
           }
         };

@@ -384,22 +384,27 @@ int arena_alloc(sg_table* t, size_t bytes, char** out) {
     t->chunk_idx = t->chunks.size() - 1;
     t->chunk_used = 0;
     t->device_bytes += (int64_t)cap;
-    CUtensorMap tm;
-    memset(&tm, 0, sizeof(tm));
+    // three views of the chunk, row pitch 128 / 64 / 32 bytes (wide / 2x / 4x narrow arrays, see col_shift):
+    // a box is always 32 rows = one warp tile, swizzled so that a lane reading its own row is conflict-free
     TmapEncodeFn enc = getenv("SG_NO_TMA") ? nullptr : tmap_encode_fn();  // SG_NO_TMA=1: plain vector loads (A/B)
-    if (enc && t->tma_ok) {
-      const cuuint64_t gdim[2] = {128, (cuuint64_t)(cap / 128)};
-      const cuuint64_t gstr[1] = {128};
-      const cuuint32_t box[2] = {128, 32};
-      const cuuint32_t estr[2] = {1, 1};
-      if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
-          CUDA_SUCCESS)
+    for (uint32_t sh = 0; sh < 3; sh++) {
+      CUtensorMap tm;
+      memset(&tm, 0, sizeof(tm));
+      if (enc && t->tma_ok) {
+        const cuuint32_t pitch = 128u >> sh;
+        const cuuint64_t gdim[2] = {pitch, (cuuint64_t)(cap / pitch)};
+        const cuuint64_t gstr[1] = {pitch};
+        const cuuint32_t box[2] = {pitch, 32};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUtensorMapSwizzle swz = sh == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : (sh == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          t->tma_ok = false;
+      } else {
         t->tma_ok = false;
-    } else {
-      t->tma_ok = false;
+      }
+      t->tmaps.push_back(tm);
     }
-    t->tmaps.push_back(tm);
     t->tmaps_dirty = true;
   }
   *out = t->chunks[t->chunk_idx].first + t->chunk_used;
@@ -659,6 +664,38 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
                (is_str ? COL_IS_STR : 0u);
     dc.oob_gid = -1;
     if (cd.encoding == SG_ENC_ABSENT) continue;
+    // narrow arrays (sybilgpu.h): element sizes of record_ids / values
+    size_t id_size = 4, val_size = is_str ? 4 : 8;
+    if (cd.encoding == SG_ENC_BUCKET) {
+      if (cd.id_bits == 16) {
+        id_size = 2;
+        dc.flags |= COL_ID16;
+      } else if (cd.id_bits != 0 && cd.id_bits != 32) {
+        c->set_err("add_block: id_bits must be 0, 16 or 32");
+        return SG_ERR_INVALID;
+      }
+    } else if (cd.encoding == SG_ENC_VALUES) {
+      const int vb = cd.value_bits;
+      if (is_str) {
+        if (vb == 16) {
+          val_size = 2;
+          dc.flags |= COL_VAL16;
+        } else if (vb != 0 && vb != 32) {
+          c->set_err("add_block: value_bits of a str column must be 0, 16 or 32");
+          return SG_ERR_INVALID;
+        }
+      } else if (vb == 32 || vb == 16) {
+        if (!cd.delta_values) {
+          c->set_err("add_block: narrow int values are deltas (delta_values must be set)");
+          return SG_ERR_INVALID;
+        }
+        val_size = vb == 32 ? 4 : 2;
+        dc.flags |= vb == 32 ? COL_VAL32 : COL_VAL16;
+      } else if (vb != 0 && vb != 64) {
+        c->set_err("add_block: value_bits of an int column must be 0, 16, 32 or 64");
+        return SG_ERR_INVALID;
+      }
+    }
     if (is_str) {
       // unpackStrCol: a string table longer than the block is "BLOCK SIZE CHANGED" (:524)
       if (cd.ndict > nrec) dc.flags |= COL_BROKEN;
@@ -738,12 +775,12 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
       }
       tm.off_bv = sw.add(tm.bin_values.data(), tm.bin_values.size() * 8);
       tm.off_bo = sw.add(tm.bin_offsets.data(), tm.bin_offsets.size() * 4);
-      if (pm.has(cd.record_ids, (size_t)cd.nrecord_ids * 4))
+      if (pm.has(cd.record_ids, (size_t)cd.nrecord_ids * id_size))
         tm.premapped = pm.dev + ((const char*)cd.record_ids - pm.host);
       else
-        tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * 4, c->is_pinned(cd.record_ids, (size_t)cd.nrecord_ids * 4));
+        tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * id_size, c->is_pinned(cd.record_ids, (size_t)cd.nrecord_ids * id_size));
       tm.has_bv = tm.has_bo = tm.has_data = true;
-      enc_bytes += (int64_t)(tm.bin_values.size() * 8 + tm.bin_offsets.size() * 4 + (size_t)cd.nrecord_ids * 4);
+      enc_bytes += (int64_t)(tm.bin_values.size() * 8 + tm.bin_offsets.size() * 4 + (size_t)cd.nrecord_ids * id_size);
       if (cd.nrecord_ids == nrec) stats_slots.push_back((uint32_t)cd.col_slot);  // candidate for COL_FULL
     } else if (cd.encoding == SG_ENC_VALUES) {
       dc.nitems = cd.nvalues;
@@ -756,21 +793,22 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
             c->set_err("add_block: values_i32 missing");
             return SG_ERR_INVALID;
           }
-          if (pm.has(cd.values_i32, (size_t)cd.nvalues * 4))
+          if (pm.has(cd.values_i32, (size_t)cd.nvalues * val_size))
             tm.premapped = pm.dev + ((const char*)cd.values_i32 - pm.host);
           else
-            tm.off_data = sw.add(cd.values_i32, (size_t)cd.nvalues * 4, c->is_pinned(cd.values_i32, (size_t)cd.nvalues * 4));
-          enc_bytes += (int64_t)cd.nvalues * 4;
+            tm.off_data = sw.add(cd.values_i32, (size_t)cd.nvalues * val_size, c->is_pinned(cd.values_i32, (size_t)cd.nvalues * val_size));
+          enc_bytes += (int64_t)cd.nvalues * (int64_t)val_size;
         } else {
           if (!cd.values_i64) {
             c->set_err("add_block: values_i64 missing");
             return SG_ERR_INVALID;
           }
-          if (pm.has(cd.values_i64, (size_t)cd.nvalues * 8))
+          if (pm.has(cd.values_i64, (size_t)cd.nvalues * val_size))
             tm.premapped = pm.dev + ((const char*)cd.values_i64 - pm.host);
           else
-            tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * 8, c->is_pinned(cd.values_i64, (size_t)cd.nvalues * 8));
-          enc_bytes += (int64_t)cd.nvalues * 8;
+            tm.off_data = sw.add(cd.values_i64, (size_t)cd.nvalues * val_size, c->is_pinned(cd.values_i64, (size_t)cd.nvalues * val_size));
+          enc_bytes += (int64_t)cd.nvalues * (int64_t)val_size;
+          if (val_size != 8) dc.vbase = cd.value_base;
           t->has_values_int[(size_t)cd.col_slot] = 1;
           stats_slots.push_back((uint32_t)cd.col_slot);
         }
@@ -835,7 +873,7 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
     const sg_column_desc& cd = b->cols[ci];
     DevCol& dc = dcs[(size_t)cd.col_slot];
     Tmp& tm = tmp[(size_t)ci];
-    if (tm.has_bv) dc.bin_values = (const int64_t*)(dev + tm.off_bv);
+    if (tm.has_bv) dc.bin_values = (const int64_t*)(dev + tm.off_bv);  // (VALUES columns keep vbase in the same field)
     if (tm.has_bo) dc.bin_offsets = (const uint32_t*)(dev + tm.off_bo);
     if (tm.has_data) {
       const size_t chunk = tm.premapped ? pm.chunk : t->chunk_idx;
@@ -892,10 +930,11 @@ int sg_table_add_blocks(sg_table* t, const sg_block_desc* const* blocks, int64_t
     for (int ci = 0; ci < b->ncols; ci++) {
       const sg_column_desc& cd = b->cols[ci];
       if (cd.encoding == SG_ENC_BUCKET)
-        see(cd.record_ids, (size_t)cd.nrecord_ids * 4);
+        see(cd.record_ids, (size_t)cd.nrecord_ids * (cd.id_bits == 16 ? 2 : 4));
       else if (cd.encoding == SG_ENC_VALUES)
         see(cd.col_type == SG_COL_STR ? (const void*)cd.values_i32 : (const void*)cd.values_i64,
-            (size_t)cd.nvalues * (cd.col_type == SG_COL_STR ? 4 : 8));
+            (size_t)cd.nvalues * (cd.col_type == SG_COL_STR ? (cd.value_bits == 16 ? 2 : 4)
+                                                            : (cd.value_bits == 32 ? 4 : (cd.value_bits == 16 ? 2 : 8))));
     }
   }
   if (lo && payload >= ((size_t)1 << 20)) {

@@ -39,6 +39,8 @@ class SynthCol:
 class SynthSpec:
     def __init__(self, name, key_table, cols, total_rows, seed, block_rows=F.SG_BLOCK_ROWS, threshold=5000):
         self.name, self.key_table, self.cols = name, key_table, cols
+        # narrow arrays (uint16 ids, int32/int16 value deltas: sybilgpu.h) unless SG_WIDE=1 asks for Go's decoded types
+        self.narrow = not os.environ.get("SG_WIDE")
         self.total_rows, self.seed, self.block_rows, self.threshold = total_rows, seed, block_rows, threshold
         self.KeyTable = {n: i for i, (n, _) in enumerate(key_table)}
         self.KeyTypes = {i: t for i, (_, t) in enumerate(key_table)}
@@ -76,6 +78,7 @@ class SynthSpec:
         s.seed, s.total_rows, s.block_rows, s.ncols = self.seed, self.total_rows, self.block_rows, len(self.cols)
         s.cardinality_threshold, s.num_col_slots = self.threshold, len(self.key_table)
         s.cols = C.cast(arr, C.POINTER(F.sbg_col))
+        s.narrow = 1 if self.narrow else 0
         self._keep = arr
         return s
 

@@ -6,24 +6,31 @@ import numpy as np
 import pytest
 
 from sybil_b200 import _ffi as F
-from sybil_b200.blocks import decode_column, encode_int_column, encode_str_column
+from sybil_b200.blocks import decode_column, encode_int_column, encode_str_column, narrow_column
 from sybil_b200 import synth
 
 
 def col_arrays(cd):
+    """The descriptor's arrays in the element types its id_bits / value_bits name (sybilgpu.h)."""
     def arr(p, n, t):
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(t)), (n,)).copy() if p and n else np.zeros(0, t)
+    idt = C.c_uint16 if cd.id_bits == 16 else C.c_uint32
+    vit = {16: C.c_int16, 32: C.c_int32}.get(cd.value_bits, C.c_int64)
+    vst = C.c_uint16 if cd.value_bits == 16 else C.c_int32
     return dict(enc=cd.encoding, delta_ids=cd.delta_ids, delta_values=cd.delta_values,
                 bin_values=arr(cd.bin_values, cd.nbins, C.c_int64),
                 bin_offsets=arr(cd.bin_offsets, cd.nbins + 1, C.c_uint32),
-                record_ids=arr(cd.record_ids, cd.nrecord_ids, C.c_uint32),
-                values_i64=arr(cd.values_i64, cd.nvalues if cd.col_type == F.SG_COL_INT else 0, C.c_int64),
-                values_i32=arr(cd.values_i32, cd.nvalues if cd.col_type == F.SG_COL_STR else 0, C.c_int32))
+                record_ids=arr(cd.record_ids, cd.nrecord_ids, idt),
+                values_i64=arr(cd.values_i64, cd.nvalues if cd.col_type == F.SG_COL_INT else 0, vit),
+                values_i32=arr(cd.values_i32, cd.nvalues if cd.col_type == F.SG_COL_STR else 0, vst),
+                value_base=cd.value_base)
 
 
+@pytest.mark.parametrize("narrow", [False, True])
 @pytest.mark.parametrize("cfg", ["c2", "c3", "c5"])
-def test_generator_matches_numpy_encoder(cfg):
+def test_generator_matches_numpy_encoder(cfg, narrow):
     spec = synth.config(cfg, total_rows=3 * 4096 + 1000, block_rows=4096)
+    spec.narrow = narrow
     store = synth.generate(spec, 0, None, nthreads=2)
     spec.threshold = spec.threshold
     g = F.gen()
@@ -46,7 +53,12 @@ def test_generator_matches_numpy_encoder(cfg):
                 blob = C.string_at(cd.dict_bytes, int(offs[-1]))
                 table = [blob[offs[i]:offs[i + 1]] for i in range(cd.ndict)]
                 assert table == ref.string_table
+            if narrow:
+                ref = narrow_column(ref)
             assert got["enc"] == ref.encoding
+            for k in ("record_ids", "values_i64", "values_i32"):  # same element types as the numpy narrowing picks
+                assert got[k].dtype == np.asarray(getattr(ref, k)).dtype or len(got[k]) == 0, (k, got[k].dtype)
+            assert got["value_base"] == getattr(ref, "value_base", 0)
             if ref.encoding == F.SG_ENC_BUCKET:
                 assert np.array_equal(got["bin_values"], ref.bin_values)
                 assert np.array_equal(got["bin_offsets"], ref.bin_offsets)
@@ -65,6 +77,8 @@ def test_encode_decode_round_trip_with_missing_rows(threshold):
     valid = rng.random(n) > 0.1
     c = encode_int_column(0, v, valid, threshold)
     dv, pop = decode_column(c, n)
+    dn, popn = decode_column(narrow_column(c), n)  # the narrow form decodes to the same rows
+    assert np.array_equal(dn, dv) and np.array_equal(popn, pop)
     if c.encoding == F.SG_ENC_BUCKET:
         assert np.array_equal(pop, valid)
         assert np.array_equal(dv[valid], v[valid])

@@ -194,13 +194,17 @@ def test_golden_rows_reproduce_reference_buckets():
         assert np.array_equal(h.Values, dense(gold["hist"]))
 
 
+@pytest.mark.parametrize("narrow", [True, False])
 @pytest.mark.parametrize("cfg,rows", [("c2", 300_000), ("c3", 400_000), ("c4", 300_000), ("c5", 300_000)])
-def test_benchmark_configs_at_reduced_size(cfg, rows):
-    """BASELINE.json configs 2-5 generated by the C++ generator at a size the oracle finishes in seconds."""
+def test_benchmark_configs_at_reduced_size(cfg, rows, narrow):
+    """BASELINE.json configs 2-5 generated by the C++ generator at a size the oracle finishes in seconds, with
+    the arrays in their narrow form (uint16 ids, int16 / int32 value deltas: 2 KiB / 1 KiB TMA tiles) and in Go's
+    decoded types (4 KiB tiles)."""
     from sybil_b200 import engine as E
     from sybil_b200 import synth
     from oracle.oracle_ffi import OracleTable
     spec = synth.config(cfg, total_rows=rows)
+    spec.narrow = narrow
     store = synth.generate(spec)
     qd = synth.query_for(spec)
     s = Spec(spec.key_table)
@@ -453,7 +457,7 @@ def _shuffle_bins(spec, seed):
             offs = np.asarray(col.bin_offsets, np.int64)
             ids = [np.asarray(col.record_ids[offs[b]:offs[b + 1]]) for b in perm]
             col.bin_values = np.asarray(col.bin_values)[perm]
-            col.record_ids = np.concatenate(ids).astype(np.uint32)
+            col.record_ids = np.concatenate(ids).astype(np.asarray(col.record_ids).dtype)  # (uint16 stays uint16)
             col.bin_offsets = np.concatenate([[0], np.cumsum([len(x) for x in ids])]).astype(np.uint32)
 
 

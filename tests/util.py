@@ -7,7 +7,9 @@ import numpy as np
 
 from sybil_b200 import _ffi as F
 from sybil_b200 import engine as E
-from sybil_b200.blocks import encode_block
+import os
+
+from sybil_b200.blocks import encode_block, narrow_column
 
 INT, STR = F.SG_COL_INT, F.SG_COL_STR
 
@@ -16,8 +18,21 @@ MEAN_TOL = 1e-9
 STD_TOL = 1e-9
 
 
+# Which columns of the test tables are handed over in their narrow form (uint16 ids, int16/int32 value deltas,
+# sybilgpu.h): "mixed" (default) = column c of block b when b + c is even, so one table — even one block —
+# mixes both forms and every test exercises both; "narrow" / "wide" = all / none (SG_TEST_FORMS).
+FORMS = os.environ.get("SG_TEST_FORMS", "mixed")
+
+
+def pick_narrow(block_index, col_slot, forms=None):
+    forms = forms or FORMS
+    return forms == "narrow" or (forms == "mixed" and (block_index + col_slot) % 2 == 0)
+
+
 class Spec:
     """A table: key_table [(name, type)], IntInfo, and SavedBlocks."""
+
+    forms = None  # None: the module default (FORMS)
 
     def __init__(self, key_table):
         self.key_table = key_table
@@ -39,7 +54,9 @@ class Spec:
                 v = vals[start:end]
                 va = valid.get(name)
                 cl.append((slot, self.KeyTypes[slot], v, None if va is None else va[start:end]))
-            self.blocks.append(encode_block(len(self.blocks), end - start, cl, threshold))
+            blk = encode_block(len(self.blocks), end - start, cl, threshold)
+            blk.cols = [narrow_column(c) if pick_narrow(blk.block_index, c.col_slot, self.forms) else c for c in blk.cols]
+            self.blocks.append(blk)
         for name, vals in cols.items():
             slot = self.KeyTable[name]
             if self.KeyTypes[slot] == INT:
