@@ -21,6 +21,7 @@ import "C"
 
 import (
 	"errors"
+	"runtime"
 	"unsafe"
 )
 
@@ -81,6 +82,13 @@ type Column struct {
 	RecordIDs   []uint32
 	ValuesI64   []int64
 	ValuesI32   []int32
+	// Narrow forms (ABI v3, sg_column_desc.id_bits / value_bits): a decoder that keeps gob's varints narrow
+	// fills these INSTEAD of the wide slices above; 2-4x fewer bytes cross PCIe and sit in HBM.
+	RecordIDs16 []uint16 // bucket columns: ids / gaps (always < 65,536 in a valid block)
+	Deltas32    []int32  // int value arrays, ValueEncoded: value k = ValueBase + Deltas[0] + ... + Deltas[k]
+	Deltas16    []int16  //   (the same, 16-bit)
+	ValueBase   int64
+	Values16    []uint16 // str value arrays: local string ids
 	DictBytes   []byte   // StringTable concatenated
 	DictOffsets []uint32 // len(StringTable)+1
 }
@@ -90,11 +98,26 @@ type IntInfo struct {
 	Min, Max int64
 }
 
+// pin makes a Go slice's backing array safe to store in C memory for the duration of the call (cgo pointer
+// rules): runtime.Pinner keeps the collector from moving it.  Slices carved from Ctx.Pinned are C memory
+// already and pinning them is a no-op.
+func pin[T any](p *runtime.Pinner, s []T) unsafe.Pointer {
+	if len(s) == 0 {
+		return nil
+	}
+	d := unsafe.SliceData(s)
+	p.Pin(d)
+	return unsafe.Pointer(d)
+}
+
 // AddBlock stages one block (LoadBlockFromDir + unpack*Col, table_block_io.go:225-310).
-// All slices are only read during the call (cgo pointer rules: the descriptor
-// arrays are allocated in C memory; the data slices are pinned for the call
-// with runtime.Pinner when they are Go-allocated).
+// Small arrays (bin values, offsets, string tables) are read during the call; the big ones (record ids,
+// values) are DMA'd asynchronously when they lie in memory from Ctx.Pinned and must stay untouched until
+// Table.Sync returns (INTEGRATION.md §3) — Go-allocated slices are copied through the library's own staging
+// before the call returns.  UNTESTED: this file has never been compiled (no Go toolchain in the build image).
 func (t *Table) AddBlock(index int64, numRecords int32, cols []Column, info []IntInfo) error {
+	var pinner runtime.Pinner
+	defer pinner.Unpin()
 	cdesc := (*C.sg_column_desc)(C.calloc(C.size_t(len(cols)+1), C.size_t(unsafe.Sizeof(C.sg_column_desc{}))))
 	defer C.free(unsafe.Pointer(cdesc))
 	cs := unsafe.Slice(cdesc, len(cols)+1)
@@ -109,17 +132,36 @@ func (t *Table) AddBlock(index int64, numRecords int32, cols []Column, info []In
 			d.encoding = C.SG_ENC_BUCKET
 			d.nbins = C.uint32_t(len(col.BinValues))
 			d.nrecord_ids = C.uint32_t(len(col.RecordIDs))
-			d.bin_values = (*C.int64_t)(unsafe.Pointer(unsafe.SliceData(col.BinValues)))
-			d.bin_offsets = (*C.uint32_t)(unsafe.Pointer(unsafe.SliceData(col.BinOffsets)))
-			d.record_ids = (*C.uint32_t)(unsafe.Pointer(unsafe.SliceData(col.RecordIDs)))
+			d.bin_values = (*C.int64_t)(pin(&pinner, col.BinValues))
+			d.bin_offsets = (*C.uint32_t)(pin(&pinner, col.BinOffsets))
+			if len(col.RecordIDs16) > 0 {
+				d.nrecord_ids = C.uint32_t(len(col.RecordIDs16))
+				d.record_ids = (*C.uint32_t)(pin(&pinner, col.RecordIDs16))
+				d.id_bits = 16
+			} else {
+				d.record_ids = (*C.uint32_t)(pin(&pinner, col.RecordIDs))
+			}
 		} else {
 			d.encoding = C.SG_ENC_VALUES
-			if col.IsStr {
+			switch {
+			case col.IsStr && len(col.Values16) > 0:
+				d.nvalues = C.uint32_t(len(col.Values16))
+				d.values_i32 = (*C.int32_t)(pin(&pinner, col.Values16))
+				d.value_bits = 16
+			case col.IsStr:
 				d.nvalues = C.uint32_t(len(col.ValuesI32))
-				d.values_i32 = (*C.int32_t)(unsafe.Pointer(unsafe.SliceData(col.ValuesI32)))
-			} else {
+				d.values_i32 = (*C.int32_t)(pin(&pinner, col.ValuesI32))
+			case len(col.Deltas16) > 0:
+				d.nvalues = C.uint32_t(len(col.Deltas16))
+				d.values_i64 = (*C.int64_t)(pin(&pinner, col.Deltas16))
+				d.value_bits, d.value_base = 16, C.int64_t(col.ValueBase)
+			case len(col.Deltas32) > 0:
+				d.nvalues = C.uint32_t(len(col.Deltas32))
+				d.values_i64 = (*C.int64_t)(pin(&pinner, col.Deltas32))
+				d.value_bits, d.value_base = 32, C.int64_t(col.ValueBase)
+			default:
 				d.nvalues = C.uint32_t(len(col.ValuesI64))
-				d.values_i64 = (*C.int64_t)(unsafe.Pointer(unsafe.SliceData(col.ValuesI64)))
+				d.values_i64 = (*C.int64_t)(pin(&pinner, col.ValuesI64))
 			}
 		}
 		if col.DeltaIDs {
@@ -130,8 +172,8 @@ func (t *Table) AddBlock(index int64, numRecords int32, cols []Column, info []In
 		}
 		if col.IsStr {
 			d.ndict = C.uint32_t(len(col.DictOffsets) - 1)
-			d.dict_bytes = (*C.char)(unsafe.Pointer(unsafe.SliceData(col.DictBytes)))
-			d.dict_offsets = (*C.uint32_t)(unsafe.Pointer(unsafe.SliceData(col.DictOffsets)))
+			d.dict_bytes = (*C.char)(pin(&pinner, col.DictBytes))
+			d.dict_offsets = (*C.uint32_t)(pin(&pinner, col.DictOffsets))
 		}
 	}
 	cinfo := (*C.sg_int_info)(C.calloc(C.size_t(len(info)+1), C.size_t(unsafe.Sizeof(C.sg_int_info{}))))
@@ -257,6 +299,9 @@ func (t *Table) Run(q *Query, allreduce bool) (*C.sg_result, error) {
 	for i, f := range q.Filters {
 		if f.Lut != nil {
 			n := C.sg_table_dict_size(t.h, C.int32_t(f.Slot))
+			if int64(len(f.Lut)) < (int64(n)+31)/32 { // one bit per global string id of the column
+				return nil, errors.New("sybilgpu: regex LUT shorter than the column's dictionary")
+			}
 			if C.sg_query_set_str_lut(h, C.int32_t(i), (*C.uint32_t)(unsafe.Pointer(&f.Lut[0])), n) != C.SG_OK {
 				return nil, t.c.err()
 			}

@@ -32,6 +32,10 @@ typedef struct sgob_block sgob_block;
 sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, const int32_t* col_types, int32_t ncols,
                                 const uint8_t* load_mask, int64_t block_index, char* err, size_t errlen);
 const sg_block_desc* sgob_block_desc(const sgob_block* b);
+/* 1: blocks read from now on keep their arrays narrow (uint16 record ids, int16 / int32 value deltas, uint16
+ * local string ids: sg_column_desc::id_bits / value_bits) instead of widening every varint to Go's uint32 /
+ * int64 / int32 — half to a quarter of the bytes over PCIe and HBM.  0 (default): Go's decoded types. */
+void sgob_set_narrow(int on);
 void sgob_block_free(sgob_block* b);
 
 /* bytes of column data decoded (sum over the arrays of the descriptor) */

@@ -24,7 +24,9 @@ def _run(cmd):
 
 
 def build_gpu(force=False):
-    """libsybilgpu.so: hand-written sm_100a kernels + runtime, cudart linked statically."""
+    """libsybilgpu.so: hand-written sm_100a kernels + runtime, cudart linked statically.  The kernel unit is
+    compiled twice (sg_internal.h): 16-warp CTAs, one per SM, and 8-warp CTAs, two per SM; the three compilations
+    run in parallel."""
     out = os.environ.get("SG_LIB_OUT") or os.path.join(CSRC, "libsybilgpu.so")
     srcs = [os.path.join(CSRC, f) for f in ("sg_kernels.cu", "sg_runtime.cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("sg_internal.h", "sg_hist.h")] + [
@@ -32,8 +34,21 @@ def build_gpu(force=False):
     if not force and not _newer(out, deps):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    _run([nvcc] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress",
-                               "186", "-o", out] + os.environ.get("SG_NVCC_FLAGS", "").split() + srcs + ["-ldl"])
+    bdir = os.path.join(CSRC, "build")
+    os.makedirs(bdir, exist_ok=True)
+    common = [nvcc] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-diag-suppress", "186"] + \
+        os.environ.get("SG_NVCC_FLAGS", "").split()
+    jobs = [(common + ["-DSG_THREADS=512", "-c", srcs[0], "-o", os.path.join(bdir, "sg_kernels_w16.o")]),
+            (common + ["-DSG_THREADS=256", "-c", srcs[0], "-o", os.path.join(bdir, "sg_kernels_w8.o")]),
+            (common + ["-c", srcs[1], "-o", os.path.join(bdir, "sg_runtime.o")])]
+    procs = [(cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for cmd in jobs]
+    for cmd, p in procs:
+        log, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), log))
+        if os.environ.get("SG_BUILD_VERBOSE"):
+            print(log)
+    _run([nvcc] + NVCC_ARCH + ["-shared", "-o", out] + [j[-1] for j in jobs] + ["-ldl"])
     return out
 
 

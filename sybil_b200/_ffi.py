@@ -216,6 +216,7 @@ GOB_SYMBOLS = {
     "sgob_read_block_dir": (P, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8),
                                 C.c_int64, C.c_char_p, C.c_size_t]),
     "sgob_block_desc": (C.POINTER(sg_block_desc), [P]),
+    "sgob_set_narrow": (None, [C.c_int]),
     "sgob_block_free": (None, [P]),
     "sgob_block_bytes": (C.c_int64, [P]),
     "sgob_table_open": (P, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),

@@ -10,6 +10,8 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <climits>
+#include <cstdint>
 #include <algorithm>
 
 #include <cstdio>
@@ -230,7 +232,51 @@ struct Column {
   std::string dict_bytes;
   std::vector<uint32_t> dict_offsets{0};
   uint32_t ndict = 0;
+  // narrow copies (sgob_set_narrow): what the varints of the file hold, not widened to Go's types
+  std::vector<uint16_t> ids16, v16;
+  std::vector<int32_t> d32;
+  std::vector<int16_t> d16;
+  int64_t vbase = 0;
+  int id_bits = 0, value_bits = 0;
 };
+
+bool g_narrow = false;
+
+// keep the arrays as narrow as their values allow (include/sybilgpu.h: id_bits / value_bits)
+void narrow_column(Column& c) {
+  if (c.encoding == SG_ENC_BUCKET) {
+    bool ok = true;
+    for (uint32_t v : c.record_ids) ok = ok && v < 65536u;
+    if (ok) {
+      c.ids16.assign(c.record_ids.begin(), c.record_ids.end());
+      c.id_bits = 16;
+    }
+  } else if (c.encoding == SG_ENC_VALUES && c.type == SG_COL_INT) {
+    if (!c.delta_values || c.values_i64.empty()) return;
+    int64_t lo = 0, hi = 0;
+    for (size_t k = 1; k < c.values_i64.size(); k++) {
+      lo = std::min(lo, c.values_i64[k]);
+      hi = std::max(hi, c.values_i64[k]);
+    }
+    c.vbase = c.values_i64[0];
+    if (lo >= INT16_MIN && hi <= INT16_MAX) {
+      c.d16.assign(c.values_i64.size(), 0);
+      for (size_t k = 1; k < c.values_i64.size(); k++) c.d16[k] = (int16_t)c.values_i64[k];
+      c.value_bits = 16;
+    } else if (lo >= INT32_MIN && hi <= INT32_MAX) {
+      c.d32.assign(c.values_i64.size(), 0);
+      for (size_t k = 1; k < c.values_i64.size(); k++) c.d32[k] = (int32_t)c.values_i64[k];
+      c.value_bits = 32;
+    }
+  } else if (c.encoding == SG_ENC_VALUES) {
+    bool ok = true;
+    for (int32_t v : c.values_i32) ok = ok && v >= 0 && v < 65536;
+    if (ok) {
+      c.v16.assign(c.values_i32.begin(), c.values_i32.end());
+      c.value_bits = 16;
+    }
+  }
+}
 
 void read_column(const std::vector<uint8_t>& raw, Column& c) {
   Reader r(raw.data(), raw.size());
@@ -295,6 +341,8 @@ struct sgob_table {
 
 extern "C" {
 
+void sgob_set_narrow(int on) { g_narrow = on != 0; }
+
 sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, const int32_t* col_types, int32_t ncols,
                                 const uint8_t* load_mask, int64_t block_index, char* err, size_t errlen) {
   auto fail = [&](const std::string& m) -> sgob_block* {
@@ -345,6 +393,7 @@ sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, c
       c.slot = s;
       c.type = col_types[s];
       read_column(raw, c);
+      if (g_narrow) narrow_column(c);
       b->cols.push_back(std::move(c));
     }
     b->descs.resize(b->cols.size());
@@ -362,16 +411,22 @@ sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, c
         cd.nrecord_ids = (uint32_t)c.record_ids.size();
         cd.bin_values = c.bin_values.data();
         cd.bin_offsets = c.bin_offsets.data();
-        cd.record_ids = c.record_ids.data();
-        b->bytes += (int64_t)c.record_ids.size() * 4 + (int64_t)c.bin_values.size() * 12;
+        cd.record_ids = c.id_bits == 16 ? reinterpret_cast<const uint32_t*>(c.ids16.data()) : c.record_ids.data();
+        cd.id_bits = c.id_bits;
+        b->bytes += (int64_t)c.record_ids.size() * (c.id_bits == 16 ? 2 : 4) + (int64_t)c.bin_values.size() * 12;
       } else if (c.type == SG_COL_INT) {
         cd.nvalues = (uint32_t)c.values_i64.size();
-        cd.values_i64 = c.values_i64.data();
-        b->bytes += (int64_t)c.values_i64.size() * 8;
+        cd.value_bits = c.value_bits;
+        cd.value_base = c.value_bits ? c.vbase : 0;
+        cd.values_i64 = c.value_bits == 16   ? reinterpret_cast<const int64_t*>(c.d16.data())
+                        : c.value_bits == 32 ? reinterpret_cast<const int64_t*>(c.d32.data())
+                                             : c.values_i64.data();
+        b->bytes += (int64_t)c.values_i64.size() * (c.value_bits ? c.value_bits / 8 : 8);
       } else {
         cd.nvalues = (uint32_t)c.values_i32.size();
-        cd.values_i32 = c.values_i32.data();
-        b->bytes += (int64_t)c.values_i32.size() * 4;
+        cd.value_bits = c.value_bits;
+        cd.values_i32 = c.value_bits == 16 ? reinterpret_cast<const int32_t*>(c.v16.data()) : c.values_i32.data();
+        b->bytes += (int64_t)c.values_i32.size() * (c.value_bits == 16 ? 2 : 4);
       }
       if (c.type == SG_COL_STR) {
         cd.ndict = c.ndict;

@@ -179,7 +179,8 @@ struct LaunchParams {
   uint32_t acc_smem;          // accumulators replicated in shared memory (plan.acc_repl > 0)
   const void* tmaps;          // CUtensorMap[chunks][3] in global memory: row pitch 128 / 64 / 32 bytes (nullptr: plain
                               // vector loads)
-  uint32_t nstage;            // TMA staging depth per warp (1 or 2)
+  uint32_t stage_units;       // TMA staging per warp in units of 2 KiB (0 none; 2 = one 4 KiB tile; 4 = two)
+  uint32_t tail_off;          // the per-pass tables: bytes from the fixed part's start (behind slots, accumulators, cache)
   unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
   uint32_t fold_every;        // blocks whose shared accumulators may be folded together (>= 1)
   uint32_t hashg;             // a group column is a value-array int column (hash lookup path; slot_bytes == 4)
@@ -198,22 +199,34 @@ __host__ __device__ static inline uint32_t vh_hash(long long v) {
   return (uint32_t)x;
 }
 
-// host-callable launchers (sg_kernels.cu)
-int launch_scan(const LaunchParams& lp, int grid, void* stream);
-// extents of value-array int columns: items[i] = index into cols[] (block * ncolslots + slot)
-int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
-                 void* stream);
-// distinct values of value-array int columns: keys[cap] (pre-filled with INT64_MIN = empty) receives every
-// distinct decoded value of the listed (block, column) items; counters[0] += new keys, counters[1] = 1 if
-// INT64_MIN itself occurred, counters[2] = 1 if the set filled up (more than cap/2 keys)
-int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,
-                    long long* keys, uint32_t cap_mask, unsigned int* counters, void* stream);
-// adds the spilled records up (see Plan::spill_naggs); nblocks = blocks of the table
-int launch_hist_apply(const Plan* plan, const uint32_t* spill, const uint16_t* counts, uint32_t nblocks, uint32_t naggs_spill,
-                      uint32_t lslots, uint32_t hist_rows, uint32_t hrw, int grid, void* stream);
-int scan_threads();
-// shared memory the kernel needs besides slots and accumulators (nstage: TMA staging depth, 0 = none)
-uint32_t scan_fixed_smem(uint32_t nstage);
+// host-callable launchers (sg_kernels.cu).  The kernel unit is compiled twice, into two namespaces:
+//   w16: CTAs of 16 warps, one per SM (up to 227 KiB of shared memory: 16-bit slot words, big accumulator sets);
+//   w8:  CTAs of 8 warps, two per SM (113 KiB each).  Two independent CTAs hide each other's barriers, look-back
+//        waits and the L2-bound histogram pass: measured on C3 +27% over one 16-warp CTA (profiles/r02_variants.md).
+#define SG_DECLARE_VARIANT(ns)                                                                                          \
+  namespace ns {                                                                                                        \
+  int launch_scan(const LaunchParams& lp, int grid, void* stream);                                                      \
+  /* extents of value-array int columns: items[i] = index into cols[] (block * ncolslots + slot) */                    \
+  int launch_stats(DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,    \
+                   void* stream);                                                                                       \
+  /* distinct values of value-array int columns: keys[cap] (pre-filled with INT64_MIN = empty) receives every          \
+   * distinct decoded value of the listed (block, column) items; counters[0] += new keys, counters[1] = 1 if          \
+   * INT64_MIN itself occurred, counters[2] = 1 if the set filled up (more than cap/2 keys) */                          \
+  int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems,               \
+                      uint32_t ncolslots, long long* keys, uint32_t cap_mask, unsigned int* counters, void* stream);    \
+  /* adds the spilled records up (see Plan::spill_naggs); nblocks = blocks of the table */                              \
+  int launch_hist_apply(const Plan* plan, const uint32_t* spill, const uint16_t* counts, uint32_t nblocks,              \
+                        uint32_t naggs_spill, uint32_t lslots, uint32_t hist_rows, uint32_t hrw, int grid, void* stream); \
+  int scan_threads();                                                                                                   \
+  /* shared memory the kernel needs besides slots and accumulators (stage_units: per-warp TMA staging, 2 KiB units) */ \
+  uint32_t scan_fixed_smem(uint32_t stage_units);                                                                       \
+  /* ... and behind them: the per-pass tables of a plan with ncand candidate passes */                                 \
+  uint32_t scan_tail_smem(uint32_t ncand);                                                                              \
+  int scan_ctas_per_sm();   /* CTAs the kernel is built to co-reside per SM */                                          \
+  uint32_t scan_max_smem(); /* dynamic shared memory one CTA may use then */                                            \
+  }
+SG_DECLARE_VARIANT(w16)
+SG_DECLARE_VARIANT(w8)
 constexpr uint32_t HROW_NONE = 0xffffffffu;
 constexpr uint32_t SMEM_BINS = 1024;  // per-bin payload entries kept in shared memory (more: global scratch)
 constexpr uint32_t TMA_TILE_BYTES = 4096;  // one warp tile: 32 rows of 128 bytes

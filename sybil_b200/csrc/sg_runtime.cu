@@ -87,7 +87,17 @@ TmapEncodeFn tmap_encode_fn() {
 
 constexpr size_t ARENA_CHUNK = (size_t)512 << 20;
 constexpr size_t STAGE_BYTES = (size_t)64 << 20;
-constexpr uint32_t MAX_DYN_SMEM = 227 * 1024;
+// the two builds of the kernel unit (sg_internal.h)
+struct Variant {
+  const char* name;
+  int warps, ctas;
+  uint32_t max_smem;  // dynamic shared memory of one CTA
+  uint32_t (*fixed_smem)(uint32_t);
+  uint32_t (*tail_smem)(uint32_t);
+  int (*launch)(const LaunchParams&, int, void*);
+};
+static const Variant V16 = {"w16", 16, w16::scan_ctas_per_sm(), w16::scan_max_smem(), w16::scan_fixed_smem, w16::scan_tail_smem, w16::launch_scan};
+static const Variant V8 = {"w8", 8, w8::scan_ctas_per_sm(), w8::scan_max_smem(), w8::scan_fixed_smem, w8::scan_tail_smem, w8::launch_scan};
 constexpr int64_t MAX_SLOTS = (int64_t)1 << 26;
 constexpr int64_t INT_DICT_CAP = (int64_t)1 << 22;
 
@@ -1117,7 +1127,9 @@ struct sg_query {
   std::vector<HistLayout> layouts;
   uint32_t slot_bytes = 2;
   uint32_t smem_bytes = 0;
+  uint32_t tail_off = 0;
   uint32_t nstage = 0;
+  const Variant* variant = &V16;  // which build of the kernel runs the plan (make_plan)
   // device state
   Plan* d_plan = nullptr;
   uint64_t* d_acc = nullptr;  // one allocation: scalars | count | per agg hcount,sum,vmax | buckets
@@ -1270,7 +1282,7 @@ int upload_table(sg_table* t) {
     size_t n = t->pending_stats.size();
     CUDA_TRY(c, pool_alloc(c, (void**)&d_items, n * 4));
     CUDA_TRY(c, cudaMemcpyAsync(d_items, t->pending_stats.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-    int rc = launch_stats(t->d_cols, t->d_blocks, d_items, (uint32_t)n, (uint32_t)t->ncols, c->stream);
+    int rc = w16::launch_stats(t->d_cols, t->d_blocks, d_items, (uint32_t)n, (uint32_t)t->ncols, c->stream);
     if (rc != 0) {
       c->set_err(std::string("stats kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
       pool_release(c, d_items);
@@ -1322,7 +1334,7 @@ int ensure_value_dict(sg_table* t, int col) {
     fill_ll<<<(unsigned)(((size_t)cap + 255) / 256), 256, 0, c->stream>>>(d_keys, cap, INT64_MIN);
     CUDA_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(d_items, items.data(), items.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    int rc = launch_distinct(t->d_cols, t->d_blocks, d_items, (uint32_t)items.size(), (uint32_t)t->ncols, d_keys, cap - 1u, d_cnt,
+    int rc = w16::launch_distinct(t->d_cols, t->d_blocks, d_items, (uint32_t)items.size(), (uint32_t)t->ncols, d_keys, cap - 1u, d_cnt,
                              c->stream);
     if (rc != 0) {
       c->set_err(std::string("distinct kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
@@ -1682,31 +1694,63 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     return ((uint64_t)P.lslots + 1) * P.acc_words * repl * 4 + ((uint64_t)P.lslots + 1) * (uint64_t)P.naggs * 4 + 8 +
            (uint64_t)P.nslots * (1 + 2 * (uint64_t)P.naggs) * 8 + 16;
   };
+  const Variant* V = &V16;  // the budget below is taken for this build of the kernel
+  const uint32_t ncand = (uint32_t)(P.nfilters + P.ngroups + (time_mode ? 1 : 0) + P.naggs);
+  const uint32_t tail_b = V16.tail_smem(ncand) + 16;  // per-pass tables behind everything else (same in both builds)
   auto repl_for = [&](uint32_t nstage) -> uint32_t {
-    const uint32_t fixed = scan_fixed_smem(nstage) + slots_b;
-    if (fixed > MAX_DYN_SMEM) return 0;
-    const uint32_t avail = MAX_DYN_SMEM - fixed;
+    const uint32_t fixed = V->fixed_smem(nstage) + slots_b + tail_b;
+    if (fixed > V->max_smem) return 0;
+    const uint32_t avail = V->max_smem - fixed;
     uint32_t repl = 32;
     while (repl >= 1 && acc_bytes(repl) > avail) repl >>= 1;
     return repl;
   };
   auto hist_rows_for = [&](uint32_t nstage, uint32_t repl) -> uint32_t {
     if (!hrow_words || !repl) return 0;
-    const uint64_t used = (uint64_t)scan_fixed_smem(nstage) + slots_b + acc_bytes(repl);
-    if (used >= MAX_DYN_SMEM) return 0;
-    return (uint32_t)std::min<uint64_t>(P.lslots, (MAX_DYN_SMEM - used) / ((uint64_t)hrow_words * 4));
+    const uint64_t used = (uint64_t)V->fixed_smem(nstage) + slots_b + tail_b + acc_bytes(repl);
+    if (used >= V->max_smem) return 0;
+    return (uint32_t)std::min<uint64_t>(P.lslots, (V->max_smem - used) / ((uint64_t)hrow_words * 4));
+  };
+  // (nstage below counts 2 KiB units per warp: 4 = two 4 KiB tiles, 2 = one — or two tiles of a narrow column —,
+  // 1 = 2 KiB: one tile of a uint16 / int32 column, two of an int16 one; wide columns then use plain loads)
+  bool all_narrow = true;  // every TMA-feedable column the plan reads is stored narrow in every listed block
+  {
+    std::vector<int> pcols;
+    for (int i = 0; i < P.nfilters; i++) pcols.push_back(q->filters[(size_t)i].col_slot);
+    for (int i = 0; i < P.ngroups; i++) pcols.push_back(q->groups[(size_t)i].col_slot);
+    for (int i = 0; i < P.naggs; i++) pcols.push_back(q->aggs[(size_t)i].col_slot);
+    if (time_mode) pcols.push_back(P.time_col);
+    for (uint32_t b : list) {
+      for (int col : pcols) {
+        if (col < 0 || col >= t->ncols) continue;
+        const DevCol& dc = t->cols[(size_t)b * (size_t)t->ncols + (size_t)col];
+        if (dc.enc == SG_ENC_ABSENT || !(dc.flags & COL_TMA)) continue;
+        if (dc.enc == SG_ENC_VALUES && (dc.flags & COL_IS_STR)) continue;  // read with plain loads anyway
+        if (col_shift(dc.flags) == 0u) all_narrow = false;
+      }
+      if (!all_narrow) break;
+    }
+  }
+  const char* force_units = getenv("SG_STAGE_UNITS");  // A/B: 0, 1, 2 or 4
+  auto pick_units = [&]() -> uint32_t {
+    uint32_t u = 0;
+    if (t->tma_ok && t->d_tmaps) {
+      auto fits = [&](uint32_t x) { return repl_for(x) >= 2 || (repl_for(x) >= 1 && repl_for(0) <= 1); };
+      if (repl_for(4) >= 32 && hist_rows_for(4, 32) >= std::min<uint32_t>(P.lslots, hrow_words ? P.lslots : 0u))
+        u = 4;
+      else if (fits(2))
+        u = 2;
+      else if (all_narrow && fits(1))
+        u = 1;
+      if (force_units) u = (uint32_t)atoi(force_units);
+    }
+    if (V->fixed_smem(u) + slots_b + tail_b > V->max_smem) u = 0;
+    return u;
   };
   uint32_t nstage = 0, repl = 0;
   for (int attempt = 0; attempt < 2; attempt++) {
     slots_b = q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u;
-    nstage = 0;
-    if (t->tma_ok && t->d_tmaps) {
-      if (repl_for(2) >= 32 && hist_rows_for(2, 32) >= std::min<uint32_t>(P.lslots, hrow_words ? P.lslots : 0u))
-        nstage = 2;
-      else if (repl_for(1) >= 2 || (repl_for(1) >= 1 && repl_for(0) <= 1))
-        nstage = 1;
-    }
-    if (scan_fixed_smem(nstage) + slots_b > MAX_DYN_SMEM) nstage = 0;
+    nstage = pick_units();
     repl = q->hashg ? 0u : repl_for(nstage);
     if (repl == 0 && time_mode && P.lslots != P.nslots) {
       // accumulators in global memory: no slot window (the kernel's global paths index whole-axis slots)
@@ -1724,6 +1768,40 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     repl >>= 1;
     hrows = hist_rows_for(nstage, repl);
   }
+  // ---- which build runs it.  Two 8-warp CTAs per SM (113 KiB each) beat one 16-warp CTA whenever their
+  // shared-memory diet costs nothing that matters: 8-bit (or global) slot words, narrow arrays (2 KiB staging per
+  // warp), at least two accumulator replicas, and no histogram row lost that the big CTA would have cached —
+  // unless most rows go to L2 either way (then the second CTA overlaps that LSU-bound pass with its own scans).
+  q->variant = &V16;
+  {
+    const char* fv = getenv("SG_VARIANT");  // A/B: 8 or 16
+    const uint32_t nstage16 = nstage, repl16 = repl, hrows16 = hrows;
+    V = &V8;
+    const uint32_t u8 = pick_units();
+    const uint32_t r8 = q->hashg ? 0u : repl_for(u8);
+    uint32_t rr = r8;
+    uint32_t h8 = hist_rows_for(u8, rr);
+    while (hrow_words && rr > 2 && h8 < P.lslots) {
+      rr >>= 1;
+      h8 = hist_rows_for(u8, rr);
+    }
+    const bool feasible = q->slot_bytes != 2 && V8.ctas >= 2 && V8.fixed_smem(u8) + slots_b + tail_b <= V8.max_smem &&
+                          (repl16 == 0 ? rr == 0 || !P.lslots : rr >= 2) && (u8 >= 1 || !(t->tma_ok && t->d_tmaps));
+    const bool hist_l2_bound = hrow_words != 0 && hrows16 < P.lslots;
+    bool use8 = feasible && all_narrow && repl16 != 0 && hist_l2_bound;
+    if (fv) use8 = feasible && atoi(fv) == 8;
+    if (use8) {
+      q->variant = &V8;
+      nstage = u8;
+      repl = repl16 == 0 ? 0u : rr;
+      hrows = repl ? h8 : 0u;
+    } else {
+      V = &V16;
+      nstage = nstage16;
+      repl = repl16;
+      hrows = hrows16;
+    }
+  }
   q->nstage = nstage;
   P.acc_repl = repl;  // 0: accumulate straight into global memory
   P.hist_rows = hrows;
@@ -1738,7 +1816,11 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     for (int i = 0; i < P.naggs; i++)
       if (P.aggs[i].hrow_off != HROW_NONE) P.aggs[i].spill_idx = P.spill_naggs++;
   }
-  q->smem_bytes = scan_fixed_smem(nstage) + slots_b + (repl ? (uint32_t)acc_bytes(repl) + hrows * hrow_words * 4 + 16 : 0u);
+  {
+    const uint32_t body = slots_b + (repl ? (uint32_t)acc_bytes(repl) + hrows * hrow_words * 4 + 16 : 0u);
+    q->tail_off = (V->fixed_smem(0) + body + 15u) & ~15u;  // relative to the fixed part (fixed_smem(0) = its size)
+    q->smem_bytes = V->fixed_smem(nstage) - V->fixed_smem(0) + q->tail_off + tail_b;
+  }
   return SG_OK;
 }
 
@@ -1752,21 +1834,22 @@ int alloc_device(sg_query* q) {
   if (!q->d_plan) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_plan, sizeof(Plan)));
   if (!q->d_work) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_work, 64));
   size_t nb = std::max<size_t>(t->blocks.size(), 1);
-  q->grid = c->sm_count > 0 ? c->sm_count : 1;
+  q->grid = (c->sm_count > 0 ? c->sm_count : 1) * q->variant->ctas;
+  const size_t grid_cap = (size_t)(c->sm_count > 0 ? c->sm_count : 1) * 2;  // per-CTA scratch: sized for either build
   if (nb > q->block_cap) {
     pool_release(c, q->d_block_status);
     pool_release(c, q->d_block_list);
     pool_release(c, q->d_item_mask);
     q->d_block_status = q->d_block_list = q->d_item_mask = nullptr;
-    const size_t items_cap = nb + (size_t)q->grid * SG_MAX_AGGS;  // tail blocks may split per aggregation
+    const size_t items_cap = nb + grid_cap * SG_MAX_AGGS;  // tail blocks may split per aggregation
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_status, nb * 4));
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_block_list, items_cap * 16));  // uint4 {block, mask, NumRecords, -}
     q->block_cap = nb;
   }
-  if (!q->d_gbinpay) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gbinpay, (size_t)q->grid * SG_BLOCK_ROWS * 4));
-  if (!q->d_gdummy) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gdummy, (size_t)q->grid * 32 * 8));
+  if (!q->d_gbinpay) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gbinpay, grid_cap * SG_BLOCK_ROWS * 4));
+  if (!q->d_gdummy) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gdummy, grid_cap * 32 * 8));
   if (q->slot_bytes == 4 && !q->d_gslots)
-    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gslots, (size_t)q->grid * SG_BLOCK_ROWS * 4));
+    CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gslots, grid_cap * SG_BLOCK_ROWS * 4));
   if (q->plan.spill_naggs) {
     const size_t need = nb * (size_t)q->plan.spill_naggs;
     if (need > q->spill_cap) {
@@ -1892,7 +1975,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.gdummy = q->d_gdummy;
   lp.smem_bytes = q->smem_bytes;
   lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
-  lp.nstage = t->d_tmaps ? q->nstage : 0u;
+  lp.stage_units = t->d_tmaps ? q->nstage : 0u;
+  lp.tail_off = q->tail_off;
   lp.dbg = nullptr;
   lp.hashg = q->hashg ? 1u : 0u;
   lp.spill = q->plan.spill_naggs ? q->d_spill : nullptr;
@@ -1945,16 +2029,16 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
       lp.dbg = d_dbg;
     }
   }
-  lp.tmaps = lp.nstage ? t->d_tmaps : nullptr;
+  lp.tmaps = lp.stage_units ? t->d_tmaps : nullptr;
   int grid = (int)std::min<size_t>((size_t)q->grid, std::max<size_t>(items.size(), 1));
   CUDA_TRY(c, cudaEventRecord(q->ev0, c->stream));
-  int rc = launch_scan(lp, grid, c->stream);
+  int rc = q->variant->launch(lp, grid, c->stream);
   if (rc != 0) {
     c->set_err(std::string("scan kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     return SG_ERR_CUDA;
   }
   if (q->plan.spill_naggs) {
-    rc = launch_hist_apply(q->d_plan, q->d_spill, q->d_spill_counts, (uint32_t)t->blocks.size(), q->plan.spill_naggs,
+    rc = w16::launch_hist_apply(q->d_plan, q->d_spill, q->d_spill_counts, (uint32_t)t->blocks.size(), q->plan.spill_naggs,
                            q->plan.lslots, q->plan.hist_rows, q->plan.hist_row_words, q->grid, c->stream);
     if (rc != 0) {
       c->set_err(std::string("hist_apply kernel launch: ") + cudaGetErrorString((cudaError_t)rc));

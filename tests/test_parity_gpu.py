@@ -643,3 +643,61 @@ def test_top_groups_of_a_high_cardinality_result():
                block_rows=65536)
     for kw in (dict(limit=100), dict(limit=100, order_by="m"), dict(limit=50, order_asc=True)):
         both(s, Q(s, groups=["k"], aggs=["m"], op="avg", **kw))
+
+
+# ---------------------------------------------------------------------------------------------------
+# SURVEY §8(f) N1 / N2 on the hot path: block directories in sybil's on-disk format -> native (C++) gob
+# reader -> sg_table_add_block -> CUDA scan, against the oracle over the blocks the directories were
+# written from
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("narrow", [False, True])
+def test_block_directories_through_the_native_reader(tmp_path, narrow):
+    """write_block_dir (gob int_*.db / str_*.db / info.db, one gzipped) -> sgob_read_block_dir -> the C ABI.
+    narrow: the reader keeps the file's varints narrow (uint16 ids, int16 / int32 deltas) instead of widening
+    them to Go's decoded types; both must give the oracle's result."""
+    import ctypes as C
+    from sybil_b200 import blockdir
+    from sybil_b200 import engine as E
+    rng = np.random.default_rng(77)
+    n = 9000
+    s = Spec([("age", INT), ("big", INT), ("lat", INT), ("host", STR), ("uid", STR), ("time", INT)])
+    s.forms = "wide"  # the directories are written from Go's decoded types; the READER decides what it hands over
+    s.add_rows({"age": rng.integers(10, 30, n), "big": rng.integers(-(1 << 40), 1 << 45, n),
+                "lat": (rng.integers(0, 65536, (n, 4)).sum(1) * 23470 // (4 * 65535) + 30),
+                "host": np.array(["h%d" % x for x in rng.integers(0, 5, n)]),
+                "uid": np.array(["u%d" % x for x in rng.integers(0, 4 * n, n)]),
+                "time": 1500000000 + np.sort(rng.integers(0, 7200, n))},
+               {"age": rng.random(n) > 0.1, "host": rng.random(n) > 0.1}, threshold=50, block_rows=4000)
+    g = F.gobread()
+    g.sgob_set_narrow(1 if narrow else 0)
+    names = (C.c_char_p * len(s.key_table))(*[nm.encode() for nm, _ in s.key_table])
+    types = (C.c_int32 * len(s.key_table))(*[t for _, t in s.key_table])
+    t = E.Table("dirs", s.key_table)
+    t.IntInfo = dict(s.IntInfo)
+    handles = []
+    try:
+        saw_narrow = False
+        for i, b in enumerate(s.blocks):
+            d = str(tmp_path / ("block%d" % i))
+            blockdir.write_block_dir(d, b, s.key_table, compress=(i % 2 == 1))
+            err = C.create_string_buffer(512)
+            h = g.sgob_read_block_dir(d.encode(), names, types, len(s.key_table), None, b.block_index, err, len(err))
+            assert h, err.value.decode()
+            handles.append(h)
+            desc = g.sgob_block_desc(h)
+            for k in range(desc.contents.ncols):
+                cd = desc.contents.cols[k]
+                saw_narrow = saw_narrow or cd.id_bits == 16 or cd.value_bits in (16, 32) and cd.col_type == INT
+            t.add_block_desc_ptr(desc)
+        assert saw_narrow == narrow
+        for q in (Q(s, groups=["host"], aggs=["lat", "big"], op="hist"),
+                  Q(s, int_filters=[("age", "gt", 15), ("big", "lt", 1 << 44)], str_filters=[("host", "neq", "h3")],
+                    groups=["age"], aggs=["lat"], op="avg"),
+                  Q(s, groups=["uid"], aggs=["age"], op="avg", limit=50),
+                  Q(s, aggs=["lat"], op="hist", time_col="time", time_bucket=600)):
+            compare(run_gpu(s, q, table=t), run_oracle(s, q), q)
+    finally:
+        g.sgob_set_narrow(0)
+        t.close()
+        for h in handles:
+            g.sgob_block_free(h)
