@@ -215,7 +215,10 @@ void sg_table_free(sg_table* t);
 /* Copies the block's arrays host->device (async on the table's copy stream),
  * interns its string tables into the table's global dictionary and its int bin
  * values into the per-column value dictionary.  Returns SG_ERR_INVALID for a
- * malformed descriptor (the block is not added). */
+ * malformed descriptor (the block is not added).
+ * Lifetime of the descriptor's arrays: everything is read during the call EXCEPT record_ids / values that lie
+ * inside a region from sg_pinned_alloc — those are DMA'd in place (no bounce copy) and must stay untouched
+ * until sg_table_sync (or the next sg_query_run) returns. */
 int sg_table_add_block(sg_table* t, const sg_block_desc* block);
 /* Batch form.  Arrays that lie inside one region from sg_pinned_alloc are mirrored into HBM with a
  * few large copies instead of one per array (full PCIe rate); otherwise as n calls above. */

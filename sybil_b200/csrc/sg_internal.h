@@ -180,7 +180,6 @@ struct LaunchParams {
   const void* tmaps;          // CUtensorMap[chunks][3] in global memory: row pitch 128 / 64 / 32 bytes (nullptr: plain
                               // vector loads)
   uint32_t stage_units;       // TMA staging per warp in units of 2 KiB (0 none; 2 = one 4 KiB tile; 4 = two)
-  uint32_t tail_off;          // the per-pass tables: bytes from the fixed part's start (behind slots, accumulators, cache)
   unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
   uint32_t fold_every;        // blocks whose shared accumulators may be folded together (>= 1)
   uint32_t hashg;             // a group column is a value-array int column (hash lookup path; slot_bytes == 4)
@@ -220,8 +219,6 @@ __host__ __device__ static inline uint32_t vh_hash(long long v) {
   int scan_threads();                                                                                                   \
   /* shared memory the kernel needs besides slots and accumulators (stage_units: per-warp TMA staging, 2 KiB units) */ \
   uint32_t scan_fixed_smem(uint32_t stage_units);                                                                       \
-  /* ... and behind them: the per-pass tables of a plan with ncand candidate passes */                                 \
-  uint32_t scan_tail_smem(uint32_t ncand);                                                                              \
   int scan_ctas_per_sm();   /* CTAs the kernel is built to co-reside per SM */                                          \
   uint32_t scan_max_smem(); /* dynamic shared memory one CTA may use then */                                            \
   }

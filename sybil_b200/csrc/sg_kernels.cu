@@ -70,18 +70,12 @@ constexpr uint32_t OFF_PUBA = OFF_BINPAY + SMEM_BINS * 4;              // u64[MA
 constexpr uint32_t OFF_PUBB = OFF_PUBA + MAX_TILES * 8;                // u64[MAX_TILES]
 constexpr uint32_t OFF_MBAR = OFF_PUBB + MAX_TILES * 8;                // u64[NWARPS][2] mbarriers
 constexpr uint32_t OFF_MISC = OFF_MBAR + NWARPS * 2 * 8;               // u32[128]
-constexpr uint32_t FIXED_SMEM = OFF_MISC + 128 * 4;
-// Behind the slot words, the accumulators and the histogram cache (LaunchParams::tail_off): the per-pass tables,
-// sized by the plan's candidate passes n (filters + group columns + time column + aggregations):
-//   u32[n][4] pass list | u32[n] candidates | u32[n][4] per-block scratch | DevCol[n] the block's candidate columns
-constexpr uint32_t TAIL_PLIST = 0;
-__host__ __device__ constexpr uint32_t tail_pcand(uint32_t n) { return TAIL_PLIST + n * 16u; }
-__host__ __device__ constexpr uint32_t tail_ptmp(uint32_t n) { return tail_pcand(n) + n * 4u; }
-__host__ __device__ constexpr uint32_t tail_colcache(uint32_t n) { return (tail_ptmp(n) + n * 16u + 15u) & ~15u; }
-__host__ __device__ constexpr uint32_t tail_bytes(uint32_t n) { return tail_colcache(n) + n * 80u; }
-uint32_t scan_tail_smem(uint32_t ncand) { return tail_bytes(ncand ? ncand : 1u); }
-constexpr uint32_t ALIAS_PER_WARP = OFF_PUBA / NWARPS;  // head bits + prefixes + per-bin payloads, cut into per-warp slices
-static_assert(OFF_HEADBITS == 0 && OFF_PUBA == 16384, "the borrowed staging area is the first 16 KiB of the fixed part");
+constexpr uint32_t PL_MAX = 48;                                        // TMA-fed column passes of one block
+constexpr uint32_t OFF_PLIST = OFF_MISC + 128 * 4;                     // u32[PL_MAX][4]
+constexpr uint32_t OFF_PCAND = OFF_PLIST + PL_MAX * 16;                // u32[PL_MAX] candidate passes of the plan
+constexpr uint32_t OFF_PTMP = OFF_PCAND + PL_MAX * 4;                  // u32[PL_MAX][4] per-block scratch
+constexpr uint32_t OFF_COLCACHE = OFF_PTMP + PL_MAX * 16;               // DevCol[PL_MAX]: the block's candidate columns
+constexpr uint32_t FIXED_SMEM = OFF_COLCACHE + PL_MAX * 80;
 // stage_units: per-warp TMA staging in units of 2 KiB (0 none, 1, 2 = one 4 KiB tile, 4 = two)
 uint32_t scan_fixed_smem(uint32_t stage_units) { return NWARPS * (TMA_TILE_BYTES / 2) * stage_units + FIXED_SMEM; }
 // CTAs of THREADS threads the kernel is built to co-reside per SM (launch bounds), and the dynamic shared
@@ -112,7 +106,6 @@ struct Ctx {
   // latency at the head of a pass overlaps the tail of the previous one
   const uint32_t* plist;
   uint32_t npass, pass_idx, pref_idx;
-  uint32_t pref_ns;  // stages of pass pref_idx the previous pass already requested
   uint32_t zero;  // 0 at run time, opaque to the compiler (see staged_reads_done)
 #ifdef SG_FINE_TIMING
   volatile unsigned long long* tacc;  // thread 0 only: [9..15] fine-grained marks
@@ -132,20 +125,10 @@ struct Ctx {
   unsigned long long t_tma, t_lb;
   __device__ __forceinline__ uint32_t buf(uint32_t st) const { return st ? buf1 : buf0; }
   // narrow arrays (col_shift > 0): a tile is 2 KiB or 1 KiB, so a 4 KiB buffer holds two of them
-  // A tile of a column with col_shift s is 4 KiB >> s: as many stages (at most two) as the warp's buffer holds;
-  // 0 = the column's tiles do not fit (plain loads).  A VALUE pass whose tiles fit the buffer only once borrows its
-  // second stage from the head-bit / per-bin payload area (16 KiB, ALIAS_PER_WARP each), which only bucket passes
-  // use: `alias` = the pass may do so.  The borrowed stage is requested by the pass's own prologue — behind the
-  // barrier that ended the previous pass — never by the previous pass's epilogue.
-  uint32_t alias0;  // this warp's slice of that area (shared-window address)
-  __device__ __forceinline__ uint32_t stages(uint32_t shift, bool alias) const {
-    const uint32_t tile = TMA_TILE_BYTES >> shift, own = stage_bytes / tile;
-    return own >= 2u ? 2u : ((own == 1u && alias && tile <= ALIAS_PER_WARP) ? 2u : own);
-  }
-  __device__ __forceinline__ uint32_t bufx(uint32_t st, uint32_t shift) const {
-    const uint32_t tile = TMA_TILE_BYTES >> shift;
-    return st == 0u ? buf0 : (2u * tile <= stage_bytes ? buf0 + tile : alias0);
-  }
+  // a tile of a column with col_shift s is 4 KiB >> s: as many stages (at most two) as the warp's buffer holds;
+  // 0 = the column's tiles do not fit (plain loads)
+  __device__ __forceinline__ uint32_t stages(uint32_t shift) const { return min(2u, stage_bytes / (TMA_TILE_BYTES >> shift)); }
+  __device__ __forceinline__ uint32_t bufx(uint32_t st, uint32_t shift) const { return buf0 + st * (TMA_TILE_BYTES >> shift); }
   __device__ __forceinline__ uint32_t mbar(uint32_t st) const { return st ? mbar1 : mbar0; }
   __device__ __forceinline__ uint32_t take_parity(uint32_t st) {
     const uint32_t p = st ? par1 : par0;
@@ -293,10 +276,10 @@ struct Feed {
 #define SG_PF_AHEAD 0  // measured on C2: 0 -> 0.677 ms, 2 -> 0.708 ms, 4 -> 0.731 ms (the scan is bandwidth-, not latency-bound)
 #endif
 constexpr uint32_t PF_AHEAD = SG_PF_AHEAD;  // L2 prefetch runs this many of the warp's tiles ahead of its staged loads (0: off)
-__device__ __forceinline__ Feed make_feed(const Ctx& cx, const DevCol& c, bool alias = false) {
+__device__ __forceinline__ Feed make_feed(const Ctx& cx, const DevCol& c) {
   Feed f;
   f.shift = col_shift(c.flags);
-  f.ns = cx.stages(f.shift, alias);
+  f.ns = cx.stages(f.shift);
   f.on = cx.tmaps != nullptr && (c.flags & COL_TMA) != 0 && f.ns != 0u;
   f.tmap = cx.tmaps + ((size_t)c.data_chunk * 3u + f.shift) * 128;
   f.row0 = c.data_row << f.shift;
@@ -333,13 +316,9 @@ __device__ __forceinline__ void feed_prologue(Ctx& cx, Feed& f, uint32_t ntiles)
     f.nrow0 = e[5];
     f.nnt = e[6];
   }
-  {
-    const uint32_t have = cx.pref_idx == cx.pass_idx ? cx.pref_ns : 0u;  // stages the previous pass requested
-    if (have < f.ns && f.ns == 2u && 2u * (TMA_TILE_BYTES >> f.shift) > cx.stage_bytes && cx.lane == 0)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the borrowed stage held head bits until the barrier
-    for (uint32_t st = have; st < f.ns; st++)
+  if (cx.pref_idx != cx.pass_idx)
+    for (uint32_t st = 0; st < f.ns; st++)
       if (cx.warp + st * NWARPS < ntiles) feed_issue(cx, f, cx.warp + st * NWARPS, st);
-  }
   // the first pass of a block has nobody before it to prefetch its head
   if (cx.pass_idx == 0)
     for (uint32_t v = f.ns; v < f.ns + PF_AHEAD; v++) feed_prefetch(cx, f, v);
@@ -356,12 +335,11 @@ __device__ __forceinline__ void feed_epilogue(Ctx& cx, const Feed& f) {
     nf.tmap = cx.tmaps + (size_t)e[0] * 128;  // e[0] = chunk * 3 + shift: the view's index
     nf.row0 = e[1];
     nf.shift = e[0] % 3u;
-    nf.ns = cx.stages(nf.shift, false);  // the stages that live in this warp's own buffer
+    nf.ns = cx.stages(nf.shift);
     const uint32_t nt = e[2];
     for (uint32_t st = 0; st < nf.ns; st++)
       if (cx.warp + st * NWARPS < nt) feed_issue(cx, nf, cx.warp + st * NWARPS, st);
     cx.pref_idx = cx.pass_idx;
-    cx.pref_ns = nf.ns;
   }
 }
 
@@ -745,7 +723,7 @@ __device__ __forceinline__ void scan_values_i64(Ctx& cx, const DevCol& c, const 
   cx.epoch++;
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   unsigned long long prev_incl = vw ? (unsigned long long)c.vbase : 0ull;
-  Feed feed = make_feed(cx, c, true);
+  Feed feed = make_feed(cx, c);
   feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
@@ -866,7 +844,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
   const uint32_t ntiles = (n + (32 * VE - 1)) / (32 * VE);
   uint32_t prev_incl = vw ? (uint32_t)(unsigned long long)c.vbase : 0u;  // decoded values are exact mod 2^32
   uint32_t hix = 0;  // xor of the high limbs read (keeps the staged loads 16 bytes wide)
-  Feed feed = make_feed(cx, c, true);
+  Feed feed = make_feed(cx, c);
   feed_prologue(cx, feed, ntiles);
   uint32_t it = 0;
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
@@ -1290,20 +1268,15 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
   cx.pubA = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBA);
   cx.pubB = reinterpret_cast<volatile unsigned long long*>(smem + OFF_PUBB);
   cx.misc = reinterpret_cast<volatile uint32_t*>(smem + OFF_MISC);
-  const uint32_t ncand_plan = (uint32_t)(PP->nfilters + PP->ngroups + (PP->time_col >= 0 ? 1 : 0) + PP->naggs);
-  const uint32_t ntail = ncand_plan ? ncand_plan : 1u;
-  unsigned char* const tail = smem + lp.tail_off;
-  uint32_t* const plist_w = reinterpret_cast<uint32_t*>(tail + TAIL_PLIST);
+  uint32_t* const plist_w = reinterpret_cast<uint32_t*>(smem + OFF_PLIST);
   cx.plist = plist_w;
   cx.timing = lp.dbg != nullptr && cx.warp == 0;
   cx.t_tma = cx.t_lb = 0;
   cx.npass = cx.pass_idx = 0;
   cx.pref_idx = 0xffffffffu;
-  cx.pref_ns = 0;
   {
     cx.buf0 = smem_u32(stage_base) + (uint32_t)cx.warp * cx.stage_bytes;
     cx.buf1 = cx.buf0 + TMA_TILE_BYTES;
-    cx.alias0 = smem_u32(smem + OFF_HEADBITS) + (uint32_t)cx.warp * ALIAS_PER_WARP;
     cx.mbar0 = smem_u32(smem + OFF_MBAR) + (uint32_t)cx.warp * 16u;
     cx.mbar1 = cx.mbar0 + 8u;
     cx.par0 = cx.par1 = 0;
@@ -1384,11 +1357,11 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
   }
   // candidate passes of the plan, in execution order: column | kind << 16 (0 filter, 1 group, 2 time,
   // 3 aggregation) | (string filter) << 24.  Built once; each block only looks its columns up.
-  uint32_t* const pcand = reinterpret_cast<uint32_t*>(tail + tail_pcand(ntail));
-  uint32_t* const ptmp = reinterpret_cast<uint32_t*>(tail + tail_ptmp(ntail));
+  uint32_t* const pcand = reinterpret_cast<uint32_t*>(smem + OFF_PCAND);
+  uint32_t* const ptmp = reinterpret_cast<uint32_t*>(smem + OFF_PTMP);
   // the block's column descriptors, one per candidate pass (same order as pcand): each pass would
   // otherwise start with two dependent global loads (plan -> column slot -> descriptor)
-  DevCol* const colcache = reinterpret_cast<DevCol*>(tail + tail_colcache(ntail));
+  DevCol* const colcache = reinterpret_cast<DevCol*>(smem + OFF_COLCACHE);
   if (cx.tid == 0) {
     uint32_t nc = 0;
     for (int fi = 0; fi < nfilters; fi++)
@@ -1570,7 +1543,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
       const uint32_t pc = pcand[cx.tid];
       const uint32_t kind = (pc >> 16) & 0xffu;
       const DevCol c = cols[pc & 0xffu];
-      bool on = cx.tmaps != nullptr && (c.flags & COL_TMA) && cx.stages(col_shift(c.flags), false) != 0u;
+      bool on = cx.tmaps != nullptr && (c.flags & COL_TMA) && cx.stages(col_shift(c.flags)) != 0u;
       bool bucket = c.enc == SG_ENC_BUCKET;
       if (kind == 0) {
         // (a bucket filter in fail mode walks only the tiles of its failing bins, with plain loads)
@@ -2456,8 +2429,6 @@ __global__ void __launch_bounds__(THREADS, 1) stats_kernel(DevCol* cols, const D
   cx.stage_bytes = 0;
   cx.zero = 0;
   cx.buf0 = cx.buf1 = cx.mbar0 = cx.mbar1 = cx.par0 = cx.par1 = 0;
-  cx.alias0 = 0;
-  cx.pref_ns = 0;
   cx.plist = nullptr;
   cx.timing = false;
   cx.t_tma = cx.t_lb = 0;
@@ -2555,8 +2526,6 @@ __global__ void __launch_bounds__(THREADS, 1) distinct_kernel(const DevCol* cols
   cx.stage_bytes = 0;
   cx.zero = 0;
   cx.buf0 = cx.buf1 = cx.mbar0 = cx.mbar1 = cx.par0 = cx.par1 = 0;
-  cx.alias0 = 0;
-  cx.pref_ns = 0;
   cx.plist = nullptr;
   cx.timing = false;
   cx.t_tma = cx.t_lb = 0;

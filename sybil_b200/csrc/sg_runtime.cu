@@ -93,11 +93,10 @@ struct Variant {
   int warps, ctas;
   uint32_t max_smem;  // dynamic shared memory of one CTA
   uint32_t (*fixed_smem)(uint32_t);
-  uint32_t (*tail_smem)(uint32_t);
   int (*launch)(const LaunchParams&, int, void*);
 };
-static const Variant V16 = {"w16", 16, w16::scan_ctas_per_sm(), w16::scan_max_smem(), w16::scan_fixed_smem, w16::scan_tail_smem, w16::launch_scan};
-static const Variant V8 = {"w8", 8, w8::scan_ctas_per_sm(), w8::scan_max_smem(), w8::scan_fixed_smem, w8::scan_tail_smem, w8::launch_scan};
+static const Variant V16 = {"w16", 16, w16::scan_ctas_per_sm(), w16::scan_max_smem(), w16::scan_fixed_smem, w16::launch_scan};
+static const Variant V8 = {"w8", 8, w8::scan_ctas_per_sm(), w8::scan_max_smem(), w8::scan_fixed_smem, w8::launch_scan};
 constexpr int64_t MAX_SLOTS = (int64_t)1 << 26;
 constexpr int64_t INT_DICT_CAP = (int64_t)1 << 22;
 
@@ -1127,7 +1126,6 @@ struct sg_query {
   std::vector<HistLayout> layouts;
   uint32_t slot_bytes = 2;
   uint32_t smem_bytes = 0;
-  uint32_t tail_off = 0;
   uint32_t nstage = 0;
   const Variant* variant = &V16;  // which build of the kernel runs the plan (make_plan)
   // device state
@@ -1695,10 +1693,8 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
            (uint64_t)P.nslots * (1 + 2 * (uint64_t)P.naggs) * 8 + 16;
   };
   const Variant* V = &V16;  // the budget below is taken for this build of the kernel
-  const uint32_t ncand = (uint32_t)(P.nfilters + P.ngroups + (time_mode ? 1 : 0) + P.naggs);
-  const uint32_t tail_b = V16.tail_smem(ncand) + 16;  // per-pass tables behind everything else (same in both builds)
   auto repl_for = [&](uint32_t nstage) -> uint32_t {
-    const uint32_t fixed = V->fixed_smem(nstage) + slots_b + tail_b;
+    const uint32_t fixed = V->fixed_smem(nstage) + slots_b;
     if (fixed > V->max_smem) return 0;
     const uint32_t avail = V->max_smem - fixed;
     uint32_t repl = 32;
@@ -1707,7 +1703,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   };
   auto hist_rows_for = [&](uint32_t nstage, uint32_t repl) -> uint32_t {
     if (!hrow_words || !repl) return 0;
-    const uint64_t used = (uint64_t)V->fixed_smem(nstage) + slots_b + tail_b + acc_bytes(repl);
+    const uint64_t used = (uint64_t)V->fixed_smem(nstage) + slots_b + acc_bytes(repl);
     if (used >= V->max_smem) return 0;
     return (uint32_t)std::min<uint64_t>(P.lslots, (V->max_smem - used) / ((uint64_t)hrow_words * 4));
   };
@@ -1744,7 +1740,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
         u = 1;
       if (force_units) u = (uint32_t)atoi(force_units);
     }
-    if (V->fixed_smem(u) + slots_b + tail_b > V->max_smem) u = 0;
+    if (V->fixed_smem(u) + slots_b > V->max_smem) u = 0;
     return u;
   };
   uint32_t nstage = 0, repl = 0;
@@ -1785,7 +1781,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
       rr >>= 1;
       h8 = hist_rows_for(u8, rr);
     }
-    const bool feasible = q->slot_bytes != 2 && V8.ctas >= 2 && V8.fixed_smem(u8) + slots_b + tail_b <= V8.max_smem &&
+    const bool feasible = q->slot_bytes != 2 && V8.ctas >= 2 && V8.fixed_smem(u8) + slots_b <= V8.max_smem &&
                           (repl16 == 0 ? rr == 0 || !P.lslots : rr >= 2) && (u8 >= 1 || !(t->tma_ok && t->d_tmaps));
     const bool hist_l2_bound = hrow_words != 0 && hrows16 < P.lslots;
     bool use8 = feasible && all_narrow && repl16 != 0 && hist_l2_bound;
@@ -1816,11 +1812,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     for (int i = 0; i < P.naggs; i++)
       if (P.aggs[i].hrow_off != HROW_NONE) P.aggs[i].spill_idx = P.spill_naggs++;
   }
-  {
-    const uint32_t body = slots_b + (repl ? (uint32_t)acc_bytes(repl) + hrows * hrow_words * 4 + 16 : 0u);
-    q->tail_off = (V->fixed_smem(0) + body + 15u) & ~15u;  // relative to the fixed part (fixed_smem(0) = its size)
-    q->smem_bytes = V->fixed_smem(nstage) - V->fixed_smem(0) + q->tail_off + tail_b;
-  }
+  q->smem_bytes = V->fixed_smem(nstage) + slots_b + (repl ? (uint32_t)acc_bytes(repl) + hrows * hrow_words * 4 + 16 : 0u);
   return SG_OK;
 }
 
@@ -1976,7 +1968,6 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.smem_bytes = q->smem_bytes;
   lp.acc_smem = q->plan.acc_repl > 0 ? 1u : 0u;
   lp.stage_units = t->d_tmaps ? q->nstage : 0u;
-  lp.tail_off = q->tail_off;
   lp.dbg = nullptr;
   lp.hashg = q->hashg ? 1u : 0u;
   lp.spill = q->plan.spill_naggs ? q->d_spill : nullptr;

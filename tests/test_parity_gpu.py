@@ -701,3 +701,58 @@ def test_block_directories_through_the_native_reader(tmp_path, narrow):
         t.close()
         for h in handles:
             g.sgob_block_free(h)
+
+
+def test_pinned_buffer_reuse_needs_sync():
+    """The zero-copy staging path (arrays inside a region from sg_pinned_alloc are DMA'd in place): a host that
+    recycles one pinned buffer for successive batches calls sg_table_sync before it overwrites the buffer
+    (INTEGRATION.md §3).  Two batches generated into the SAME pinned arena, one after the other; the table must
+    hold both, bit for bit (oracle over all blocks)."""
+    from sybil_b200 import engine as E
+    from sybil_b200 import synth
+    from oracle.oracle_ffi import OracleTable
+    spec = synth.config("c3", total_rows=6 * 30000, block_rows=30000)
+    s = Spec(spec.key_table)
+    s.IntInfo = dict(spec.IntInfo)
+    q = Q(s, **synth.query_for(spec))
+    ot = OracleTable(spec.key_table)
+    t = E.Table("pin", spec.key_table)
+    t.IntInfo = dict(spec.IntInfo)
+    nbytes = 64 << 20
+    arena = t.lib.sg_pinned_alloc(t.ctx.h, nbytes)
+    assert arena
+    try:
+        for first in (0, 3):
+            store = synth.generate(spec, first, 3, nthreads=2, arena_ptr=arena, arena_bytes=nbytes)
+            for i in range(store.num_blocks()):
+                ot.add_block(store.block(i))  # (the oracle copies the arrays)
+            ptrs, n = store.block_ptrs()
+            t.add_blocks(ptrs, n)
+            t.sync()  # the DMA out of the arena has finished: the next batch may overwrite it
+            store.close()
+        d, keep = q.desc()
+        compare(run_gpu(s, q, table=t), ot.query(d, q.aggs, nthreads=2), q)
+    finally:
+        t.lib.sg_pinned_free(t.ctx.h, arena)
+        t.close()
+        ot.close()
+
+
+@pytest.mark.parametrize("variant", ["8", "16"])
+def test_both_kernel_builds_agree_with_the_oracle(variant, monkeypatch):
+    """The library holds two builds of the scan kernel (16-warp CTAs, one per SM; 8-warp CTAs, two per SM) and
+    picks one per plan; SG_VARIANT forces either.  Both must give the oracle's result on plans of every shape:
+    filters + two group columns + histogram (the C3 shape, whose default is the 8-warp build), time rollup with
+    the histogram cache, high-cardinality group-by with global accumulators, MultiHist."""
+    monkeypatch.setenv("SG_VARIANT", variant)
+    s = _wide_spec(5, 70000, 35000, nulls=False)
+    for q in (Q(s, int_filters=[("f0", "gt", 100), ("f1", "lt", 900000)], str_filters=[("s0", "neq", "v3")],
+                groups=["s1", "d"], aggs=["lat"], op="hist"),
+              Q(s, aggs=["lat"], op="hist", time_col="time", time_bucket=3600),
+              Q(s, groups=["s1"], aggs=["f1", "lat"], op="avg")):
+        compare(run_gpu(s, q), run_oracle(s, q), q)
+    r = random_spec(6, nrows=12000, block_rows=5000, threshold=40)
+    for q in (Q(r, groups=["uid"], aggs=["age", "lat"], op="avg"),
+              Q(r, int_filters=[("age", "gt", 12)], groups=["host", "age"], aggs=["lat", "big"], op="hist", loghist=True),
+              Q(r, str_filters=[("state", "re", "^s1")], groups=["state"], aggs=["big"], op="hist")):
+        compare(run_gpu(r, q), run_oracle(r, q), q)
