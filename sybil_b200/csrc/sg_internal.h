@@ -105,7 +105,7 @@ struct KAgg {
                       // kernel then skips the hist-Count reductions; accumulators-in-global plans only)
   uint32_t hrow_off;  // offset of this aggregation's counters inside a slot's row of the shared-memory
                       // histogram cache (HROW_NONE: its buckets go straight to L2)
-  uint32_t spill_idx; // index among the aggregations whose cache misses are spilled as records (HROW_NONE: none)
+  uint32_t _pad2;
   uint64_t* buckets;  // [nslots][nvals_total]
   uint64_t* hcount;   // [nslots]
   uint64_t* sum;      // [nslots]
@@ -148,13 +148,6 @@ struct Plan {
   // to the 64-bit bucket arrays in L2 when the window moves and when the CTA runs out of work
   uint32_t hist_rows;
   uint32_t hist_row_words;
-  // ---- deferred histogram (plans whose cache cannot hold every slot's row): a bucket increment that
-  // misses the cache is written as a 32-bit record (local slot * hist_row_words + hrow_off + bucket) into
-  // the (block, aggregation, value tile)'s 512-record region; hist_apply_kernel adds the records up in
-  // 16-bit shared-memory counters afterwards — one coalesced store + one shared atomic per increment
-  // instead of a 64-bit reduction to L2 (45 cycles of LSU time per warp instruction)
-  uint32_t spill_naggs;  // 0: off
-  uint32_t _pad3;
   uint64_t* count;      // [nslots]
   uint64_t* scalars;    // [0] matched rows, [1] broken blocks, [2] time overflow rows, [3] blocks done
   uint32_t* block_status;  // per table block: 1 = broken in this query
@@ -183,11 +176,7 @@ struct LaunchParams {
   unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
   uint32_t fold_every;        // blocks whose shared accumulators may be folded together (>= 1)
   uint32_t hashg;             // a group column is a value-array int column (hash lookup path; slot_bytes == 4)
-  uint32_t* spill;            // [table block][spill agg][SPILL_TILES][SPILL_TILE_RECS] records (plan.spill_naggs > 0)
-  uint16_t* spill_counts;     // [table block][spill agg][SPILL_TILES] records written (zeroed before the launch)
 };
-constexpr uint32_t SPILL_TILES = 128;      // value tiles of one block (65,536 rows / 512)
-constexpr uint32_t SPILL_TILE_RECS = 512;  // rows of one value tile
 
 // the hash both sides of the value -> code table use
 __host__ __device__ static inline uint32_t vh_hash(long long v) {
@@ -213,9 +202,6 @@ __host__ __device__ static inline uint32_t vh_hash(long long v) {
    * INT64_MIN itself occurred, counters[2] = 1 if the set filled up (more than cap/2 keys) */                          \
   int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems,               \
                       uint32_t ncolslots, long long* keys, uint32_t cap_mask, unsigned int* counters, void* stream);    \
-  /* adds the spilled records up (see Plan::spill_naggs); nblocks = blocks of the table */                              \
-  int launch_hist_apply(const Plan* plan, const uint32_t* spill, const uint16_t* counts, uint32_t nblocks,              \
-                        uint32_t naggs_spill, uint32_t lslots, uint32_t hist_rows, uint32_t hrw, int grid, void* stream); \
   int scan_threads();                                                                                                   \
   /* shared memory the kernel needs besides slots and accumulators (stage_units: per-warp TMA staging, 2 KiB units) */ \
   uint32_t scan_fixed_smem(uint32_t stage_units);                                                                       \

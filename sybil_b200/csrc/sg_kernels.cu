@@ -832,8 +832,11 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t x, unsigned long long M) 
 
 // value-array int column whose decoded values are known (COL_STATS) to lie in [0, 2^32): the same
 // tiles and look-back, in 32-bit arithmetic.  tile_visit(idx0, a[VE] (uint32), nvalid)
+// `pf`: when not null, the tile's 32-bit slot words (global scratch, one per row) are prefetched into L1 before
+// the tile is waited for, so that the loads behind the scan find them there (high-cardinality plans)
 template <class TileVisit>
-__device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const uint32_t nrec, TileVisit tile_visit) {
+__device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const uint32_t nrec, TileVisit tile_visit,
+                                                const uint32_t* pf = nullptr) {
   uint32_t n = c.nitems;
   if (n > nrec) n = nrec;
   const unsigned long long* __restrict__ vals = reinterpret_cast<const unsigned long long*>(c.data);
@@ -850,6 +853,7 @@ __device__ __forceinline__ void scan_values_u32(Ctx& cx, const DevCol& c, const 
   for (uint32_t t = warp; t < ntiles; t += NWARPS, it++) {
     const uint32_t idx0 = t * (32 * VE) + lane * VE;
     uint32_t a[VE];
+    if (pf != nullptr && idx0 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + idx0));  // 16 words = 64 bytes
     if (feed.on) {
       const uint32_t st = it & (feed.ns - 1u);
 #ifdef SG_WAIT_TIMING
@@ -1758,9 +1762,17 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
         }
       } else if (c.enc == SG_ENC_VALUES && G.is_str) {
         const uint32_t stride = G.stride;
-        scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
-          slot[row] = (SlotT)(slot[row] + ((uint32_t)str_gid(c, local) + 1u) * stride);
-        });
+        if (nfilters == 0 && gi == 0) {
+          // first pass to touch the zeroed slot words: a store, not a read-modify-write (with the slot words in
+          // the global scratch the load was the top stall of the high-cardinality plan, profiles/r02_c5.md)
+          scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
+            slot[row] = (SlotT)(((uint32_t)str_gid(c, local) + 1u) * stride);
+          });
+        } else {
+          scan_values_i32(cx, c, nrec, [&](uint32_t row, int32_t local) {
+            slot[row] = (SlotT)(slot[row] + ((uint32_t)str_gid(c, local) + 1u) * stride);
+          });
+        }
       }
       else if (HASHG && c.enc == SG_ENC_VALUES && !G.is_str) {
         // value-array int group column: decoded value -> dense code through the table-wide value
@@ -2006,10 +2018,6 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
       const uint32_t hrows = (hist32 && hoff != HROW_NONE) ? hist_rows : 0u;
       const uint32_t hcache_s = hist_s + hoff * 4u, hrw_b = hrw * 4u;
       unsigned long long* const bkt_w = bkt + (size_t)tb * nvt;  // the window's first row of bucket counters
-      // deferred histogram: where this aggregation's cache misses of value tile t of this block go
-      const uint32_t sp_idx = KA->spill_idx;
-      const bool spill_on = hrows != 0u && hrows < lslots && PP->spill_naggs != 0u && sp_idx != HROW_NONE && lp.spill != nullptr;
-      const size_t sp_tile0 = ((size_t)bid * PP->spill_naggs + sp_idx) * SPILL_TILES;
       auto hist_add = [&](uint32_t e, uint32_t b) {
         if (e < hrows)
           sred_add(hcache_s + e * hrw_b + b * 4u, 1u);
@@ -2101,29 +2109,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
               if (!fr && e != trash) agg_slow(&AS, e, (long long)a[k], 0);
             }
           }
-          if (nsub > 0 && hist32 && spill_on) {
-            // cache hit: shared reduction; miss: one record, written with the other lanes' records of the
-            // same step to consecutive words of the tile's region (rank = lanes below with a record)
-            const uint32_t t = idx0 >> 9;
-            uint32_t* const rec = lp.spill + (sp_tile0 + t) * SPILL_TILE_RECS;
-            const uint32_t ltmask = (1u << cx.lane) - 1u;
-            uint32_t off = 0;
-#pragma unroll
-            for (int k = 0; k < VE; k++) {
-              const uint32_t e = NOFILT ? sw[k] : min(sw[k] ^ passbits, trash);
-              const bool fr = ALLFAST || (a[k] - fmin32) <= fspan32;
-              const uint32_t e2 = fr ? e : trash;
-              const uint32_t x = a[k] - fmin32 + hdelta;
-              const uint32_t b = min(bsize0 == 1u ? x : div_magic(x, magic0), nvals0 - 1);
-              const bool miss = e2 >= hrows && e2 != trash;
-              if (e2 < hrows) sred_add(hcache_s + e2 * hrw_b + b * 4u, 1u);
-              const uint32_t m = __ballot_sync(FULL, miss);
-              if (miss)  // streaming store: the records are read once, much later — keep them out of the way in L2
-                asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(rec + off + __popc(m & ltmask)), "r"(e2 * hrw + hoff + b) : "memory");
-              off += __popc(m);
-            }
-            if (cx.lane == 0) lp.spill_counts[sp_tile0 + t] = (uint16_t)off;
-          } else if (nsub > 0 && hist32) {
+          if (nsub > 0 && hist32) {
             // Straight-line bucket step: x / BucketSize by multiply-high (BucketSize 1 has no magic: b = x), then
             // ONE predicated shared reduction (the slot's row is in the cache) and, unless every row is, ONE
             // predicated 64-bit reduction to L2.  (With `magic ? mulhi : x / bsize` and if / else-if the compiler
@@ -2227,7 +2213,7 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
             }
           }
         };
-        scan_values_u32(cx, c, nrec, tile32g);
+        scan_values_u32(cx, c, nrec, tile32g, sizeof(SlotT) == 4 ? reinterpret_cast<const uint32_t*>(slot) : nullptr);
         const uint32_t nv = c.nitems < nrec ? c.nitems : nrec;
         for (uint32_t r = nv + cx.tid; r < nrec; r += THREADS) {
           const uint32_t s = (uint32_t)slot[r];
@@ -2573,116 +2559,6 @@ __global__ void __launch_bounds__(THREADS, 1) distinct_kernel(const DevCol* cols
         }
     });
   }
-}
-
-// ---------------------------------------------------------------------------
-// deferred histogram: add the spilled records up.  Every CTA takes a contiguous range of table blocks and
-// counts their records in 16-bit shared-memory counters (two per word; a half that reaches 2^15 sends the
-// increment straight to L2 instead, so no half can wrap: at most THREADS * 16 increments are in flight
-// between the add and its check); the counters are flushed once per pass with 64-bit reductions.  The
-// counter space [hist_rows * hrw, lslots * hrw) is covered in as many passes as 16-bit counters fit.
-// ---------------------------------------------------------------------------
-constexpr uint32_t APPLY_SMEM = 224u * 1024u;
-// one bucket counter's 64-bit home in L2, from its index in the [local slot][hist_row_words] space
-__device__ __forceinline__ unsigned long long* bucket_home(const Plan* __restrict__ PP, uint32_t idx, uint32_t hrw) {
-  const uint32_t row = idx / hrw, off = idx - row * hrw;
-  for (int a = 0; a < PP->naggs; a++) {
-    const uint32_t ho = PP->aggs[a].hrow_off, nv = PP->aggs[a].nvals_total;
-    if (ho != HROW_NONE && off >= ho && off - ho < nv)
-      return reinterpret_cast<unsigned long long*>(PP->aggs[a].buckets) + ((size_t)row * nv + (off - ho));
-  }
-  return nullptr;
-}
-__global__ void __launch_bounds__(THREADS, 1) hist_apply_kernel(const Plan* __restrict__ PP, const uint32_t* __restrict__ spill,
-                                                                const uint16_t* __restrict__ counts, uint32_t nblocks,
-                                                                uint32_t naggs_spill, uint32_t lslots, uint32_t hist_rows,
-                                                                uint32_t hrw) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* const cnt = reinterpret_cast<uint32_t*>(smem_raw);
-  const uint32_t cnt_s = smem_u32(cnt);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t first = hist_rows * hrw, total = lslots * hrw - first;  // counters the records can name
-  const uint32_t cap = APPLY_SMEM / 2u;                                  // 16-bit counters per pass
-  const uint32_t per = (nblocks + gridDim.x - 1) / gridDim.x;
-  const uint32_t b0 = min(blockIdx.x * per, nblocks), b1 = min(b0 + per, nblocks);
-  const size_t ntile = (size_t)(b1 - b0) * naggs_spill * SPILL_TILES;
-  const size_t tile0 = (size_t)b0 * naggs_spill * SPILL_TILES;
-  for (uint32_t lo = 0; lo < total; lo += cap) {
-    const uint32_t n = min(cap, total - lo), base = first + lo;
-    for (uint32_t i = tid; i < (n + 1u) / 2u; i += THREADS) cnt[i] = 0;
-    __syncthreads();
-    // a warp's tiles, one ahead: the next tile's count and records (all 2 KiB of its region — what lies past
-    // the count is masked) are in flight while the current tile's 512 candidates are counted
-    size_t ti = warp;
-    uint32_t nrec_n = 0;
-    uint4 qn[4];
-    auto fetch = [&](size_t t) {
-      nrec_n = counts[tile0 + t];
-      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(spill + (tile0 + t) * SPILL_TILE_RECS);
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(qn[j].x), "=r"(qn[j].y), "=r"(qn[j].z), "=r"(qn[j].w)
-                     : "l"(src + j * 32 + lane));
-    };
-    if (ti < ntile) fetch(ti);
-    while (ti < ntile) {
-      const uint32_t nrec = nrec_n;
-      uint4 q[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) q[j] = qn[j];
-      const size_t tn = ti + NWARPS;
-      if (tn < ntile) fetch(tn);
-      uint32_t hot = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t r[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint32_t pos = (uint32_t)(j * 32 + lane) * 4u + (uint32_t)i;
-          const uint32_t c = r[i] - base;  // counter inside this pass (unsigned: the others land far out of range)
-          if (pos < nrec && c < n) {
-            const uint32_t sh = (c & 1u) << 4;
-            const uint32_t old = satom_add(cnt_s + (c >> 1) * 4u, 1u << sh);
-            hot |= ((old >> sh) & 0x8000u) ? (1u << (j * 4 + i)) : 0u;
-          }
-        }
-      }
-      if (hot) {  // rare: a half at 2^15 or above keeps its value, the increment goes straight to L2
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t r[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            if ((hot >> (j * 4 + i)) & 1u) {
-              const uint32_t c = r[i] - base;
-              sred_add(cnt_s + (c >> 1) * 4u, 0u - (1u << ((c & 1u) << 4)));
-              unsigned long long* const home = bucket_home(PP, r[i], hrw);
-              if (home) gred_add(home, 1ull);
-            }
-        }
-      }
-      ti = tn;
-    }
-    __syncthreads();
-    for (uint32_t w = tid; w < (n + 1u) / 2u; w += THREADS) {
-      const uint32_t v = cnt[w];
-      if (!v) continue;
-      if (v & 0xffffu) gred_add(bucket_home(PP, base + 2u * w, hrw), (unsigned long long)(v & 0xffffu));
-      if (v >> 16) gred_add(bucket_home(PP, base + 2u * w + 1u, hrw), (unsigned long long)(v >> 16));
-    }
-    __syncthreads();
-  }
-}
-
-int launch_hist_apply(const Plan* plan, const uint32_t* spill, const uint16_t* counts, uint32_t nblocks, uint32_t naggs_spill,
-                      uint32_t lslots, uint32_t hist_rows, uint32_t hrw, int grid, void* stream) {
-  if (nblocks == 0 || naggs_spill == 0) return 0;
-  cudaError_t e = cudaFuncSetAttribute(hist_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  hist_apply_kernel<<<grid, THREADS, APPLY_SMEM, (cudaStream_t)stream>>>(plan, spill, counts, nblocks, naggs_spill, lslots,
-                                                                        hist_rows, hrw);
-  return (int)cudaGetLastError();
 }
 
 int launch_distinct(const DevCol* cols, const DevBlock* blocks, const uint32_t* items, uint32_t nitems, uint32_t ncolslots,

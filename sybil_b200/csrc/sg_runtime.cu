@@ -1143,9 +1143,6 @@ struct sg_query {
   uint32_t* d_gslots = nullptr;
   uint32_t* d_gbinpay = nullptr;
   unsigned long long* d_gdummy = nullptr;
-  uint32_t* d_spill = nullptr;         // deferred-histogram records (Plan::spill_naggs)
-  uint16_t* d_spill_counts = nullptr;
-  size_t spill_cap = 0;                // table blocks x spill aggregations the buffers hold
   std::vector<uint32_t*> d_luts;
   size_t block_cap = 0;
   int grid = 0;
@@ -1196,11 +1193,6 @@ void free_device(sg_query* q) {
   pool_release(c, q->d_gslots);
   pool_release(c, q->d_gbinpay);
   pool_release(c, q->d_gdummy);
-  pool_release(c, q->d_spill);
-  pool_release(c, q->d_spill_counts);
-  q->d_spill = nullptr;
-  q->d_spill_counts = nullptr;
-  q->spill_cap = 0;
   for (auto p : q->d_luts) pool_release(c, p);
   q->d_luts.clear();
   q->d_plan = nullptr;
@@ -1669,7 +1661,6 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   for (int i = 0; i < P.naggs; i++) {
     KAgg& ka = P.aggs[i];
     ka.hrow_off = HROW_NONE;
-    ka.spill_idx = HROW_NONE;
     if (!P.hist_mode || ka.nsub != 1 || getenv("SG_NO_HIST_CACHE")) continue;
     const long long fmin = ka.info_min > 0 ? ka.info_min : 0;
     long long fmax = ka.info_max < 0xffffffffll ? ka.info_max : 0xffffffffll;
@@ -1738,6 +1729,14 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
         u = 2;
       else if (all_narrow && fits(1))
         u = 1;
+      // accumulators that cannot live in shared memory at any size (high-cardinality plans): nothing competes
+      // with the staging buffers — take the deepest that fits (round 1 left such plans on plain loads)
+      if (u == 0 && (q->hashg || repl_for(0) == 0))
+        for (uint32_t x : {4u, 2u, 1u})
+          if (V->fixed_smem(x) + slots_b <= V->max_smem && (x >= 2 || all_narrow)) {
+            u = x;
+            break;
+          }
       if (force_units) u = (uint32_t)atoi(force_units);
     }
     if (V->fixed_smem(u) + slots_b > V->max_smem) u = 0;
@@ -1801,17 +1800,6 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   q->nstage = nstage;
   P.acc_repl = repl;  // 0: accumulate straight into global memory
   P.hist_rows = hrows;
-  // deferred histogram for the rows the cache cannot hold (whole-axis plans only: records carry local slots)
-  P.spill_naggs = 0;
-  for (int i = 0; i < P.naggs; i++) P.aggs[i].spill_idx = HROW_NONE;
-  // Off unless SG_SPILL=1: measured on C3 (profiles/r02_c3.md) the scan kernel gets 9% faster, but the
-  // records' extra HBM traffic slows the bandwidth-bound value passes of the other CTAs and the apply kernel
-  // takes the rest: no net gain at 117 slots x 1,002 buckets.
-  if (hrow_words && repl && hrows > 0 && hrows < P.lslots && P.lslots == P.nslots && getenv("SG_SPILL") && !getenv("SG_NO_SPILL") &&
-      (uint64_t)P.lslots * hrow_words < 0xffffffffull) {
-    for (int i = 0; i < P.naggs; i++)
-      if (P.aggs[i].hrow_off != HROW_NONE) P.aggs[i].spill_idx = P.spill_naggs++;
-  }
   q->smem_bytes = V->fixed_smem(nstage) + slots_b + (repl ? (uint32_t)acc_bytes(repl) + hrows * hrow_words * 4 + 16 : 0u);
   return SG_OK;
 }
@@ -1842,27 +1830,6 @@ int alloc_device(sg_query* q) {
   if (!q->d_gdummy) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gdummy, grid_cap * 32 * 8));
   if (q->slot_bytes == 4 && !q->d_gslots)
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gslots, grid_cap * SG_BLOCK_ROWS * 4));
-  if (q->plan.spill_naggs) {
-    const size_t need = nb * (size_t)q->plan.spill_naggs;
-    if (need > q->spill_cap) {
-      pool_release(c, q->d_spill);
-      pool_release(c, q->d_spill_counts);
-      q->d_spill = nullptr;
-      q->d_spill_counts = nullptr;
-      q->spill_cap = 0;
-      if (pool_alloc(c, (void**)&q->d_spill, need * SPILL_TILES * SPILL_TILE_RECS * 4) != cudaSuccess ||
-          pool_alloc(c, (void**)&q->d_spill_counts, need * SPILL_TILES * 2) != cudaSuccess) {
-        // no room for the record buffers: cache misses go straight to L2 as before
-        cudaGetLastError();
-        pool_release(c, q->d_spill);
-        q->d_spill = nullptr;
-        q->plan.spill_naggs = 0;
-        for (int i = 0; i < q->plan.naggs; i++) q->plan.aggs[i].spill_idx = HROW_NONE;
-      } else {
-        q->spill_cap = need;
-      }
-    }
-  }
   if (!q->ev0) {
     CUDA_TRY(c, cudaEventCreate(&q->ev0));
     CUDA_TRY(c, cudaEventCreate(&q->ev1));
@@ -1928,7 +1895,10 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   }
   // parameters go up from pinned scratch (truly asynchronous); the same scratch later receives the
   // accumulators when they are small
-  const size_t acc_back = q->acc_words * 8 <= ((size_t)4 << 20) ? q->acc_words * 8 : 64;
+  // small accumulator arrays come back right behind the scan (build_result then needs no further copy) — unless a
+  // cross-GPU merge follows, which reads the MERGED array back itself: then only the scalars (broken blocks) do
+  const bool merge_follows = c->comm != nullptr && c->nranks > 1;
+  const size_t acc_back = (!merge_follows && q->acc_words * 8 <= ((size_t)4 << 20)) ? q->acc_words * 8 : 64;
   const size_t off_items = (sizeof(Plan) + 255) & ~(size_t)255;
   const size_t off_acc = off_items + ((items.size() * 16 + 255) & ~(size_t)255);
   char* hp = c->scratch(off_acc + acc_back);
@@ -1970,11 +1940,6 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.stage_units = t->d_tmaps ? q->nstage : 0u;
   lp.dbg = nullptr;
   lp.hashg = q->hashg ? 1u : 0u;
-  lp.spill = q->plan.spill_naggs ? q->d_spill : nullptr;
-  lp.spill_counts = q->plan.spill_naggs ? q->d_spill_counts : nullptr;
-  if (q->plan.spill_naggs)
-    CUDA_TRY(c, cudaMemsetAsync(q->d_spill_counts, 0, std::max<size_t>(t->blocks.size(), 1) * q->plan.spill_naggs * SPILL_TILES * 2,
-                                c->stream));
   // Deferred fold: the replicated 32-bit accumulators of up to fold_every consecutive blocks are
   // folded together.  Needs one encoding per aggregation column across the listed blocks (word0
   // counts accepted rows for bucket columns, rejected ones for value arrays) and keeps the hot
@@ -2027,15 +1992,6 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   if (rc != 0) {
     c->set_err(std::string("scan kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     return SG_ERR_CUDA;
-  }
-  if (q->plan.spill_naggs) {
-    rc = w16::launch_hist_apply(q->d_plan, q->d_spill, q->d_spill_counts, (uint32_t)t->blocks.size(), q->plan.spill_naggs,
-                           q->plan.lslots, q->plan.hist_rows, q->plan.hist_row_words, q->grid, c->stream);
-    if (rc != 0) {
-      c->set_err(std::string("hist_apply kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-      return SG_ERR_CUDA;
-    }
-    q->launches += 1;
   }
   CUDA_TRY(c, cudaEventRecord(q->ev1, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(hp + off_acc, q->d_acc, acc_back, cudaMemcpyDeviceToHost, c->stream));
@@ -2969,56 +2925,122 @@ int sg_query_allreduce(sg_query* q) {
     // differing axes: every rank sees that in the same gathered data and takes the exchange path
     CUDA_TRY(c, cudaMemsetAsync(q->d_acc + 8, 0, 64, c->stream));
   }
-  // One small all-reduce (sum) carries the job-wide block counters AND answers "do the ranks agree on
-  // the slot space?": with two independent 30-bit signatures s of the serialised axes, every rank
-  // checks  sum(s) == n*s_mine  and  sum(s^2) == n*s_mine^2  (exact in 64 bits for n <= 8); if the
-  // signatures differ, the variance is positive and the second test fails on EVERY rank, so all
-  // ranks take the same branch.
+  // ---- larger plans: element-wise all-reduces (sums: scalars, count, hcount, sum, buckets; max: vmax) --------
   std::vector<uint8_t> mine;
   serialise_axes(q, mine);
   const uint64_t sig = fnv64(0xcbf29ce484222325ull, mine.data(), mine.size());
   const uint64_t sa = sig & 0x3fffffffull, sb = (sig >> 32) & 0x3fffffffull;
-  uint64_t hc[8] = {(uint64_t)q->broken_staged, (uint64_t)q->skipped, (uint64_t)q->rows_scanned, (uint64_t)q->blocks_scanned,
-                    sa, sa * sa, sb, sb * sb};
-  int rc = SG_OK;
-  if (c->nranks <= 8) {
-    rc = comm_allreduce_host(c, hc, 8, ncclUint64, ncclSum);
-    if (rc != SG_OK) return rc;
-  } else {
-    // more ranks than the exact-moment test covers: max of sig and of ~sig (equal iff all equal)
-    uint64_t pr[2] = {sig, ~sig};
-    rc = comm_allreduce_host(c, pr, 2, ncclUint64, ncclMax);
-    if (rc != SG_OK) return rc;
-    rc = comm_allreduce_host(c, hc, 4, ncclUint64, ncclSum);
-    if (rc != SG_OK) return rc;
-    const bool same = pr[0] == ~pr[1];
-    hc[4] = same ? sa * (uint64_t)c->nranks : ~0ull;
-    hc[5] = sa * sa * (uint64_t)c->nranks;
-    hc[6] = sb * (uint64_t)c->nranks;
-    hc[7] = sb * sb * (uint64_t)c->nranks;
-  }
   const uint64_t n = (uint64_t)c->nranks;
-  const bool agree = hc[4] == n * sa && hc[5] == n * sa * sa && hc[6] == n * sb && hc[7] == n * sb * sb;
-  q->broken_staged = (int64_t)hc[0];
-  q->skipped = (int64_t)hc[1];
-  q->rows_scanned = (int64_t)hc[2];
-  q->blocks_scanned = (int64_t)hc[3];
-  if (!agree) {
-    rc = remap_to_union(q);
-    if (rc != SG_OK) return rc;
-  }
-  // element-wise merge.  sums: scalars, count, hcount, sum, buckets; max: vmax.
-  auto ar = [&](uint64_t* p, size_t n, int dtype, int op) -> int {
-    ncclResult_t r = g_nccl.AllReduce(p, p, n, dtype, op, c->comm, c->stream);
+  auto ar = [&](const uint64_t* src, uint64_t* dst, size_t cnt, int dtype, int op) -> int {
+    ncclResult_t r = g_nccl.AllReduce(src, dst, cnt, dtype, op, c->comm, c->stream);
     return r != 0 ? nccl_fail(c, "ncclAllReduce", r) : (int)SG_OK;
   };
-  rc = ar(q->d_acc, q->sum_words, ncclUint64, ncclSum);
+  const bool whole = q->acc_words * 8 <= ((size_t)4 << 20);  // small enough to read back right behind the merge
+  int rc = SG_OK;
+  if (c->nranks <= 8 && !getenv("SG_MERGE_TWO_STEP")) {
+    // The job-wide block counters and the answer to "do the ranks agree on the slot space?" ride in spare scalar
+    // words of the SUM all-reduce itself: with two independent 30-bit signatures s of the serialised axes, every
+    // rank checks  sum(s) == n*s_mine  and  sum(s^2) == n*s_mine^2  (exact in 64 bits for n <= 8) on the merged
+    // copy; if the signatures differ the variance is positive and the test fails on EVERY rank, so all ranks take
+    // the same branch.  The reduction is out of place: a rank's own accumulators survive for the dictionary
+    // exchange of that (rare) case.  No host-synchronous collective ahead of the merge (it cost ~80 us a query).
+    char* hp = c->scratch(64 + (whole ? q->acc_words * 8 : 128));
+    uint64_t* d_merged = nullptr;
+    if (!hp) {
+      c->set_err("cudaHostAlloc (merge scratch) failed");
+      return SG_ERR_CUDA;
+    }
+    CUDA_TRY(c, pool_alloc(c, (void**)&d_merged, q->acc_words * 8));
+    uint64_t* hc = (uint64_t*)hp;
+    hc[0] = (uint64_t)q->broken_staged;
+    hc[1] = (uint64_t)q->skipped;
+    hc[2] = (uint64_t)q->rows_scanned;
+    hc[3] = (uint64_t)q->blocks_scanned;
+    hc[4] = sa;
+    hc[5] = sa * sa;
+    hc[6] = sb;
+    hc[7] = sb * sb;
+    uint64_t* hm = (uint64_t*)(hp + 64);
+    cudaError_t ce = cudaMemcpyAsync(q->d_acc + 8, hc, 64, cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess) {
+      rc = ar(q->d_acc, d_merged, q->sum_words, ncclUint64, ncclSum);
+      if (rc == SG_OK && q->acc_words > q->sum_words)
+        rc = ar(q->d_acc + q->sum_words, d_merged + q->sum_words, q->acc_words - q->sum_words, ncclInt64, ncclMax);
+    }
+    if (ce == cudaSuccess && rc == SG_OK) ce = cudaMemsetAsync(q->d_acc + 8, 0, 64, c->stream);  // own copy as it was
+    if (ce == cudaSuccess && rc == SG_OK)
+      ce = cudaMemcpyAsync(hm, d_merged, whole ? q->acc_words * 8 : 128, cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess && rc == SG_OK) ce = cudaStreamSynchronize(c->stream);
+    if (ce != cudaSuccess || rc != SG_OK) {
+      pool_release(c, d_merged);
+      if (rc != SG_OK) return rc;
+      c->set_err(std::string("merge: ") + cudaGetErrorString(ce));
+      return SG_ERR_CUDA;
+    }
+    const uint64_t* m = hm + 8;
+    const bool agree = m[4] == n * sa && m[5] == n * sa * sa && m[6] == n * sb && m[7] == n * sb * sb;
+    q->broken_staged = (int64_t)m[0];
+    q->skipped = (int64_t)m[1];
+    q->rows_scanned = (int64_t)m[2];
+    q->blocks_scanned = (int64_t)m[3];
+    if (agree) {
+      // the merged copy becomes the query's accumulator array (the plan's device pointers name q->d_acc)
+      ce = cudaMemsetAsync(d_merged + 8, 0, 64, c->stream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(q->d_acc, d_merged, q->acc_words * 8, cudaMemcpyDeviceToDevice, c->stream);
+      if (ce == cudaSuccess && !whole) ce = cudaStreamSynchronize(c->stream);
+      pool_release(c, d_merged);  // (stream-ordered pool: reuse waits for the copy queued above)
+      if (ce != cudaSuccess) {
+        c->set_err(std::string("merge: ") + cudaGetErrorString(ce));
+        return SG_ERR_CUDA;
+      }
+      if (whole) {
+        for (int k = 8; k < 16; k++) hm[k] = 0;
+        q->h_acc.assign(hm, hm + q->acc_words);
+        q->h_acc_valid = true;
+        q->d2h_bytes += (int64_t)q->acc_words * 8;
+      }
+      return SG_OK;
+    }
+    pool_release(c, d_merged);
+    rc = remap_to_union(q);  // differing dictionaries / time axes: re-lay this rank's accumulators by the union
+    if (rc != SG_OK) return rc;
+  } else {
+    uint64_t hc[8] = {(uint64_t)q->broken_staged, (uint64_t)q->skipped, (uint64_t)q->rows_scanned, (uint64_t)q->blocks_scanned,
+                      sa, sa * sa, sb, sb * sb};
+    if (c->nranks <= 8) {
+      rc = comm_allreduce_host(c, hc, 8, ncclUint64, ncclSum);
+      if (rc != SG_OK) return rc;
+    } else {
+      // more ranks than the exact-moment test covers: max of sig and of ~sig (equal iff all equal)
+      uint64_t pr[2] = {sig, ~sig};
+      rc = comm_allreduce_host(c, pr, 2, ncclUint64, ncclMax);
+      if (rc != SG_OK) return rc;
+      rc = comm_allreduce_host(c, hc, 4, ncclUint64, ncclSum);
+      if (rc != SG_OK) return rc;
+      const bool same = pr[0] == ~pr[1];
+      hc[4] = same ? sa * n : ~0ull;
+      hc[5] = sa * sa * n;
+      hc[6] = sb * n;
+      hc[7] = sb * sb * n;
+    }
+    const bool agree = hc[4] == n * sa && hc[5] == n * sa * sa && hc[6] == n * sb && hc[7] == n * sb * sb;
+    q->broken_staged = (int64_t)hc[0];
+    q->skipped = (int64_t)hc[1];
+    q->rows_scanned = (int64_t)hc[2];
+    q->blocks_scanned = (int64_t)hc[3];
+    if (!agree) {
+      rc = remap_to_union(q);
+      if (rc != SG_OK) return rc;
+    }
+  }
+  // in place (after a dictionary exchange, or the two-step path): the counters are already job totals
+  rc = ar(q->d_acc, q->d_acc, q->sum_words, ncclUint64, ncclSum);
   if (rc == SG_OK && q->acc_words > q->sum_words)
-    rc = ar(q->d_acc + q->sum_words, q->acc_words - q->sum_words, ncclInt64, ncclMax);
+    rc = ar(q->d_acc + q->sum_words, q->d_acc + q->sum_words, q->acc_words - q->sum_words, ncclInt64, ncclMax);
   if (rc != SG_OK) return rc;
   // read the merged accumulators back behind the all-reduces (small plans): build_result then needs
   // no further copy
-  if (q->acc_words * 8 <= ((size_t)4 << 20)) {
+  if (whole) {
     char* hp = c->scratch(q->acc_words * 8);
     if (hp) {
       CUDA_TRY(c, cudaMemcpyAsync(hp, q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost, c->stream));
