@@ -11,6 +11,7 @@
 #include <zlib.h>
 
 #include <climits>
+#include <limits>
 #include <cstdint>
 #include <algorithm>
 
@@ -110,7 +111,16 @@ struct Reader {
       f(t.fields[(size_t)idx].first, t.fields[(size_t)idx].second);
     }
   }
+  int depth = 0;  // nesting of skip(): a crafted stream with self-referential type ids must not overflow the stack
+  struct Nest {
+    int& d;
+    explicit Nest(int& x) : d(x) {
+      if (++d > 64) throw Err("gob: value nested too deeply");
+    }
+    ~Nest() { --d; }
+  };
   void skip(int64_t tid) {
+    Nest nest(depth);
     switch (tid) {
       case T_BOOL: case T_INT: case T_UINT: case T_FLOAT: u(); return;
       case T_BYTES: case T_STRING: str(); return;
@@ -190,12 +200,24 @@ struct Reader {
     const TypeDef& t = def(tid);
     if (t.kind != TypeDef::SLICE && t.kind != TypeDef::ARRAY) throw Err("gob: expected a slice");
     uint64_t n = u();
-    if (n > ((uint64_t)1 << 28)) throw Err("gob: slice too long");
+    // every element takes at least one byte: a length prefix beyond the bytes left is corrupt (and must not reserve)
+    if (n > (uint64_t)(end - p)) throw Err("gob: slice longer than the stream");
     out.reserve(out.size() + (size_t)n);
-    if (t.elem == T_UINT || (is_unsigned && t.elem != T_INT))
-      for (uint64_t k = 0; k < n; k++) out.push_back((T)u());
-    else
-      for (uint64_t k = 0; k < n; k++) out.push_back((T)i());
+    // Go's decoder raises an overflow error when a value does not fit the destination type: so does this one
+    if (t.elem == T_UINT || (is_unsigned && t.elem != T_INT)) {
+      for (uint64_t k = 0; k < n; k++) {
+        const uint64_t v = u();
+        if (v > (uint64_t)std::numeric_limits<T>::max()) throw Err("gob: value overflows the column's element type");
+        out.push_back((T)v);
+      }
+    } else {
+      for (uint64_t k = 0; k < n; k++) {
+        const int64_t v = i();
+        if (v < (int64_t)std::numeric_limits<T>::min() || (v > 0 && (uint64_t)v > (uint64_t)std::numeric_limits<T>::max()))
+          throw Err("gob: value overflows the column's element type");
+        out.push_back((T)v);
+      }
+    }
   }
 };
 
@@ -288,6 +310,7 @@ void read_column(const std::vector<uint8_t>& raw, Column& c) {
     else if (f == "BucketEncoded") bucket = r.u() != 0;
     else if (f == "Bins") {
       const TypeDef& st = r.def(ft);
+      if (st.kind != TypeDef::SLICE && st.kind != TypeDef::ARRAY) throw Err("gob: Bins is not a slice");
       uint64_t n = r.u();
       for (uint64_t k = 0; k < n; k++) {
         int64_t value = 0;

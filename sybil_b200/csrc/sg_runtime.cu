@@ -334,6 +334,9 @@ struct sg_table {
   std::vector<DevCol> cols;  // [nblocks][ncols] host mirror (device pointers inside)
   std::vector<StrDict> sdict;
   std::vector<IntDict> idict;
+  // entries each dictionary held after its last sg_table_dict_seed_* call (-1: never seeded).  A dictionary that
+  // is still exactly its seed has the same size and numbering on every rank that seeded it alike.
+  std::vector<int64_t> sseed, iseed;
   std::vector<char> has_values_int;  // an int column that is value-array encoded somewhere
   // group-by on such a column: its value-array blocks' distinct values join the column's IntDict
   // (on demand, kernel-side distinct set) and a device open-addressing table maps value -> code
@@ -572,6 +575,8 @@ sg_table* sg_table_create(sg_ctx* c, int32_t num_col_slots, const int32_t* col_t
   t->idict.resize((size_t)num_col_slots);
   t->has_values_int.assign((size_t)num_col_slots, 0);
   t->vhash.assign((size_t)num_col_slots, sg_table::ValueHash());
+  t->sseed.assign((size_t)num_col_slots, -1);
+  t->iseed.assign((size_t)num_col_slots, -1);
   t->srank.assign((size_t)num_col_slots, std::vector<uint32_t>());
   t->irank.assign((size_t)num_col_slots, std::vector<uint32_t>());
   cudaSetDevice(c->device);
@@ -1022,12 +1027,14 @@ int sg_table_dict_get(sg_table* t, int32_t col, int64_t id, const char** bytes, 
 int sg_table_dict_seed_str(sg_table* t, int32_t col, const char* bytes, const uint32_t* offsets, int64_t n) {
   if (!t || col < 0 || col >= t->ncols || n < 0 || (n > 0 && (!bytes || !offsets))) return SG_ERR_INVALID;
   for (int64_t i = 0; i < n; i++) t->sdict[(size_t)col].intern(bytes + offsets[i], offsets[i + 1] - offsets[i]);
+  t->sseed[(size_t)col] = (int64_t)t->sdict[(size_t)col].strs.size();
   t->version++;
   return SG_OK;
 }
 int sg_table_dict_seed_int(sg_table* t, int32_t col, const int64_t* values, int64_t n) {
   if (!t || col < 0 || col >= t->ncols || n < 0 || (n > 0 && !values)) return SG_ERR_INVALID;
   for (int64_t i = 0; i < n; i++) t->idict[(size_t)col].intern(values[i]);
+  t->iseed[(size_t)col] = (int64_t)t->idict[(size_t)col].vals.size();
   t->version++;
   return SG_OK;
 }
@@ -1240,7 +1247,8 @@ int upload_table(sg_table* t) {
       CUDA_TRY(c, cudaMalloc(&t->d_tmaps, cap * sizeof(CUtensorMap)));
       t->d_tmaps_cap = cap;
     }
-    CUDA_TRY(c, cudaMemcpy(t->d_tmaps, t->tmaps.data(), t->tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpyAsync(t->d_tmaps, t->tmaps.data(), t->tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (H2D on the stream the kernels run on: see remap_to_union)
     t->tmaps_dirty = false;
   }
   if (!t->dirty && t->d_blocks) return SG_OK;
@@ -1262,8 +1270,10 @@ int upload_table(sg_table* t) {
     hb[i]._pad = 0;
   }
   if (nb) {
-    CUDA_TRY(c, cudaMemcpy(t->d_blocks, hb.data(), nb * sizeof(DevBlock), cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(t->d_cols, t->cols.data(), nb * (size_t)t->ncols * sizeof(DevCol), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpyAsync(t->d_blocks, hb.data(), nb * sizeof(DevBlock), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (H2D on the stream the kernels run on: see remap_to_union)
+    CUDA_TRY(c, cudaMemcpyAsync(t->d_cols, t->cols.data(), nb * (size_t)t->ncols * sizeof(DevCol), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (H2D on the stream the kernels run on: see remap_to_union)
   }
   if (!t->pending_stats.empty()) {
     // exact extents of the newly staged value-array int columns (one more read of those
@@ -1372,8 +1382,10 @@ int ensure_value_dict(sg_table* t, int col) {
     vh.d_ids = nullptr;
     CUDA_TRY(c, cudaMalloc((void**)&vh.d_keys, (size_t)cap * 8));
     CUDA_TRY(c, cudaMalloc((void**)&vh.d_ids, (size_t)cap * 4));
-    CUDA_TRY(c, cudaMemcpy(vh.d_keys, keys.data(), (size_t)cap * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(vh.d_ids, ids.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpyAsync(vh.d_keys, keys.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (H2D on the stream the kernels run on: see remap_to_union)
+    CUDA_TRY(c, cudaMemcpyAsync(vh.d_ids, ids.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (H2D on the stream the kernels run on: see remap_to_union)
     vh.mask = cap - 1u;
     vh.dict_size = D.vals.size();
   }
@@ -1849,6 +1861,107 @@ int alloc_device(sg_query* q) {
   return SG_OK;
 }
 
+// ---- top-K selection on the device (results with very many groups and a limit) ------------------------------
+// The order value of a slot as a 64-bit key whose unsigned order is the value's order: Count, or the mean of
+// one aggregation (the IEEE double the host computes: sum / hist Count, -inf without a histogram).
+struct TopkArgs {
+  const uint64_t* acc;
+  size_t off_count, off_hc, off_sum;  // of the ordering aggregation (off_hc unused when hc_is_count)
+  int order_by;                       // < 0: Count
+  int hc_is_count;
+  uint32_t nslots;
+};
+struct TopkTotals {
+  unsigned long long live, count, max_key;
+  unsigned long long hc[SG_MAX_AGGS], sum[SG_MAX_AGGS];
+  unsigned int n_out, overflow;
+};
+__device__ __forceinline__ unsigned long long topk_key(const TopkArgs& A, uint32_t s, unsigned long long cnt) {
+  if (A.order_by < 0) return cnt;
+  const unsigned long long hc = A.hc_is_count ? cnt : A.acc[A.off_hc + s];
+  const double v = hc ? (double)(long long)A.acc[A.off_sum + s] / (double)(long long)hc : -INFINITY;
+  const long long b = __double_as_longlong(v);
+  return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+// pass 0: Cumulative totals of every live slot and the largest key
+__global__ void topk_totals(TopkArgs A, int naggs, const size_t* off_hc_all, const size_t* off_sum_all, const int* hc_is_count_all,
+                            TopkTotals* tot) {
+  unsigned long long live = 0, count = 0, mx = 0;
+  unsigned long long hc[SG_MAX_AGGS], sm[SG_MAX_AGGS];
+  for (int a = 0; a < naggs; a++) hc[a] = sm[a] = 0;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < A.nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long c = A.acc[A.off_count + s];
+    if (!c) continue;
+    live++;
+    count += c;
+    const unsigned long long k = topk_key(A, s, c);
+    mx = k > mx ? k : mx;
+    for (int a = 0; a < naggs; a++) {
+      const unsigned long long h = hc_is_count_all[a] ? c : A.acc[off_hc_all[a] + s];
+      if (!h) continue;
+      hc[a] += h;
+      sm[a] += A.acc[off_sum_all[a] + s];
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    live += __shfl_xor_sync(0xffffffffu, live, d);
+    count += __shfl_xor_sync(0xffffffffu, count, d);
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, d);
+    mx = o > mx ? o : mx;
+    for (int a = 0; a < naggs; a++) {
+      hc[a] += __shfl_xor_sync(0xffffffffu, hc[a], d);
+      sm[a] += __shfl_xor_sync(0xffffffffu, sm[a], d);
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && live) {
+    atomicAdd(&tot->live, live);
+    atomicAdd(&tot->count, count);
+    atomicMax(&tot->max_key, mx);
+    for (int a = 0; a < naggs; a++) {
+      atomicAdd(&tot->hc[a], hc[a]);
+      atomicAdd(&tot->sum[a], sm[a]);
+    }
+  }
+}
+// one radix digit (`bits` wide at `shift`) of the keys whose higher bits equal `prefix`
+__global__ void topk_hist(TopkArgs A, unsigned long long prefix, int shift, int bits, int has_prefix, unsigned int* hist) {
+  __shared__ unsigned int sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const unsigned long long mask = (1ull << bits) - 1ull;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < A.nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long c = A.acc[A.off_count + s];
+    if (!c) continue;
+    const unsigned long long k = topk_key(A, s, c);
+    if (has_prefix && (k >> (shift + bits)) != prefix) continue;
+    atomicAdd(&sh[(k >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// every live slot whose key is >= lower: {slot, count, (hist Count, sum) per aggregation} appended to `rows`
+__global__ void topk_emit(TopkArgs A, unsigned long long lower, int naggs, const size_t* off_hc_all, const size_t* off_sum_all,
+                          const int* hc_is_count_all, unsigned long long* rows, unsigned int cap, TopkTotals* tot) {
+  const int w = 2 + 2 * naggs;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < A.nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long c = A.acc[A.off_count + s];
+    if (!c || topk_key(A, s, c) < lower) continue;
+    const unsigned int i = atomicAdd(&tot->n_out, 1u);
+    if (i >= cap) {
+      tot->overflow = 1u;
+      continue;
+    }
+    unsigned long long* r = rows + (size_t)i * w;
+    r[0] = s;
+    r[1] = c;
+    for (int a = 0; a < naggs; a++) {
+      r[2 + 2 * a] = hc_is_count_all[a] ? c : A.acc[off_hc_all[a] + s];
+      r[3 + 2 * a] = A.acc[off_sum_all[a] + s];
+    }
+  }
+}
+
 __global__ void fill_i64(int64_t* p, size_t n, int64_t v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -2136,11 +2249,9 @@ static const std::vector<uint32_t>& axis_ranks(sg_query* q, size_t di, std::vect
 }
 
 // one group's ResultGroup from the accumulators of dense slot s (h: words [0, have))
-static void make_group(const sg_query* q, const uint64_t* h, uint32_t s, ResultGroup& g, int64_t* tbucket) {
+// key words and rendered key of dense slot s
+static void group_key(const sg_query* q, uint32_t s, ResultGroup& g, int64_t* tbucket) {
   const Plan& P = q->plan;
-  const int naggs = P.naggs;
-  init_group(g, naggs);
-  g.count = (int64_t)h[q->off_count + s];
   for (size_t di = 0; di < q->dims.size(); di++) {
     const GroupDim& d = q->dims[di];
     uint32_t code = (s / d.stride) % d.radix;
@@ -2158,6 +2269,13 @@ static void make_group(const sg_query* q, const uint64_t* h, uint32_t s, ResultG
       g.key.push_back((uint64_t)q->table->idict[(size_t)d.col].vals[code - 1]);
   }
   g.skey = render_key(q, g.key);
+}
+static void make_group(const sg_query* q, const uint64_t* h, uint32_t s, ResultGroup& g, int64_t* tbucket) {
+  const Plan& P = q->plan;
+  const int naggs = P.naggs;
+  init_group(g, naggs);
+  g.count = (int64_t)h[q->off_count + s];
+  group_key(q, s, g, tbucket);
   const bool want_max = P.hist_mode || q->d.hist_kind == SG_HIST_MULTI;
   for (int a = 0; a < naggs; a++) {
     g.hc(a) = (size_t)a < q->hc_is_count.size() && q->hc_is_count[(size_t)a] ? g.count : (int64_t)h[q->off_hcount[(size_t)a] + s];
@@ -2189,9 +2307,175 @@ static void parallel_slots(uint32_t n, int want, Fn fn) {
   for (auto& x : th) x.join();
 }
 
+// Results with very many groups and a limit (the 1M-key group-by: `-limit 100`): the first `limit` groups of
+// the sorted list are selected on the device — Cumulative totals + largest key, a radix descent over the order
+// keys (11 bits a pass, from the top set bit down) to the key of the limit-th group, then every slot at or above
+// it with its values — instead of reading a 40 MB accumulator array back and scanning a million slots on the
+// host.  Ties at the cut are all emitted and broken on the host exactly as sort_groups does.
+// Returns SG_OK with *out set, 1 when the query is not of that shape (or the tie group is huge): host path.
+static int build_result_topk(sg_query* q, sg_result** out) {
+  sg_ctx* c = q->ctx;
+  const Plan& P = q->plan;
+  const int naggs = P.naggs, ob = q->d.order_by_agg;
+  const int64_t limit = q->d.limit;
+  if (P.time_col >= 0 || P.hist_mode || q->d.hist_kind == SG_HIST_MULTI) return 1;
+  if (limit <= 0 || limit > 65536 || ob == SG_ORDER_NONE || q->d.order_asc) return 1;
+  if (P.nslots < (1u << 17) || q->h_acc_valid || getenv("SG_NO_GPU_TOPK")) return 1;
+  const unsigned cap = (unsigned)limit + 8192u;
+  const size_t w = 2 + 2 * (size_t)naggs;
+  const size_t off_tot = 0, off_hist = 512, off_offs = off_hist + 8192, off_scal = off_offs + 512, off_rows = off_scal + 128;
+  const size_t total = off_rows + (size_t)cap * w * 8;
+  char* hp = c->scratch(total);
+  PoolTmp dev(c);
+  if (!hp || pool_alloc(c, &dev.p, total) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  char* dp = (char*)dev.p;
+  size_t* h_offs = (size_t*)(hp + off_offs);
+  int* h_hcic = (int*)(h_offs + 2 * SG_MAX_AGGS);
+  for (int a = 0; a < naggs; a++) {
+    h_offs[a] = q->off_hcount[(size_t)a];
+    h_offs[SG_MAX_AGGS + a] = q->off_sum[(size_t)a];
+    h_hcic[a] = (size_t)a < q->hc_is_count.size() && q->hc_is_count[(size_t)a] ? 1 : 0;
+  }
+  TopkArgs A;
+  A.acc = q->d_acc;
+  A.off_count = q->off_count;
+  A.order_by = ob;
+  A.off_hc = ob >= 0 ? q->off_hcount[(size_t)ob] : 0;
+  A.off_sum = ob >= 0 ? q->off_sum[(size_t)ob] : 0;
+  A.hc_is_count = ob >= 0 ? h_hcic[ob] : 1;
+  A.nslots = P.nslots;
+  const size_t* d_off_hc = (const size_t*)(dp + off_offs);
+  const size_t* d_off_sum = d_off_hc + SG_MAX_AGGS;
+  const int* d_hcic = (const int*)(d_off_hc + 2 * SG_MAX_AGGS);
+  TopkTotals* d_tot = (TopkTotals*)(dp + off_tot);
+  unsigned int* d_hist = (unsigned int*)(dp + off_hist);
+  unsigned long long* d_rows = (unsigned long long*)(dp + off_rows);
+  const int grid = std::max(1, c->sm_count) * 4;
+  static_assert(sizeof(TopkTotals) <= 512, "TopkTotals");
+  CUDA_TRY(c, cudaMemsetAsync(dp, 0, off_offs, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(dp + off_offs, hp + off_offs, 512, cudaMemcpyHostToDevice, c->stream));
+  topk_totals<<<grid, 256, 0, c->stream>>>(A, naggs, d_off_hc, d_off_sum, d_hcic, d_tot);
+  CUDA_TRY(c, cudaMemcpyAsync(hp + off_tot, d_tot, sizeof(TopkTotals), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(hp + off_scal, q->d_acc, 128, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  q->launches += 1;
+  TopkTotals T = *(const TopkTotals*)(hp + off_tot);
+  if (T.live == 0 || T.max_key == 0) return 1;
+  // radix descent to the key of the limit-th group
+  int hi = 64 - __builtin_clzll(T.max_key);  // keys have no bit at or above `hi`
+  unsigned long long prefix = 0, lower = 0;
+  int has_prefix = 0;
+  uint64_t need = (uint64_t)limit;
+  for (;;) {
+    const int bits = std::min(11, hi), shift = hi - bits;
+    CUDA_TRY(c, cudaMemsetAsync(d_hist, 0, 8192, c->stream));
+    topk_hist<<<grid, 256, 0, c->stream>>>(A, prefix, shift, bits, has_prefix, d_hist);
+    CUDA_TRY(c, cudaMemcpyAsync(hp + off_hist, d_hist, 8192, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    q->launches += 1;
+    const unsigned int* hist = (const unsigned int*)(hp + off_hist);
+    uint64_t cum = 0;
+    int b = (1 << bits) - 1;
+    for (; b > 0; b--) {
+      if (cum + hist[b] >= need) break;
+      cum += hist[b];
+    }
+    // (b == 0 also when fewer than `need` keys exist under this prefix: then everything under it qualifies)
+    const unsigned long long np = (prefix << bits) | (unsigned long long)b;
+    if (hist[b] <= 8192u - 1u || shift == 0 || cum + hist[b] < need) {
+      lower = np << shift;
+      break;
+    }
+    need -= cum;
+    prefix = np;
+    has_prefix = 1;
+    hi = shift;
+  }
+  topk_emit<<<grid, 256, 0, c->stream>>>(A, lower, naggs, d_off_hc, d_off_sum, d_hcic, d_rows, cap, d_tot);
+  CUDA_TRY(c, cudaMemcpyAsync(hp + off_tot, d_tot, sizeof(TopkTotals), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  q->launches += 1;
+  T = *(const TopkTotals*)(hp + off_tot);
+  if (T.overflow || T.n_out > cap) return 1;  // a huge group of ties at the cut: the host path sorts them all
+  const size_t n = T.n_out;
+  CUDA_TRY(c, cudaMemcpyAsync(hp + off_rows, d_rows, n * w * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  q->d2h_bytes += (int64_t)(n * w * 8 + 8192 + 1024);
+  const unsigned long long* rows = (const unsigned long long*)(hp + off_rows);
+  const uint64_t* scal = (const uint64_t*)(hp + off_scal);
+
+  // exact order of the candidates: value descending, ties by GroupByKey ascending (ranks of the rendered fields)
+  std::vector<std::vector<uint32_t>> scratch(q->dims.size());
+  std::vector<const std::vector<uint32_t>*> ranks(q->dims.size(), nullptr);
+  for (size_t di = 0; di < q->dims.size(); di++) ranks[di] = &axis_ranks(q, di, scratch[di]);
+  struct Ent {
+    double v;
+    uint64_t tie;
+    uint32_t row;
+  };
+  std::vector<Ent> ents(n);
+  for (size_t i = 0; i < n; i++) {
+    const unsigned long long* r = rows + i * w;
+    const uint32_t sl = (uint32_t)r[0];
+    uint64_t tie = 0;
+    for (size_t di = 0; di < q->dims.size(); di++) {
+      const GroupDim& d = q->dims[di];
+      const uint32_t code = (sl / d.stride) % d.radix;
+      tie = tie * d.radix + (code ? (uint64_t)(*ranks[di])[code - 1] + 1u : 0u);
+    }
+    ents[i].v = order_value(q, (int64_t)r[1], ob >= 0 ? (int64_t)r[2 + 2 * ob] : 0, ob >= 0 ? (int64_t)r[3 + 2 * ob] : 0);
+    ents[i].tie = tie;
+    ents[i].row = (uint32_t)i;
+  }
+  std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.v != b.v ? a.v > b.v : a.tie < b.tie; });
+  if ((int64_t)ents.size() > limit) ents.resize((size_t)limit);
+
+  std::unique_ptr<sg_result> r(new sg_result());
+  r->q = q;
+  r->layouts = q->layouts;
+  r->hist_mode = false;
+  r->ngroups_cols = P.ngroups;
+  r->naggs = naggs;
+  r->broken = q->broken_staged + (int64_t)scal[1];
+  r->skipped = q->skipped;
+  init_group(r->total, naggs);
+  r->total.skey = "TOTAL";
+  for (int i = 1; i < P.ngroups; i++) r->total.skey += "\t";
+  r->has_total_hists = true;
+  r->total.count = (int64_t)T.count;
+  for (int a = 0; a < naggs; a++) {
+    r->total.hc(a) = (int64_t)T.hc[a];
+    r->total.sm(a) = (int64_t)T.sum[a];
+  }
+  r->matched = (int64_t)T.count;  // no time column: every matched row is counted in exactly one group
+  r->ngroups_total = (int64_t)T.live;
+  r->groups.resize(ents.size());
+  for (size_t i = 0; i < ents.size(); i++) {
+    const unsigned long long* rw = rows + (size_t)ents[i].row * w;
+    ResultGroup& g = r->groups[i];
+    init_group(g, naggs);
+    g.count = (int64_t)rw[1];
+    group_key(q, (uint32_t)rw[0], g, nullptr);
+    for (int a = 0; a < naggs; a++) {
+      g.hc(a) = (int64_t)rw[2 + 2 * a];
+      g.sm(a) = (int64_t)rw[3 + 2 * a];
+      g.vx(a) = INT64_MIN;
+    }
+  }
+  *out = r.release();
+  return SG_OK;
+}
+
 int build_result(sg_query* q, sg_result** out) {
   sg_ctx* c = q->ctx;
   const Plan& P = q->plan;
+  {
+    const int rc = build_result_topk(q, out);
+    if (rc != 1) return rc;
+  }
   const bool time_mode = P.time_col >= 0;
   const int naggs = P.naggs;
   // what the result reads: without bucket counters, without hist Min/Max tracking and with every hist Count
@@ -2479,7 +2763,8 @@ int sg_query_set_str_lut(sg_query* q, int32_t fi, const uint32_t* bits, int64_t 
   pool_release(c, q->d_luts[(size_t)fi]);
   q->d_luts[(size_t)fi] = nullptr;
   CUDA_TRY(c, pool_alloc(c, (void**)&q->d_luts[(size_t)fi], std::max<size_t>(words, 1) * 4));
-  if (words) CUDA_TRY(c, cudaMemcpy(q->d_luts[(size_t)fi], bits, words * 4, cudaMemcpyHostToDevice));
+  if (words) CUDA_TRY(c, cudaMemcpyAsync(q->d_luts[(size_t)fi], bits, words * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (H2D on the stream the kernels run on: see remap_to_union)
   q->planned = false;
   return SG_OK;
 }
@@ -2813,7 +3098,10 @@ static int remap_to_union(sg_query* q) {
     const uint32_t old_slots = P.nslots, new_slots = (uint32_t)stride;
     // old accumulators to the host, re-laid by the union, back to the device
     std::vector<uint64_t> h_old(q->acc_words);
-    CUDA_TRY(c, cudaMemcpy(h_old.data(), q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost));
+    // (on the query's own stream: it does not synchronise with the legacy default stream, and a pageable
+    // cudaMemcpy may return before its DMA has landed)
+    CUDA_TRY(c, cudaMemcpyAsync(h_old.data(), q->d_acc, q->acc_words * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     q->d2h_bytes += (int64_t)q->acc_words * 8;
     const size_t o_count = q->off_count;
     const std::vector<size_t> o_hc = q->off_hcount, o_sum = q->off_sum, o_vmax = q->off_vmax, o_bk = q->off_buckets;
@@ -2844,7 +3132,8 @@ static int remap_to_union(sg_query* q) {
     pool_release(c, q->d_acc);
     q->d_acc = nullptr;
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_acc, q->acc_words * 8));
-    CUDA_TRY(c, cudaMemcpy(q->d_acc, h_new.data(), q->acc_words * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpyAsync(q->d_acc, h_new.data(), q->acc_words * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     q->dims = ndims;
     P.nslots = new_slots;
     if (have_time) P.time_first = g_first;
@@ -2937,7 +3226,20 @@ int sg_query_allreduce(sg_query* q) {
   };
   const bool whole = q->acc_words * 8 <= ((size_t)4 << 20);  // small enough to read back right behind the merge
   int rc = SG_OK;
-  if (c->nranks <= 8 && !getenv("SG_MERGE_TWO_STEP")) {
+  // ... which is only safe when every rank's accumulator array has the same length BY CONSTRUCTION (an element-wise
+  // collective with different counts on different ranks is undefined): every group axis is a dictionary still
+  // exactly as the host seeded it (sg_table_dict_seed_*) or the time axis (planned from the query's IntInfo).
+  // Otherwise a small host-synchronous collective compares the signatures first, as before.
+  bool sized_alike = !q->merged;
+  for (const GroupDim& d : q->dims) {
+    if (d.is_time) continue;
+    const sg_table* t = q->table;
+    const int64_t have = d.is_str ? (int64_t)t->sdict[(size_t)d.col].strs.size() : (int64_t)t->idict[(size_t)d.col].vals.size();
+    const int64_t seeded = d.is_str ? t->sseed[(size_t)d.col] : t->iseed[(size_t)d.col];
+    if (seeded < 0 || seeded != have) sized_alike = false;
+  }
+  if (getenv("SG_MERGE_ONE_STEP")) sized_alike = true;  // (diagnostics: the caller vouches for equal sizes)
+  if (c->nranks <= 8 && sized_alike && !getenv("SG_MERGE_TWO_STEP")) {
     // The job-wide block counters and the answer to "do the ranks agree on the slot space?" ride in spare scalar
     // words of the SUM all-reduce itself: with two independent 30-bit signatures s of the serialised axes, every
     // rank checks  sum(s) == n*s_mine  and  sum(s^2) == n*s_mine^2  (exact in 64 bits for n <= 8) on the merged

@@ -59,7 +59,9 @@ def _binary_key(r):
     if isinstance(b, str):
         return b
     # key words (uint64) -> the 8-byte little-endian fields of aggregate.go:125-143, one per group column
-    return b"".join(int(w).to_bytes(8, "little") for w in b).decode("latin-1")
+    # (the gob writer encodes str as utf-8 with surrogateescape: decoding the raw bytes the same way makes every byte,
+    # including those >= 0x80, come out as ONE byte on the wire)
+    return b"".join(int(w).to_bytes(8, "little") for w in b).decode("utf-8", "surrogateescape")
 
 
 def _result(r, agg_names, int_info, ngroups):
@@ -76,7 +78,8 @@ def _result(r, agg_names, int_info, ngroups):
         hists[name] = hist_value(h.Count, h.Avg, mn, mx, h.NumBuckets, h.BucketSize, list(h.Values), lo, hi, getattr(h, "Samples", 0))
     key = _binary_key(r)
     if not isinstance(getattr(r, "BinaryByKey", ""), str):
-        key = key[:8 * ngroups]
+        raw = key.encode("utf-8", "surrogateescape")[:8 * ngroups]  # GROUP_BY_WIDTH bytes per group column
+        key = raw.decode("utf-8", "surrogateescape")
     return {"Hists": hists, "GroupByKey": r.GroupByKey, "BinaryByKey": key, "Count": int(r.Count), "Samples": int(r.Samples)}
 
 

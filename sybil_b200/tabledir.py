@@ -65,14 +65,18 @@ def load_blocks(info, sink, columns=None):
     A block directory that cannot be decoded is skipped, as LoadBlockFromDir returning nil is
     (table_query.go:134-139)."""
     rows = 0
+    info.skipped_blocks = 0
     for i, d in enumerate(info.block_dirs):
         try:
             blk = blockdir.read_block_dir(d, info.key_table, columns, block_index=i)
-        except (gob.GobError, EOFError, FileNotFoundError, OSError):
+            if blk.num_records <= 0:
+                continue
+            # a block the sink rejects (NumRecords above the block size, inconsistent bins, ids that do not fit
+            # their array type) is one bad block, not a failed table load
+            sink.add_block(blk)
+        except (gob.GobError, EOFError, FileNotFoundError, OSError, OverflowError, ValueError, RuntimeError):
+            info.skipped_blocks += 1
             continue
-        if blk.num_records <= 0:
-            continue
-        sink.add_block(blk)
         rows += blk.num_records
     return rows
 

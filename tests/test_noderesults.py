@@ -83,3 +83,15 @@ def test_oracle_results_round_trip_as_node_results():
         assert c["Values"] == [int(v) for v in h.Values] and c["PercentileMode"] is True
         assert (c["Info"].get("Min", 0), c["Info"].get("Max", 0)) == tuple(s.IntInfo["lat"])
     assert qr["Cumulative"]["Count"] == o.Cumulative.Count
+
+
+def test_binary_key_bytes_survive_the_wire():
+    """BinaryByKey is 8 little-endian bytes per group column (aggregate.go:125-143); key words >= 128 hold bytes
+    >= 0x80, which must stay single bytes in the gob string (latin-1 decoding doubled them)."""
+    from sybil_b200 import noderesults as NR
+
+    class R:
+        BinaryByKey = [200, 0xFFFFFFFFFFFFFFFF, 5]
+    key = NR._binary_key(R())
+    assert len(key.encode("utf-8", "surrogateescape")) == 24
+    assert key.encode("utf-8", "surrogateescape")[:8] == (200).to_bytes(8, "little")

@@ -638,6 +638,16 @@ def test_top_groups_of_a_high_cardinality_result():
                block_rows=65536)
     for kw in (dict(limit=100), dict(limit=100, order_by="m"), dict(limit=50, order_asc=True)):
         both(s, Q(s, groups=["k"], aggs=["m"], op="avg", **kw))
+    # The first `limit` groups of such a result are selected on the device (radix descent over the order keys,
+    # sg_runtime.cu build_result_topk).  Uniform keys above: thousands of groups tie at the cut for $COUNT, the
+    # selection gives up and the host sorts (same answer).  Skewed keys here: distinct counts at the top, few ties
+    # at the cut — the device path end to end, for Count, for a mean, with and without a second aggregation.
+    keys = (rng.pareto(1.1, n) * 40).astype(np.int64) % 300_000
+    s2 = Spec([("k", STR), ("m", INT), ("w", INT)])
+    s2.add_rows({"k": np.array(["key%d" % v for v in keys]), "m": rng.integers(0, 10000, n), "w": rng.integers(-500, 500, n)},
+                block_rows=65536)
+    for kw in (dict(limit=100), dict(limit=1000, order_by="w"), dict(limit=7, order_by="m")):
+        both(s2, Q(s2, groups=["k"], aggs=["m", "w"], op="avg", **kw))
 
 
 # ---------------------------------------------------------------------------------------------------
