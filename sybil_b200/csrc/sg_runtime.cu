@@ -337,6 +337,21 @@ struct sg_table {
   // entries each dictionary held after its last sg_table_dict_seed_* call (-1: never seeded).  A dictionary that
   // is still exactly its seed has the same size and numbering on every rank that seeded it alike.
   std::vector<int64_t> sseed, iseed;
+  // the previous block's string table / bin values of each column and the global ids they interned to: blocks of one
+  // table mostly repeat them (the same 12 strings, the same 1,000 bin values), and then the per-block hash lookups
+  // — the host-side cost of staging once the arrays are narrow — shrink to one memcmp
+  struct LastDict {
+    std::string bytes;
+    std::vector<uint32_t> offsets;
+    std::vector<int32_t> remap;
+  };
+  struct LastBins {
+    std::vector<int64_t> values;
+    std::vector<int32_t> remap;
+    int64_t mn = 0, mx = 0;
+  };
+  std::vector<LastDict> last_dict;
+  std::vector<LastBins> last_bins;
   std::vector<char> has_values_int;  // an int column that is value-array encoded somewhere
   // group-by on such a column: its value-array blocks' distinct values join the column's IntDict
   // (on demand, kernel-side distinct set) and a device open-addressing table maps value -> code
@@ -575,6 +590,8 @@ sg_table* sg_table_create(sg_ctx* c, int32_t num_col_slots, const int32_t* col_t
   t->idict.resize((size_t)num_col_slots);
   t->has_values_int.assign((size_t)num_col_slots, 0);
   t->vhash.assign((size_t)num_col_slots, sg_table::ValueHash());
+  t->last_dict.assign((size_t)num_col_slots, sg_table::LastDict());
+  t->last_bins.assign((size_t)num_col_slots, sg_table::LastBins());
   t->sseed.assign((size_t)num_col_slots, -1);
   t->iseed.assign((size_t)num_col_slots, -1);
   t->srank.assign((size_t)num_col_slots, std::vector<uint32_t>());
@@ -718,15 +735,28 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
         return SG_ERR_INVALID;
       }
       StrDict& sd = t->sdict[(size_t)cd.col_slot];
-      tm.remap.resize(cd.ndict);
-      // duplicate strings inside one table keep the first id (bucket_replace, :536-545)
-      for (uint32_t k = 0; k < cd.ndict; k++) {
-        uint32_t o0 = cd.dict_offsets[k], o1 = cd.dict_offsets[k + 1];
-        if (o1 < o0) {
-          c->set_err("add_block: string offsets not monotone");
-          return SG_ERR_INVALID;
+      sg_table::LastDict& ld = t->last_dict[(size_t)cd.col_slot];
+      const size_t nbytes = cd.ndict ? cd.dict_offsets[cd.ndict] : 0;
+      if (cd.ndict > 0 && ld.offsets.size() == (size_t)cd.ndict + 1 && ld.bytes.size() == nbytes &&
+          memcmp(ld.offsets.data(), cd.dict_offsets, ((size_t)cd.ndict + 1) * 4) == 0 &&
+          memcmp(ld.bytes.data(), cd.dict_bytes, nbytes) == 0) {
+        tm.remap = ld.remap;  // the same string table as the column's previous block
+      } else {
+        tm.remap.resize(cd.ndict);
+        // duplicate strings inside one table keep the first id (bucket_replace, :536-545)
+        for (uint32_t k = 0; k < cd.ndict; k++) {
+          uint32_t o0 = cd.dict_offsets[k], o1 = cd.dict_offsets[k + 1];
+          if (o1 < o0) {
+            c->set_err("add_block: string offsets not monotone");
+            return SG_ERR_INVALID;
+          }
+          tm.remap[k] = sd.intern(cd.dict_bytes + o0, o1 - o0);
         }
-        tm.remap[k] = sd.intern(cd.dict_bytes + o0, o1 - o0);
+        if (cd.ndict > 0 && cd.ndict <= 4096) {  // (a 60,000-string table is not worth a copy per block)
+          ld.offsets.assign(cd.dict_offsets, cd.dict_offsets + cd.ndict + 1);
+          ld.bytes.assign(cd.dict_bytes, nbytes);
+          ld.remap = tm.remap;
+        }
       }
       dc.oob_gid = sd.intern("", 0);
       dc.nremap = cd.ndict;
@@ -775,12 +805,24 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
       }
       if (!is_str) {
         IntDict& id = t->idict[(size_t)cd.col_slot];
-        tm.remap.resize(dc.nbins);
+        sg_table::LastBins& lb = t->last_bins[(size_t)cd.col_slot];
         int64_t mn = INT64_MAX, mx = INT64_MIN;
-        for (uint32_t k = 0; k < dc.nbins; k++) {
-          tm.remap[k] = id.intern(tm.bin_values[k]);
-          mn = std::min(mn, tm.bin_values[k]);
-          mx = std::max(mx, tm.bin_values[k]);
+        if (lb.values.size() == tm.bin_values.size() && !id.overflow &&
+            memcmp(lb.values.data(), tm.bin_values.data(), tm.bin_values.size() * 8) == 0) {
+          tm.remap = lb.remap;  // the same bin values as the column's previous block
+          mn = lb.mn;
+          mx = lb.mx;
+        } else {
+          tm.remap.resize(dc.nbins);
+          for (uint32_t k = 0; k < dc.nbins; k++) {
+            tm.remap[k] = id.intern(tm.bin_values[k]);
+            mn = std::min(mn, tm.bin_values[k]);
+            mx = std::max(mx, tm.bin_values[k]);
+          }
+          lb.values = tm.bin_values;
+          lb.remap = tm.remap;
+          lb.mn = mn;
+          lb.mx = mx;
         }
         dc.nremap = dc.nbins;
         dc.vmin = mn;
