@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 3 /* 2: order_by_agg / order_asc / limit in sg_query_desc; 3: narrow arrays (id_bits / value_bits) */
+#define SG_ABI_VERSION 4 /* 2: order_by_agg / order_asc / limit in sg_query_desc; 3: narrow arrays (id_bits / value_bits); \
+                            4: set columns + SetFilter (SG_COL_SET, SG_OP_IN / SG_OP_NIN), sg_query_set_str_replace */
 
 /* limits of one query (reference has none; beyond these -> SG_ERR_UNSUPPORTED) */
 #define SG_MAX_FILTERS 15
@@ -49,8 +50,9 @@ typedef enum sg_status {
   SG_ERR_STATE = -6        /* call out of order */
 } sg_status;
 
-/* record.go:14-19 (INT_VAL = 1, STR_VAL = 2); set columns are out of scope */
-typedef enum sg_coltype { SG_COL_INT = 1, SG_COL_STR = 2 } sg_coltype;
+/* record.go:14-19 (INT_VAL = 1, STR_VAL = 2, SET_VAL = 3).  A set column (SavedSetColumn, column_store.go:66-74)
+ * can be filtered on (SetFilter); like the reference it cannot be grouped by or aggregated. */
+typedef enum sg_coltype { SG_COL_INT = 1, SG_COL_STR = 2, SG_COL_SET = 3 } sg_coltype;
 
 /* SavedIntColumn.BucketEncoded / Values (column_store.go:46-64) */
 typedef enum sg_encoding {
@@ -66,7 +68,9 @@ typedef enum sg_filter_op {
   SG_OP_EQ = 2,
   SG_OP_NEQ = 3,
   SG_OP_RE = 4,  /* str only: matches iff lut bit of the value's global id is set */
-  SG_OP_NRE = 5  /* str only: populated and lut bit clear */
+  SG_OP_NRE = 5, /* str only: populated and lut bit clear */
+  SG_OP_IN = 6,  /* set only (SetFilter "in", filter.go:252-285): the row's set holds str_value */
+  SG_OP_NIN = 7  /* set only ("nin"): the row has a set and it does not hold str_value */
 } sg_filter_op;
 
 /* FLAGS.OP (hist_basic.go:79) and FLAGS.LOG_HIST (hist.go:29) */
@@ -83,14 +87,14 @@ typedef struct sg_result sg_result;
 
 /* ---- descriptors -------------------------------------------------------- */
 
-/* IntFilter / StrFilter (filter.go:143-169). */
+/* IntFilter / StrFilter / SetFilter (filter.go:143-169). */
 typedef struct sg_filter_desc {
   int32_t col_slot;
   int32_t col_type;      /* sg_coltype */
   int32_t op;            /* sg_filter_op */
   int32_t _pad;
   int64_t int_value;     /* IntFilter.Value */
-  const char* str_value; /* StrFilter.Value for EQ/NEQ (not NUL-terminated) */
+  const char* str_value; /* StrFilter.Value for EQ/NEQ, SetFilter.Value for IN/NIN (not NUL-terminated) */
   int64_t str_len;
 } sg_filter_desc;
 
@@ -138,7 +142,14 @@ typedef struct sg_query_desc {
   const sg_agg_desc* aggs;
 } sg_query_desc;
 
-/* One column of one block: the post-gob form of SavedIntColumn / SavedStrColumn.
+/* One column of one block: the post-gob form of SavedIntColumn / SavedStrColumn / SavedSetColumn.
+ *
+ * Set columns (col_type SG_COL_SET, unpackSetCol column_store_io.go:611-688) come in the bucket form only:
+ * Bins[i].Value = local string id of a tag, Bins[i].Records = the rows whose set holds it (a row may be listed
+ * in several bins, never twice in one); at most SG_BLOCK_ROWS (bin,row) pairs per block in this build
+ * (more: SG_ERR_UNSUPPORTED).  The host turns the non-bucketed file form (Values [][]int32, written for more
+ * than 5,000 distinct tags, column_store_io.go:183-192) into bins and passes len(Values) as `nvalues`: the
+ * reference marks every row below it as populated, even with an empty set (column_store_io.go:672-682).
  *
  * Narrow arrays.  On disk the arrays are gob varints (1-3 bytes per small gap); a decoder
  * that keeps them narrow instead of widening every element to Go's uint32 / int64 moves 2-3x fewer bytes
@@ -254,6 +265,17 @@ void sg_query_free(sg_query* q);
 /* host-evaluated regex for filter #filter_index (filter.go:215-237): bitset over the
  * GLOBAL string ids of that column, nbits = sg_table_dict_size at call time */
 int sg_query_set_str_lut(sg_query* q, int32_t filter_index, const uint32_t* bits, int64_t nbits);
+/* StrReplace (FLAGS.STR_REPLACE "col:pattern:replacement", table_query.go:34-50): the reference rewrites a str
+ * column's string table with regexp.ReplaceAllString while it unpacks a block (column_store_io.go:515-549), so
+ * filters and group keys see the rewritten strings and rows whose strings rewrite to the same text fall into
+ * one group.  As for RE/NRE the regexp runs on the host, once per distinct string: bytes/offsets hold the
+ * rewritten text of every string of the column's GLOBAL dictionary (n == sg_table_dict_size at call time, n+1
+ * offsets).  Group keys of that column are then rendered from the rewritten strings and groups that rewrite to
+ * the same key are combined (their str id in sg_result_group is the smallest global id of the class).  Filters
+ * on a rewritten column must be sent by the host as RE / NRE with a bitset evaluated on the rewritten strings
+ * (EQ "x" = RE bitset of the strings that rewrite to "x").  Call between sg_query_begin and sg_query_finish;
+ * n == 0 removes the rewrite.  Not combinable with a cross-GPU merge over differing dictionaries. */
+int sg_query_set_str_replace(sg_query* q, int32_t col_slot, const char* bytes, const uint32_t* offsets, int64_t n);
 /* ShouldLoadBlockFromDir (table_block_io.go:110-182): 1 = load, 0 = pruned */
 int sg_query_should_load(sg_query* q, const sg_block_desc* block);
 /* Resident path: run the scan over every staged block of the table

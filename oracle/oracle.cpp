@@ -61,7 +61,7 @@
 namespace {
 
 // record.go:14-19
-enum : int8_t { NO_VAL = 0, INT_VAL = 1, STR_VAL = 2 };
+enum : int8_t { NO_VAL = 0, INT_VAL = 1, STR_VAL = 2, SET_VAL = 3 };  // record.go:14-19
 // aggregate.go:15-16,31 ; hist.go:3
 const int INTERNAL_RESULT_LIMIT = 100000;
 const int GROUP_BY_WIDTH = 8;
@@ -462,6 +462,7 @@ struct SavedColumn {  // SavedIntColumn / SavedStrColumn, column_store.go:46-64
   std::vector<int64_t> values_i64;
   std::vector<int32_t> values_i32;
   std::vector<std::string> StringTable;
+  uint32_t set_nvalues = 0;  // SavedSetColumn in its non-bucketed form: len(Values) (sybilgpu.h hands it over as bins + this)
 };
 struct SavedBlock {
   int64_t block_index = 0;
@@ -498,12 +499,18 @@ struct Block {  // TableBlock with its AoS slab (record_slab.go:28-122)
   std::vector<int32_t> Strs;      // n * ncols
   std::vector<int8_t> Populated;  // n * ncols
   std::vector<TableColumn> columns;
+  std::map<int, std::vector<std::vector<int32_t>>> SetMap;  // Record.SetMap (record.go): col -> per row the tag ids
 };
 
+struct StrReplace {  // config.go:102-105
+  std::regex re;
+  std::string Replace;
+};
 struct Table {
   int ncols = 0;
   std::vector<int32_t> KeyTypes;
   std::vector<SavedBlock> blocks;
+  std::map<int, StrReplace> str_replacements;  // OPTS.STR_REPLACEMENTS by column (table_query.go:34-50)
 };
 
 // column_store_io.go:690-780.  Returns false on "BLOCK SIZE CHANGED DURING QUERY".
@@ -537,8 +544,10 @@ static bool unpackIntCol(Block& tb, const SavedColumn& into) {
   return true;
 }
 
-// column_store_io.go:493-609 (StrReplace is a CLI feature outside the path: no replacements)
-static bool unpackStrCol(Block& tb, const SavedColumn& into) {
+// column_store_io.go:493-609.  str_replace: OPTS.STR_REPLACEMENTS[into.Name] (nullptr: none).  The regexp dialect is
+// std::regex ECMAScript, not Go's RE2, and the replacement template is std::regex_replace's ($1, $& ...), not Go's
+// Expand ($1, ${1}, $name): the same for plain patterns and $N templates — dialect unpinned.
+static bool unpackStrCol(Block& tb, const SavedColumn& into, const StrReplace* str_replace) {
   const int col_id = into.col_slot;
   const uint32_t num_records = (uint32_t)tb.n;
   const int K = tb.ncols;
@@ -547,7 +556,8 @@ static bool unpackStrCol(Block& tb, const SavedColumn& into) {
   std::unordered_map<int32_t, int32_t> bucket_replace;
   if ((uint32_t)into.StringTable.size() > num_records) return false;
   for (size_t k = 0; k < into.StringTable.size(); k++) {
-    const std::string& v = into.StringTable[k];
+    std::string v = into.StringTable[k];
+    if (str_replace) v = std::regex_replace(v, str_replace->re, str_replace->Replace);  // re.ReplaceAllString (:531)
     auto ex = col.StringTable.find(v);
     if (ex != col.StringTable.end()) {
       bucket_replace[(int32_t)k] = ex->second;
@@ -589,6 +599,40 @@ static bool unpackStrCol(Block& tb, const SavedColumn& into) {
   return true;
 }
 
+// column_store_io.go:611-688.  (A later duplicate in the string table overwrites the earlier id in col.StringTable,
+// :632-635 — unlike unpackStrCol, where the first wins.)
+static bool unpackSetCol(Block& tb, const SavedColumn& into) {
+  const int col_id = into.col_slot;
+  const uint32_t num_records = (uint32_t)tb.n;
+  const int K = tb.ncols;
+  TableColumn& col = tb.columns[(size_t)col_id];
+  std::vector<std::string> tr_string_lookup(into.StringTable.size());
+  for (size_t k = 0; k < into.StringTable.size(); k++) {
+    col.StringTable[into.StringTable[k]] = (int32_t)k;
+    tr_string_lookup[k] = into.StringTable[k];
+  }
+  col.val_string_id_lookup = tr_string_lookup;
+  auto& sets = tb.SetMap[col_id];
+  sets.resize((size_t)tb.n);
+  // BucketEncoded
+  for (size_t b = 0; b + 1 < into.bin_offsets.size(); b++) {
+    uint32_t prev = 0;
+    for (uint32_t j = into.bin_offsets[b]; j < into.bin_offsets[b + 1]; j++) {
+      uint32_t r = into.record_ids[j];
+      if (into.delta_ids) r = r + prev;
+      if (r >= num_records) return false;
+      sets[r].push_back((int32_t)into.bin_values[b]);
+      tb.Populated[(size_t)r * K + col_id] = SET_VAL;
+      prev = r;
+    }
+  }
+  // the non-bucketed form (Values [][]int32, :670-683): every listed row is populated, empty set or not.  The tags
+  // themselves arrive as bins (sybilgpu.h); the reference's "len(Values) > num_records" error is kept.
+  if (into.set_nvalues > num_records) return false;
+  for (uint32_t r = 0; r < into.set_nvalues; r++) tb.Populated[(size_t)r * K + col_id] = SET_VAL;
+  return true;
+}
+
 // LoadBlockFromDir, table_block_io.go:225-310: only files named in the LoadSpec are unpacked
 static bool LoadBlock(const Table& t, const SavedBlock& sb, const std::vector<char>& wanted, Block& tb) {
   if (sb.NumRecords <= 0) return false;
@@ -603,10 +647,13 @@ static bool LoadBlock(const Table& t, const SavedBlock& sb, const std::vector<ch
     if (c.col_slot < 0 || c.col_slot >= t.ncols) continue;
     if (!wanted[(size_t)c.col_slot]) continue;
     bool ok = true;
-    if (c.col_type == SG_COL_STR)
-      ok = unpackStrCol(tb, c);
-    else if (c.col_type == SG_COL_INT)
+    if (c.col_type == SG_COL_STR) {
+      auto sr = t.str_replacements.find(c.col_slot);
+      ok = unpackStrCol(tb, c, sr == t.str_replacements.end() ? nullptr : &sr->second);
+    } else if (c.col_type == SG_COL_INT)
       ok = unpackIntCol(tb, c);
+    else if (c.col_type == SG_COL_SET)
+      ok = unpackSetCol(tb, c);
     if (!ok) return false;  // "ERROR DURING COLUMN UNPACK ... SKIPPING BLOCK"
   }
   return true;
@@ -653,6 +700,29 @@ static bool StrFilterFilter(const Filter& f, Block& tb, size_t r) {
     }
     case SG_OP_EQ: ret = (int64_t)val == filterval; break;
     case SG_OP_NEQ: ret = (int64_t)val != filterval; break;
+    default: break;
+  }
+  return ret;
+}
+
+// filter.go:252-285
+static bool SetFilterFilter(const Filter& f, Block& tb, size_t r) {
+  size_t K = (size_t)tb.ncols;
+  TableColumn& col = tb.columns[(size_t)f.col];
+  bool ret = false;
+  if (tb.Populated[r * K + f.col] != SET_VAL) return false;
+  const std::vector<int32_t>& sets = tb.SetMap[f.col][r];
+  int32_t val_id = col.get_val_id(f.svalue);
+  switch (f.op) {
+    case SG_OP_IN:
+      for (int32_t tag : sets)
+        if (tag == val_id) return true;
+      break;
+    case SG_OP_NIN:
+      ret = true;
+      for (int32_t tag : sets)
+        if (tag == val_id) return false;
+      break;
     default: break;
   }
   return ret;
@@ -753,7 +823,8 @@ static int64_t FilterAndAggRecords(QuerySpec& qs, Block& tb) {
     if (F.weight_col && tb.Populated[i * K + F.weight_col_id] == INT_VAL) weight = tb.Ints[i * K + F.weight_col_id];
 
     for (auto& f : qs.Filters) {
-      bool ok = f.type == SG_COL_INT ? IntFilterFilter(f, tb, i) : StrFilterFilter(f, tb, i);
+      bool ok = f.type == SG_COL_INT ? IntFilterFilter(f, tb, i)
+                                     : (f.type == SG_COL_SET ? SetFilterFilter(f, tb, i) : StrFilterFilter(f, tb, i));
       if (!ok) {
         add = false;
         break;
@@ -927,6 +998,22 @@ orc_table* orc_table_create(int32_t num_col_slots, const int32_t* col_types) {
   return t;
 }
 void orc_table_free(orc_table* t) { delete t; }
+// FLAGS.STR_REPLACE for one column (table_query.go:34-50); pattern == NULL removes it
+int orc_table_set_str_replace(orc_table* t, int32_t col_slot, const char* pattern, const char* replacement) {
+  if (!pattern) {
+    t->t.str_replacements.erase(col_slot);
+    return 0;
+  }
+  try {
+    StrReplace sr;
+    sr.re = std::regex(pattern, std::regex::ECMAScript);
+    sr.Replace = replacement ? replacement : "";
+    t->t.str_replacements[col_slot] = sr;
+  } catch (const std::regex_error&) {
+    return -1;
+  }
+  return 0;
+}
 
 int orc_table_add_block(orc_table* t, const sg_block_desc* d) {
   SavedBlock sb;
@@ -971,7 +1058,8 @@ int orc_table_add_block(orc_table* t, const sg_block_desc* d) {
         sc.values_i32.assign(c.values_i32, c.values_i32 + c.nvalues);
       }
     }
-    if (c.col_type == SG_COL_STR)
+    if (c.col_type == SG_COL_SET) sc.set_nvalues = c.nvalues;
+    if (c.col_type == SG_COL_STR || c.col_type == SG_COL_SET)
       for (uint32_t k = 0; k < c.ndict; k++)
         sc.StringTable.emplace_back(c.dict_bytes + c.dict_offsets[k], c.dict_offsets[k + 1] - c.dict_offsets[k]);
     sb.cols.push_back(std::move(sc));

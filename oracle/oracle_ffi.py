@@ -20,6 +20,7 @@ SYMBOLS = {
     "orc_table_create": (P, [C.c_int32, C.POINTER(C.c_int32)]),
     "orc_table_free": (None, [P]),
     "orc_table_add_block": (C.c_int, [P, C.POINTER(F.sg_block_desc)]),
+    "orc_table_set_str_replace": (C.c_int, [P, C.c_int32, C.c_char_p, C.c_char_p]),
     "orc_query": (P, [P, C.POINTER(F.sg_query_desc), C.c_int, C.c_int64]),
     "orc_result_free": (None, [P]),
     "orc_result_seconds": (C.c_double, [P]),
@@ -84,6 +85,13 @@ class OracleTable:
     def add_block(self, blk):
         d = blk.desc() if hasattr(blk, "desc") else blk
         self.lib.orc_table_add_block(self.h, C.byref(d) if not isinstance(d, C._Pointer) else d)
+
+    def set_str_replace(self, col_slot, pattern, replacement):
+        """FLAGS.STR_REPLACE for one column (pattern None: off)."""
+        rc = self.lib.orc_table_set_str_replace(self.h, col_slot, None if pattern is None else pattern.encode(),
+                                                None if replacement is None else replacement.encode())
+        if rc != 0:
+            raise ValueError("bad pattern %r" % pattern)
 
     def close(self):
         if self.h:

@@ -14,20 +14,21 @@ LIB_PATH = os.environ.get("SG_LIB") or os.path.join(_HERE, "csrc", "libsybilgpu.
 GEN_PATH = os.path.join(_HERE, "csrc", "libsybilblockgen.so")
 GOB_PATH = os.path.join(_HERE, "csrc", "libsybilgob.so")
 
-SG_ABI_VERSION = 3
+SG_ABI_VERSION = 4
 SG_ORDER_COUNT, SG_ORDER_NONE = -1, -2
 SG_MAX_FILTERS, SG_MAX_GROUPS, SG_MAX_AGGS, SG_MAX_COLS = 15, 8, 16, 64
 SG_BLOCK_ROWS = 65536
 SG_MISSING_KEY = 0xFFFFFFFFFFFFFFFF
 
 SG_OK, SG_ERR_INVALID, SG_ERR_CUDA, SG_ERR_UNSUPPORTED, SG_ERR_NOMEM, SG_ERR_NCCL, SG_ERR_STATE = 0, -1, -2, -3, -4, -5, -6
-SG_COL_INT, SG_COL_STR = 1, 2
+SG_COL_INT, SG_COL_STR, SG_COL_SET = 1, 2, 3
 SG_ENC_ABSENT, SG_ENC_BUCKET, SG_ENC_VALUES = 0, 1, 2
-SG_OP_GT, SG_OP_LT, SG_OP_EQ, SG_OP_NEQ, SG_OP_RE, SG_OP_NRE = 0, 1, 2, 3, 4, 5
+SG_OP_GT, SG_OP_LT, SG_OP_EQ, SG_OP_NEQ, SG_OP_RE, SG_OP_NRE, SG_OP_IN, SG_OP_NIN = 0, 1, 2, 3, 4, 5, 6, 7
 SG_MODE_AVG, SG_MODE_HIST = 0, 1
 SG_HIST_BASIC, SG_HIST_MULTI = 0, 1
 
-OPS = {"gt": SG_OP_GT, "lt": SG_OP_LT, "eq": SG_OP_EQ, "neq": SG_OP_NEQ, "re": SG_OP_RE, "nre": SG_OP_NRE}
+OPS = {"gt": SG_OP_GT, "lt": SG_OP_LT, "eq": SG_OP_EQ, "neq": SG_OP_NEQ, "re": SG_OP_RE, "nre": SG_OP_NRE,
+       "in": SG_OP_IN, "nin": SG_OP_NIN}
 
 
 class sg_filter_desc(C.Structure):
@@ -115,6 +116,7 @@ SYMBOLS = {
     "sg_query_begin": (P, [P, P, C.POINTER(sg_query_desc)]),
     "sg_query_free": (None, [P]),
     "sg_query_set_str_lut": (C.c_int, [P, C.c_int32, P, C.c_int64]),
+    "sg_query_set_str_replace": (C.c_int, [P, C.c_int32, P, P, C.c_int64]),
     "sg_query_should_load": (C.c_int, [P, C.POINTER(sg_block_desc)]),
     "sg_query_run": (C.c_int, [P]),
     "sg_query_submit_block": (C.c_int, [P, C.POINTER(sg_block_desc)]),

@@ -74,7 +74,9 @@ class SavedColumn:
                     self.values_i32 = np.ascontiguousarray(self.values_i32, np.int32)
                 d.nvalues = len(self.values_i32)
                 d.values_i32 = _ptr(self.values_i32)
-        if self.col_type == F.SG_COL_STR:
+        if self.col_type == F.SG_COL_SET:
+            d.nvalues = int(getattr(self, "set_nvalues", 0))  # len(Values) of the non-bucketed file form
+        if self.col_type in (F.SG_COL_STR, F.SG_COL_SET):
             blob = b"".join(self.string_table)
             offs = np.zeros(len(self.string_table) + 1, np.uint32)
             if self.string_table:
@@ -173,6 +175,70 @@ def encode_str_column(col_slot, strings, valid, threshold=CARDINALITY_THRESHOLD)
     return col
 
 
+def encode_set_column(col_slot, sets, valid, threshold=CARDINALITY_THRESHOLD):
+    """SaveSetsToColumns (column_store_io.go:139-217) for one block.  sets: per row a list of tags (strings).
+    At most `threshold` distinct tags: Bins[tag] = rows holding it.  More: the file holds Values [][]int32 (one id
+    list per row up to the last populated row); the C ABI takes that form as bins too, plus len(Values) in
+    `nvalues` (sybilgpu.h) — `set_values_to_bins` below is that conversion."""
+    valid = np.asarray(valid, bool)
+    col = SavedColumn(col_slot, F.SG_COL_SET)
+    table, rows_of = {}, {}
+    max_r = 0
+    for r, tags in enumerate(sets):
+        if not valid[r]:
+            continue
+        for tag in tags:
+            b = tag if isinstance(tag, bytes) else str(tag).encode()
+            k = table.setdefault(b, len(table))
+            rows_of.setdefault(k, []).append(r)
+            max_r = max(max_r, r + 1)
+    if not table:
+        return None  # a row with an empty set never reaches same_sets: no file without any tag
+    col.string_table = list(table.keys())
+    col.encoding = F.SG_ENC_BUCKET
+    col.delta_ids = True
+    vals, offs, ids = [], [0], []
+    for k in sorted(rows_of):
+        rows = np.asarray(sorted(set(rows_of[k])), np.int64)  # (a tag listed twice in one row counts once)
+        gaps = rows.copy()
+        gaps[1:] -= rows[:-1]
+        vals.append(k)
+        ids.append(gaps)
+        offs.append(offs[-1] + len(rows))
+    col.bin_values = np.asarray(vals, np.int64)
+    col.bin_offsets = np.asarray(offs, np.uint32)
+    col.record_ids = np.concatenate(ids).astype(np.uint32)
+    if len(table) > threshold:
+        col.set_nvalues = max_r  # was written as Values[:max_r]: every row below max_r reads back as populated
+    return col
+
+
+def set_values_to_bins(col_slot, values, string_table):
+    """SavedSetColumn in its non-bucketed form (Values [][]int32) as the bins the C ABI takes: what a host does
+    with a set_*.db file whose BucketEncoded is false."""
+    col = SavedColumn(col_slot, F.SG_COL_SET)
+    col.string_table = [s if isinstance(s, bytes) else str(s).encode() for s in string_table]
+    rows_of = {}
+    for r, tags in enumerate(values):
+        for k in (tags or []):
+            rows_of.setdefault(int(k), []).append(r)
+    col.encoding = F.SG_ENC_BUCKET
+    col.delta_ids = True
+    vals, offs, ids = [], [0], []
+    for k in sorted(rows_of):
+        rows = np.asarray(sorted(set(rows_of[k])), np.int64)
+        gaps = rows.copy()
+        gaps[1:] -= rows[:-1]
+        vals.append(k)
+        ids.append(gaps)
+        offs.append(offs[-1] + len(rows))
+    col.bin_values = np.asarray(vals, np.int64)
+    col.bin_offsets = np.asarray(offs, np.uint32)
+    col.record_ids = (np.concatenate(ids) if ids else np.zeros(0)).astype(np.uint32)
+    col.set_nvalues = len(values)
+    return col
+
+
 def encode_block(block_index, num_records, columns, threshold=CARDINALITY_THRESHOLD):
     """columns: list of (col_slot, col_type, values, valid).  Returns a SavedBlock."""
     blk = SavedBlock(block_index, num_records)
@@ -184,6 +250,8 @@ def encode_block(block_index, num_records, columns, threshold=CARDINALITY_THRESH
             v = np.asarray(values, np.int64)[np.asarray(valid, bool)]
             if len(v):
                 blk.info[slot] = (int(v.min()), int(v.max()))
+        elif typ == F.SG_COL_SET:
+            c = encode_set_column(slot, values, valid, threshold)
         else:
             c = encode_str_column(slot, values, valid, threshold)
         if c is not None:

@@ -24,6 +24,9 @@ enum : uint32_t {
   COL_ID16 = 128u,        //   uint16 record ids / gaps
   COL_VAL32 = 256u,       //   int32 deltas relative to vbase (int VALUES)
   COL_VAL16 = 512u,       //   int16 deltas relative to vbase (int VALUES) / uint16 local string ids (str VALUES)
+  COL_SET = 1024u,        // set column (SavedSetColumn): bucket form, a row may sit in several bins; vmin holds the
+                          // number of leading rows that are populated whatever the bins say (len(Values) of the
+                          // non-bucketed file form, column_store_io.go:672-682)
 };
 // log2(4-byte-id or 8-byte-value width / stored width): the row pitch of the arena view a column's tiles are
 // fetched through is 128 >> shift bytes, so a warp tile always holds 1024 ids / 512 values
@@ -70,6 +73,10 @@ struct KFilter {
   int64_t ival;
   const uint32_t* lut;  // RE/NRE: bitset over global ids
   int64_t lut_bits;
+  // SetFilter (IN / NIN, filter.go:252-285): sticky bits of the slot word, already shifted into place.  Every bin of
+  // the set column ORs set_pbit ("the row has a set"; 0 for IN) into its rows, the bin of the literal also set_tbit
+  // ("the set holds the literal"); the plan's filt_target asks for pbit set and tbit set (IN) / clear (NIN).
+  uint32_t set_pbit, set_tbit;
 };
 
 struct KGroup {

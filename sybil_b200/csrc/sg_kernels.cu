@@ -1635,6 +1635,31 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
       sp.gid = F.str_gid;
       sp.lut = F.lut;
       sp.lut_bits = F.lut_bits;
+      if (F.op >= SG_OP_IN) {
+        // SetFilter (filter.go:252-285) over a set column in its bucket form (unpackSetCol, column_store_io.go:641-668):
+        // sticky bits instead of a pass count — a row may be listed in several bins.  The planner keeps such a query
+        // in count mode (fail_mode == 0).
+        if (c.enc == SG_ENC_BUCKET) {
+          uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
+          for (uint32_t b = cx.tid; b < c.nbins; b += THREADS)
+            pay[b] = F.set_pbit | (str_gid(c, c.bin_values[b]) == F.str_gid ? F.set_tbit : 0u);
+          __syncthreads();
+          scan_bucket<SlotT>(
+              cx, c, nrec, [&](uint32_t bin) { return (SlotT)pay[bin]; },
+              [&](uint32_t row, SlotT cur) {
+                if (cur) slot_or(slot, slot_s, row, (uint32_t)cur);
+              });
+        }
+        // rows the non-bucketed file form listed (even with an empty set) are populated (a column of nothing but
+        // empty sets is staged as ABSENT + COL_SET)
+        const uint32_t npop = (c.flags & COL_SET) ? (uint32_t)min((long long)nrec, max(0ll, (long long)c.vmin)) : 0u;
+        if (F.set_pbit && npop) {
+          for (uint32_t r = cx.tid; r < npop; r += THREADS) slot_or(slot, slot_s, r, F.set_pbit);
+          __syncthreads();
+        }
+        pass_mark(pass_no++);
+        continue;
+      }
       if (c.enc == SG_ENC_BUCKET) {
         uint32_t* pay = c.nbins <= SMEM_BINS ? cx.binpay_s : gbinpay;
         const bool push_down = PP->fail_mode == 1u;

@@ -683,16 +683,23 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
       c->set_err("add_block: column type differs from the table's KeyTypes");
       return SG_ERR_INVALID;
     }
-    if (cd.col_type != SG_COL_INT && cd.col_type != SG_COL_STR) {
-      c->set_err("add_block: unsupported column type (set columns are out of scope)");
-      return SG_ERR_UNSUPPORTED;
+    if (cd.col_type != SG_COL_INT && cd.col_type != SG_COL_STR && cd.col_type != SG_COL_SET) {
+      c->set_err("add_block: unknown column type");
+      return SG_ERR_INVALID;
     }
     DevCol& dc = dcs[(size_t)cd.col_slot];
     Tmp& tm = tmp[(size_t)ci];
-    const bool is_str = cd.col_type == SG_COL_STR;
+    // a set column (SavedSetColumn) is staged like a bucket-encoded str column: tags are strings of the column's
+    // global dictionary, bins list the rows whose set holds the tag (unpackSetCol, column_store_io.go:611-688)
+    const bool is_set = cd.col_type == SG_COL_SET;
+    const bool is_str = cd.col_type == SG_COL_STR || is_set;
+    if (is_set && cd.encoding == SG_ENC_VALUES) {
+      c->set_err("add_block: a set column comes in the bucket form (sybilgpu.h); nvalues carries len(Values)");
+      return SG_ERR_INVALID;
+    }
     dc.enc = (uint32_t)cd.encoding;
     dc.flags = (cd.delta_ids ? COL_DELTA_IDS : 0u) | (cd.delta_values ? COL_DELTA_VALUES : 0u) |
-               (is_str ? COL_IS_STR : 0u);
+               (is_str ? COL_IS_STR : 0u) | (is_set ? COL_SET : 0u);
     dc.oob_gid = -1;
     if (cd.encoding == SG_ENC_ABSENT) continue;
     // narrow arrays (sybilgpu.h): element sizes of record_ids / values
@@ -728,8 +735,9 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
       }
     }
     if (is_str) {
-      // unpackStrCol: a string table longer than the block is "BLOCK SIZE CHANGED" (:524)
-      if (cd.ndict > nrec) dc.flags |= COL_BROKEN;
+      // unpackStrCol: a string table longer than the block is "BLOCK SIZE CHANGED" (:524); unpackSetCol has no
+      // such check
+      if (cd.ndict > nrec && !is_set) dc.flags |= COL_BROKEN;
       if (cd.ndict > 0 && (!cd.dict_bytes || !cd.dict_offsets)) {
         c->set_err("add_block: string table missing");
         return SG_ERR_INVALID;
@@ -775,6 +783,10 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
         return SG_ERR_INVALID;
       }
       if (cd.nrecord_ids > SG_BLOCK_ROWS) {
+        if (is_set) {
+          c->set_err("add_block: set column with more than 65,536 (tag,row) pairs in one block (not in this build)");
+          return SG_ERR_UNSUPPORTED;
+        }
         // more (bin,row) pairs than a block has rows: some row would be listed twice
         c->set_err("add_block: more record ids than rows in a block");
         return SG_ERR_INVALID;
@@ -799,8 +811,9 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
       tm.bin_offsets.push_back(cd.nrecord_ids);
       dc.nbins = (uint32_t)tm.bin_values.size();
       dc.nitems = cd.nrecord_ids;
+      if (is_set) dc.vmin = (int64_t)std::min<uint32_t>(cd.nvalues, nrec);  // rows populated whatever the bins say
       if (dc.nbins == 0) {
-        dc.enc = SG_ENC_ABSENT;
+        dc.enc = SG_ENC_ABSENT;  // (a set column of nothing but empty sets keeps COL_SET + vmin: see the kernel)
         continue;
       }
       if (!is_str) {
@@ -837,7 +850,7 @@ static int add_block_impl(sg_table* t, const sg_block_desc* b, const Premap& pm)
         tm.off_data = sw.add(cd.record_ids, (size_t)cd.nrecord_ids * id_size, c->is_pinned(cd.record_ids, (size_t)cd.nrecord_ids * id_size));
       tm.has_bv = tm.has_bo = tm.has_data = true;
       enc_bytes += (int64_t)(tm.bin_values.size() * 8 + tm.bin_offsets.size() * 4 + (size_t)cd.nrecord_ids * id_size);
-      if (cd.nrecord_ids == nrec) stats_slots.push_back((uint32_t)cd.col_slot);  // candidate for COL_FULL
+      if (cd.nrecord_ids == nrec && !is_set) stats_slots.push_back((uint32_t)cd.col_slot);  // candidate for COL_FULL
     } else if (cd.encoding == SG_ENC_VALUES) {
       dc.nitems = cd.nvalues;
       if (cd.nvalues > nrec) {
@@ -1222,6 +1235,13 @@ struct sg_query {
   bool h_acc_valid = false;
   std::vector<std::vector<std::string>> m_strs;
   std::vector<std::vector<int64_t>> m_ints;
+  // StrReplace (sg_query_set_str_replace): per str column slot the rewritten text of every global string and the
+  // smallest global id that rewrites to the same text (the class representative the groups are folded onto)
+  struct Replace {
+    std::vector<std::string> strs;
+    std::vector<uint32_t> canon;
+  };
+  std::map<int, Replace> repl;
 };
 
 sg_result::~sg_result() {
@@ -1508,6 +1528,10 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
       c->set_err("query: group column out of range");
       return SG_ERR_INVALID;
     }
+    if (t->types[(size_t)gd.col] == SG_COL_SET) {
+      c->set_err("query: a set column cannot be grouped by (aggregate.go:125-143 reads Ints / Strs only)");
+      return SG_ERR_INVALID;
+    }
     gd.is_str = t->types[(size_t)gd.col] == SG_COL_STR;
     if (!gd.is_str && t->has_values_int[(size_t)gd.col]) {
       int rc = ensure_value_dict(t, gd.col);
@@ -1574,6 +1598,17 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   // bucket column whose bins were checked to list each row once) -> one sticky FAIL bit instead of a
   // pass count, and bucket filters walk the failing bins only
   bool fail_mode = P.nfilters > 0 && !getenv("SG_NO_FAIL_MODE");
+  // SetFilters (IN / NIN) do not count passes: each owns sticky bits above the pass counter (one for IN: "the set
+  // holds the literal"; two for NIN: "the row has a set", "the set holds the literal"); they keep the query in
+  // count mode
+  uint32_t nset_in = 0, nset_nin = 0;
+  for (auto& f : q->filters) {
+    if (f.op == SG_OP_IN) nset_in++;
+    if (f.op == SG_OP_NIN) nset_nin++;
+  }
+  const uint32_t ncount = (uint32_t)P.nfilters - nset_in - nset_nin;  // filters that count passes
+  const uint32_t sbits = nset_in + 2u * nset_nin;
+  if (sbits) fail_mode = false;
   for (size_t i = 0; i < q->filters.size() && fail_mode; i++) {
     const int col = q->filters[i].col_slot;
     if (!col_ok(col)) break;  // reported below
@@ -1617,9 +1652,27 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   P.time_magic = 0;
   if (time_mode && P.time_bucket >= 2 && P.time_bucket < 0x100000000ll)
     P.time_magic = (uint64_t)(((unsigned __int128)1 << 64) / (unsigned __int128)P.time_bucket) + 1u;
-  uint32_t fbits = 0;
+  uint32_t fbits = 0, cbits = 0;
+  uint32_t sticky_target = 0;  // the sticky bits (relative to gbits + cbits) a passing row shows
   auto slot_layout = [&]() -> int {
-    fbits = fail_mode ? 1u : bits_for((uint64_t)P.nfilters + 1);
+    cbits = fail_mode ? 1u : (ncount ? bits_for((uint64_t)ncount + 1) : 0u);
+    fbits = cbits + sbits;
+    sticky_target = 0;
+    for (uint32_t i = 0, k = 0; i < (uint32_t)P.nfilters && P.gbits + fbits <= 32; i++) {
+      KFilter& kf = P.filters[i];
+      const int op = q->filters[i].op;
+      kf.set_pbit = kf.set_tbit = 0;
+      if (op == SG_OP_IN) {
+        kf.set_tbit = 1u << (P.gbits + cbits + k);
+        sticky_target |= 1u << k;
+        k += 1;
+      } else if (op == SG_OP_NIN) {
+        kf.set_pbit = 1u << (P.gbits + cbits + k);
+        kf.set_tbit = 1u << (P.gbits + cbits + k + 1);
+        sticky_target |= 1u << k;
+        k += 2;
+      }
+    }
     const uint32_t tbit = time_mode ? 1u : 0u;
     const uint32_t total_bits = P.gbits + fbits + tbit;
     if (total_bits > 32) {
@@ -1629,8 +1682,8 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     q->slot_bytes = total_bits <= 8 ? 1u : (total_bits <= 16 ? 2u : 4u);
     if (q->hashg) q->slot_bytes = 4;  // the hashed group pass exists for 32-bit slot words + global accumulators only
     P.finc = 1u << P.gbits;
-    P.filt_mask = (1u << fbits) - 1u;
-    P.filt_target = fail_mode ? 0u : (uint32_t)P.nfilters;
+    P.filt_mask = (uint32_t)(((uint64_t)1 << fbits) - 1u);
+    P.filt_target = fail_mode ? 0u : (ncount | (sticky_target << cbits));
     P.time_ok = time_mode ? (1u << (P.gbits + fbits)) : 0u;
     P.pass_target = P.filt_target | (time_mode ? (1u << fbits) : 0u);
     return SG_OK;
@@ -1649,8 +1702,8 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     }
     KFilter& kf = P.filters[i];
     kf.col = f.col_slot;
-    kf.is_str = t->types[(size_t)f.col_slot] == SG_COL_STR;
-    if ((f.col_type == SG_COL_STR) != (kf.is_str != 0)) {
+    kf.is_str = t->types[(size_t)f.col_slot] != SG_COL_INT;
+    if (f.col_type != t->types[(size_t)f.col_slot]) {
       c->set_err("query: filter type does not match the column's KeyTypes");
       return SG_ERR_INVALID;
     }
@@ -1659,7 +1712,18 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     kf.str_gid = -1;
     kf.lut = nullptr;
     kf.lut_bits = 0;
-    if (kf.is_str) {
+    if (f.col_type == SG_COL_SET) {
+      if (f.op != SG_OP_IN && f.op != SG_OP_NIN) {
+        c->set_err("query: op not valid for a set filter");
+        return SG_ERR_INVALID;
+      }
+      // a literal absent from the dictionary is in no row's set (get_val_id hands out a fresh id, filter.go:264)
+      kf.str_gid = t->sdict[(size_t)f.col_slot].find(q->filter_strs[(size_t)i]);
+      // (its sticky bits: slot_layout)
+    } else if (f.op == SG_OP_IN || f.op == SG_OP_NIN) {
+      c->set_err("query: IN / NIN are set filter ops");
+      return SG_ERR_INVALID;
+    } else if (kf.is_str) {
       if (f.op == SG_OP_EQ || f.op == SG_OP_NEQ) {
         kf.str_gid = t->sdict[(size_t)f.col_slot].find(q->filter_strs[(size_t)i]);
       } else if (f.op == SG_OP_RE || f.op == SG_OP_NRE) {
@@ -2194,6 +2258,9 @@ std::string render_key(const sg_query* q, const std::vector<uint64_t>& key) {
         s += std::to_string((int64_t)v);
       else if (q->merged) {
         if (v < q->m_strs[i].size()) s += q->m_strs[i][(size_t)v];
+      } else if (q->repl.count(col)) {  // StrReplace: the rewritten text (column_store_io.go:529-547)
+        const auto& rs = q->repl.at(col).strs;
+        if (v < rs.size()) s += rs[(size_t)v];
       } else if (v < t->sdict[(size_t)col].strs.size())
         s += t->sdict[(size_t)col].strs[(size_t)v];
     }
@@ -2272,6 +2339,10 @@ static const std::vector<uint32_t>& axis_ranks(sg_query* q, size_t di, std::vect
       for (int64_t v : q->m_ints[di]) r.push_back(std::to_string(v));
       ranks_of(r, scratch);
     }
+    return scratch;
+  }
+  if (d.is_str && q->repl.count(d.col)) {
+    ranks_of(q->repl.at(d.col).strs, scratch);
     return scratch;
   }
   if (d.is_str) {
@@ -2361,6 +2432,7 @@ static int build_result_topk(sg_query* q, sg_result** out) {
   const int naggs = P.naggs, ob = q->d.order_by_agg;
   const int64_t limit = q->d.limit;
   if (P.time_col >= 0 || P.hist_mode || q->d.hist_kind == SG_HIST_MULTI) return 1;
+  if (!q->repl.empty()) return 1;  // StrReplace folds groups on the host before anything is ordered
   if (limit <= 0 || limit > 65536 || ob == SG_ORDER_NONE || q->d.order_asc) return 1;
   if (P.nslots < (1u << 17) || q->h_acc_valid || getenv("SG_NO_GPU_TOPK")) return 1;
   const unsigned cap = (unsigned)limit + 8192u;
@@ -2511,6 +2583,51 @@ static int build_result_topk(sg_query* q, sg_result** out) {
   return SG_OK;
 }
 
+// StrReplace: strings of a group column that rewrite to the same text are one group in the reference (the block's
+// string table is rewritten before any row is read, column_store_io.go:529-547).  The scan grouped by the original
+// global ids; here every dense slot whose code on a rewritten axis is not its class representative is added onto
+// the representative's slot (counts, hist counts, sums, bucket counters: +; max: max) and cleared.
+static int fold_replaced(sg_query* q, uint64_t* h, size_t have) {
+  const Plan& P = q->plan;
+  sg_ctx* c = q->ctx;
+  for (size_t di = 0; di < q->dims.size(); di++) {
+    const GroupDim& d = q->dims[di];
+    if (!d.is_str || d.is_time) continue;
+    auto it = q->repl.find(d.col);
+    if (it == q->repl.end()) continue;
+    const auto& canon = it->second.canon;
+    if (canon.size() + 1 != (size_t)d.radix) {
+      c->set_err("query: the dictionary of a StrReplace column grew after sg_query_set_str_replace");
+      return SG_ERR_STATE;
+    }
+    auto fold_array = [&](size_t off, size_t per_slot, bool is_max) {
+      if (off + (size_t)P.nslots * per_slot > have) return;  // not read back: the result does not use it
+      for (uint32_t s = 0; s < P.nslots; s++) {
+        const uint32_t code = (s / d.stride) % d.radix;
+        if (code == 0 || canon[code - 1] == code - 1) continue;
+        const uint32_t to = s - (code - 1 - canon[code - 1]) * d.stride;
+        uint64_t* src = h + off + (size_t)s * per_slot;
+        uint64_t* dst = h + off + (size_t)to * per_slot;
+        for (size_t k = 0; k < per_slot; k++) {
+          if (is_max)
+            dst[k] = (uint64_t)std::max((int64_t)dst[k], (int64_t)src[k]), src[k] = (uint64_t)INT64_MIN;
+          else
+            dst[k] += src[k], src[k] = 0;
+        }
+      }
+    };
+    for (int a = 0; a < P.naggs; a++) {
+      fold_array(q->off_hcount[(size_t)a], 1, false);
+      fold_array(q->off_sum[(size_t)a], 1, false);
+      fold_array(q->off_vmax[(size_t)a], 1, true);
+      const uint32_t nv = q->layouts[(size_t)a].nvals_total;
+      if (nv) fold_array(q->off_buckets[(size_t)a], nv, false);
+    }
+    fold_array(q->off_count, 1, false);  // last: nothing above reads it, but keep the order obvious
+  }
+  return SG_OK;
+}
+
 int build_result(sg_query* q, sg_result** out) {
   sg_ctx* c = q->ctx;
   const Plan& P = q->plan;
@@ -2549,6 +2666,14 @@ int build_result(sg_query* q, sg_result** out) {
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     q->d2h_bytes += (int64_t)have * 8;
     h = (const uint64_t*)r->pin;
+  }
+  if (!q->repl.empty()) {
+    if (q->merged) {
+      c->set_err("query: StrReplace cannot follow a cross-GPU merge over differing dictionaries (seed them)");
+      return SG_ERR_UNSUPPORTED;
+    }
+    const int rc = fold_replaced(q, const_cast<uint64_t*>(h), have);  // (h is this call's own copy of the read-back)
+    if (rc != SG_OK) return rc;
   }
   r->layouts = q->layouts;
   r->hist_mode = P.hist_mode != 0;
@@ -2808,6 +2933,38 @@ int sg_query_set_str_lut(sg_query* q, int32_t fi, const uint32_t* bits, int64_t 
   if (words) CUDA_TRY(c, cudaMemcpyAsync(q->d_luts[(size_t)fi], bits, words * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // (H2D on the stream the kernels run on: see remap_to_union)
   q->planned = false;
+  return SG_OK;
+}
+
+int sg_query_set_str_replace(sg_query* q, int32_t col, const char* bytes, const uint32_t* offsets, int64_t n) {
+  if (!q || n < 0) return SG_ERR_INVALID;
+  sg_ctx* c = q->ctx;
+  sg_table* t = q->table;
+  if (col < 0 || col >= t->ncols || t->types[(size_t)col] != SG_COL_STR) {
+    c->set_err("sg_query_set_str_replace: not a str column");
+    return SG_ERR_INVALID;
+  }
+  if (n == 0) {
+    q->repl.erase(col);
+    return SG_OK;
+  }
+  if (!bytes || !offsets || (size_t)n != t->sdict[(size_t)col].strs.size()) {
+    c->set_err("sg_query_set_str_replace: one rewritten string per entry of the column's dictionary is needed");
+    return SG_ERR_INVALID;
+  }
+  sg_query::Replace R;
+  R.strs.reserve((size_t)n);
+  R.canon.resize((size_t)n);
+  std::unordered_map<std::string, uint32_t> first;
+  for (int64_t i = 0; i < n; i++) {
+    if (offsets[i + 1] < offsets[i]) {
+      c->set_err("sg_query_set_str_replace: offsets not monotone");
+      return SG_ERR_INVALID;
+    }
+    R.strs.emplace_back(bytes + offsets[i], offsets[i + 1] - offsets[i]);
+    R.canon[(size_t)i] = first.emplace(R.strs.back(), (uint32_t)i).first->second;
+  }
+  q->repl[col] = std::move(R);
   return SG_OK;
 }
 

@@ -101,6 +101,25 @@ class StrFilter:  # filter.go:152-160
         self.regex = re.compile(Value) if Op in ("re", "nre") else None
 
 
+class SetFilter:  # filter.go:162-169
+    def __init__(self, Field, FieldId, Op, Value):
+        self.Field, self.FieldId, self.Op, self.Value = Field, FieldId, Op, Value
+
+
+class StrReplace:  # config.go:102-105; FLAGS.STR_REPLACE "col:pattern:replacement" (table_query.go:34-50)
+    def __init__(self, Pattern, Replace):
+        self.Pattern, self.Replace = Pattern, Replace
+        self.regex = re.compile(Pattern)
+        # Go's Expand template ($1, ${1}, ${name}) as Python's (\g<1>); a literal backslash stays one
+        t = Replace.replace("\\", "\\\\")
+        t = re.sub(r"\$\{(\w+)\}", r"\\g<\1>", t)
+        t = re.sub(r"\$(\d+)", r"\\g<\1>", t)
+        self._template = t
+
+    def apply(self, s):  # regexp.ReplaceAllString (column_store_io.go:531)
+        return self.regex.sub(self._template, s)
+
+
 class Grouping:  # query_spec.go:73-76
     def __init__(self, Name, name_id):
         self.Name, self.name_id = Name, name_id
@@ -127,6 +146,10 @@ class LoadSpec:  # table_load_spec.go:5-72
     def Str(self, name):
         self.columns[name] = True
         self.files["str_" + name + ".db"] = True
+
+    def Set(self, name):
+        self.columns[name] = True
+        self.files["set_" + name + ".db"] = True
 
 
 class Hist:
@@ -242,7 +265,9 @@ class _ResultHandle:
 
 
 class QueryParams:  # query_spec.go:25-41
-    def __init__(self, Filters=None, Groups=None, Aggregations=None, TimeBucket=0, OrderBy="$COUNT", OrderAsc=False, Limit=0):
+    def __init__(self, Filters=None, Groups=None, Aggregations=None, TimeBucket=0, OrderBy="$COUNT", OrderAsc=False, Limit=0,
+                 StrReplace=None):
+        self.StrReplace = StrReplace or {}  # column name -> StrReplace (query_spec.go:30)
         self.Filters = Filters or []
         self.Groups = Groups or []
         self.Aggregations = Aggregations or []
@@ -255,7 +280,7 @@ class QueryParams:  # query_spec.go:25-41
 class QuerySpec:  # query_spec.go:60-67
     def __init__(self, params=None, **kw):
         self.QueryParams = params or QueryParams(**kw)
-        for k in ("Filters", "Groups", "Aggregations", "TimeBucket", "OrderBy", "OrderAsc", "Limit"):
+        for k in ("Filters", "Groups", "Aggregations", "TimeBucket", "OrderBy", "OrderAsc", "Limit", "StrReplace"):
             setattr(self, k, getattr(self.QueryParams, k))
         self.Results = {}
         self.TimeResults = {}
@@ -280,7 +305,7 @@ def make_query_desc(KeyTable, KeyTypes, IntInfo, qs):
             fl[i].col_type = F.SG_COL_INT
             fl[i].int_value = f.Value
         else:
-            fl[i].col_type = F.SG_COL_STR
+            fl[i].col_type = F.SG_COL_SET if isinstance(f, SetFilter) else F.SG_COL_STR
             b = f.Value if isinstance(f.Value, bytes) else f.Value.encode()
             keep.append(b)
             fl[i].str_value = b
@@ -401,6 +426,9 @@ class Table:
     def StrFilter(self, name, op, value):
         return StrFilter(name, self.get_key_id(name), op, value)
 
+    def SetFilter(self, name, op, value):
+        return SetFilter(name, self.get_key_id(name), op, value)
+
     def Grouping(self, name):
         return Grouping(name, self.get_key_id(name))
 
@@ -462,17 +490,39 @@ class PreparedQuery:
                 if name not in loadSpec.columns:
                     raise ValueError("%s column %r is not in the LoadSpec: sybil would not load it" % (what, name))
         d, self._keep = table._desc(qs)
+        # StrReplace (table_query.go:34-50, column_store_io.go:515-549): the strings of a rewritten column are
+        # rewritten on the host, once per distinct string; its filters travel as RE / NRE bitsets evaluated on
+        # the rewritten strings (sybilgpu.h, sg_query_set_str_replace)
+        repl = {name: sr for name, sr in (getattr(qs, "StrReplace", None) or {}).items()
+                if name in table.KeyTable and table.KeyTypes[table.KeyTable[name]] == F.SG_COL_STR}
+        rewritten = {}
+        for name, sr in repl.items():
+            rewritten[name] = [sr.apply(s.decode("utf-8", "surrogateescape")).encode("utf-8", "surrogateescape")
+                               for s in table.dict_strings(name)]
+        fl = self._keep[0]
+        for i, f in enumerate(qs.Filters):
+            if isinstance(f, StrFilter) and f.Field in repl and f.Op in ("eq", "neq"):
+                fl[i].op = F.SG_OP_RE if f.Op == "eq" else F.SG_OP_NRE
         self.q = lib.sg_query_begin(ctx.h, table.h, C.byref(d))
         if not self.q:
             raise SybilGpuError(F.SG_ERR_INVALID, ctx.err())
         try:
+            for name, strs in rewritten.items():
+                blob = b"".join(strs)
+                offs = np.zeros(len(strs) + 1, np.uint32)
+                if strs:
+                    offs[1:] = np.cumsum([len(x) for x in strs])
+                buf = np.frombuffer(blob if blob else b"\0", dtype=np.uint8).copy()
+                ctx.check(lib.sg_query_set_str_replace(self.q, table.KeyTable[name], buf.ctypes.data, offs.ctypes.data, len(strs)))
             for i, f in enumerate(qs.Filters):
-                if isinstance(f, StrFilter) and f.regex is not None:
+                if isinstance(f, StrFilter) and (f.regex is not None or f.Field in repl):
                     # the host evaluates the regexp once per distinct string (filter.go:215-237)
-                    strs = table.dict_strings(f.Field)
+                    strs = rewritten[f.Field] if f.Field in repl else table.dict_strings(f.Field)
                     bits = np.zeros((len(strs) + 31) // 32 + 1, np.uint32)
+                    lit = f.Value if isinstance(f.Value, bytes) else f.Value.encode()
                     for gid, s in enumerate(strs):
-                        if f.regex.search(s.decode("utf-8", "replace")):
+                        hit = f.regex.search(s.decode("utf-8", "replace")) if f.regex is not None else s == lit
+                        if hit:
                             bits[gid >> 5] |= np.uint32(1 << (gid & 31))
                     ctx.check(lib.sg_query_set_str_lut(self.q, i, bits.ctypes.data, len(strs)))
         except Exception:

@@ -1,0 +1,98 @@
+"""The oracle's SetFilter / set-column decode (filter.go:252-285, column_store_io.go:611-688) and StrReplace
+(column_store_io.go:515-549) against a row-by-row evaluation of the raw rows in plain Python: the reference holds
+no test vector for either, so the restatement is pinned to its definition (parity otherwise unpinned)."""
+import re
+from collections import Counter
+
+import numpy as np
+
+from sybil_b200 import blocks as B
+from sybil_b200 import _ffi as F
+from tests.util import INT, SET, STR, Q, Spec, run_oracle
+
+
+def _table(seed=5, nrows=4000, block_rows=1500, threshold=5000):
+    rng = np.random.default_rng(seed)
+    s = Spec([("v", INT), ("host", STR), ("tags", SET)])
+    ntag = rng.integers(0, 4, nrows)
+    rows = {
+        "v": rng.integers(0, 1000, nrows),
+        "host": np.array(["web-%02d.dc%d" % (a, b) for a, b in zip(rng.integers(0, 12, nrows), rng.integers(1, 4, nrows))]),
+        "tags": [["t%d" % t for t in rng.choice(9, int(k), replace=False)] for k in ntag],
+    }
+    valid = {"host": rng.random(nrows) > 0.1}
+    s.add_rows(rows, valid, threshold=threshold, block_rows=block_rows)
+    return s, rows, valid
+
+
+def test_set_filters_in_nin_absent_literal():
+    s, rows, valid = _table()
+    for op, tag in (("in", "t3"), ("nin", "t3"), ("in", "nope"), ("nin", "nope")):
+        q = Q(s, set_filters=[("tags", op, tag)], groups=["host"], aggs=["v"])
+        o = run_oracle(s, q)
+        want = Counter()
+        for i in range(len(rows["v"])):
+            tags = rows["tags"][i]
+            ok = (tag in tags) if op == "in" else (len(tags) > 0 and tag not in tags)  # no set: both ops say false
+            if ok:
+                want[(rows["host"][i] if valid["host"][i] else "") + "\t"] += 1
+        assert o.MatchedCount == sum(want.values()), (op, tag)
+        assert {k: r.Count for k, r in o.Results.items()} == dict(want), (op, tag)
+    # two set filters and an int filter together
+    q = Q(s, int_filters=[("v", "lt", 500)], set_filters=[("tags", "in", "t1"), ("tags", "nin", "t2")])
+    o = run_oracle(s, q)
+    n = sum(1 for i in range(len(rows["v"])) if rows["v"][i] < 500 and "t1" in rows["tags"][i] and "t2" not in rows["tags"][i])
+    assert o.MatchedCount == n and n > 0
+
+
+def test_set_column_values_form_marks_listed_rows_populated():
+    # the non-bucketed file form: every row below len(Values) is populated, even with an empty set
+    s = Spec([("v", INT), ("tags", SET)])
+    n = 50
+    vals = [[0], [], [1, 0], None, [1]] * 6  # 30 listed rows, 20 beyond len(Values)
+    blk = B.SavedBlock(0, n)
+    blk.cols.append(B.encode_int_column(0, np.arange(n), np.ones(n, bool)))
+    blk.cols.append(B.set_values_to_bins(1, vals, ["a", "b"]))
+    s.blocks.append(blk)
+    s.IntInfo["v"] = (0, n - 1)
+    assert run_oracle(s, Q(s, set_filters=[("tags", "nin", "a")])).MatchedCount == 18  # [], None, [1] x 6
+    assert run_oracle(s, Q(s, set_filters=[("tags", "in", "a")])).MatchedCount == 12
+    assert run_oracle(s, Q(s, set_filters=[("tags", "nin", "zzz")])).MatchedCount == 30
+
+
+def test_str_replace_merges_groups_and_rewrites_filters():
+    s, rows, valid = _table()
+    pat, rep = r"^web-(\d+)\.dc\d$", "web-$1"
+    py = lambda x: re.sub(pat, r"web-\1", x)
+    q = Q(s, groups=["host"], aggs=["v"], str_replace={"host": (pat, rep)})
+    o = run_oracle(s, q)
+    want, sums = Counter(), Counter()
+    for i in range(len(rows["v"])):
+        k = (py(rows["host"][i]) if valid["host"][i] else "") + "\t"
+        want[k] += 1
+        sums[k] += int(rows["v"][i])
+    assert {k: r.Count for k, r in o.Results.items()} == dict(want)
+    assert {k: r.Hists["v"].ExactSum for k, r in o.Results.items()} == dict(sums)
+    assert len(want) == 13  # 12 hosts (the dc suffix is gone) + rows without the column
+    # filters see the rewritten strings: eq on a rewritten name, neq, and a regexp over it
+    for op, lit in (("eq", "web-03"), ("neq", "web-03"), ("re", "^web-0[12]$")):
+        o = run_oracle(s, Q(s, str_filters=[("host", op, lit)], str_replace={"host": (pat, rep)}))
+        def ok(i):
+            if not valid["host"][i]:
+                return False
+            h = py(rows["host"][i])
+            return {"eq": h == lit, "neq": h != lit, "re": re.search(lit, h) is not None}[op]
+        assert o.MatchedCount == sum(1 for i in range(len(rows["v"])) if ok(i)), (op, lit)
+
+
+def test_str_replace_absent_literal_aliases_an_id_like_the_reference():
+    # get_val_id gives an absent literal the id len(col.StringTable) (table_column.go:27-48).  After a rewrite that
+    # merged strings the map is shorter than the block's string table, so that id belongs to another string and
+    # `eq <absent literal>` matches ITS rows (column_store_io.go:536-546 + filter.go:205).  The oracle restates it;
+    # the CUDA path answers "no row" (documented divergence).
+    s = Spec([("v", INT), ("name", STR)])
+    names = np.array(["a1", "a2", "b"] * 10)
+    s.add_rows({"v": np.arange(30), "name": names})
+    o = run_oracle(s, Q(s, str_filters=[("name", "eq", "zz")], str_replace={"name": (r"^a\d$", "a")}))
+    assert o.MatchedCount == 10  # the rows of "b": local id 2 == len({"a": 0, "b": 2})
+    assert run_oracle(s, Q(s, str_filters=[("name", "eq", "zz")])).MatchedCount == 0

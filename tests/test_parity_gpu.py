@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from sybil_b200 import _ffi as F
-from tests.util import compare_group, INT, STR, Q, Spec, compare, random_spec, run_gpu, run_oracle
+from tests.util import compare_group, INT, SET, STR, Q, Spec, compare, random_spec, run_gpu, run_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -775,3 +775,67 @@ def test_both_kernel_builds_agree_with_the_oracle(variant, monkeypatch):
               Q(r, int_filters=[("age", "gt", 12)], groups=["host", "age"], aggs=["lat", "big"], op="hist", loghist=True),
               Q(r, str_filters=[("state", "re", "^s1")], groups=["state"], aggs=["big"], op="hist")):
         compare(run_gpu(r, q), run_oracle(r, q), q)
+
+
+def test_set_filters_in_nin_like_filter_go():
+    # SetFilter (filter.go:252-285) over set columns (unpackSetCol, column_store_io.go:611-688): sticky bits in
+    # the slot word; alone, two at once, mixed with pass-counting int / str filters, with groups, hist and time
+    s = random_spec(31, nrows=6000, block_rows=1700, sets=True)
+    for op, tag in (("in", "t3"), ("nin", "t3"), ("in", "nope"), ("nin", "nope")):
+        g, o = both(s, Q(s, set_filters=[("tags", op, tag)], groups=["host"], aggs=["lat"], op="avg"))
+    assert g.MatchedCount > 0
+    both(s, Q(s, set_filters=[("tags", "in", "t1"), ("tags", "nin", "t2")], groups=["state"], aggs=["lat"], op="hist"))
+    g, o = both(s, Q(s, int_filters=[("age", "gt", 12)], str_filters=[("state", "neq", "s3")],
+                     set_filters=[("tags", "nin", "t5"), ("tags", "in", "t0")], groups=["host", "age"], aggs=["lat", "big"],
+                     op="hist"))
+    assert 0 < g.MatchedCount < 6000
+    both(s, Q(s, set_filters=[("tags", "in", "t4")], groups=["host"], aggs=["lat"], op="hist", time_col="time", time_bucket=600))
+    both(s, Q(s, set_filters=[("tags", "nin", "t4")]))
+
+
+def test_set_column_values_form_and_many_tags():
+    # the non-bucketed file form (more than `threshold` distinct tags): rows below len(Values) count as populated
+    # even with an empty set; and a set column next to fail-mode-capable filters keeps the query in count mode
+    from sybil_b200 import blocks as B
+    n = 3000
+    rng = np.random.default_rng(9)
+    s = Spec([("v", INT), ("tags", SET)])
+    s.forms = "wide"
+    vals = [list(rng.choice(400, int(k), replace=False)) if k else ([] if i % 2 else None)
+            for i, k in enumerate(rng.integers(0, 5, n - 500))]
+    blk = B.SavedBlock(0, n)
+    blk.cols.append(B.encode_int_column(0, rng.integers(0, 100000, n), np.ones(n, bool), threshold=10))
+    blk.cols.append(B.set_values_to_bins(1, vals, ["tag%d" % i for i in range(400)]))
+    s.blocks.append(blk)
+    s.IntInfo["v"] = (0, 99999)
+    for op, tag in (("in", "tag7"), ("nin", "tag7"), ("nin", "zzz")):
+        g, o = both(s, Q(s, int_filters=[("v", "lt", 50000)], set_filters=[("tags", op, tag)], aggs=["v"], op="hist"))
+    assert g.MatchedCount > 0
+
+
+def test_set_column_limits_and_misuse():
+    from sybil_b200 import engine as E
+    s = random_spec(33, nrows=500, block_rows=500, sets=True)
+    with pytest.raises(E.SybilGpuError):  # a set column cannot be grouped by (aggregate.go:125-143)
+        run_gpu(s, Q(s, groups=["tags"]))
+    with pytest.raises(E.SybilGpuError):  # IN / NIN are set ops
+        run_gpu(s, Q(s, str_filters=[("host", "in", "h1")]))
+
+
+def test_str_replace_like_table_query_go():
+    # FLAGS.STR_REPLACE (table_query.go:34-50, column_store_io.go:515-549): group keys and filters see the
+    # rewritten strings; strings that rewrite to the same text are one group
+    s = random_spec(41, nrows=6000, block_rows=1700)
+    rep = {"state": (r"^s(\d)\d*$", "S$1")}  # s0..s11 -> S0, S1 (s1, s10, s11), S2 ... S9
+    g, o = both(s, Q(s, groups=["state"], aggs=["lat", "big"], op="hist", str_replace=rep))
+    assert "S1\t" in g.Results and len(g.Results) == 11  # 10 rewritten names + the rows without the column
+    both(s, Q(s, groups=["host", "state"], aggs=["lat"], op="avg", str_replace=rep, order_by="lat", limit=5))
+    both(s, Q(s, groups=["state", "age"], aggs=["lat"], op="hist", str_replace=rep, time_col="time", time_bucket=900))
+    # (a literal that no rewritten string equals is left out: the reference hands it the id len(StringTable), which
+    # after a merging rewrite is some other string's id — tests/test_oracle_sets_replace.py)
+    for op, lit in (("eq", "S1"), ("neq", "S1"), ("re", "^S[12]$"), ("nre", "^S[12]$")):
+        both(s, Q(s, str_filters=[("state", op, lit)], groups=["state"], aggs=["lat"], op="avg", str_replace=rep))
+    # a high-cardinality value-array column folded onto few keys, two rewritten columns at once
+    rep2 = {"uid": (r"^u(\d).*$", "U$1"), "host": ("h", "node-")}
+    g, o = both(s, Q(s, groups=["uid", "host"], aggs=["lat"], op="avg", str_replace=rep2))
+    assert len(g.Results) <= 9 * 6 + 6

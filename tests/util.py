@@ -11,7 +11,7 @@ import os
 
 from sybil_b200.blocks import encode_block, narrow_column
 
-INT, STR = F.SG_COL_INT, F.SG_COL_STR
+INT, STR, SET = F.SG_COL_INT, F.SG_COL_STR, F.SG_COL_SET
 
 # tolerances of SURVEY.md §8(d): mean |d| <= 1e-9*max(1,|mean|); stddev rel <= 1e-9
 MEAN_TOL = 1e-9
@@ -75,8 +75,11 @@ class Q:
     """A query in the reference's vocabulary, buildable without a GPU."""
 
     def __init__(self, spec, int_filters=(), str_filters=(), groups=(), aggs=(), op="avg", loghist=False,
-                 time_col=None, time_bucket=0, hist_bucket=0, order_by="$COUNT", order_asc=False, limit=0):
+                 time_col=None, time_bucket=0, hist_bucket=0, order_by="$COUNT", order_asc=False, limit=0,
+                 set_filters=(), str_replace=None):
         self.spec = spec
+        self.set_filters = list(set_filters)      # (column, "in" | "nin", tag)
+        self.str_replace = dict(str_replace or {})  # column -> (pattern, replacement): FLAGS.STR_REPLACE
         self.order_by, self.order_asc, self.limit = order_by, order_asc, limit
         self.int_filters, self.str_filters = list(int_filters), list(str_filters)
         self.groups, self.aggs = list(groups), list(aggs)
@@ -96,10 +99,12 @@ class Q:
         self.set_flags()
         filters = [E.IntFilter(c, s.KeyTable[c], op, v) for c, op, v in self.int_filters]
         filters += [E.StrFilter(c, s.KeyTable[c], op, v) for c, op, v in self.str_filters]
+        filters += [E.SetFilter(c, s.KeyTable[c], op, v) for c, op, v in self.set_filters]
         groups = [E.Grouping(c, s.KeyTable[c]) for c in self.groups]
         aggs = [E.Aggregation(c, s.KeyTable[c], self.op) for c in self.aggs]
         return E.QuerySpec(Filters=filters, Groups=groups, Aggregations=aggs, TimeBucket=self.time_bucket if self.time_col else 0,
-                           OrderBy=self.order_by, OrderAsc=self.order_asc, Limit=self.limit)
+                           OrderBy=self.order_by, OrderAsc=self.order_asc, Limit=self.limit,
+                           StrReplace={c: E.StrReplace(p, r) for c, (p, r) in self.str_replace.items()})
 
     def desc(self):
         qs = self.query_spec()
@@ -111,6 +116,8 @@ def run_oracle(spec, q, nthreads=1):
     ot = OracleTable(spec.key_table)
     for b in spec.blocks:
         ot.add_block(b)
+    for c, (pat, rep) in q.str_replace.items():
+        ot.set_str_replace(spec.KeyTable[c], pat, rep)
     d, keep = q.desc()
     try:
         return ot.query(d, q.aggs, nthreads=nthreads)
@@ -133,6 +140,8 @@ def run_gpu(spec, q, table=None):
             ls.Int(c)
         for c, _, _ in q.str_filters:
             ls.Str(c)
+        for c, _, _ in q.set_filters:
+            ls.Set(c)
         for c in q.groups + q.aggs:
             ls.Int(c)
         table.LoadAndQueryRecords(ls, qs)
@@ -204,10 +213,13 @@ def compare(qs, oq, q):
             compare_group(qs.TimeResults[tb][k], o, q.aggs, op_hist, ("TimeResults", tb, k), q.loghist)
 
 
-def random_spec(seed, nrows=3000, block_rows=1000, nulls=True, threshold=5000, wide=False):
-    """A small random table exercising both encodings, missing values and several string columns."""
+def random_spec(seed, nrows=3000, block_rows=1000, nulls=True, threshold=5000, wide=False, sets=False):
+    """A small random table exercising both encodings, missing values and several string columns
+    (sets: plus a set column `tags`, 0-3 of 9 tags per row, some rows without the column)."""
     rng = np.random.default_rng(seed)
     kt = [("age", INT), ("lat", INT), ("big", INT), ("host", STR), ("state", STR), ("time", INT), ("uid", STR)]
+    if sets:
+        kt.append(("tags", SET))
     s = Spec(kt)
     cols = {
         "age": rng.integers(10, 30, nrows),
@@ -219,6 +231,9 @@ def random_spec(seed, nrows=3000, block_rows=1000, nulls=True, threshold=5000, w
         "uid": np.array(["u%d" % v for v in rng.integers(0, nrows * 4, nrows)]),
     }
     valid = {}
+    if sets:
+        ntag = rng.integers(0, 4, nrows)
+        cols["tags"] = [["t%d" % v for v in rng.choice(9, int(k), replace=False)] for k in ntag]
     if nulls:
         for name in ("age", "lat", "host", "state", "big"):
             valid[name] = rng.random(nrows) > 0.07
