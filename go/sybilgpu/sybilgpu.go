@@ -74,6 +74,11 @@ func (c *Ctx) NewTable(colTypes []int32) (*Table, error) {
 type Column struct {
 	Slot        int32
 	IsStr       bool
+	// IsSet: a SavedSetColumn (column_store.go:66-74, ABI v4).  Handed over in the bucket form only (BinValues =
+	// tag ids of StringTable, a row may sit in several bins); a file in the non-bucketed form (Values [][]int32) is
+	// turned into bins by the caller, len(Values) goes into SetNumValues (sybilgpu.h).
+	IsSet        bool
+	SetNumValues uint32
 	BucketEnc   bool // BucketEncoded
 	DeltaIDs    bool // DeltaEncodedIDs
 	DeltaValues bool // ValueEncoded
@@ -128,6 +133,9 @@ func (t *Table) AddBlock(index int64, numRecords int32, cols []Column, info []In
 		if col.IsStr {
 			d.col_type = C.SG_COL_STR
 		}
+		if col.IsSet {
+			d.col_type = C.SG_COL_SET
+		}
 		if col.BucketEnc {
 			d.encoding = C.SG_ENC_BUCKET
 			d.nbins = C.uint32_t(len(col.BinValues))
@@ -170,7 +178,10 @@ func (t *Table) AddBlock(index int64, numRecords int32, cols []Column, info []In
 		if col.DeltaValues {
 			d.delta_values = 1
 		}
-		if col.IsStr {
+		if col.IsSet {
+			d.nvalues = C.uint32_t(col.SetNumValues)
+		}
+		if col.IsStr || col.IsSet {
 			d.ndict = C.uint32_t(len(col.DictOffsets) - 1)
 			d.dict_bytes = (*C.char)(pin(&pinner, col.DictBytes))
 			d.dict_offsets = (*C.uint32_t)(pin(&pinner, col.DictOffsets))
@@ -197,6 +208,7 @@ func (t *Table) AddBlock(index int64, numRecords int32, cols []Column, info []In
 type Filter struct {
 	Slot   int32
 	IsStr  bool
+	IsSet  bool  // SetFilter (filter.go:162-169): Op is SG_OP_IN / SG_OP_NIN, StrVal the tag
 	Op     int32 // SG_OP_*
 	IntVal int64
 	StrVal string
@@ -223,6 +235,15 @@ type Query struct {
 	TimeBucket int64
 	TimeMin    int64
 	TimeMax    int64
+	StrReplace []StrReplaced // OPTS.STR_REPLACEMENTS, one entry per rewritten str column
+}
+
+// StrReplaced carries, for one str column, the rewritten text of every string of its global dictionary
+// (sg_table_dict_size / sg_table_dict_get order): Offsets has one more entry than there are strings.
+type StrReplaced struct {
+	Slot    int32
+	Bytes   []byte
+	Offsets []uint32
 }
 
 // Run is LoadAndQueryRecords for the staged blocks: returns the result handle.
@@ -241,8 +262,11 @@ func (t *Table) Run(q *Query, allreduce bool) (*C.sg_result, error) {
 	for i, f := range q.Filters {
 		fs[i].col_slot, fs[i].op, fs[i].int_value = C.int32_t(f.Slot), C.int32_t(f.Op), C.int64_t(f.IntVal)
 		fs[i].col_type = C.SG_COL_INT
-		if f.IsStr {
+		if f.IsStr || f.IsSet {
 			fs[i].col_type = C.SG_COL_STR
+			if f.IsSet {
+				fs[i].col_type = C.SG_COL_SET
+			}
 			p := C.CString(f.StrVal)
 			cstrs = append(cstrs, unsafe.Pointer(p))
 			fs[i].str_value, fs[i].str_len = p, C.int64_t(len(f.StrVal))
@@ -305,6 +329,17 @@ func (t *Table) Run(q *Query, allreduce bool) (*C.sg_result, error) {
 			if C.sg_query_set_str_lut(h, C.int32_t(i), (*C.uint32_t)(unsafe.Pointer(&f.Lut[0])), n) != C.SG_OK {
 				return nil, t.c.err()
 			}
+		}
+	}
+	// StrReplace (table_query.go:34-50): the caller rewrote every string of the column's dictionary with
+	// regexp.ReplaceAllString (and built the Luts of that column's filters on the rewritten strings)
+	for _, sr := range q.StrReplace {
+		var pinner runtime.Pinner
+		rc := C.sg_query_set_str_replace(h, C.int32_t(sr.Slot), (*C.char)(pin(&pinner, sr.Bytes)),
+			(*C.uint32_t)(pin(&pinner, sr.Offsets)), C.int64_t(len(sr.Offsets)-1))
+		pinner.Unpin()
+		if rc != C.SG_OK {
+			return nil, t.c.err()
 		}
 	}
 	if C.sg_query_run(h) != C.SG_OK {

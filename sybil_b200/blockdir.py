@@ -3,6 +3,7 @@
 A block directory holds one gob file per column, named by the column's type and name, and `info.db`:
     <block>/int_<col>.db   gob(SavedIntColumn)    column_store.go:46-54, column_store_io.go:117-134
     <block>/str_<col>.db   gob(SavedStrColumn)    column_store.go:56-64, column_store_io.go:280-299
+    <block>/set_<col>.db   gob(SavedSetColumn)    column_store.go:66-74, column_store_io.go:139-217
     <block>/info.db        gob(SavedColumnInfo)   column_store.go:39-44, column_store_io.go:308-358
 (`.db.gz` is accepted like `file_decoder.go:35-53` does.)  `read_block_dir` is what
 `LoadBlockFromDir` + `unpack*Col` do up to the point where the reference starts scattering values
@@ -33,6 +34,10 @@ INT_COLUMN = ("struct", "SavedIntColumn", [("Name", "string"), ("DeltaEncodedIDs
 STR_COLUMN = ("struct", "SavedStrColumn", [("Name", "string"), ("DeltaEncodedIDs", "bool"), ("BucketEncoded", "bool"),
                                             ("Bins", ("slice", STR_BUCKET)), ("Values", ("slice", "int")),
                                             ("StringTable", ("slice", "string")), ("VERSION", "int")])
+SET_BUCKET = ("struct", "SavedSetBucket", [("Value", "int"), ("Records", ("slice", "uint"))])
+SET_COLUMN = ("struct", "SavedSetColumn", [("Name", "string"), ("Bins", ("slice", SET_BUCKET)),
+                                            ("Values", ("slice", ("slice", "int"))), ("StringTable", ("slice", "string")),
+                                            ("DeltaEncodedIDs", "bool"), ("BucketEncoded", "bool"), ("VERSION", "int")])
 INT_INFO = ("struct", "IntInfo", [("Min", "int"), ("Max", "int"), ("Avg", "float"), ("M2", "float"), ("Count", "int")])
 STR_INFO = ("struct", "StrInfo", [("TopStringCount", ("map", "int", "int")), ("Cardinality", "int")])
 COLUMN_INFO = ("struct", "SavedColumnInfo", [("NumRecords", "int"), ("StrInfoMap", ("map", "string", STR_INFO)),
@@ -85,6 +90,24 @@ def str_column_from_gob(col_slot, v):
     return c
 
 
+def set_column_from_gob(col_slot, v):
+    """SavedSetColumn -> SavedColumn in the bucket form the C ABI takes (sybilgpu.h): the non-bucketed file form
+    (Values [][]int32) is turned into bins, len(Values) kept as set_nvalues."""
+    from .blocks import set_values_to_bins
+    table = v.get("StringTable", [])
+    if v.get("BucketEncoded", False):
+        c = SavedColumn(col_slot, F.SG_COL_SET)
+        c.string_table = [s.encode("utf-8", "surrogateescape") for s in table]
+        c.encoding = F.SG_ENC_BUCKET
+        c.delta_ids = bool(v.get("DeltaEncodedIDs", False))
+        _bins(c, v.get("Bins", []))
+        return c
+    return set_values_to_bins(col_slot, v.get("Values", []), [s.encode("utf-8", "surrogateescape") for s in table])
+
+
+_PREFIX = {F.SG_COL_INT: "int", F.SG_COL_STR: "str", F.SG_COL_SET: "set"}
+
+
 def read_block_dir(dirname, key_table, columns=None, block_index=0):
     """The block at `dirname` as a SavedBlock.  key_table: [(name, SG_COL_INT|SG_COL_STR)] (the table's
     KeyTable/KeyTypes); columns: names to load (the LoadSpec; default all).  A column whose file is
@@ -101,12 +124,12 @@ def read_block_dir(dirname, key_table, columns=None, block_index=0):
     for i, (name, typ) in enumerate(key_table):
         if columns is not None and name not in columns:
             continue
-        prefix = "int" if typ == F.SG_COL_INT else "str"
-        raw = _read(os.path.join(dirname, "%s_%s.db" % (prefix, name)))
+        raw = _read(os.path.join(dirname, "%s_%s.db" % (_PREFIX[typ], name)))
         if raw is None:
             continue
         v = gob.decode(raw)
-        blk.cols.append(int_column_from_gob(i, v) if typ == F.SG_COL_INT else str_column_from_gob(i, v))
+        blk.cols.append({F.SG_COL_INT: int_column_from_gob, F.SG_COL_STR: str_column_from_gob,
+                         F.SG_COL_SET: set_column_from_gob}[typ](i, v))
     return blk
 
 
@@ -128,6 +151,18 @@ def column_to_gob(c, name):
             v.update(ValueEncoded=bool(c.delta_values), Values=np.asarray(c.values_i64).tolist())
         return INT_COLUMN, v
     v["StringTable"] = [s.decode("utf-8", "surrogateescape") for s in c.string_table]
+    if c.col_type == F.SG_COL_SET:
+        nv = int(getattr(c, "set_nvalues", 0))
+        if nv:  # written un-bucketed (more than CARDINALITY_THRESHOLD tags, column_store_io.go:183-192)
+            rows = [[] for _ in range(nv)]
+            for b in range(len(c.bin_values)):
+                ids = np.asarray(c.record_ids[int(c.bin_offsets[b]):int(c.bin_offsets[b + 1])], np.int64)
+                for r in (np.cumsum(ids) if c.delta_ids else ids):
+                    rows[int(r)].append(int(c.bin_values[b]))
+            v.update(DeltaEncodedIDs=True, Values=rows)
+        else:
+            v.update(BucketEncoded=True, DeltaEncodedIDs=bool(c.delta_ids), Bins=_bins_to_gob(c))
+        return SET_COLUMN, v
     if c.encoding == F.SG_ENC_BUCKET:
         v.update(BucketEncoded=True, DeltaEncodedIDs=bool(c.delta_ids), Bins=_bins_to_gob(c))
     else:
@@ -146,7 +181,7 @@ def write_block_dir(dirname, blk, key_table, compress=False):
             continue
         name, typ = key_table[c.col_slot]
         t, v = column_to_gob(c, name)
-        with op(os.path.join(dirname, "%s_%s.db%s" % ("int" if typ == F.SG_COL_INT else "str", name, ext)), "wb") as f:
+        with op(os.path.join(dirname, "%s_%s.db%s" % (_PREFIX[typ], name, ext)), "wb") as f:
             f.write(gob.encode(v, t))
         if typ == F.SG_COL_STR:
             str_info[name] = {"Cardinality": len(c.string_table)}

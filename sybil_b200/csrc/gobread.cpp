@@ -260,6 +260,7 @@ struct Column {
   std::vector<int16_t> d16;
   int64_t vbase = 0;
   int id_bits = 0, value_bits = 0;
+  uint32_t set_nvalues = 0;  // set column read from its non-bucketed form: len(Values)
 };
 
 bool g_narrow = false;
@@ -304,6 +305,7 @@ void read_column(const std::vector<uint8_t>& raw, Column& c) {
   Reader r(raw.data(), raw.size());
   const int64_t tid = r.next_value();
   bool bucket = false;
+  std::vector<std::vector<int32_t>> set_rows;
   r.structure(tid, [&](const std::string& f, int64_t ft) {
     if (f == "DeltaEncodedIDs") c.delta_ids = r.u() != 0;
     else if (f == "ValueEncoded") c.delta_values = r.u() != 0;
@@ -322,6 +324,15 @@ void read_column(const std::vector<uint8_t>& raw, Column& c) {
         c.bin_values.push_back(value);
         c.bin_offsets.push_back((uint32_t)c.record_ids.size());
       }
+    } else if (f == "Values" && c.type == SG_COL_SET) {
+      // SavedSetColumn.Values [][]int32 (more than 5,000 distinct tags, column_store_io.go:183-192): kept per row
+      // here, turned into bins below (the C ABI takes set columns in the bucket form, sybilgpu.h)
+      const TypeDef& st = r.def(ft);
+      if (st.kind != TypeDef::SLICE && st.kind != TypeDef::ARRAY) throw Err("gob: set Values is not a slice");
+      uint64_t n = r.u();
+      if (n > (uint64_t)SG_BLOCK_ROWS) throw Err("gob: set Values longer than a block");
+      set_rows.resize((size_t)n);
+      for (uint64_t k = 0; k < n; k++) r.ints(st.elem, set_rows[(size_t)k], false);
     } else if (f == "Values") {
       if (c.type == SG_COL_INT) r.ints(ft, c.values_i64, false);
       else r.ints(ft, c.values_i32, false);
@@ -341,6 +352,28 @@ void read_column(const std::vector<uint8_t>& raw, Column& c) {
     c.bin_values.clear();
     c.bin_offsets.assign(1, 0);
     c.record_ids.clear();
+  }
+  if (c.type == SG_COL_SET && !bucket) {
+    // rows -> bins (tag id ascending, rows ascending, gaps); len(Values) travels as nvalues: the reference marks
+    // every listed row populated, empty set or not (column_store_io.go:672-682)
+    std::map<int32_t, std::vector<uint32_t>> rows_of;
+    for (size_t r2 = 0; r2 < set_rows.size(); r2++)
+      for (int32_t tag : set_rows[r2]) {
+        auto& v = rows_of[tag];
+        if (v.empty() || v.back() != (uint32_t)r2) v.push_back((uint32_t)r2);
+      }
+    for (auto& kv : rows_of) {
+      uint32_t prev = 0;
+      for (size_t k = 0; k < kv.second.size(); k++) {
+        c.record_ids.push_back(k == 0 ? kv.second[k] : kv.second[k] - prev);
+        prev = kv.second[k];
+      }
+      c.bin_values.push_back(kv.first);
+      c.bin_offsets.push_back((uint32_t)c.record_ids.size());
+    }
+    c.delta_ids = true;
+    c.encoding = SG_ENC_BUCKET;
+    c.set_nvalues = (uint32_t)set_rows.size();
   }
 }
 
@@ -409,8 +442,9 @@ sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, c
     }
     for (int32_t s = 0; s < ncols; s++) {
       if (load_mask && !load_mask[s]) continue;
-      if (col_types[s] != SG_COL_INT && col_types[s] != SG_COL_STR) continue;
-      const std::string path = d + "/" + (col_types[s] == SG_COL_INT ? "int_" : "str_") + col_names[s] + ".db";
+      if (col_types[s] != SG_COL_INT && col_types[s] != SG_COL_STR && col_types[s] != SG_COL_SET) continue;
+      const std::string path =
+          d + "/" + (col_types[s] == SG_COL_INT ? "int_" : (col_types[s] == SG_COL_STR ? "str_" : "set_")) + col_names[s] + ".db";
       if (!read_file(path, raw)) continue;  // the block does not hold that column
       Column c;
       c.slot = s;
@@ -437,6 +471,7 @@ sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, c
         cd.record_ids = c.id_bits == 16 ? reinterpret_cast<const uint32_t*>(c.ids16.data()) : c.record_ids.data();
         cd.id_bits = c.id_bits;
         b->bytes += (int64_t)c.record_ids.size() * (c.id_bits == 16 ? 2 : 4) + (int64_t)c.bin_values.size() * 12;
+        if (c.type == SG_COL_SET) cd.nvalues = c.set_nvalues;
       } else if (c.type == SG_COL_INT) {
         cd.nvalues = (uint32_t)c.values_i64.size();
         cd.value_bits = c.value_bits;
@@ -451,7 +486,7 @@ sgob_block* sgob_read_block_dir(const char* dir, const char* const* col_names, c
         cd.values_i32 = c.value_bits == 16 ? reinterpret_cast<const int32_t*>(c.v16.data()) : c.values_i32.data();
         b->bytes += (int64_t)c.values_i32.size() * (c.value_bits == 16 ? 2 : 4);
       }
-      if (c.type == SG_COL_STR) {
+      if (c.type == SG_COL_STR || c.type == SG_COL_SET) {
         cd.ndict = c.ndict;
         cd.dict_bytes = c.dict_bytes.empty() ? "" : c.dict_bytes.data();
         cd.dict_offsets = c.dict_offsets.data();

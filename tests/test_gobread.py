@@ -160,3 +160,43 @@ def test_native_example_host_compiles_and_fails_loudly_without_a_gpu(tmp_path):
     if not torch.cuda.is_available():
         p = subprocess.run([exe, str(tmp_path), "nosuchtable", "g", "a"], capture_output=True, text=True)
         assert p.returncode != 0 and "info.db" in p.stderr
+
+
+@pytest.mark.parametrize("threshold", [5000, 4])
+def test_native_reader_set_columns(tmp_path, threshold):
+    # set_<col>.db in both file forms (bucketed; Values [][]int32 turned into bins + nvalues): the native reader's
+    # descriptor gives the oracle the same answers as the in-memory blocks
+    from tests.util import SET
+    from oracle.oracle_ffi import OracleTable
+    rng = np.random.default_rng(3)
+    n = 2500
+    s = Spec([("v", INT), ("tags", SET)])
+    s.forms = "wide"  # (write_block_dir lays out the post-gob arrays as they are)
+    s.add_rows({"v": rng.integers(0, 100, n),
+                "tags": [["t%d" % t for t in rng.choice(9, int(k), replace=False)] for k in rng.integers(0, 4, n)]},
+               threshold=threshold, block_rows=900)
+    ot = OracleTable(s.key_table)
+    keep = []
+    try:
+        for i, b in enumerate(s.blocks):
+            d = str(tmp_path / ("block%d" % i))
+            blockdir.write_block_dir(d, b, s.key_table, compress=i % 2 == 0)
+            g, h, err = _read_native(d, s.key_table, block_index=b.block_index)
+            assert h, err
+            keep.append((g, h))
+            desc = g.sgob_block_desc(h).contents
+            cd = [desc.cols[k] for k in range(desc.ncols) if desc.cols[k].col_type == SET][0]
+            assert cd.encoding == F.SG_ENC_BUCKET and cd.ndict == 9
+            assert (cd.nvalues > 0) == (threshold == 4)
+            ot.add_block(g.sgob_block_desc(h))
+        for op, tag in (("in", "t3"), ("nin", "t3"), ("nin", "nope")):
+            q = Q(s, set_filters=[("tags", op, tag)], aggs=["v"])
+            want = run_oracle(s, q)
+            d, _keep = q.desc()
+            got = ot.query(d, q.aggs)
+            assert got.MatchedCount == want.MatchedCount > 0
+            assert got.Cumulative.Hists["v"].ExactSum == want.Cumulative.Hists["v"].ExactSum
+    finally:
+        ot.close()
+        for g, h in keep:
+            g.sgob_block_free(h)
