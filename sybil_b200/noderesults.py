@@ -13,8 +13,9 @@ Only what the merge reads is sent (gob receivers bind by field name and zero the
 Aggregations, OrderBy/Limit/TimeBucket; per group GroupByKey, BinaryByKey, Count, Samples and, per
 aggregation, a `*sybil.HistCompat` (the name the reference registers, `query_cache.go:18-27`) holding
 the BasicHist state `Combine` uses (`hist_basic.go:259-279`): NumBuckets, BucketSize, Values,
-PercentileMode, Max, Min, Count, Avg, Info{Min, Max}.  Log-scale histograms (`*sybil.MultiHistCompat`)
-are not emitted yet.
+PercentileMode, Max, Min, Count, Avg, Info{Min, Max}.  Log-scale histograms (FLAGS.LOG_HIST) travel as
+`*sybil.MultiHistCompat` with one such state per sub-histogram (`multi_hist_value`).  The receiving side —
+`CombineResults` under `OPTS.MERGE_TABLE`, i.e. `fullMergeHist` — is restated in `stitch.py`.
 
 Field layouts follow the type definitions Go itself sent in the reference's golden stream
 (`testdata/TestDecodeGoldenFiles/node_results.golden.gob`); `tests/test_noderesults.py` decodes that
@@ -44,6 +45,12 @@ TABLE = ("struct", "Table", [("Name", "string")])
 NODE_RESULTS = ("struct", "NodeResults", [("Table", TABLE), ("Tables", ("slice", "string")), ("QuerySpec", QUERY_SPEC)])
 
 HIST_NAME = "*sybil.HistCompat"
+# hist_multi.go:6-18 (table is unexported); MultiHistCompat embeds *MultiHist and names it again as Histogram
+# (hist_compat.go:50-54): gob flattens both pointers, the state travels twice
+MULTI_HIST = ("struct", "MultiHist", [("Max", "int"), ("Min", "int"), ("Samples", "int"), ("Count", "int"), ("Avg", "float"),
+                                      ("PercentileMode", "bool"), ("Subhists", ("slice", HIST_COMPAT)), ("Info", INT_INFO)])
+MULTI_COMPAT = ("struct", "MultiHistCompat", [("MultiHist", MULTI_HIST), ("Histogram", MULTI_HIST)])
+MULTI_NAME = "*sybil.MultiHistCompat"
 
 
 def hist_value(count, avg, vmin, vmax, num_buckets, bucket_size, values, info_min, info_max, samples=0):
@@ -52,6 +59,28 @@ def hist_value(count, avg, vmin, vmax, num_buckets, bucket_size, values, info_mi
               "PercentileMode": len(values) > 0, "Max": int(vmax), "Min": int(vmin), "Samples": int(samples), "Count": int(count),
               "Avg": float(avg), "Info": {"Min": int(info_min), "Max": int(info_max)}}
     return (HIST_NAME, HIST_COMPAT, {"BasicHist": {"BasicHistCachedInfo": cached}})
+
+
+def multi_hist_value(count, avg, vmin, vmax, values, info_min, info_max, samples=0, hist_bucket=0):
+    """A log-scale histogram (FLAGS.LOG_HIST) as `*sybil.MultiHistCompat`: `values` are the bucket counters of all
+    sub-histograms concatenated in Subhists order (the engine's layout, sg_hist.h::make_layout ==
+    TrackPercentiles, hist_multi.go:223-257).  Each sub-histogram is sent with its own layout, its counters and
+    Count = their sum; the engine keeps no per-sub-histogram mean, so their Avg is sent as 0 — nothing the
+    reference prints or merges reads it (percentiles, buckets and stddev of a MultiHist come from the counters and
+    the outer Avg, hist_multi.go:90-158)."""
+    from .stitch import BasicHist, multi_layout
+    subs, at = [], 0
+    for lo, hi in multi_layout(int(info_min), int(info_max)):
+        lay = BasicHist(lo, hi, hist_bucket)
+        n = len(lay.Values)
+        vals = [int(v) for v in values[at:at + n]]
+        at += n
+        subs.append(hist_value(sum(vals), 0.0, lo, hi, lay.NumBuckets, lay.BucketSize, vals, lo, hi)[2])
+    if at != len(values):
+        raise ValueError("MultiHist: %d counters for a layout of %d" % (len(values), at))
+    m = {"Max": int(vmax), "Min": int(vmin), "Samples": int(samples), "Count": int(count), "Avg": float(avg),
+         "PercentileMode": len(values) > 0, "Subhists": subs, "Info": {"Min": int(info_min), "Max": int(info_max)}}
+    return (MULTI_NAME, MULTI_COMPAT, {"MultiHist": m, "Histogram": m})
 
 
 def _binary_key(r):
@@ -70,11 +99,12 @@ def _result(r, agg_names, int_info, ngroups):
         h = r.Hists.get(name)
         if h is None:
             continue
-        if getattr(h, "nsubhists", 1) > 1:
-            raise NotImplementedError("MultiHist results are not emitted yet")
         mn = h.Min() if callable(getattr(h, "Min", None)) else h.Min
         mx = h.Max() if callable(getattr(h, "Max", None)) else h.Max
         lo, hi = int_info.get(name, (mn, mx))
+        if getattr(h, "nsubhists", 0) >= 1:  # FLAGS.LOG_HIST: *sybil.MultiHistCompat
+            hists[name] = multi_hist_value(h.Count, h.Avg, mn, mx, list(h.Values), lo, hi, getattr(h, "Samples", 0))
+            continue
         hists[name] = hist_value(h.Count, h.Avg, mn, mx, h.NumBuckets, h.BucketSize, list(h.Values), lo, hi, getattr(h, "Samples", 0))
     key = _binary_key(r)
     if not isinstance(getattr(r, "BinaryByKey", ""), str):
@@ -83,7 +113,8 @@ def _result(r, agg_names, int_info, ngroups):
     return {"Hists": hists, "GroupByKey": r.GroupByKey, "BinaryByKey": key, "Count": int(r.Count), "Samples": int(r.Samples)}
 
 
-def node_results_value(qs, table_name, groups, aggs, int_info, op="hist", order_by="$COUNT", limit=100, time_bucket=0):
+def node_results_value(qs, table_name, groups, aggs, int_info, op="hist", order_by="$COUNT", limit=100, time_bucket=0,
+                       loghist=False):
     """The NodeResults value (a dict matching NODE_RESULTS) of a finished query.
     groups / aggs: column names; int_info: name -> (Min, Max) of the table (hist.go:27-38)."""
     res = lambda r: _result(r, aggs, int_info, len(groups))  # noqa: E731
@@ -94,7 +125,7 @@ def node_results_value(qs, table_name, groups, aggs, int_info, op="hist", order_
     if getattr(qs, "TimeResults", None):
         qr["TimeResults"] = {int(tb): {k: res(r) for k, r in m.items()} for tb, m in qs.TimeResults.items()}
     qp = {"Groups": [{"Name": g} for g in groups],
-          "Aggregations": [{"Op": op, "Name": a, "HistType": "basic" if op == "hist" else ""} for a in aggs],
+          "Aggregations": [{"Op": op, "Name": a, "HistType": ("multi" if loghist else "basic") if op == "hist" else ""} for a in aggs],
           "OrderBy": order_by, "Limit": int(limit), "TimeBucket": int(time_bucket)}
     return {"Table": {"Name": table_name}, "Tables": [table_name], "QuerySpec": {"QueryParams": qp, "QueryResults": qr}}
 

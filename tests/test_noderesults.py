@@ -95,3 +95,89 @@ def test_binary_key_bytes_survive_the_wire():
     key = NR._binary_key(R())
     assert len(key.encode("utf-8", "surrogateescape")) == 24
     assert key.encode("utf-8", "surrogateescape")[:8] == (200).to_bytes(8, "little")
+
+
+def _halves(seed=4, n=4000):
+    rng = np.random.default_rng(seed)
+    rows = {"lat": rng.integers(30, 5000, n), "host": np.array(["h%d" % x for x in rng.integers(0, 4, n)])}
+    whole, a, b = Spec([("lat", INT), ("host", STR)]), Spec([("lat", INT), ("host", STR)]), Spec([("lat", INT), ("host", STR)])
+    whole.add_rows(rows, block_rows=1000)
+    a.add_rows({k: v[:n // 2] for k, v in rows.items()}, block_rows=1000)
+    b.add_rows({k: v[n // 2:] for k, v in rows.items()}, block_rows=1000)
+    return whole, a, b
+
+
+def test_stitch_with_equal_extents_reproduces_the_whole_table_counters():
+    """`sybil aggregate` over two nodes' NodeResults (stitch.combine_node_results == CombineResults under
+    MERGE_TABLE, fullMergeHist query_spec.go:118-135): with the same extents on both nodes every (bucket start,
+    count) pair lands in its own bucket again, so counts and all bucket counters equal one node scanning it all."""
+    from sybil_b200 import stitch
+    whole, a, b = _halves()
+    info = {"lat": whole.IntInfo["lat"]}
+    for sp in (a, b):
+        sp.IntInfo = dict(whole.IntInfo)  # both nodes build their histograms from the table's extents
+    mk = lambda sp: Q(sp, groups=["host"], aggs=["lat"], op="hist")
+    streams = [NR.encode_node_results(run_oracle(sp, mk(sp)), "t", ["host"], ["lat"], info) for sp in (a, b)]
+    merged = stitch.combine_node_results(streams)
+    want = run_oracle(whole, mk(whole))
+    assert merged["MatchedCount"] == want.MatchedCount and set(merged["Results"]) == set(want.Results)
+    for k, r in want.Results.items():
+        g = merged["Results"][k]
+        kind, h = g["Hists"]["lat"]
+        assert kind == "basic" and g["Count"] == r.Count
+        assert h.Count == r.Hists["lat"].Count and h.Values == [int(v) for v in r.Hists["lat"].Values]
+        assert (h.NumBuckets, h.BucketSize) == (r.Hists["lat"].NumBuckets, r.Hists["lat"].BucketSize)
+        # the merged mean is the mean of BUCKET STARTS (what the reference computes; values beyond the last bucket
+        # were clamped into it): the weighted mean of the whole-table result's own sparse buckets
+        ib = r.Hists["lat"].IntBuckets
+        assert abs(h.Avg - sum(k2 * c for k2, c in ib.items()) / sum(ib.values())) < 1e-6
+    assert merged["Cumulative"]["Count"] == want.Cumulative.Count
+
+
+def test_stitch_rebuckets_histograms_of_different_extents():
+    from sybil_b200 import stitch
+    whole, a, b = _halves(seed=6)
+    a.IntInfo, b.IntInfo = {"lat": (0, 2000)}, {"lat": (30, 6000)}
+    mk = lambda sp: Q(sp, aggs=["lat"], op="hist")
+    oa, ob = run_oracle(a, mk(a)), run_oracle(b, mk(b))
+    streams = [NR.encode_node_results(o, "t", [], ["lat"], {"lat": sp.IntInfo["lat"]}) for o, sp in ((oa, a), (ob, b))]
+    merged = stitch.combine_node_results(streams)
+    kind, h = merged["Cumulative"]["Hists"]["lat"]
+    assert (h.InfoMin, h.InfoMax) == (0, 6000)
+    ref = stitch.BasicHist(0, 6000)
+    assert (h.NumBuckets, h.BucketSize) == (ref.NumBuckets, ref.BucketSize) == (1001, 6)
+    # every accepted value of both nodes is still counted, in the bucket of its node-side bucket start
+    assert h.Count == oa.Cumulative.Hists["lat"].Count + ob.Cumulative.Hists["lat"].Count == sum(h.Values)
+    want = [0] * len(h.Values)
+    for o in (oa, ob):
+        for start, cnt in o.Cumulative.Hists["lat"].IntBuckets.items():
+            want[min(start // 6, len(want) - 1)] += cnt
+    assert h.Values == want
+
+
+def test_multihist_results_travel_as_multihistcompat():
+    from sybil_b200 import stitch
+    whole, a, b = _halves(seed=7)
+    info = {"lat": whole.IntInfo["lat"]}
+    q = Q(whole, groups=["host"], aggs=["lat"], op="hist", loghist=True)
+    o = run_oracle(whole, q)
+    raw = NR.encode_node_results(o, "t", ["host"], ["lat"], info, loghist=True)
+    back = gob.decode(raw)
+    assert back["QuerySpec"]["QueryParams"]["Aggregations"][0]["HistType"] == "multi"
+    lay = stitch.multi_layout(*info["lat"])
+    for k, r in o.Results.items():
+        v = back["QuerySpec"]["QueryResults"]["Results"][k]["Hists"]["lat"]
+        assert v["__type__"] == NR.MULTI_NAME and v["MultiHist"] == v["Histogram"]
+        m = v["MultiHist"]
+        assert m["Count"] == r.Hists["lat"].Count and m["Avg"] == r.Hists["lat"].Avg and len(m["Subhists"]) == len(lay)
+        flat = []
+        for sh, (lo, hi) in zip(m["Subhists"], lay):
+            c = sh["BasicHist"]["BasicHistCachedInfo"]
+            assert (c["Info"].get("Min", 0), c["Info"].get("Max", 0)) == (lo, hi)
+            flat += c.get("Values", [])
+        assert flat == [int(x) for x in r.Hists["lat"].Values] and sum(flat) == r.Hists["lat"].Count
+    # and the aggregator merges two such streams into BasicHists over the union range
+    merged = stitch.combine_node_results([raw, raw])
+    for k, r in o.Results.items():
+        kind, h = merged["Results"][k]["Hists"]["lat"]
+        assert kind == "basic" and h.Count == 2 * r.Hists["lat"].Count == sum(h.Values)
