@@ -37,7 +37,7 @@ def looks_like_block(name):
 class TableInfo:
     def __init__(self, name, key_table, int_info, block_dirs):
         self.name = name
-        self.key_table = key_table      # [(column name, SG_COL_INT | SG_COL_STR | 0)] by slot
+        self.key_table = key_table      # [(column name, SG_COL_INT | SG_COL_STR | SG_COL_SET | 0)] by slot
         self.IntInfo = int_info         # column name -> (Min, Max)
         self.block_dirs = block_dirs    # absolute paths, in the order the reference visits them
 
@@ -51,8 +51,9 @@ def read_table(dbdir, name):
     by_slot = {int(s): n for n, s in t.get("KeyTable", {}).items()}
     types = {int(s): int(v) for s, v in t.get("KeyTypes", {}).items()}
     nslots = (max(by_slot) + 1) if by_slot else 0
-    # record.go:14-19: INT_VAL = 1, STR_VAL = 2 (SET_VAL = 3 is outside this engine's path)
-    key_table = [(by_slot.get(s, "_unused_%d" % s), types.get(s, 0) if types.get(s, 0) in (F.SG_COL_INT, F.SG_COL_STR) else 0)
+    # record.go:14-19: INT_VAL = 1, STR_VAL = 2, SET_VAL = 3
+    key_table = [(by_slot.get(s, "_unused_%d" % s),
+                  types.get(s, 0) if types.get(s, 0) in (F.SG_COL_INT, F.SG_COL_STR, F.SG_COL_SET) else 0)
                  for s in range(nslots)]
     int_info = {by_slot[int(s)]: (int(ii.get("Min", 0)), int(ii.get("Max", 0)))
                 for s, ii in t.get("IntInfo", {}).items() if int(s) in by_slot}
