@@ -1118,6 +1118,7 @@ struct GroupDim {  // one axis of the dense slot space
   int col = -1;
   bool is_str = false;
   bool is_time = false;
+  bool is_weight = false;  // the hidden axis of a weighted query (OPTS.WEIGHT_COL): folded away before the result
   uint32_t radix = 1, stride = 1;
 };
 
@@ -1125,6 +1126,7 @@ struct ResultGroup {
   std::vector<uint64_t> key;
   std::string skey;
   int64_t count = 0;
+  int64_t samples = -1;  // Result.Samples when it differs from Count (weighted queries); -1: == count
   // per aggregation a: agg[3a] = hist Count, agg[3a+1] = exact sum, agg[3a+2] = max above info_max
   // (one allocation per group: a high-cardinality result holds a million of these)
   std::vector<int64_t> agg;
@@ -1167,6 +1169,8 @@ struct sg_result {
   std::vector<uint32_t> order;
   int64_t ngroups_total = 0;
   std::unordered_map<int64_t, std::unique_ptr<ResultGroup>> cache;
+  // weighted queries: rows (Result.Samples) per dense slot — Count holds the weights' sum (aggregate.go:202-203)
+  std::vector<uint64_t> samples;
 };
 
 struct sg_query {
@@ -1178,6 +1182,8 @@ struct sg_query {
   std::vector<sg_filter_desc> filters;
   std::vector<std::string> filter_strs;
   std::vector<sg_group_desc> groups;
+  // the group columns the PLAN scans: `groups`, plus the weight column of a weighted query as a last, hidden axis
+  std::vector<sg_group_desc> pgroups;
   std::vector<sg_agg_desc> aggs;
   std::vector<std::vector<uint32_t>> luts;  // per filter (host copy)
   std::vector<int64_t> lut_bits;
@@ -1510,7 +1516,28 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   memset(&P, 0, sizeof(P));
   q->hashg = false;
   P.nfilters = (int32_t)q->filters.size();
-  P.ngroups = (int32_t)q->groups.size();
+  // Weighted queries (OPTS.WEIGHT_COL, aggregate.go:68,100-102,202-203; hist_basic.go:111-151): Count += weight,
+  // hist Count += weight, Values[bucket] += weight, mean weighted.  All of these are linear in the weight, so the
+  // scan groups by the weight VALUE as one more (hidden, last) axis — the ordinary int group-by — and the host
+  // folds that axis away with a multiplication per slot (fold_axes).  Rows WITHOUT the weight column would reuse
+  // the previous row's weight in the reference (Q13): such a query is refused when the result is built.
+  q->pgroups = q->groups;
+  const bool weighted = q->d.weight_col_slot >= 0;
+  if (weighted) {
+    if (q->d.weight_col_slot >= t->ncols || t->types[(size_t)q->d.weight_col_slot] != SG_COL_INT) {
+      c->set_err("query: the weight column must be an int column");
+      return SG_ERR_INVALID;
+    }
+    if (q->pgroups.size() >= SG_MAX_GROUPS) {
+      c->set_err("query: a weighted query takes one group axis: at most SG_MAX_GROUPS - 1 group columns");
+      return SG_ERR_UNSUPPORTED;
+    }
+    sg_group_desc wg;
+    wg.col_slot = q->d.weight_col_slot;
+    wg.col_type = SG_COL_INT;
+    q->pgroups.push_back(wg);
+  }
+  P.ngroups = (int32_t)q->pgroups.size();
   P.naggs = (int32_t)q->aggs.size();
   P.ncolslots = t->ncols;
   P.hist_mode = q->d.op_mode == SG_MODE_HIST;
@@ -1521,9 +1548,10 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   // ---- slot space ------------------------------------------------------------
   q->dims.clear();
   uint64_t stride = 1;
-  for (size_t i = 0; i < q->groups.size(); i++) {
+  for (size_t i = 0; i < q->pgroups.size(); i++) {
     GroupDim gd;
-    gd.col = q->groups[i].col_slot;
+    gd.col = q->pgroups[i].col_slot;
+    gd.is_weight = weighted && i + 1 == q->pgroups.size();
     if (!col_ok(gd.col)) {
       c->set_err("query: group column out of range");
       return SG_ERR_INVALID;
@@ -1822,7 +1850,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   {
     std::vector<int> pcols;
     for (int i = 0; i < P.nfilters; i++) pcols.push_back(q->filters[(size_t)i].col_slot);
-    for (int i = 0; i < P.ngroups; i++) pcols.push_back(q->groups[(size_t)i].col_slot);
+    for (int i = 0; i < P.ngroups; i++) pcols.push_back(q->pgroups[(size_t)i].col_slot);
     for (int i = 0; i < P.naggs; i++) pcols.push_back(q->aggs[(size_t)i].col_slot);
     if (time_mode) pcols.push_back(P.time_col);
     for (uint32_t b : list) {
@@ -2372,6 +2400,7 @@ static void group_key(const sg_query* q, uint32_t s, ResultGroup& g, int64_t* tb
       if (tbucket) *tbucket = (P.time_first + (int64_t)code - 1) * P.time_bucket;
       continue;
     }
+    if (d.is_weight) continue;  // (folded away: every live slot has code 0 here)
     if (code == 0)
       g.key.push_back(SG_MISSING_KEY);
     else if (d.is_str)
@@ -2383,11 +2412,13 @@ static void group_key(const sg_query* q, uint32_t s, ResultGroup& g, int64_t* tb
   }
   g.skey = render_key(q, g.key);
 }
-static void make_group(const sg_query* q, const uint64_t* h, uint32_t s, ResultGroup& g, int64_t* tbucket) {
+static void make_group(const sg_query* q, const uint64_t* h, uint32_t s, ResultGroup& g, int64_t* tbucket,
+                       const std::vector<uint64_t>* samples = nullptr) {
   const Plan& P = q->plan;
   const int naggs = P.naggs;
   init_group(g, naggs);
   g.count = (int64_t)h[q->off_count + s];
+  if (samples && s < samples->size()) g.samples = (int64_t)(*samples)[s];
   group_key(q, s, g, tbucket);
   const bool want_max = P.hist_mode || q->d.hist_kind == SG_HIST_MULTI;
   for (int a = 0; a < naggs; a++) {
@@ -2432,7 +2463,7 @@ static int build_result_topk(sg_query* q, sg_result** out) {
   const int naggs = P.naggs, ob = q->d.order_by_agg;
   const int64_t limit = q->d.limit;
   if (P.time_col >= 0 || P.hist_mode || q->d.hist_kind == SG_HIST_MULTI) return 1;
-  if (!q->repl.empty()) return 1;  // StrReplace folds groups on the host before anything is ordered
+  if (!q->repl.empty() || q->d.weight_col_slot >= 0) return 1;  // StrReplace / weights fold slots on the host first
   if (limit <= 0 || limit > 65536 || ob == SG_ORDER_NONE || q->d.order_asc) return 1;
   if (P.nslots < (1u << 17) || q->h_acc_valid || getenv("SG_NO_GPU_TOPK")) return 1;
   const unsigned cap = (unsigned)limit + 8192u;
@@ -2551,13 +2582,13 @@ static int build_result_topk(sg_query* q, sg_result** out) {
   r->q = q;
   r->layouts = q->layouts;
   r->hist_mode = false;
-  r->ngroups_cols = P.ngroups;
+  r->ngroups_cols = (int)q->groups.size();
   r->naggs = naggs;
   r->broken = q->broken_staged + (int64_t)scal[1];
   r->skipped = q->skipped;
   init_group(r->total, naggs);
   r->total.skey = "TOTAL";
-  for (int i = 1; i < P.ngroups; i++) r->total.skey += "\t";
+  for (int i = 1; i < (int)q->groups.size(); i++) r->total.skey += "\t";
   r->has_total_hists = true;
   r->total.count = (int64_t)T.count;
   for (int a = 0; a < naggs; a++) {
@@ -2583,36 +2614,79 @@ static int build_result_topk(sg_query* q, sg_result** out) {
   return SG_OK;
 }
 
+// Host-side folds of the dense accumulators before the result is built.
+//
 // StrReplace: strings of a group column that rewrite to the same text are one group in the reference (the block's
 // string table is rewritten before any row is read, column_store_io.go:529-547).  The scan grouped by the original
-// global ids; here every dense slot whose code on a rewritten axis is not its class representative is added onto
-// the representative's slot (counts, hist counts, sums, bucket counters: +; max: max) and cleared.
-static int fold_replaced(sg_query* q, uint64_t* h, size_t have) {
+// global ids; every dense slot whose code on a rewritten axis is not its class representative is added onto the
+// representative's slot (counts, hist counts, sums, bucket counters: +; max: max) and cleared.
+//
+// Weights (OPTS.WEIGHT_COL): the scan grouped by the weight value as a hidden last axis (make_plan); the slots of
+// weight w are multiplied by w and added onto code 0 of that axis — Count / hist Count / Values[] += weight
+// (aggregate.go:203, hist_basic.go:111-116,146), exact sum += value * weight; Result.Samples keeps the rows.
+// A row without the weight column would reuse the previous row's weight (Q13, aggregate.go:68,100-102): refused.
+static int fold_axes(sg_query* q, uint64_t* h, size_t have, sg_result* r, int64_t* matched_rows) {
   const Plan& P = q->plan;
   sg_ctx* c = q->ctx;
   for (size_t di = 0; di < q->dims.size(); di++) {
     const GroupDim& d = q->dims[di];
-    if (!d.is_str || d.is_time) continue;
-    auto it = q->repl.find(d.col);
-    if (it == q->repl.end()) continue;
-    const auto& canon = it->second.canon;
-    if (canon.size() + 1 != (size_t)d.radix) {
-      c->set_err("query: the dictionary of a StrReplace column grew after sg_query_set_str_replace");
-      return SG_ERR_STATE;
+    if (d.is_time) continue;
+    const std::vector<uint32_t>* canon = nullptr;
+    std::vector<uint64_t> wmul;  // weight axis: multiplier per code - 1
+    if (d.is_weight) {
+      const std::vector<int64_t>& vals = q->merged ? q->m_ints[di] : q->table->idict[(size_t)d.col].vals;
+      if (vals.size() + 1 != (size_t)d.radix) {
+        c->set_err("query: the weight column's value dictionary changed under the query");
+        return SG_ERR_STATE;
+      }
+      wmul.assign(vals.begin(), vals.end());
+      const uint64_t* cnt = h + q->off_count;
+      r->samples.assign(P.nslots, 0);
+      int64_t rows = 0;
+      for (uint32_t s = 0; s < P.nslots; s++) {
+        if (!cnt[s]) continue;
+        const uint32_t code = (s / d.stride) % d.radix;
+        if (code == 0) {
+          c->set_err("query: rows without the weight column (the reference reuses the previous row's weight, "
+                     "aggregate.go:68,100-102): not reproduced by this engine");
+          return SG_ERR_UNSUPPORTED;
+        }
+        r->samples[s - code * d.stride] += cnt[s];
+        rows += (int64_t)cnt[s];
+      }
+      if (matched_rows) *matched_rows = rows;
+    } else if (d.is_str) {
+      auto it = q->repl.find(d.col);
+      if (it == q->repl.end()) continue;
+      canon = &it->second.canon;
+      if (canon->size() + 1 != (size_t)d.radix) {
+        c->set_err("query: the dictionary of a StrReplace column grew after sg_query_set_str_replace");
+        return SG_ERR_STATE;
+      }
+    } else {
+      continue;
     }
     auto fold_array = [&](size_t off, size_t per_slot, bool is_max) {
       if (off + (size_t)P.nslots * per_slot > have) return;  // not read back: the result does not use it
       for (uint32_t s = 0; s < P.nslots; s++) {
         const uint32_t code = (s / d.stride) % d.radix;
-        if (code == 0 || canon[code - 1] == code - 1) continue;
-        const uint32_t to = s - (code - 1 - canon[code - 1]) * d.stride;
+        if (code == 0) continue;
+        uint32_t to;
+        uint64_t mul = 1;
+        if (canon) {
+          if ((*canon)[code - 1] == code - 1) continue;
+          to = s - (code - 1 - (*canon)[code - 1]) * d.stride;
+        } else {
+          to = s - code * d.stride;
+          mul = wmul[code - 1];
+        }
         uint64_t* src = h + off + (size_t)s * per_slot;
         uint64_t* dst = h + off + (size_t)to * per_slot;
         for (size_t k = 0; k < per_slot; k++) {
           if (is_max)
             dst[k] = (uint64_t)std::max((int64_t)dst[k], (int64_t)src[k]), src[k] = (uint64_t)INT64_MIN;
           else
-            dst[k] += src[k], src[k] = 0;
+            dst[k] += src[k] * mul, src[k] = 0;  // (wrapping, like the reference's int64 arithmetic)
         }
       }
     };
@@ -2623,7 +2697,7 @@ static int fold_replaced(sg_query* q, uint64_t* h, size_t have) {
       const uint32_t nv = q->layouts[(size_t)a].nvals_total;
       if (nv) fold_array(q->off_buckets[(size_t)a], nv, false);
     }
-    fold_array(q->off_count, 1, false);  // last: nothing above reads it, but keep the order obvious
+    fold_array(q->off_count, 1, false);
   }
   return SG_OK;
 }
@@ -2667,24 +2741,26 @@ int build_result(sg_query* q, sg_result** out) {
     q->d2h_bytes += (int64_t)have * 8;
     h = (const uint64_t*)r->pin;
   }
-  if (!q->repl.empty()) {
-    if (q->merged) {
+  int64_t w_rows = -1;  // weighted queries: matched ROWS (MatchedCount counts records, aggregate.go:117)
+  if (!q->repl.empty() || q->d.weight_col_slot >= 0) {
+    if (q->merged && !q->repl.empty()) {
       c->set_err("query: StrReplace cannot follow a cross-GPU merge over differing dictionaries (seed them)");
       return SG_ERR_UNSUPPORTED;
     }
-    const int rc = fold_replaced(q, const_cast<uint64_t*>(h), have);  // (h is this call's own copy of the read-back)
+    // (h is this call's own copy of the read-back)
+    const int rc = fold_axes(q, const_cast<uint64_t*>(h), have, r.get(), &w_rows);
     if (rc != SG_OK) return rc;
   }
   r->layouts = q->layouts;
   r->hist_mode = P.hist_mode != 0;
-  r->ngroups_cols = P.ngroups;
+  r->ngroups_cols = (int)q->groups.size();
   r->naggs = naggs;
   r->matched = (int64_t)h[0];
   r->broken = q->broken_staged + (int64_t)h[1];
   r->skipped = q->skipped;
   init_group(r->total, naggs);
   r->total.skey = "TOTAL";
-  for (int i = 1; i < P.ngroups; i++) r->total.skey += "\t";
+  for (int i = 1; i < (int)q->groups.size(); i++) r->total.skey += "\t";
   r->has_total_hists = !time_mode;
   const uint64_t* cnt = h + q->off_count;
 
@@ -2803,7 +2879,8 @@ int build_result(sg_query* q, sg_result** out) {
     r->ngroups_total = live;
     // without a time column every matched row is counted in exactly one group, so the kernel does not
     // count matches separately (MatchedCount, aggregate.go:117)
-    r->matched = r->total.count;
+    r->matched = w_rows >= 0 ? w_rows : r->total.count;
+    if (w_rows >= 0) r->total.samples = w_rows;
     r->lazy = true;
     r->acc_have = have;
     if (!r->pin) {
@@ -2823,7 +2900,7 @@ int build_result(sg_query* q, sg_result** out) {
     if (cnt[s] == 0) continue;
     ResultGroup g;
     int64_t tbucket = 0;
-    make_group(q, h, s, g, &tbucket);
+    make_group(q, h, s, g, &tbucket, r->samples.empty() ? nullptr : &r->samples);
     // Results[key]: Count/Samples only (aggregate.go:156-171); hists live per bucket
     auto it = by_key.find(g.key);
     if (it == by_key.end()) {
@@ -2837,13 +2914,18 @@ int build_result(sg_query* q, sg_result** out) {
     }
     r->groups[it->second].count += g.count;
     r->total.count += g.count;
+    if (g.samples >= 0) {  // weighted: Samples are rows
+      ResultGroup& bg = r->groups[it->second];
+      bg.samples = (bg.samples < 0 ? 0 : bg.samples) + g.samples;
+      r->total.samples = (r->total.samples < 0 ? 0 : r->total.samples) + g.samples;
+    }
     auto& sl = slices[tbucket];
     if (!sl) {
       sl.reset(new sg_result());
       sl->q = q;
       sl->layouts = q->layouts;
       sl->hist_mode = r->hist_mode;
-      sl->ngroups_cols = P.ngroups;
+      sl->ngroups_cols = (int)q->groups.size();
       sl->naggs = naggs;
       init_group(sl->total, naggs);
     }
@@ -2879,10 +2961,6 @@ sg_query* sg_query_begin(sg_ctx* c, sg_table* t, const sg_query_desc* d) {
   if (d->nfilters < 0 || d->nfilters > SG_MAX_FILTERS || d->ngroups < 0 || d->ngroups > SG_MAX_GROUPS ||
       d->naggs < 0 || d->naggs > SG_MAX_AGGS) {
     c->set_err("sg_query_begin: too many filters / groups / aggregations for this build");
-    return nullptr;
-  }
-  if (d->weight_col_slot >= 0) {
-    c->set_err("sg_query_begin: weighted queries (OPTS.WEIGHT_COL) are not supported in this build");
     return nullptr;
   }
   if (!t) {
@@ -3003,6 +3081,7 @@ int sg_query_run(sg_query* q) {
   };
   for (auto& f : q->filters) want(f.col_slot);
   for (auto& g : q->groups) want(g.col_slot);
+  if (q->d.weight_col_slot >= 0) want(q->d.weight_col_slot);
   for (auto& a : q->aggs) want(a.col_slot);
   if (q->d.time_col_slot >= 0 && q->d.time_bucket > 0) want(q->d.time_col_slot);
   q->skipped = q->stream_skipped;
@@ -3606,7 +3685,7 @@ static ResultGroup* pick_group(sg_result* r, int64_t i) {
     auto it = r->cache.find(i);
     if (it == r->cache.end()) {
       std::unique_ptr<ResultGroup> g(new ResultGroup());
-      make_group(r->q, r->accp, r->order[(size_t)i], *g, nullptr);
+      make_group(r->q, r->accp, r->order[(size_t)i], *g, nullptr, r->samples.empty() ? nullptr : &r->samples);
       it = r->cache.emplace(i, std::move(g)).first;
     }
     return it->second.get();
@@ -3621,7 +3700,7 @@ int sg_result_group(sg_result* r, int64_t i, uint64_t* key_out, int64_t* count, 
   if (key_out)
     for (size_t k = 0; k < g->key.size(); k++) key_out[k] = g->key[k];
   if (count) *count = g->count;
-  if (samples) *samples = g->count;  // unweighted: Samples == Count (aggregate.go:202-203)
+  if (samples) *samples = g->samples >= 0 ? g->samples : g->count;  // unweighted: Samples == Count (aggregate.go:202-203)
   return SG_OK;
 }
 int sg_result_group_key(sg_result* r, int64_t i, const char** bytes, int64_t* len) {

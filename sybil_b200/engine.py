@@ -35,6 +35,7 @@ class _Flags:
         self.TIME_COL = ""
         self.TIME_BUCKET = 0
         self.LIMIT = 100
+        self.WEIGHT_COL = ""  # config.go:81; OPTS.WEIGHT_COL / WEIGHT_COL_ID follow from it (cmd_query.go:317-320)
 
 
 FLAGS = _Flags()
@@ -328,7 +329,7 @@ def make_query_desc(KeyTable, KeyTypes, IntInfo, qs):
     d.filters = C.cast(fl, C.POINTER(F.sg_filter_desc))
     d.groups = C.cast(gr, C.POINTER(F.sg_group_desc))
     d.aggs = C.cast(ag, C.POINTER(F.sg_agg_desc))
-    d.weight_col_slot = -1
+    d.weight_col_slot = KeyTable[FLAGS.WEIGHT_COL] if FLAGS.WEIGHT_COL else -1
     # SortResults(OrderBy, OrderAsc) (aggregate.go:497-525)
     order = getattr(qs, "OrderBy", "$COUNT")
     if order == "$COUNT":

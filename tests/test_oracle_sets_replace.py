@@ -119,3 +119,29 @@ def test_set_columns_round_trip_through_block_directories(tmp_path):
         if threshold == 4:  # the Values form marks rows below len(Values) populated: "nin" also takes the empty sets
             n = sum(1 for r in s.blocks[0].cols if r.col_type == SET and getattr(r, "set_nvalues", 0) > 0)
             assert n == 1
+
+
+def test_weights_in_the_oracle_match_a_row_by_row_evaluation():
+    # OPTS.WEIGHT_COL (aggregate.go:68,100-102,202-203; hist_basic.go:111-116): Count += weight, Samples = rows,
+    # hist Count / bucket counters += weight, exact sum += value * weight; and the carry-over of Q13
+    rng = np.random.default_rng(4)
+    n = 3000
+    s = Spec([("v", INT), ("host", STR), ("w", INT)])
+    rows = {"v": rng.integers(0, 1000, n), "host": np.array(["h%d" % x for x in rng.integers(0, 4, n)]),
+            "w": rng.choice(np.asarray([1, 2, 5, 10]), n)}
+    valid = {"w": rng.random(n) > 0.2}
+    s.add_rows(rows, valid, block_rows=1100)
+    o = run_oracle(s, Q(s, groups=["host"], aggs=["v"], op="hist", weight_col="w"))
+    cnt, smp, sm = Counter(), Counter(), Counter()
+    for start in range(0, n, 1100):
+        weight = 1  # declared outside the row loop of one block: carries over to rows without the column
+        for i in range(start, min(n, start + 1100)):
+            if valid["w"][i]:
+                weight = int(rows["w"][i])
+            k = rows["host"][i] + "\t"
+            cnt[k] += weight
+            smp[k] += 1
+            sm[k] += int(rows["v"][i]) * weight
+    assert o.MatchedCount == n
+    assert {k: (r.Count, r.Samples, r.Hists["v"].Count, r.Hists["v"].ExactSum, int(r.Hists["v"].Values.sum()))
+            for k, r in o.Results.items()} == {k: (cnt[k], smp[k], cnt[k], sm[k], cnt[k]) for k in cnt}

@@ -76,8 +76,9 @@ class Q:
 
     def __init__(self, spec, int_filters=(), str_filters=(), groups=(), aggs=(), op="avg", loghist=False,
                  time_col=None, time_bucket=0, hist_bucket=0, order_by="$COUNT", order_asc=False, limit=0,
-                 set_filters=(), str_replace=None):
+                 set_filters=(), str_replace=None, weight_col=None):
         self.spec = spec
+        self.weight_col = weight_col  # FLAGS.WEIGHT_COL
         self.set_filters = list(set_filters)      # (column, "in" | "nin", tag)
         self.str_replace = dict(str_replace or {})  # column -> (pattern, replacement): FLAGS.STR_REPLACE
         self.order_by, self.order_asc, self.limit = order_by, order_asc, limit
@@ -93,6 +94,7 @@ class Q:
         if self.time_col:
             E.FLAGS.TIME_COL = self.time_col
             E.FLAGS.TIME_BUCKET = self.time_bucket
+        E.FLAGS.WEIGHT_COL = self.weight_col or ""
 
     def query_spec(self):
         s = self.spec
@@ -142,7 +144,7 @@ def run_gpu(spec, q, table=None):
             ls.Str(c)
         for c, _, _ in q.set_filters:
             ls.Set(c)
-        for c in q.groups + q.aggs:
+        for c in q.groups + q.aggs + ([q.weight_col] if q.weight_col else []):
             ls.Int(c)
         table.LoadAndQueryRecords(ls, qs)
         return qs
