@@ -41,13 +41,25 @@ def build_gpu(force=False):
     jobs = [(common + ["-DSG_THREADS=512", "-c", srcs[0], "-o", os.path.join(bdir, "sg_kernels_w16.o")]),
             (common + ["-DSG_THREADS=256", "-c", srcs[0], "-o", os.path.join(bdir, "sg_kernels_w8.o")]),
             (common + ["-c", srcs[1], "-o", os.path.join(bdir, "sg_runtime.o")])]
-    procs = [(cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for cmd in jobs]
+    # an object whose own sources are older than it is kept (the two kernel units take minutes each); the flags
+    # it was built with are part of the check
+    hdrs = [os.path.join(CSRC, "sg_internal.h"), os.path.join(ROOT, "include", "sybilgpu.h")]
+    obj_deps = [[srcs[0]] + hdrs, [srcs[0]] + hdrs, [srcs[1], os.path.join(CSRC, "sg_hist.h")] + hdrs]
+    stale = []
+    for cmd, deps_o in zip(jobs, obj_deps):
+        stamp = cmd[-1] + ".cmd"
+        same_cmd = os.path.exists(stamp) and open(stamp).read() == " ".join(cmd)
+        stale.append(force or not same_cmd or _newer(cmd[-1], deps_o))
+    todo = [cmd for cmd, st in zip(jobs, stale) if st]
+    procs = [(cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for cmd in todo]
     for cmd, p in procs:
         log, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), log))
         if os.environ.get("SG_BUILD_VERBOSE"):
             print(log)
+        with open(cmd[-1] + ".cmd", "w") as f:
+            f.write(" ".join(cmd))
     _run([nvcc] + NVCC_ARCH + ["-shared", "-o", out] + [j[-1] for j in jobs] + ["-ldl"])
     return out
 

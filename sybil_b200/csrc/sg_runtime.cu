@@ -1239,6 +1239,11 @@ struct sg_query {
   // accumulators as read back right behind the kernel (small plans): spares build_result a blocking copy
   std::vector<uint64_t> h_acc;
   bool h_acc_valid = false;
+  // ... larger ones (tens of KB to 4 MiB: a C3-shaped result is 0.94 MB) land in a pinned buffer of the context's
+  // pool that the result then OWNS — no copy out of the scratch area (that copy cost as much as the D2H itself)
+  char* h_pin = nullptr;
+  size_t h_pin_bytes = 0;
+  bool h_pin_valid = false;
   std::vector<std::vector<std::string>> m_strs;
   std::vector<std::vector<int64_t>> m_ints;
   // StrReplace (sg_query_set_str_replace): per str column slot the rewritten text of every global string and the
@@ -2241,10 +2246,26 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
     return SG_ERR_CUDA;
   }
   CUDA_TRY(c, cudaEventRecord(q->ev1, c->stream));
-  CUDA_TRY(c, cudaMemcpyAsync(hp + off_acc, q->d_acc, acc_back, cudaMemcpyDeviceToHost, c->stream));
+  const bool to_pin = acc_back == q->acc_words * 8 && acc_back >= ((size_t)32 << 10);
+  q->h_pin_valid = false;
+  if (to_pin) {
+    if (q->h_pin && q->h_pin_bytes < acc_back) {
+      c->pin_put(q->h_pin, q->h_pin_bytes);
+      q->h_pin = nullptr;
+    }
+    if (!q->h_pin) q->h_pin = c->pin_get(acc_back, &q->h_pin_bytes);
+  }
+  char* const back = to_pin && q->h_pin ? q->h_pin : hp + off_acc;
+  CUDA_TRY(c, cudaMemcpyAsync(back, q->d_acc, acc_back, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  q->h_acc.assign((const uint64_t*)(hp + off_acc), (const uint64_t*)(hp + off_acc + acc_back));
-  q->h_acc_valid = acc_back == q->acc_words * 8;
+  if (back == q->h_pin) {
+    q->h_acc.assign((const uint64_t*)back, (const uint64_t*)back + 8);  // the scalars (sg_query_run reads them)
+    q->h_acc_valid = false;
+    q->h_pin_valid = true;
+  } else {
+    q->h_acc.assign((const uint64_t*)back, (const uint64_t*)(back + acc_back));
+    q->h_acc_valid = acc_back == q->acc_words * 8;
+  }
   q->d2h_bytes += (int64_t)acc_back;
   float ms = 0;
   CUDA_TRY(c, cudaEventElapsedTime(&ms, q->ev0, q->ev1));
@@ -2465,7 +2486,7 @@ static int build_result_topk(sg_query* q, sg_result** out) {
   if (P.time_col >= 0 || P.hist_mode || q->d.hist_kind == SG_HIST_MULTI) return 1;
   if (!q->repl.empty() || q->d.weight_col_slot >= 0) return 1;  // StrReplace / weights fold slots on the host first
   if (limit <= 0 || limit > 65536 || ob == SG_ORDER_NONE || q->d.order_asc) return 1;
-  if (P.nslots < (1u << 17) || q->h_acc_valid || getenv("SG_NO_GPU_TOPK")) return 1;
+  if (P.nslots < (1u << 17) || q->h_acc_valid || q->h_pin_valid || getenv("SG_NO_GPU_TOPK")) return 1;
   const unsigned cap = (unsigned)limit + 8192u;
   const size_t w = 2 + 2 * (size_t)naggs;
   const size_t off_tot = 0, off_hist = 512, off_offs = off_hist + 8192, off_scal = off_offs + 512, off_rows = off_scal + 128;
@@ -2723,7 +2744,14 @@ int build_result(sg_query* q, sg_result** out) {
   r->q = q;
   std::vector<uint64_t> hv;
   const uint64_t* h = nullptr;
-  if (q->h_acc_valid && q->h_acc.size() == q->acc_words) {
+  if (q->h_pin_valid && q->h_pin) {  // read back behind the kernel into a pinned buffer: the result takes it over
+    r->pin = q->h_pin;
+    r->pin_bytes = q->h_pin_bytes;
+    q->h_pin = nullptr;
+    q->h_pin_valid = false;
+    have = q->acc_words;
+    h = (const uint64_t*)r->pin;
+  } else if (q->h_acc_valid && q->h_acc.size() == q->acc_words) {
     hv.swap(q->h_acc);
     q->h_acc_valid = false;
     have = q->acc_words;
@@ -2993,6 +3021,7 @@ void sg_query_free(sg_query* q) {
   if (!q) return;
   cudaSetDevice(q->ctx->device);
   free_device(q);
+  if (q->h_pin) q->ctx->pin_put(q->h_pin, q->h_pin_bytes);
   if (q->ev0) cudaEventDestroy(q->ev0);
   if (q->ev1) cudaEventDestroy(q->ev1);
   delete q;
@@ -3431,6 +3460,7 @@ int sg_query_allreduce(sg_query* q) {
   if (!c->comm || c->nranks <= 1) return SG_OK;
   cudaSetDevice(c->device);
   q->h_acc_valid = false;  // the device copy is about to change
+  q->h_pin_valid = false;
   // Small plans (the usual case: a few hundred groups): ONE collective.  Every rank writes a header
   // (block counters, signature of its axes) into its scalars and all-gathers its whole accumulator
   // array; each rank then reduces the gathered copies on the host (sum region, max region) — or, if
