@@ -1244,6 +1244,11 @@ struct sg_query {
   char* h_pin = nullptr;
   size_t h_pin_bytes = 0;
   bool h_pin_valid = false;
+  uint64_t axes_sig = 0, axes_sig_version = 0;  // axes_signature(): valid for table version axes_sig_version - 1
+  size_t axes_size = 0;
+  // multi-GPU: aggregations whose hist Count the kernel skipped on THIS rank (== Count here); the count array is
+  // copied over the hist-Count array behind the scan so that the element-wise merge sums real values
+  std::vector<char> hc_fill;
   std::vector<std::vector<std::string>> m_strs;
   std::vector<std::vector<int64_t>> m_ints;
   // StrReplace (sg_query_set_str_replace): per str column slot the rewritten text of every global string and the
@@ -3141,7 +3146,9 @@ int sg_query_run(sg_query* q) {
   // array covering every row whose exact extents lie inside the accepted range: the kernel then
   // skips that reduction (accumulators-in-global plans) and the result takes Count
   q->hc_is_count.assign((size_t)q->plan.naggs, 0);
-  if (q->plan.acc_repl == 0 && c->nranks <= 1) {  // multi-GPU: ranks would have to agree first
+  q->hc_fill.assign((size_t)q->plan.naggs, 0);
+  const bool multi = c->comm != nullptr && c->nranks > 1;
+  if (q->plan.acc_repl == 0) {  // (multi-GPU: the proof is per rank — see hc_fill)
     for (int a = 0; a < q->plan.naggs; a++) {
       const KAgg& ka = q->plan.aggs[a];
       const int64_t amax = std::min(ka.reject_hi, ka.info_max);
@@ -3154,7 +3161,8 @@ int sg_query_run(sg_query* q) {
           break;
         }
       }
-      q->hc_is_count[(size_t)a] = ok ? 1 : 0;
+      q->hc_is_count[(size_t)a] = ok && !multi ? 1 : 0;
+      q->hc_fill[(size_t)a] = ok && multi ? 1 : 0;
       q->plan.aggs[a]._pad = ok ? 1u : 0u;
     }
   }
@@ -3193,6 +3201,12 @@ int sg_query_run(sg_query* q) {
     }
     list.swap(next);
   }
+  // multi-GPU: hist Counts this rank's kernel did not accumulate (they equal Count on this rank) are filled in
+  // from the count array, so that every rank's array holds real values for the element-wise merge
+  for (int a = 0; a < q->plan.naggs; a++)
+    if ((size_t)a < q->hc_fill.size() && q->hc_fill[(size_t)a])
+      CUDA_TRY(c, cudaMemcpyAsync(q->d_acc + q->off_hcount[(size_t)a], q->d_acc + q->off_count, (size_t)q->plan.nslots * 8,
+                                  cudaMemcpyDeviceToDevice, c->stream));
   q->last_list = list;
   q->ran = true;
   q->host_run_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_planned).count();
@@ -3454,6 +3468,25 @@ corrupt:
   return SG_ERR_NCCL;
 }
 
+// signature (and serialised size) of the query's axes; hashing a 1M-string dictionary costs ~15 ms, so it is kept
+// per (table version) — the axes of an un-merged query only change when blocks are staged
+static uint64_t axes_signature(sg_query* q, size_t* size_out) {
+  if (!q->merged && q->axes_sig_version == q->table->version + 1) {
+    if (size_out) *size_out = q->axes_size;
+    return q->axes_sig;
+  }
+  std::vector<uint8_t> axes;
+  serialise_axes(q, axes);
+  const uint64_t sig = fnv64(0xcbf29ce484222325ull, axes.data(), axes.size());
+  if (!q->merged) {
+    q->axes_sig = sig;
+    q->axes_size = axes.size();
+    q->axes_sig_version = q->table->version + 1;
+  }
+  if (size_out) *size_out = axes.size();
+  return sig;
+}
+
 int sg_query_allreduce(sg_query* q) {
   if (!q || !q->ran) return SG_ERR_STATE;
   sg_ctx* c = q->ctx;
@@ -3465,10 +3498,12 @@ int sg_query_allreduce(sg_query* q) {
   // (block counters, signature of its axes) into its scalars and all-gathers its whole accumulator
   // array; each rank then reduces the gathered copies on the host (sum region, max region) — or, if
   // the signatures differ, falls through to the dictionary exchange below with its own copy intact.
-  if (q->acc_words * 8 * (size_t)c->nranks <= ((size_t)2 << 20)) {
-    std::vector<uint8_t> axes;
-    serialise_axes(q, axes);
-    const uint64_t sig = fnv64(0xcbf29ce484222325ull, axes.data(), axes.size());
+  static const bool force_allreduce = getenv("SG_MERGE_ALLREDUCE") != nullptr;  // (tests: the large-plan path at any size)
+  // (measured on 2 B200s, C3's 0.94 MB per rank: all-gather + host reduce 0.46 ms per query on top of the scan, the
+  // all-reduce path below 0.38 ms — the host-reduce path is kept for plans whose gathered copies are a few pages)
+  if (q->acc_words * 8 * (size_t)c->nranks <= ((size_t)256 << 10) && !force_allreduce) {
+    size_t axes_size = 0;
+    const uint64_t sig = axes_signature(q, &axes_size);
     const size_t aw = q->acc_words, nr = (size_t)c->nranks;
     char* hp = c->scratch(64 + aw * 8 * nr);
     uint64_t* d_all = nullptr;
@@ -3483,7 +3518,7 @@ int sg_query_allreduce(sg_query* q) {
     hdr[2] = (uint64_t)q->rows_scanned;
     hdr[3] = (uint64_t)q->blocks_scanned;
     hdr[4] = sig;
-    hdr[5] = (uint64_t)axes.size();
+    hdr[5] = (uint64_t)axes_size;
     hdr[6] = hdr[7] = 0;
     CUDA_TRY(c, cudaMemcpyAsync(q->d_acc + 8, hdr, 64, cudaMemcpyHostToDevice, c->stream));
     ncclResult_t r = g_nccl.AllGather(q->d_acc, d_all, aw * 8, ncclUint8, c->comm, c->stream);
@@ -3494,7 +3529,7 @@ int sg_query_allreduce(sg_query* q) {
     pool_release(c, d_all);
     q->d2h_bytes += (int64_t)(aw * 8 * nr);
     bool agree = true;
-    for (size_t k = 0; k < nr; k++) agree = agree && all[k * aw + 12] == sig && all[k * aw + 13] == (uint64_t)axes.size();
+    for (size_t k = 0; k < nr; k++) agree = agree && all[k * aw + 12] == sig && all[k * aw + 13] == (uint64_t)axes_size;
     // the counters are job totals on either path
     uint64_t tot[4] = {0, 0, 0, 0};
     for (size_t k = 0; k < nr; k++)
@@ -3523,9 +3558,7 @@ int sg_query_allreduce(sg_query* q) {
     CUDA_TRY(c, cudaMemsetAsync(q->d_acc + 8, 0, 64, c->stream));
   }
   // ---- larger plans: element-wise all-reduces (sums: scalars, count, hcount, sum, buckets; max: vmax) --------
-  std::vector<uint8_t> mine;
-  serialise_axes(q, mine);
-  const uint64_t sig = fnv64(0xcbf29ce484222325ull, mine.data(), mine.size());
+  const uint64_t sig = axes_signature(q, nullptr);
   const uint64_t sa = sig & 0x3fffffffull, sb = (sig >> 32) & 0x3fffffffull;
   const uint64_t n = (uint64_t)c->nranks;
   auto ar = [&](const uint64_t* src, uint64_t* dst, size_t cnt, int dtype, int op) -> int {
@@ -3571,6 +3604,20 @@ int sg_query_allreduce(sg_query* q) {
     hc[6] = sb;
     hc[7] = sb * sb;
     uint64_t* hm = (uint64_t*)(hp + 64);
+    // a whole merged array of some size goes straight into a pinned buffer the result will own (no copy out of
+    // the scratch area afterwards: see run_list)
+    bool to_pin = false;
+    if (whole && q->acc_words * 8 >= ((size_t)32 << 10)) {
+      if (q->h_pin && q->h_pin_bytes < q->acc_words * 8) {
+        c->pin_put(q->h_pin, q->h_pin_bytes);
+        q->h_pin = nullptr;
+      }
+      if (!q->h_pin) q->h_pin = c->pin_get(q->acc_words * 8, &q->h_pin_bytes);
+      if (q->h_pin) {
+        hm = (uint64_t*)q->h_pin;
+        to_pin = true;
+      }
+    }
     cudaError_t ce = cudaMemcpyAsync(q->d_acc + 8, hc, 64, cudaMemcpyHostToDevice, c->stream);
     if (ce == cudaSuccess) {
       rc = ar(q->d_acc, d_merged, q->sum_words, ncclUint64, ncclSum);
@@ -3605,8 +3652,13 @@ int sg_query_allreduce(sg_query* q) {
       }
       if (whole) {
         for (int k = 8; k < 16; k++) hm[k] = 0;
-        q->h_acc.assign(hm, hm + q->acc_words);
-        q->h_acc_valid = true;
+        if (to_pin) {
+          q->h_acc.assign(hm, hm + 8);
+          q->h_pin_valid = true;
+        } else {
+          q->h_acc.assign(hm, hm + q->acc_words);
+          q->h_acc_valid = true;
+        }
         q->d2h_bytes += (int64_t)q->acc_words * 8;
       }
       return SG_OK;
