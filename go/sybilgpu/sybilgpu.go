@@ -235,6 +235,7 @@ type Query struct {
 	TimeBucket int64
 	TimeMin    int64
 	TimeMax    int64
+	WeightSlot int32 // OPTS.WEIGHT_COL_ID, -1: unweighted (a zero-valued Query must set -1 explicitly)
 	StrReplace []StrReplaced // OPTS.STR_REPLACEMENTS, one entry per rewritten str column
 }
 
@@ -299,7 +300,7 @@ func (t *Table) Run(q *Query, allreduce bool) (*C.sg_result, error) {
 	d.filters, d.groups, d.aggs = fl, gr, ag
 	d.time_col_slot, d.time_bucket = C.int32_t(q.TimeSlot), C.int64_t(q.TimeBucket)
 	d.time_min, d.time_max = C.int64_t(q.TimeMin), C.int64_t(q.TimeMax)
-	d.weight_col_slot = -1
+	d.weight_col_slot = C.int32_t(q.WeightSlot) // -1: unweighted; rows without the column: SG_ERR_UNSUPPORTED at finish
 	// SortResults(OrderBy, OrderAsc) and FLAGS.LIMIT (ABI v2)
 	d.order_by_agg = C.SG_ORDER_COUNT
 	if spec.OrderBy == "" {
