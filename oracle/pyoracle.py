@@ -6,7 +6,9 @@ the Go sources and must agree on every field.  Same citations as oracle.cpp:
 unpack*Col column_store_io.go:493-609,690-780; filters filter.go:171-250;
 FilterAndAggRecords aggregate.go:56-282; BasicHist hist_basic.go:34-279; MultiHist
 hist_multi.go:22-257; Result.Combine query_spec.go:138-193; CombineResults
-aggregate.go:414-467.
+aggregate.go:414-467; unpackSetCol column_store_io.go:611-688; SetFilter filter.go:252-285;
+weights aggregate.go:68,100-102,202-203 + AddWeightedValue; StrReplace
+column_store_io.go:515-549.
 """
 import math
 import re
@@ -56,12 +58,12 @@ class PyBasicHist:
             self.NumBuckets, self.BucketSize = nb, bs
             self.Values = [0] * (nb + 1)
 
-    def add(self, v):
+    def add(self, v, weight=1, weight_col=False):  # AddWeightedValue, hist_basic.go:101-151
         if v > _i64(self.info[1] * 10) or v < self.info[0]:
             return
-        self.Count += 1
-        self.ExactSum = _i64(self.ExactSum + v)
-        self.Avg = self.Avg + (float(v) - self.Avg) / float(self.Count)
+        self.Count += weight if (weight_col or weight > 1) else 1
+        self.ExactSum = _i64(self.ExactSum + v * weight)
+        self.Avg = self.Avg + _fdiv(float(v) - self.Avg, float(self.Count)) * float(weight)
         self.Max = max(self.Max, v)
         self.Min = min(self.Min, v)
         if not self.pm:
@@ -73,7 +75,7 @@ class PyBasicHist:
         if b < 0:
             self.Underliers.append(v)
             b = 0
-        self.Values[b] += 1
+        self.Values[b] += weight
 
     def combine(self, o):
         for k, v in enumerate(o.Values):
@@ -141,16 +143,16 @@ class PyMultiHist:
                 right = right - size
             self.subs.append(PyBasicHist(mn, right, True))
 
-    def add(self, v):
+    def add(self, v, weight=1, weight_col=False):  # hist_multi.go:48-88
         if v > _i64(self.info[1] * 10) or v < self.info[0]:
             return
-        self.Count += 1
-        self.ExactSum = _i64(self.ExactSum + v)
-        self.Avg = self.Avg + (float(v) - self.Avg) / float(self.Count)
+        self.Count += weight if (weight_col or weight > 1) else 1
+        self.ExactSum = _i64(self.ExactSum + v * weight)
+        self.Avg = self.Avg + _fdiv(float(v) - self.Avg, float(self.Count)) * float(weight)
         self.Max, self.Min = max(self.Max, v), min(self.Min, v)
         for sh in self.subs:
             if sh.info[0] <= v <= sh.info[1]:
-                sh.add(v)
+                sh.add(v, weight, weight_col)
                 break
 
     def combine(self, o):
@@ -224,15 +226,42 @@ def _combine(into, r):
     into.Samples += r.Samples
 
 
+def _set_rows(c, n):
+    """unpackSetCol (column_store_io.go:611-688): per row the tag strings and whether the row has a set; None when
+    the block is broken (a row id beyond the block)."""
+    import numpy as np
+    tags = [[] for _ in range(n)]
+    pop = [False] * n
+    for b in range(len(c.bin_values)):
+        ids = np.asarray(c.record_ids[c.bin_offsets[b]:c.bin_offsets[b + 1]]).astype(np.int64)
+        rows = np.cumsum(ids) if c.delta_ids else ids
+        for r in rows:
+            if r >= n:
+                return None
+            tags[int(r)].append(c.string_table[int(c.bin_values[b])])
+            pop[int(r)] = True
+    nv = int(getattr(c, "set_nvalues", 0))
+    if nv > n:
+        return None
+    for r in range(nv):  # the non-bucketed file form lists the row: populated, empty set or not
+        pop[r] = True
+    return tags, pop
+
+
 def query(blocks, key_types, filters, groups, aggs, op_hist=False, log_hist=False, time_col=None, time_bucket=0,
-          hist_bucket=0):
-    """blocks: list of sybil_b200.blocks.SavedBlock.  filters: (slot, 'int'|'str', op, value);
-    groups: slots; aggs: (slot, info_min, info_max).  Returns (results, time_results, cumulative, matched, broken)."""
+          hist_bucket=0, weight_col=None, str_replace=None):
+    """blocks: list of sybil_b200.blocks.SavedBlock.  filters: (slot, 'int'|'str'|'set', op, value);
+    groups: slots; aggs: (slot, info_min, info_max); weight_col: slot (OPTS.WEIGHT_COL); str_replace: {slot:
+    (pattern, python replacement template)} — the rewritten strings are what filters and keys see.  A merging rewrite
+    is restated by its INTENT only for literals the rewritten table holds (see DESIGN.md §7 for the reference's id
+    aliasing with other literals).  Returns (results, time_results, cumulative, matched, broken)."""
+    str_replace = str_replace or {}
     master, tmaster = {}, {}
     cumulative = PyResult()
     cumulative.GroupByKey = "TOTAL" + "\t" * max(len(groups) - 1, 0)
     matched_total = broken = 0
-    wanted = set([f[0] for f in filters] + list(groups) + [a[0] for a in aggs] + ([time_col] if time_col is not None else []))
+    wanted = set([f[0] for f in filters] + list(groups) + [a[0] for a in aggs] + ([time_col] if time_col is not None else []) +
+                 ([weight_col] if weight_col is not None else []))
     for blk in blocks:
         n = blk.num_records
         cols, bad = {}, False
@@ -252,15 +281,40 @@ def query(blocks, key_types, filters, groups, aggs, op_hist=False, log_hist=Fals
                         bad = True
             if bad:
                 break
+            if c.col_type == F.SG_COL_SET:
+                sr = _set_rows(c, n)
+                if sr is None:
+                    bad = True
+                    break
+                cols[c.col_slot] = (sr, c)
+                continue
+            if c.col_slot in str_replace:  # re.ReplaceAllString over the block's string table (:529-531)
+                import copy
+                pat, rep = str_replace[c.col_slot]
+                c = copy.copy(c)
+                c.string_table = [re.sub(pat, rep, t.decode()).encode() for t in c.string_table]
             cols[c.col_slot] = (decode_column(c, n), c)
         if bad:
             broken += 1
             continue
         res, tres = {}, {}
         matched = 0
+        weight = 1  # declared outside the row loop: a row without the weight column reuses the last one (Q13)
         for r in range(n):
+            if weight_col is not None and weight_col in cols and cols[weight_col][0][1][r]:
+                weight = int(cols[weight_col][0][0][r])
             ok = True
             for slot, kind, op, val in filters:
+                if kind == "set":  # SetFilter, filter.go:252-285
+                    if slot not in cols or not cols[slot][0][1][r]:
+                        ok = False
+                        break
+                    lit = val if isinstance(val, bytes) else val.encode()
+                    has = lit in cols[slot][0][0][r]
+                    ok = has if op == "in" else not has
+                    if not ok:
+                        break
+                    continue
                 if slot not in cols or not cols[slot][0][1][r]:
                     ok = False
                     break
@@ -301,19 +355,19 @@ def query(blocks, key_types, filters, groups, aggs, op_hist=False, log_hist=Fals
                     continue
                 big = res.setdefault(skey, PyResult())
                 big.GroupByKey = skey
-                big.Count += 1
+                big.Count += weight
                 big.Samples += 1
                 tv = int(cols[time_col][0][0][r])
                 target = tres.setdefault(_tdiv(tv, time_bucket) * time_bucket, {})
             rec = target.setdefault(skey, PyResult())
             rec.GroupByKey = skey
-            rec.Count += 1
+            rec.Count += weight
             rec.Samples += 1
             for ai, (slot, mn, mx) in enumerate(aggs):
                 if slot in cols and cols[slot][0][1][r] and key_types[slot] == F.SG_COL_INT:
                     if ai not in rec.Hists:
                         rec.Hists[ai] = PyMultiHist(mn, mx, op_hist) if log_hist else PyBasicHist(mn, mx, op_hist, hist_bucket)
-                    rec.Hists[ai].add(int(cols[slot][0][0][r]))
+                    rec.Hists[ai].add(int(cols[slot][0][0][r]), weight, weight_col is not None)
         matched_total += matched
         for k, r in res.items():
             if k not in master:

@@ -10,11 +10,16 @@ from tests.util import INT, STR, Q, Spec, random_spec, run_oracle
 def py_query(spec, q):
     filters = [(spec.KeyTable[c], "int", op, v) for c, op, v in q.int_filters]
     filters += [(spec.KeyTable[c], "str", op, v) for c, op, v in q.str_filters]
+    filters += [(spec.KeyTable[c], "set", op, v) for c, op, v in q.set_filters]
     aggs = [(spec.KeyTable[a],) + tuple(spec.IntInfo.get(a, (0, 0))) for a in q.aggs]
+    import re as _re
+    # Go's $1 template as Python's \g<1>
+    repl = {spec.KeyTable[c]: (p, _re.sub(r"\$(\d+)", r"\\g<\1>", r)) for c, (p, r) in q.str_replace.items()}
     return pyoracle.query(spec.blocks, spec.KeyTypes, filters, [spec.KeyTable[g] for g in q.groups], aggs,
                           op_hist=q.op == "hist", log_hist=q.loghist,
                           time_col=spec.KeyTable[q.time_col] if q.time_col else None, time_bucket=q.time_bucket,
-                          hist_bucket=q.hist_bucket)
+                          hist_bucket=q.hist_bucket, weight_col=spec.KeyTable[q.weight_col] if q.weight_col else None,
+                          str_replace=repl)
 
 
 def check(spec, q):
@@ -95,3 +100,35 @@ def test_no_groups_is_total_key():
     o = run_oracle(s, Q(s, aggs=["age"], op="hist"))
     assert list(o.Results) == ["total"]
     check(s, Q(s, aggs=["age"], op="hist"))
+
+
+def test_set_filters_in_both_restatements():
+    s = random_spec(8, nrows=1200, block_rows=400, sets=True)
+    for op, tag in (("in", "t3"), ("nin", "t3"), ("nin", "nope"), ("in", "nope")):
+        check(s, Q(s, set_filters=[("tags", op, tag)], groups=["host"], aggs=["lat"], op="hist"))
+    check(s, Q(s, int_filters=[("age", "gt", 12)], set_filters=[("tags", "in", "t1"), ("tags", "nin", "t2")],
+               groups=["state"], aggs=["lat"], op="avg"))
+
+
+def test_weights_with_carry_over_in_both_restatements():
+    # OPTS.WEIGHT_COL incl. the carry-over of Q13 (rows without the weight column), Count / Samples / weighted
+    # histograms, the float running mean bit for bit
+    import numpy as np
+    rng = np.random.default_rng(9)
+    n = 1500
+    s = Spec([("lat", INT), ("host", STR), ("time", INT), ("w", INT)])
+    s.add_rows({"lat": rng.integers(30, 9000, n), "host": np.array(["h%d" % x for x in rng.integers(0, 4, n)]),
+                "time": 1500000000 + np.sort(rng.integers(0, 3600, n)), "w": rng.choice(np.asarray([1, 2, 5, 10]), n)},
+               {"w": rng.random(n) > 0.15, "lat": rng.random(n) > 0.05}, block_rows=500)
+    check(s, Q(s, groups=["host"], aggs=["lat"], op="hist", weight_col="w"))
+    check(s, Q(s, groups=["host"], aggs=["lat"], op="avg", weight_col="w"))
+    check(s, Q(s, groups=["host"], aggs=["lat"], op="hist", loghist=True, weight_col="w"))
+    check(s, Q(s, aggs=["lat"], op="hist", weight_col="w", time_col="time", time_bucket=600))
+
+
+def test_str_replace_in_both_restatements():
+    s = random_spec(10, nrows=1200, block_rows=400)
+    rep = {"state": (r"^s(\d)\d*$", "S$1")}
+    check(s, Q(s, groups=["state"], aggs=["lat"], op="hist", str_replace=rep))
+    check(s, Q(s, str_filters=[("state", "eq", "S1")], groups=["state", "host"], aggs=["lat"], op="avg", str_replace=rep))
+    check(s, Q(s, str_filters=[("state", "neq", "S1")], groups=["state"], aggs=["lat"], op="avg", str_replace=rep))
