@@ -73,12 +73,15 @@ def update_int_info(table, name, val, skip_outliers=True):
 
 
 def digest(rows, key_table, time_col=None, valid=None, table_info=None, threshold=CARDINALITY_THRESHOLD,
-           chunk_size=CHUNK_SIZE, skip_outliers=True, first_block_index=0, ingest_info=True):
+           chunk_size=CHUNK_SIZE, skip_outliers=True, first_block_index=0, ingest_info=True, partial=None):
     """rows: {column: values in ingestion order}; valid: {column: bool mask} (a row lacking a column).
     Returns (blocks, table_info): SavedBlocks whose `info` is the block's IntInfoMap (Min, Max), and the table's
     IntInfo (dict name -> IntInfo) after AddIntField (per row, ingestion order; `ingest_info`) and the save-time
     updates.  time_col: the column Record.Timestamp is read from (OPTS.TIME_COL); None leaves the order alone
-    (every Timestamp 0: the stable sort is the identity)."""
+    (every Timestamp 0: the stable sort is the identity).
+    partial: (rows, valid) of the table's last, short block (FillPartialBlock, table_block_io.go:48-110): its rows
+    stay in front, in the order they were stored, the time-sorted new rows fill it up to chunk_size and the rest goes
+    on in new blocks; the first returned block then REPLACES that block (give its index as first_block_index)."""
     slot = {n: i for i, (n, _) in enumerate(key_table)}
     typ = {n: t for n, t in key_table}
     valid = dict(valid or {})
@@ -98,6 +101,23 @@ def digest(rows, key_table, time_col=None, valid=None, table_info=None, threshol
         if time_col in valid:
             ts = np.where(np.asarray(valid[time_col], bool), ts, 0)  # a record without the column keeps Timestamp 0
         order = np.argsort(ts, kind="stable")
+    if partial is not None:
+        prow, pvalid = partial
+        pn = len(next(iter(prow.values()))) if prow else 0
+        if pn >= chunk_size:
+            pn, prow = 0, {}
+        # one row space: the partial block's rows first (indices 0..pn-1), then the new rows shifted by pn
+        rows = {k: (list(prow.get(k, [None] * pn)) + list(v)) if typ[k] == F.SG_COL_SET
+                else np.concatenate([np.asarray(prow[k]) if k in prow else np.zeros(pn, np.asarray(v).dtype), np.asarray(v)])
+                for k, v in rows.items()}
+        merged_valid = {}
+        for k in rows:
+            a = np.asarray((pvalid or {}).get(k, np.ones(pn, bool) if k in prow else np.zeros(pn, bool)), bool)
+            b = np.asarray(valid.get(k, np.ones(n, bool)), bool)
+            merged_valid[k] = np.concatenate([a, b])
+        valid = merged_valid
+        order = np.concatenate([np.arange(pn), order + pn])
+        n += pn
     blocks = []
     for start in range(0, n, chunk_size):
         idx = order[start:start + chunk_size]

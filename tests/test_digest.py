@@ -77,3 +77,21 @@ def test_digest_sorts_by_time_chunks_and_queries_like_the_unsorted_rows(tmp_path
     cut = int(np.sort(rows["time"])[1200])
     o = run_oracle(digested, Q(digested, int_filters=[("time", "gt", cut)]))
     assert o.SkippedBlocks >= 1 and o.MatchedCount == int((rows["time"] > cut).sum())
+
+
+def test_fill_partial_block_keeps_old_rows_in_front():
+    # FillPartialBlock (table_block_io.go:48-110): the last short block is topped up with the first of the sorted new
+    # rows; what does not fit goes on in new blocks
+    kt = [("time", INT), ("v", INT)]
+    old = {"time": np.array([50, 40, 60]), "v": np.array([1, 2, 3])}            # stored order of the short block
+    new = {"time": np.array([30, 10, 20, 70, 5]), "v": np.array([10, 11, 12, 13, 14])}
+    blocks, info = D.digest(new, kt, time_col="time", chunk_size=5, partial=(old, None), first_block_index=7)
+    assert [b.block_index for b in blocks] == [7, 8] and [b.num_records for b in blocks] == [5, 3]
+    from sybil_b200.blocks import decode_column
+    tcol = [c for c in blocks[0].cols if c.col_slot == 0][0]
+    t0, pop = decode_column(tcol, 5)
+    assert list(t0) == [50, 40, 60, 5, 10] and pop.all()      # old rows first, then the two earliest new rows
+    t1, _ = decode_column([c for c in blocks[1].cols if c.col_slot == 0][0], 3)
+    assert list(t1) == [20, 30, 70]
+    v1, _ = decode_column([c for c in blocks[1].cols if c.col_slot == 1][0], 3)
+    assert list(v1) == [12, 10, 13]
