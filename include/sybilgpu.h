@@ -30,7 +30,9 @@ extern "C" {
 #define SG_ABI_VERSION 4 /* 2: order_by_agg / order_asc / limit in sg_query_desc; 3: narrow arrays (id_bits / value_bits); \
                             4: set columns + SetFilter (SG_COL_SET, SG_OP_IN / SG_OP_NIN), sg_query_set_str_replace */
 
-/* limits of one query (reference has none; beyond these -> SG_ERR_UNSUPPORTED) */
+/* limits of one query (reference has none; beyond these -> SG_ERR_UNSUPPORTED).  Group keys: the product of the
+ * group columns' distinct-value counts (x time buckets) may reach 2^31; up to 2^26 it is a dense array, beyond that
+ * a hash table on the device keyed by the combined code (single GPU; at most 2^25 distinct groups per query). */
 #define SG_MAX_FILTERS 15
 #define SG_MAX_GROUPS 8
 #define SG_MAX_AGGS 16

@@ -183,7 +183,21 @@ struct LaunchParams {
   unsigned long long* dbg;    // optional [grid][16] cycle counters per phase (SG_PHASE_TIMING=1)
   uint32_t fold_every;        // blocks whose shared accumulators may be folded together (>= 1)
   uint32_t hashg;             // a group column is a value-array int column (hash lookup path; slot_bytes == 4)
+  // Hashed slot space (group-by products beyond the dense 2^26 slots): after the group / time passes a row's
+  // mixed-radix code (< 2^31) is looked up / inserted in this open-addressing table (key = code + 1, 0 = empty) and the
+  // slot word's group bits are replaced by the table index, which is what the accumulators are indexed by
+  // (plan.nslots == hmask + 1).  nullptr: the slot space is dense.  scalars[4] counts rows that found the table full.
+  uint32_t* hkeys;
+  uint32_t hmask;
 };
+__host__ __device__ static inline uint32_t slot_hash(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
 
 // the hash both sides of the value -> code table use
 __host__ __device__ static inline uint32_t vh_hash(long long v) {

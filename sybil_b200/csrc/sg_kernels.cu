@@ -1937,6 +1937,32 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) scan_kernel(const Launch
     __syncthreads();
     if (time_col >= 0) pass_mark(pass_no++);
 
+    // ---- hashed slot space (LaunchParams::hkeys): code -> index of an open-addressing table in global memory.
+    // Only rows that passed every filter (and carry a time code in time mode) take a slot.  The reference keys a Go
+    // map with the row's key bytes (aggregate.go:186-203); this is that map, shared by all blocks.
+    if (sizeof(SlotT) == 4 && lp.hkeys != nullptr) {
+      uint32_t* const hk = lp.hkeys;
+      const uint32_t hmask = lp.hmask;
+      for (uint32_t r = cx.tid; r < nrec; r += THREADS) {
+        const uint32_t s = (uint32_t)slot[r];
+        if ((s >> gbits) != pass_target) continue;
+        const uint32_t key = (s & gmask) + 1u;
+        uint32_t idx = slot_hash(key) & hmask, probes = 0;
+        for (;;) {
+          const uint32_t old = atomicCAS(hk + idx, 0u, key);
+          if (old == 0u || old == key) break;
+          idx = (idx + 1u) & hmask;
+          if (++probes > hmask) {  // table full: the host fails the query (scalars[4])
+            gred_add(g_scalars + 4, 1ull);
+            idx = 0u;
+            break;
+          }
+        }
+        slot[r] = (SlotT)((s & ~gmask) | idx);
+      }
+      __syncthreads();
+    }
+
     phase(3);
     // ---- Count / Samples (aggregate.go:202-203), MatchedCount (:117), aggregations
     // (:246-261).  The count is taken inside the first aggregation pass when that column

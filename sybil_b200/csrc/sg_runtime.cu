@@ -98,6 +98,7 @@ struct Variant {
 static const Variant V16 = {"w16", 16, w16::scan_ctas_per_sm(), w16::scan_max_smem(), w16::scan_fixed_smem, w16::launch_scan};
 static const Variant V8 = {"w8", 8, w8::scan_ctas_per_sm(), w8::scan_max_smem(), w8::scan_fixed_smem, w8::launch_scan};
 constexpr int64_t MAX_SLOTS = (int64_t)1 << 26;
+constexpr uint64_t MAX_CODE_SPACE = ((uint64_t)1 << 31) - 2;  // codes of a hashed slot space (key = code + 1 in 32 bits)
 constexpr int64_t INT_DICT_CAP = (int64_t)1 << 22;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
@@ -1280,6 +1281,12 @@ struct sg_query {
   // accumulators are laid out by (per entry of dims; empty for the time axis)
   bool merged = false;
   bool hashg = false;  // a group column goes through the value -> code hash table
+  // hashed slot space: the product of the group axes exceeds the dense slot space; accumulators are indexed by
+  // the index of the row's mixed-radix code in an open-addressing table on the device (LaunchParams::hkeys)
+  bool hashed = false;
+  uint64_t code_space = 0;  // product of the axes' radices
+  uint32_t* d_hkeys = nullptr;
+  std::vector<uint32_t> h_hkeys;  // read back for the result: slot -> code + 1 (0: empty)
   // accumulators as read back right behind the kernel (small plans): spares build_result a blocking copy
   std::vector<uint64_t> h_acc;
   bool h_acc_valid = false;
@@ -1320,6 +1327,8 @@ void free_device(sg_query* q) {
   q->d_item_mask = nullptr;
   pool_release(c, q->d_work);
   pool_release(c, q->d_gslots);
+  pool_release(c, q->d_hkeys);
+  q->d_hkeys = nullptr;
   pool_release(c, q->d_gbinpay);
   pool_release(c, q->d_gdummy);
   for (auto p : q->d_luts) pool_release(c, p);
@@ -1631,8 +1640,8 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     gd.radix = (uint32_t)(card + 1);
     gd.stride = (uint32_t)stride;
     stride *= gd.radix;
-    if (stride > (uint64_t)MAX_SLOTS) {
-      c->set_err("query: group-by cardinality product exceeds the dense slot space");
+    if (stride > MAX_CODE_SPACE) {
+      c->set_err("query: group-by cardinality product exceeds 2^31 (the hashed slot space keys 31-bit codes)");
       return SG_ERR_UNSUPPORTED;
     }
     q->dims.push_back(gd);
@@ -1661,8 +1670,8 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     P.time_bucket = q->d.time_bucket;
     P.time_first = tmin / P.time_bucket;
     int64_t nb = tmax / P.time_bucket - P.time_first + 1;
-    if (nb <= 0 || (uint64_t)nb * stride > (uint64_t)MAX_SLOTS) {
-      c->set_err("query: time axis too large for the dense slot space");
+    if (nb <= 0 || nb > (int64_t)MAX_SLOTS || (uint64_t)nb * stride > MAX_CODE_SPACE) {
+      c->set_err("query: time axis too large for the slot space");
       return SG_ERR_UNSUPPORTED;
     }
     P.time_radix = (uint32_t)nb + 1;
@@ -1676,6 +1685,21 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     stride *= P.time_radix;
   }
   P.nslots = (uint32_t)stride;
+  // ---- hashed slot space: more codes than dense slots.  The table gets twice as many entries as rows can make
+  // groups (every scanned row its own group at worst), within [2^16, 2^26]; a table that fills up fails the query.
+  q->code_space = stride;
+  q->hashed = stride > (uint64_t)MAX_SLOTS && !getenv("SG_NO_HASHED_SLOTS");
+  if (stride > (uint64_t)MAX_SLOTS && !q->hashed) {
+    c->set_err("query: group-by cardinality product exceeds the dense slot space");
+    return SG_ERR_UNSUPPORTED;
+  }
+  if (q->hashed) {
+    uint64_t rows = 0;
+    for (uint32_t b : list) rows += t->blocks[b].num_records;
+    uint64_t cap = (uint64_t)1 << 16;
+    while (cap < 2 * std::min<uint64_t>(rows, stride) && cap < (uint64_t)MAX_SLOTS) cap <<= 1;
+    P.nslots = (uint32_t)cap;
+  }
   // ---- fail mode: every filter column populates every row of every listed block (value array, or a
   // bucket column whose bins were checked to list each row once) -> one sticky FAIL bit instead of a
   // pass count, and bucket filters walk the failing bins only
@@ -1730,7 +1754,11 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
     P.lslots = time_mode ? group_slots * (win + 1u) : P.nslots;
     P.gbits = bits_for(P.lslots);
   };
-  window_for(true);
+  window_for(!q->hashed);
+  if (q->hashed) {  // the slot word carries the whole code; the accumulators are indexed by the table index
+    P.lslots = P.nslots;
+    P.gbits = bits_for(q->code_space);
+  }
   P.time_magic = 0;
   if (time_mode && P.time_bucket >= 2 && P.time_bucket < 0x100000000ll)
     P.time_magic = (uint64_t)(((unsigned __int128)1 << 64) / (unsigned __int128)P.time_bucket) + 1u;
@@ -1762,7 +1790,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
       return SG_ERR_UNSUPPORTED;
     }
     q->slot_bytes = total_bits <= 8 ? 1u : (total_bits <= 16 ? 2u : 4u);
-    if (q->hashg) q->slot_bytes = 4;  // the hashed group pass exists for 32-bit slot words + global accumulators only
+    if (q->hashg || q->hashed) q->slot_bytes = 4;  // these passes exist for 32-bit slot words + global accumulators only
     P.finc = 1u << P.gbits;
     P.filt_mask = (uint32_t)(((uint64_t)1 << fbits) - 1u);
     P.filt_target = fail_mode ? 0u : (ncount | (sticky_target << cbits));
@@ -1946,7 +1974,7 @@ int make_plan(sg_query* q, const std::vector<uint32_t>& list) {
   for (int attempt = 0; attempt < 2; attempt++) {
     slots_b = q->slot_bytes < 4 ? SG_BLOCK_ROWS * q->slot_bytes : 0u;
     nstage = pick_units();
-    repl = q->hashg ? 0u : repl_for(nstage);
+    repl = (q->hashg || q->hashed) ? 0u : repl_for(nstage);
     if (repl == 0 && time_mode && P.lslots != P.nslots) {
       // accumulators in global memory: no slot window (the kernel's global paths index whole-axis slots)
       window_for(false);
@@ -2030,6 +2058,9 @@ int alloc_device(sg_query* q) {
   if (!q->d_gdummy) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gdummy, grid_cap * 32 * 8));
   if (q->slot_bytes == 4 && !q->d_gslots)
     CUDA_TRY(c, pool_alloc(c, (void**)&q->d_gslots, grid_cap * SG_BLOCK_ROWS * 4));
+  pool_release(c, q->d_hkeys);
+  q->d_hkeys = nullptr;
+  if (q->hashed) CUDA_TRY(c, pool_alloc(c, (void**)&q->d_hkeys, (size_t)q->plan.nslots * 4));
   if (!q->ev0) {
     CUDA_TRY(c, cudaEventCreate(&q->ev0));
     CUDA_TRY(c, cudaEventCreate(&q->ev1));
@@ -2158,6 +2189,7 @@ __global__ void fill_i64(int64_t* p, size_t n, int64_t v) {
 int reset_accumulators(sg_query* q) {
   sg_ctx* c = q->ctx;
   CUDA_TRY(c, cudaMemsetAsync(q->d_acc, 0, q->sum_words * 8, c->stream));
+  if (q->hashed && q->d_hkeys) CUDA_TRY(c, cudaMemsetAsync(q->d_hkeys, 0, (size_t)q->plan.nslots * 4, c->stream));
   if (q->acc_words > q->sum_words) {
     size_t n = q->acc_words - q->sum_words;
     fill_i64<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int64_t*)(q->d_acc + q->sum_words), n, INT64_MIN);
@@ -2241,6 +2273,8 @@ int run_list(sg_query* q, const std::vector<uint32_t>& list) {
   lp.stage_units = t->d_tmaps ? q->nstage : 0u;
   lp.dbg = nullptr;
   lp.hashg = q->hashg ? 1u : 0u;
+  lp.hkeys = q->hashed ? q->d_hkeys : nullptr;
+  lp.hmask = q->hashed ? q->plan.nslots - 1u : 0u;
   // Deferred fold: the replicated 32-bit accumulators of up to fold_every consecutive blocks are
   // folded together.  Needs one encoding per aggregation column across the listed blocks (word0
   // counts accepted rows for bucket columns, rejected ones for value arrays) and keeps the hot
@@ -2459,13 +2493,19 @@ static const std::vector<uint32_t>& axis_ranks(sg_query* q, size_t di, std::vect
   return cache;
 }
 
+// the mixed-radix code of accumulator slot s: the slot itself in a dense slot space, the table's key otherwise
+static inline uint32_t slot_code(const sg_query* q, uint32_t s) {
+  if (!q->hashed) return s;
+  return s < q->h_hkeys.size() && q->h_hkeys[s] ? q->h_hkeys[s] - 1u : 0u;
+}
 // one group's ResultGroup from the accumulators of dense slot s (h: words [0, have))
 // key words and rendered key of dense slot s
 static void group_key(const sg_query* q, uint32_t s, ResultGroup& g, int64_t* tbucket) {
   const Plan& P = q->plan;
+  const uint32_t cs = slot_code(q, s);
   for (size_t di = 0; di < q->dims.size(); di++) {
     const GroupDim& d = q->dims[di];
-    uint32_t code = (s / d.stride) % d.radix;
+    uint32_t code = (cs / d.stride) % d.radix;
     if (d.is_time) {
       if (tbucket) *tbucket = (P.time_first + (int64_t)code - 1) * P.time_bucket;
       continue;
@@ -2534,6 +2574,7 @@ static int build_result_topk(sg_query* q, sg_result** out) {
   const int64_t limit = q->d.limit;
   if (P.time_col >= 0 || P.hist_mode || q->d.hist_kind == SG_HIST_MULTI) return 1;
   if (!q->repl.empty() || q->d.weight_col_slot >= 0) return 1;  // StrReplace / weights fold slots on the host first
+  if (q->hashed) return 1;                                       // keys come from the table read-back (build_result)
   if (limit <= 0 || limit > 65536 || ob == SG_ORDER_NONE || q->d.order_asc) return 1;
   if (P.nslots < (1u << 17) || q->h_acc_valid || q->h_pin_valid || getenv("SG_NO_GPU_TOPK")) return 1;
   const unsigned cap = (unsigned)limit + 8192u;
@@ -2818,6 +2859,20 @@ int build_result(sg_query* q, sg_result** out) {
     q->d2h_bytes += (int64_t)have * 8;
     h = (const uint64_t*)r->pin;
   }
+  if (q->hashed) {
+    if (h[4] != 0) {
+      c->set_err("query: the hashed slot space filled up (more distinct group keys than its table holds)");
+      return SG_ERR_UNSUPPORTED;
+    }
+    if (!q->repl.empty() || q->d.weight_col_slot >= 0) {
+      c->set_err("query: StrReplace / weights over a hashed slot space are not in this build");
+      return SG_ERR_UNSUPPORTED;
+    }
+    q->h_hkeys.resize(P.nslots);
+    CUDA_TRY(c, cudaMemcpyAsync(q->h_hkeys.data(), q->d_hkeys, (size_t)P.nslots * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    q->d2h_bytes += (int64_t)P.nslots * 4;
+  }
   int64_t w_rows = -1;  // weighted queries: matched ROWS (MatchedCount counts records, aggregate.go:117)
   if (!q->repl.empty() || q->d.weight_col_slot >= 0) {
     if (q->merged && !q->repl.empty()) {
@@ -2855,9 +2910,10 @@ int build_result(sg_query* q, sg_result** out) {
       for (size_t di = 0; di < q->dims.size(); di++) ranks[di] = &axis_ranks(q, di, scratch[di]);
     auto tie_of = [&](uint32_t s) {
       uint64_t tie = 0;
+      const uint32_t cs = slot_code(q, s);
       for (size_t di = 0; di < q->dims.size(); di++) {
         const GroupDim& d = q->dims[di];
-        const uint32_t code = (s / d.stride) % d.radix;
+        const uint32_t code = (cs / d.stride) % d.radix;
         tie = tie * d.radix + (code ? (uint64_t)(*ranks[di])[code - 1] + 1u : 0u);
       }
       return tie;
@@ -3536,6 +3592,10 @@ int sg_query_allreduce(sg_query* q) {
   sg_ctx* c = q->ctx;
   if (!c->comm || c->nranks <= 1) return SG_OK;
   cudaSetDevice(c->device);
+  if (q->hashed) {
+    c->set_err("allreduce: a hashed slot space (group-by product beyond 2^26) is merged on one GPU only in this build");
+    return SG_ERR_UNSUPPORTED;
+  }
   q->h_acc_valid = false;  // the device copy is about to change
   q->h_pin_valid = false;
   // Small plans (the usual case: a few hundred groups): ONE collective.  Every rank writes a header

@@ -888,3 +888,35 @@ def test_weighted_query_refuses_rows_without_a_weight():
     with pytest.raises(E.SybilGpuError) as e:
         run_gpu(s, Q(s, aggs=["lat"], weight_col="w"))
     assert e.value.status == F.SG_ERR_UNSUPPORTED
+
+
+def test_hashed_slot_space_for_group_by_products_beyond_the_dense_space():
+    # two group columns of 9,000 distinct strings each: 81M codes > 2^26 dense slots.  The scan keys an open-addressing
+    # table on the device with the row's mixed-radix code (the reference's Go map over the key bytes,
+    # aggregate.go:186-203) and the accumulators are indexed by the table index.
+    rng = np.random.default_rng(61)
+    n = 30000
+    s = Spec([("a", STR), ("b", STR), ("v", INT), ("f", INT), ("time", INT)])
+    s.add_rows({"a": np.array(["a%d" % x for x in rng.integers(0, 9000, n)]),
+                "b": np.array(["b%d" % x for x in rng.integers(0, 9000, n)]),
+                "v": rng.integers(0, 100000, n), "f": rng.integers(0, 100, n),
+                "time": 1500000000 + np.sort(rng.integers(0, 3600, n))},
+               {"a": rng.random(n) > 0.05, "v": rng.random(n) > 0.05}, block_rows=10000)
+    # (8,648 and 8,713 of the 9,000 strings are drawn: with the missing-value code and "" that is 75.4M codes)
+    g, o = both(s, Q(s, groups=["a", "b"], aggs=["v"], op="avg"))
+    assert g.NumGroups > 25000
+    both(s, Q(s, int_filters=[("f", "lt", 50)], str_filters=[("a", "neq", "a7")], groups=["a", "b"], aggs=["v", "f"], op="avg",
+              order_by="v", limit=20))
+    both(s, Q(s, groups=["b", "a"], aggs=["v"], op="avg", time_col="time", time_bucket=1800))
+
+
+def test_hashed_slot_space_with_histograms():
+    rng = np.random.default_rng(62)
+    n = 12000
+    s = Spec([("a", STR), ("b", STR), ("c", INT), ("v", INT)])
+    s.add_rows({"a": np.array(["a%d" % x for x in rng.integers(0, 8300, n)]),
+                "b": np.array(["b%d" % x for x in rng.integers(0, 8300, n)]),
+                "c": rng.integers(0, 4, n), "v": rng.integers(0, 5000, n)}, block_rows=6000)
+    # ~6,300 x 6,300 x 5 codes: three axes, one of them a bucket-encoded int column
+    g, o = both(s, Q(s, groups=["a", "c", "b"], aggs=["v"], op="hist", limit=50))
+    assert g.NumGroups > 11000
