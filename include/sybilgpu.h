@@ -128,7 +128,10 @@ typedef struct sg_query_desc {
   int64_t time_bucket;     /* QuerySpec.TimeBucket, 0 = no time series */
   int64_t time_min;        /* table IntInfo of the time column: bounds the */
   int64_t time_max;        /*   dense time-bucket axis (rows outside are counted in overflow) */
-  int32_t weight_col_slot; /* OPTS.WEIGHT_COL_ID, -1 = unweighted (v1 rejects others) */
+  int32_t weight_col_slot; /* OPTS.WEIGHT_COL_ID, -1 = unweighted.  Count / hist Count / bucket counters / sums are
+                            * weighted, Samples and MatchedCount count rows (aggregate.go:100-102,202-203).  A scanned
+                            * row WITHOUT the column fails the query at sg_query_finish (SG_ERR_UNSUPPORTED): the
+                            * reference reuses the previous row's weight there */
   /* SortResults (aggregate.go:43-54,497-525): QuerySpec.OrderBy = "$COUNT" (SG_ORDER_COUNT), the name of an
    * aggregation (its index: groups ordered by Hists[col].Mean(), descending) or "" (SG_ORDER_NONE: no sort,
    * groups come in slot order); OrderAsc reverses the sorted list.  Ties (Go's sort is unstable): GroupByKey
