@@ -181,3 +181,30 @@ def test_multihist_results_travel_as_multihistcompat():
     for k, r in o.Results.items():
         kind, h = merged["Results"][k]["Hists"]["lat"]
         assert kind == "basic" and h.Count == 2 * r.Hists["lat"].Count == sum(h.Values)
+
+
+def test_stitch_merges_time_results_per_bucket():
+    from sybil_b200 import stitch
+    rng = np.random.default_rng(12)
+    n = 3000
+    rows = {"lat": rng.integers(30, 3000, n), "host": np.array(["h%d" % x for x in rng.integers(0, 3, n)]),
+            "time": 1500000000 + np.sort(rng.integers(0, 3600, n))}
+    kt = [("lat", INT), ("host", STR), ("time", INT)]
+    whole, a, b = Spec(kt), Spec(kt), Spec(kt)
+    whole.add_rows(rows, block_rows=1000)
+    a.add_rows({k: v[::2] for k, v in rows.items()}, block_rows=1000)   # every other row: both nodes see every bucket
+    b.add_rows({k: v[1::2] for k, v in rows.items()}, block_rows=1000)
+    for sp in (a, b):
+        sp.IntInfo = dict(whole.IntInfo)
+    mk = lambda sp: Q(sp, groups=["host"], aggs=["lat"], op="hist", time_col="time", time_bucket=900)
+    info = {"lat": whole.IntInfo["lat"]}
+    streams = [NR.encode_node_results(run_oracle(sp, mk(sp)), "t", ["host"], ["lat"], info, time_bucket=900) for sp in (a, b)]
+    merged = stitch.combine_node_results(streams)
+    want = run_oracle(whole, mk(whole))
+    assert set(merged["TimeResults"]) == set(want.TimeResults) and len(want.TimeResults) == 4
+    for tb, m in want.TimeResults.items():
+        for k, r in m.items():
+            g = merged["TimeResults"][tb][k]
+            assert g["Count"] == r.Count
+            assert g["Hists"]["lat"][1].Values == [int(v) for v in r.Hists["lat"].Values]
+    assert {k: g["Count"] for k, g in merged["Results"].items()} == {k: r.Count for k, r in want.Results.items()}
