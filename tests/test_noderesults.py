@@ -201,7 +201,7 @@ def test_stitch_merges_time_results_per_bucket():
     streams = [NR.encode_node_results(run_oracle(sp, mk(sp)), "t", ["host"], ["lat"], info, time_bucket=900) for sp in (a, b)]
     merged = stitch.combine_node_results(streams)
     want = run_oracle(whole, mk(whole))
-    assert set(merged["TimeResults"]) == set(want.TimeResults) and len(want.TimeResults) == 4
+    assert set(merged["TimeResults"]) == set(want.TimeResults) and len(want.TimeResults) == 5
     for tb, m in want.TimeResults.items():
         for k, r in m.items():
             g = merged["TimeResults"][tb][k]
